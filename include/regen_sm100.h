@@ -1,0 +1,154 @@
+/*
+ * regen_sm100.h -- C ABI of libregen_sm100.so, the B200 (sm_100a) implementation of the
+ * ReGenNet diffusion-sampling hot path.
+ *
+ * The reference (liangxuy/ReGenNet) is pure Python/PyTorch and has no FFI layer; the drop-in
+ * boundary is its Python API (CMDM.forward, SpacedDiffusion.p_sample_loop / ddim_sample_loop,
+ * ClassifierFreeSampleModel.forward, rotation_6d_to_matrix).  The Python classes in
+ * regennet_b200/ keep those signatures and bind the entry points below with ctypes; each
+ * entry point names the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative REGEN_E* code otherwise; no C++ exception
+ *     crosses the ABI.  regen_last_error() returns a thread-local message for the last failure.
+ *   - all tensor pointers are DEVICE pointers owned by the caller (contiguous, fp32 / int64),
+ *     unless a parameter is documented as host memory.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises the device, everything is CUDA-graph capturable.
+ *   - layouts:  BJFT = [B, J, F, T] (T innermost, the reference's user-facing layout)
+ *               TBI  = [T, B, I=J*F] (token-major, seq-first; the reference's internal
+ *                      layout, model/cmdm.py:312-313, and the memory order of the permuted
+ *                      tensors its sampler carries from step 2 on)
+ */
+#ifndef REGEN_SM100_H
+#define REGEN_SM100_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REGEN_OK 0
+#define REGEN_EINVAL (-1)   /* bad argument */
+#define REGEN_ECUDA (-2)    /* CUDA runtime / driver error */
+#define REGEN_ESTATE (-3)   /* call order violated (e.g. denoise before load_weights) */
+#define REGEN_EUNSUPPORTED (-4)
+
+#define REGEN_MAX_LAYERS 16
+
+/* library / build info: "regen_sm100 <version> sm_100a" */
+const char* regen_version(void);
+const char* regen_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Handle-free elementwise operators (HBM-bound; coalesced, vectorised)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Ancestral posterior update.  Replaces diffusion/gaussian_diffusion.py:265-287
+ * (q_posterior_mean_variance), :366-388 (process_xstart + mean) and :544-559 (p_sample):
+ *     x0c  = clip ? clamp(x0,-1,1) : x0
+ *     out  = coef1[t_b]*x0c + coef2[t_b]*x + (t_b != 0) * exp(0.5*logvar[t_b]) * noise
+ * Tables are fp32 device arrays built on the host in fp64 and then cast, exactly as
+ * _extract_into_tensor does (:1604-1617).  t is int64[B] on the device (indices into the
+ * tables).  Element e belongs to sample b = (e / inner) % B: inner = J*F*T for BJFT,
+ * inner = I for TBI.  pred_xstart (nullable) receives x0c.  noise == NULL gives the posterior
+ * mean only (p_mean_variance's "mean").  out may alias x. */
+int regen_p_sample_update(const float* x, const float* x0, const float* noise, float* out,
+                          float* pred_xstart, const int64_t* t, const float* coef1,
+                          const float* coef2, const float* logvar, int64_t n_elem, int64_t inner,
+                          int32_t B, int32_t clip_denoised, void* stream);
+
+/* DDIM update.  Replaces diffusion/gaussian_diffusion.py:744-794 (ddim_sample) with
+ * :418-423 (_predict_eps_from_xstart):
+ *     eps   = (sqrt_recip_ac[t]*x - x0c) / sqrt_recipm1_ac[t]
+ *     sigma = eta*sqrt((1-ac_prev[t])/(1-ac[t]))*sqrt(1-ac[t]/ac_prev[t])
+ *     out   = x0c*sqrt(ac_prev[t]) + sqrt(1-ac_prev[t]-sigma^2)*eps + (t!=0)*sigma*noise    */
+int regen_ddim_update(const float* x, const float* x0, const float* noise, float* out,
+                      float* pred_xstart, const int64_t* t, const float* sqrt_recip_ac,
+                      const float* sqrt_recipm1_ac, const float* ac, const float* ac_prev,
+                      float eta, int64_t n_elem, int64_t inner, int32_t B, int32_t clip_denoised,
+                      void* stream);
+
+/* Classifier-free guidance combine.  Replaces model/cfg_sampler.py:31:
+ *     out = uncond + scale[b]*(cond - uncond)                                            */
+int regen_cfg_combine(const float* cond, const float* uncond, const float* scale, float* out,
+                      int64_t n_elem, int64_t inner, int32_t B, void* stream);
+
+/* rot6d -> rotation matrix (Gram-Schmidt).  Replaces utils/rotation_conversions.py:513-534.
+ * d6 [n,6] contiguous -> R [n,3,3] contiguous, rows (b1,b2,b3).                         */
+int regen_rot6d_to_matrix(const float* d6, float* R, int64_t n, void* stream);
+
+/* Layout conversion between the user-facing BJFT and the internal TBI layout.  Replaces the
+ * permute/reshape of model/cmdm.py:312-313 (InputProcess) and :353-354 (OutputProcess). */
+int regen_bjft_to_tbi(const float* src, float* dst, int32_t B, int32_t I, int32_t T, void* stream);
+int regen_tbi_to_bjft(const float* src, float* dst, int32_t B, int32_t I, int32_t T, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The denoiser: CMDM.forward, arch='online'  (model/cmdm.py:173-252)
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct regen_handle regen_handle;
+
+typedef struct {
+  int32_t latent_dim;      /* D, must be 512 */
+  int32_t num_heads;       /* H, must be 4 (head_dim 128) */
+  int32_t ff_size;         /* F, must be 1024 */
+  int32_t num_layers;      /* <= REGEN_MAX_LAYERS */
+  int32_t input_feats;     /* I = njoints*nfeats */
+  int32_t cm_mode;         /* 0 = 'add', 1 = 'concat' (model/cmdm.py:207-211) */
+  int32_t max_batch;       /* largest effective batch (2x the user batch under CFG) */
+  int32_t max_frames;      /* largest T */
+  int32_t num_table_steps; /* size of the timestep-embedding table; timesteps must be < this */
+  int32_t precision;       /* 0 = bf16x3 split (parity mode), 1 = single-pass bf16 (fast) */
+} regen_model_desc;
+
+typedef struct {
+  const float *qkv_w, *qkv_b;   /* self_attn.in_proj_{weight[3D,D],bias[3D]} */
+  const float *o_w, *o_b;       /* self_attn.out_proj */
+  const float *xv_w, *xv_b;     /* multihead_attn.in_proj_weight[2D:3D], in_proj_bias[2D:3D] */
+  const float *xo_w, *xo_b;     /* multihead_attn.out_proj */
+  const float *l1_w, *l1_b;     /* linear1 [F,D] */
+  const float *l2_w, *l2_b;     /* linear2 [D,F] */
+  const float *n1_w, *n1_b, *n2_w, *n2_b, *n3_w, *n3_b; /* norm1..3 */
+} regen_layer_weights;
+
+typedef struct {
+  const float *in_w, *in_b;     /* input_process.poseEmbedding [D,I] */
+  const float *cmo_w, *cmo_b;   /* cmo_process.poseEmbedding [D,I] */
+  const float *fuse_w, *fuse_b; /* fuse_process [D,2D]; NULL for cm_mode 'add' */
+  const float *t0_w, *t0_b;     /* embed_timestep.time_embed.0 */
+  const float *t2_w, *t2_b;     /* embed_timestep.time_embed.2 */
+  const float *pe;              /* sequence_pos_encoder.pe [pe_len, D] */
+  int32_t pe_len;
+  const float *out_w, *out_b;   /* output_process.poseFinal [I,D] */
+  regen_layer_weights layers[REGEN_MAX_LAYERS];
+} regen_weight_ptrs;
+
+/* Replaces CMDM.__init__ (model/cmdm.py:13-111) for the device-side state. */
+int regen_create(regen_handle** out, int32_t device, const regen_model_desc* desc);
+void regen_destroy(regen_handle* h);
+
+/* Replaces load_state_dict (utils/model_util.py:5-8): packs fp32 weights into the library's own
+ * bf16 hi/lo operand buffers, folds fuse_process into the input projection, folds the 1-token
+ * cross-attention (value+out projection) and builds the timestep-embedding table. */
+int regen_load_weights(regen_handle* h, const regen_weight_ptrs* w, void* stream);
+
+/* Loop-invariant conditioning, once per sampling loop (or per forward in the generic route).
+ * cmotion: actor motion, BJFT [B,J,F,T].  cond_emb: [B,D] action / text embedding already
+ * masked for `uncond` (NULL = zeros).  guidance != 0 doubles the batch internally: rows [0,B)
+ * conditional, rows [B,2B) unconditional (cond_emb treated as zero) -- model/cfg_sampler.py:24-31.
+ * Replaces model/cmdm.py:181-187, :202 (cmo_process) and the cmotion half of :207-211, :218. */
+int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const float* cond_emb,
+                       int32_t B, int32_t T, int32_t guidance, void* stream);
+
+/* CMDM.forward (model/cmdm.py:173-252) after regen_prepare_cond.  x_tbi [T,B,I]; t int64[B] device,
+ * original (un-respaced) timesteps; x0_tbi [T,B,I] (with guidance: the guided combination
+ * uncond + scale[b]*(cond-uncond), scale = cfg_scale[B] device). */
+int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const float* cfg_scale,
+                  float* x0_tbi, int32_t B, int32_t T, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REGEN_SM100_H */

@@ -1,0 +1,66 @@
+// Shared helpers for libregen_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/regen_sm100.h"
+
+namespace regen {
+
+// thread-local last-error text returned by regen_last_error()
+void set_error(const char* fmt, ...);
+
+#define REGEN_CHECK_ARG(cond, ...)            \
+  do {                                        \
+    if (!(cond)) {                            \
+      ::regen::set_error(__VA_ARGS__);        \
+      return REGEN_EINVAL;                    \
+    }                                         \
+  } while (0)
+
+#define REGEN_CUDA(expr)                                                                      \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::regen::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,    \
+                         __LINE__);                                                           \
+      return REGEN_ECUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+#define REGEN_LAUNCH_CHECK()                                                                  \
+  do {                                                                                        \
+    cudaError_t _e = cudaGetLastError();                                                      \
+    if (_e != cudaSuccess) {                                                                  \
+      ::regen::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),          \
+                         __FILE__, __LINE__);                                                 \
+      return REGEN_ECUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// fp32 -> (hi, lo) bf16 pair with hi + lo ~= v to 16 significand bits (bf16x3 operand split)
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace regen

@@ -1,0 +1,364 @@
+// Handle-free elementwise operators of the sampling hot path (HBM-bound).
+//
+// Every kernel here moves each byte exactly once: float4-vectorised, coalesced, grid sized as a
+// multiple of the SM count.  Arithmetic mirrors the reference's fp32 operation order with explicit
+// round-to-nearest intrinsics (no FMA contraction), so the update is bit-comparable with the
+// eager PyTorch sequence it replaces.
+#include "common.cuh"
+
+namespace regen {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kBlocksPerSM = 8;
+
+inline int grid_for(int64_t work_items) {
+  int64_t blocks = ceil_div(work_items, kThreads);
+  int64_t cap = (int64_t)kNumSMs * kBlocksPerSM;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+__device__ __forceinline__ float clampf(float v, bool clip) { return clip ? fminf(fmaxf(v, -1.f), 1.f) : v; }
+
+struct PSampleCoef {
+  float c1, c2, sig;
+};
+
+// diffusion/gaussian_diffusion.py:273-276, :549-559
+__device__ __forceinline__ PSampleCoef load_psample(const int64_t* t, const float* coef1, const float* coef2,
+                                                    const float* logvar, int b) {
+  int64_t tb = t[b];
+  PSampleCoef c;
+  c.c1 = __ldg(coef1 + tb);
+  c.c2 = __ldg(coef2 + tb);
+  float nz = tb != 0 ? 1.f : 0.f;
+  c.sig = __fmul_rn(nz, expf(__fmul_rn(0.5f, __ldg(logvar + tb))));
+  return c;
+}
+
+__device__ __forceinline__ float psample_one(float x, float x0, float nz, const PSampleCoef& c) {
+  float mean = __fadd_rn(__fmul_rn(c.c1, x0), __fmul_rn(c.c2, x));
+  return __fadd_rn(mean, __fmul_rn(c.sig, nz));
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) p_sample_update_kernel(
+    const float* __restrict__ x, const float* __restrict__ x0, const float* __restrict__ noise,
+    float* __restrict__ out, float* __restrict__ pred, const int64_t* __restrict__ t,
+    const float* __restrict__ coef1, const float* __restrict__ coef2, const float* __restrict__ logvar,
+    uint32_t n_items, uint32_t inner_items, uint32_t B, int clip) {
+  // one item = one float4 (VEC) or one float; inner_items = items per (sample, outer index)
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n_items; i += gridDim.x * kThreads) {
+    int b = (int)((i / inner_items) % B);
+    PSampleCoef c = load_psample(t, coef1, coef2, logvar, b);
+    if (VEC) {
+      float4 vx = reinterpret_cast<const float4*>(x)[i];
+      float4 v0 = reinterpret_cast<const float4*>(x0)[i];
+      float4 vn = noise ? reinterpret_cast<const float4*>(noise)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      v0.x = clampf(v0.x, clip); v0.y = clampf(v0.y, clip); v0.z = clampf(v0.z, clip); v0.w = clampf(v0.w, clip);
+      float4 o;
+      o.x = psample_one(vx.x, v0.x, vn.x, c);
+      o.y = psample_one(vx.y, v0.y, vn.y, c);
+      o.z = psample_one(vx.z, v0.z, vn.z, c);
+      o.w = psample_one(vx.w, v0.w, vn.w, c);
+      reinterpret_cast<float4*>(out)[i] = o;
+      if (pred) reinterpret_cast<float4*>(pred)[i] = v0;
+    } else {
+      float v0 = clampf(x0[i], clip);
+      out[i] = psample_one(x[i], v0, noise ? noise[i] : 0.f, c);
+      if (pred) pred[i] = v0;
+    }
+  }
+}
+
+struct DdimCoef {
+  float sra, srm1, sqrt_abp, dir, sig;
+};
+
+// diffusion/gaussian_diffusion.py:769-793 with :418-423
+__device__ __forceinline__ DdimCoef load_ddim(const int64_t* t, const float* sra, const float* srm1,
+                                              const float* ac, const float* acp, float eta, int b) {
+  int64_t tb = t[b];
+  DdimCoef c;
+  c.sra = __ldg(sra + tb);
+  c.srm1 = __ldg(srm1 + tb);
+  float ab = __ldg(ac + tb), abp = __ldg(acp + tb);
+  float sigma = __fmul_rn(__fmul_rn(eta, __fsqrt_rn(__fdiv_rn(__fsub_rn(1.f, abp), __fsub_rn(1.f, ab)))),
+                          __fsqrt_rn(__fsub_rn(1.f, __fdiv_rn(ab, abp))));
+  c.sqrt_abp = __fsqrt_rn(abp);
+  c.dir = __fsqrt_rn(__fsub_rn(__fsub_rn(1.f, abp), __fmul_rn(sigma, sigma)));
+  float nz = tb != 0 ? 1.f : 0.f;
+  c.sig = __fmul_rn(nz, sigma);
+  return c;
+}
+
+__device__ __forceinline__ float ddim_one(float x, float x0, float nz, const DdimCoef& c) {
+  float eps = __fdiv_rn(__fsub_rn(__fmul_rn(c.sra, x), x0), c.srm1);
+  float mean = __fadd_rn(__fmul_rn(x0, c.sqrt_abp), __fmul_rn(c.dir, eps));
+  return __fadd_rn(mean, __fmul_rn(c.sig, nz));
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) ddim_update_kernel(
+    const float* __restrict__ x, const float* __restrict__ x0, const float* __restrict__ noise,
+    float* __restrict__ out, float* __restrict__ pred, const int64_t* __restrict__ t,
+    const float* __restrict__ sra, const float* __restrict__ srm1, const float* __restrict__ ac,
+    const float* __restrict__ acp, float eta, uint32_t n_items, uint32_t inner_items, uint32_t B, int clip) {
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n_items; i += gridDim.x * kThreads) {
+    int b = (int)((i / inner_items) % B);
+    DdimCoef c = load_ddim(t, sra, srm1, ac, acp, eta, b);
+    if (VEC) {
+      float4 vx = reinterpret_cast<const float4*>(x)[i];
+      float4 v0 = reinterpret_cast<const float4*>(x0)[i];
+      float4 vn = noise ? reinterpret_cast<const float4*>(noise)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      v0.x = clampf(v0.x, clip); v0.y = clampf(v0.y, clip); v0.z = clampf(v0.z, clip); v0.w = clampf(v0.w, clip);
+      float4 o;
+      o.x = ddim_one(vx.x, v0.x, vn.x, c);
+      o.y = ddim_one(vx.y, v0.y, vn.y, c);
+      o.z = ddim_one(vx.z, v0.z, vn.z, c);
+      o.w = ddim_one(vx.w, v0.w, vn.w, c);
+      reinterpret_cast<float4*>(out)[i] = o;
+      if (pred) reinterpret_cast<float4*>(pred)[i] = v0;
+    } else {
+      float v0 = clampf(x0[i], clip);
+      out[i] = ddim_one(x[i], v0, noise ? noise[i] : 0.f, c);
+      if (pred) pred[i] = v0;
+    }
+  }
+}
+
+// model/cfg_sampler.py:31
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) cfg_combine_kernel(const float* __restrict__ cond,
+                                                               const float* __restrict__ uncond,
+                                                               const float* __restrict__ scale,
+                                                               float* __restrict__ out, uint32_t n_items,
+                                                               uint32_t inner_items, uint32_t B) {
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n_items; i += gridDim.x * kThreads) {
+    float s = __ldg(scale + (i / inner_items) % B);
+    if (VEC) {
+      float4 c = reinterpret_cast<const float4*>(cond)[i];
+      float4 u = reinterpret_cast<const float4*>(uncond)[i];
+      float4 o;
+      o.x = __fadd_rn(u.x, __fmul_rn(s, __fsub_rn(c.x, u.x)));
+      o.y = __fadd_rn(u.y, __fmul_rn(s, __fsub_rn(c.y, u.y)));
+      o.z = __fadd_rn(u.z, __fmul_rn(s, __fsub_rn(c.z, u.z)));
+      o.w = __fadd_rn(u.w, __fmul_rn(s, __fsub_rn(c.w, u.w)));
+      reinterpret_cast<float4*>(out)[i] = o;
+    } else {
+      out[i] = __fadd_rn(uncond[i], __fmul_rn(s, __fsub_rn(cond[i], uncond[i])));
+    }
+  }
+}
+
+// utils/rotation_conversions.py:529-534.  One rotation per thread; the block's 6-float inputs and
+// 9-float outputs are staged through shared memory so global traffic is float4-coalesced.
+constexpr int kRotPerBlock = 256;
+__global__ void __launch_bounds__(kRotPerBlock) rot6d_kernel(const float* __restrict__ d6, float* __restrict__ R,
+                                                             int64_t n) {
+  __shared__ __align__(16) float s_in[kRotPerBlock * 6];
+  __shared__ __align__(16) float s_out[kRotPerBlock * 9];
+  for (int64_t base = (int64_t)blockIdx.x * kRotPerBlock; base < n; base += (int64_t)gridDim.x * kRotPerBlock) {
+    int cnt = (int)min((int64_t)kRotPerBlock, n - base);
+    const float* src = d6 + base * 6;  // 24*base bytes: 16B aligned because kRotPerBlock*24 % 16 == 0
+    int nin = cnt * 6;
+    for (int i = threadIdx.x * 4; i < nin; i += kRotPerBlock * 4) {
+      if (i + 4 <= nin) {
+        *reinterpret_cast<float4*>(s_in + i) = *reinterpret_cast<const float4*>(src + i);
+      } else {
+        for (int k = i; k < nin; ++k) s_in[k] = src[k];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < cnt) {
+      const float* a = s_in + threadIdx.x * 6;
+      float a1x = a[0], a1y = a[1], a1z = a[2], a2x = a[3], a2y = a[4], a2z = a[5];
+      // F.normalize: v / max(||v||, 1e-12)
+      float n1 = fmaxf(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(a1x, a1x), __fmul_rn(a1y, a1y)), __fmul_rn(a1z, a1z))), 1e-12f);
+      float b1x = __fdiv_rn(a1x, n1), b1y = __fdiv_rn(a1y, n1), b1z = __fdiv_rn(a1z, n1);
+      float d = __fadd_rn(__fadd_rn(__fmul_rn(b1x, a2x), __fmul_rn(b1y, a2y)), __fmul_rn(b1z, a2z));
+      float b2x = __fsub_rn(a2x, __fmul_rn(d, b1x)), b2y = __fsub_rn(a2y, __fmul_rn(d, b1y)), b2z = __fsub_rn(a2z, __fmul_rn(d, b1z));
+      float n2 = fmaxf(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(b2x, b2x), __fmul_rn(b2y, b2y)), __fmul_rn(b2z, b2z))), 1e-12f);
+      b2x = __fdiv_rn(b2x, n2); b2y = __fdiv_rn(b2y, n2); b2z = __fdiv_rn(b2z, n2);
+      float* o = s_out + threadIdx.x * 9;
+      o[0] = b1x; o[1] = b1y; o[2] = b1z;
+      o[3] = b2x; o[4] = b2y; o[5] = b2z;
+      o[6] = __fsub_rn(__fmul_rn(b1y, b2z), __fmul_rn(b1z, b2y));
+      o[7] = __fsub_rn(__fmul_rn(b1z, b2x), __fmul_rn(b1x, b2z));
+      o[8] = __fsub_rn(__fmul_rn(b1x, b2y), __fmul_rn(b1y, b2x));
+    }
+    __syncthreads();
+    float* dst = R + base * 9;  // 36*base bytes: 16B aligned because kRotPerBlock*36 % 16 == 0
+    int nout = cnt * 9;
+    for (int i = threadIdx.x * 4; i < nout; i += kRotPerBlock * 4) {
+      if (i + 4 <= nout) {
+        *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(s_out + i);
+      } else {
+        for (int k = i; k < nout; ++k) dst[k] = s_out[k];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// [B, I, T] <-> [T, B, I] through a padded shared-memory tile (per b: an I x T matrix transpose).
+constexpr int kTile = 32;
+template <bool TO_TBI>
+__global__ void __launch_bounds__(kTile * 8) transpose_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                              int B, int I, int T) {
+  __shared__ float tile[kTile][kTile + 1];
+  int b = blockIdx.z;
+  int i0 = blockIdx.y * kTile, t0 = blockIdx.x * kTile;
+  int tx = threadIdx.x % kTile, ty = threadIdx.x / kTile;  // 32 x 8
+  if (TO_TBI) {
+    // read src[b, i, t] with t fastest; write dst[t, b, i] with i fastest
+    for (int r = ty; r < kTile; r += 8) {
+      int i = i0 + r, t = t0 + tx;
+      if (i < I && t < T) tile[r][tx] = src[((int64_t)b * I + i) * T + t];
+    }
+    __syncthreads();
+    for (int r = ty; r < kTile; r += 8) {
+      int t = t0 + r, i = i0 + tx;
+      if (i < I && t < T) dst[((int64_t)t * B + b) * I + i] = tile[tx][r];
+    }
+  } else {
+    for (int r = ty; r < kTile; r += 8) {
+      int t = t0 + r, i = i0 + tx;
+      if (i < I && t < T) tile[r][tx] = src[((int64_t)t * B + b) * I + i];
+    }
+    __syncthreads();
+    for (int r = ty; r < kTile; r += 8) {
+      int i = i0 + r, t = t0 + tx;
+      if (i < I && t < T) dst[((int64_t)b * I + i) * T + t] = tile[tx][r];
+    }
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+}  // namespace regen
+
+using namespace regen;
+
+extern "C" {
+
+const char* regen_version(void) { return "regen_sm100 0.1.0 sm_100a"; }
+const char* regen_last_error(void) { return regen::g_err; }
+
+int regen_p_sample_update(const float* x, const float* x0, const float* noise, float* out, float* pred_xstart,
+                          const int64_t* t, const float* coef1, const float* coef2, const float* logvar,
+                          int64_t n_elem, int64_t inner, int32_t B, int32_t clip_denoised, void* stream) {
+  REGEN_CHECK_ARG(x && x0 && out && t && coef1 && coef2 && logvar, "p_sample_update: null pointer");
+  REGEN_CHECK_ARG(n_elem >= 0 && inner > 0 && B > 0, "p_sample_update: bad sizes");
+  REGEN_CHECK_ARG(n_elem < (int64_t)1 << 32, "p_sample_update: n_elem too large");
+  if (n_elem == 0) return REGEN_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  bool vec = (inner % 4 == 0) && (n_elem % 4 == 0) && aligned16(x) && aligned16(x0) && (!noise || aligned16(noise)) &&
+             aligned16(out) && (!pred_xstart || aligned16(pred_xstart));
+  if (vec) {
+    uint32_t items = (uint32_t)(n_elem / 4);
+    p_sample_update_kernel<true><<<grid_for(items), kThreads, 0, s>>>(x, x0, noise, out, pred_xstart, t, coef1, coef2,
+                                                                      logvar, items, (uint32_t)(inner / 4), (uint32_t)B,
+                                                                      clip_denoised);
+  } else {
+    p_sample_update_kernel<false><<<grid_for(n_elem), kThreads, 0, s>>>(x, x0, noise, out, pred_xstart, t, coef1, coef2,
+                                                                        logvar, (uint32_t)n_elem, (uint32_t)inner,
+                                                                        (uint32_t)B, clip_denoised);
+  }
+  REGEN_LAUNCH_CHECK();
+  return REGEN_OK;
+}
+
+int regen_ddim_update(const float* x, const float* x0, const float* noise, float* out, float* pred_xstart,
+                      const int64_t* t, const float* sqrt_recip_ac, const float* sqrt_recipm1_ac, const float* ac,
+                      const float* ac_prev, float eta, int64_t n_elem, int64_t inner, int32_t B, int32_t clip_denoised,
+                      void* stream) {
+  REGEN_CHECK_ARG(x && x0 && out && t && sqrt_recip_ac && sqrt_recipm1_ac && ac && ac_prev,
+                  "ddim_update: null pointer");
+  REGEN_CHECK_ARG(n_elem >= 0 && inner > 0 && B > 0, "ddim_update: bad sizes");
+  REGEN_CHECK_ARG(n_elem < (int64_t)1 << 32, "ddim_update: n_elem too large");
+  if (n_elem == 0) return REGEN_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  bool vec = (inner % 4 == 0) && (n_elem % 4 == 0) && aligned16(x) && aligned16(x0) && (!noise || aligned16(noise)) &&
+             aligned16(out) && (!pred_xstart || aligned16(pred_xstart));
+  if (vec) {
+    uint32_t items = (uint32_t)(n_elem / 4);
+    ddim_update_kernel<true><<<grid_for(items), kThreads, 0, s>>>(x, x0, noise, out, pred_xstart, t, sqrt_recip_ac,
+                                                                  sqrt_recipm1_ac, ac, ac_prev, eta, items,
+                                                                  (uint32_t)(inner / 4), (uint32_t)B, clip_denoised);
+  } else {
+    ddim_update_kernel<false><<<grid_for(n_elem), kThreads, 0, s>>>(x, x0, noise, out, pred_xstart, t, sqrt_recip_ac,
+                                                                    sqrt_recipm1_ac, ac, ac_prev, eta, (uint32_t)n_elem,
+                                                                    (uint32_t)inner, (uint32_t)B, clip_denoised);
+  }
+  REGEN_LAUNCH_CHECK();
+  return REGEN_OK;
+}
+
+int regen_cfg_combine(const float* cond, const float* uncond, const float* scale, float* out, int64_t n_elem,
+                      int64_t inner, int32_t B, void* stream) {
+  REGEN_CHECK_ARG(cond && uncond && scale && out, "cfg_combine: null pointer");
+  REGEN_CHECK_ARG(n_elem >= 0 && inner > 0 && B > 0, "cfg_combine: bad sizes");
+  REGEN_CHECK_ARG(n_elem < (int64_t)1 << 32, "cfg_combine: n_elem too large");
+  if (n_elem == 0) return REGEN_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  bool vec = (inner % 4 == 0) && (n_elem % 4 == 0) && aligned16(cond) && aligned16(uncond) && aligned16(out);
+  if (vec) {
+    uint32_t items = (uint32_t)(n_elem / 4);
+    cfg_combine_kernel<true><<<grid_for(items), kThreads, 0, s>>>(cond, uncond, scale, out, items,
+                                                                  (uint32_t)(inner / 4), (uint32_t)B);
+  } else {
+    cfg_combine_kernel<false><<<grid_for(n_elem), kThreads, 0, s>>>(cond, uncond, scale, out, (uint32_t)n_elem,
+                                                                    (uint32_t)inner, (uint32_t)B);
+  }
+  REGEN_LAUNCH_CHECK();
+  return REGEN_OK;
+}
+
+int regen_rot6d_to_matrix(const float* d6, float* R, int64_t n, void* stream) {
+  REGEN_CHECK_ARG(n >= 0, "rot6d_to_matrix: negative n");
+  if (n == 0) return REGEN_OK;
+  REGEN_CHECK_ARG(d6 && R, "rot6d_to_matrix: null pointer");
+  REGEN_CHECK_ARG(aligned16(d6) && aligned16(R), "rot6d_to_matrix: pointers must be 16-byte aligned");
+  int64_t blocks = ceil_div(n, kRotPerBlock);
+  int64_t cap = (int64_t)kNumSMs * 8;
+  if (blocks > cap) blocks = cap;
+  rot6d_kernel<<<(int)blocks, kRotPerBlock, 0, (cudaStream_t)stream>>>(d6, R, n);
+  REGEN_LAUNCH_CHECK();
+  return REGEN_OK;
+}
+
+static int launch_transpose(bool to_tbi, const float* src, float* dst, int32_t B, int32_t I, int32_t T, void* stream) {
+  REGEN_CHECK_ARG(B >= 0 && I >= 0 && T >= 0, "layout: negative size");
+  if (B == 0 || I == 0 || T == 0) return REGEN_OK;
+  REGEN_CHECK_ARG(src && dst, "layout: null pointer");
+  REGEN_CHECK_ARG(B <= 65535 && ceil_div(I, kTile) <= 65535, "layout: B or I too large for one launch");
+  dim3 grid((unsigned)ceil_div(T, kTile), (unsigned)ceil_div(I, kTile), (unsigned)B);
+  if (to_tbi)
+    transpose_kernel<true><<<grid, kTile * 8, 0, (cudaStream_t)stream>>>(src, dst, B, I, T);
+  else
+    transpose_kernel<false><<<grid, kTile * 8, 0, (cudaStream_t)stream>>>(src, dst, B, I, T);
+  REGEN_LAUNCH_CHECK();
+  return REGEN_OK;
+}
+
+int regen_bjft_to_tbi(const float* src, float* dst, int32_t B, int32_t I, int32_t T, void* stream) {
+  return launch_transpose(true, src, dst, B, I, T, stream);
+}
+int regen_tbi_to_bjft(const float* src, float* dst, int32_t B, int32_t I, int32_t T, void* stream) {
+  return launch_transpose(false, src, dst, B, I, T, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+"""Golden-vector case table shared by make_golden.py (writer) and the tests (readers).
+
+Model kwargs are exactly what the reference's utils/model_util.py:20-72 (get_model_args)
+produces for the named dataset; the forward arithmetic only depends on
+njoints/nfeats/cond_mode/num_actions/cm_mode.
+"""
+
+COMMON = dict(modeltype="", translation=True, pose_rep="rot6d", glob=True, glob_rot=True,
+              latent_dim=512, ff_size=1024, num_layers=8, num_heads=4, dropout=0.1, activation="gelu",
+              action_emb="tensor", arch="online", cm_mode="concat", body_model="smplx",
+              wo_pos_emb=False, emb_trans_dec=False, clip_version="ViT-B/32")
+
+MODELS = {
+    # README.md:96 NTU120-AS online unconstrained (BASELINE.json configs 1, 2, 4)
+    "ntu": dict(COMMON, njoints=56, nfeats=6, num_actions=26, num_frames=60, data_rep="rot6d",
+                cond_mode="no_cond", cond_mask_prob=0.0, dataset="ntu"),
+    # Chi3D action-conditioned with classifier-free guidance (config 3)
+    "chi3d": dict(COMMON, njoints=56, nfeats=6, num_actions=8, num_frames=150, data_rep="rot6d",
+                  cond_mode="action", cond_mask_prob=0.1, dataset="chi3d"),
+    # HumanML-shaped text-conditioned (config 5); CLIP features injected
+    "hml": dict(COMMON, njoints=263, nfeats=1, num_actions=1, num_frames=196, data_rep="hml_vec",
+                cond_mode="text", cond_mask_prob=0.1, dataset="humanml"),
+}
+
+
+def synth_kw(name):
+    m = MODELS[name]
+    return dict(njoints=m["njoints"], nfeats=m["nfeats"], latent_dim=m["latent_dim"], ff_size=m["ff_size"],
+                num_layers=m["num_layers"], cond_mode=m["cond_mode"], num_actions=m["num_actions"],
+                clip_dim=512, cm_mode=m["cm_mode"])
+
+
+# name -> dict(model, B, T, t (list) | loop spec)
+FORWARD_CASES = {
+    "fwd_ntu": dict(model="ntu", B=2, T=60, t=[999, 3], wseed=0, xseed=10),
+    "fwd_ntu_b1_t0": dict(model="ntu", B=1, T=60, t=[0], wseed=1, xseed=11),
+    "fwd_ntu_ragged_T37": dict(model="ntu", B=3, T=37, t=[5, 500, 77], wseed=0, xseed=12),
+    "fwd_chi3d_cond": dict(model="chi3d", B=2, T=150, t=[640, 12], wseed=2, xseed=13),
+    "fwd_chi3d_uncond": dict(model="chi3d", B=2, T=150, t=[640, 12], wseed=2, xseed=13, uncond=True),
+    "fwd_chi3d_cfg": dict(model="chi3d", B=2, T=150, t=[640, 12], wseed=2, xseed=13, cfg_scale=2.5),
+    "fwd_hml_text": dict(model="hml", B=2, T=196, t=[321, 900], wseed=3, xseed=14),
+}
+
+LOOP_CASES = {
+    # ancestral sampling, 20 respaced steps (README.md:134-137 uses ddimK respacing with p_sample_loop)
+    "loop_ntu_p20": dict(model="ntu", B=2, T=60, respacing="ddim20", ddim=False, wseed=0, xseed=10, seed=10),
+    # full-length schedule, first 6 steps only is not expressible through the reference API; use 1000->'25'
+    "loop_ntu_p25frac": dict(model="ntu", B=1, T=60, respacing="25", ddim=False, wseed=1, xseed=11, seed=3),
+    "loop_chi3d_cfg_p10": dict(model="chi3d", B=2, T=150, respacing="ddim10", ddim=False, wseed=2, xseed=13,
+                               seed=5, cfg_scale=2.5),
+    "loop_hml_ddim10": dict(model="hml", B=2, T=196, respacing="ddim10", ddim=True, wseed=3, xseed=14,
+                            seed=7, cfg_scale=2.5),
+}
+
+RESPACINGS = ["", "ddim5", "ddim20", "ddim100", "25", "10,15,20", "1000"]

@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the ReGenNet diffusion-sampling hot path on B200 (see BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): NTU120-AS online unconstrained CMDM (8 layers, d=512, SMPL-X
+rot6d 56x6), T=60, B=256 per GPU, 1000-step cosine DDPM ancestral sampling; synthetic seeded weights
+and actor motion (no checkpoints / datasets are distributable).  One "step" = one denoising step of
+the loop over the whole per-GPU batch: noise draw + CMDM forward + posterior update.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline      dominant kernel class (tcgen05 GEMMs): algorithmic FLOPs / measured device time
+  roofline_hbm  the fused posterior-update kernel against the measured HBM copy bandwidth
+  cpu_baseline  the CPU oracle (port of the reference algorithm) on this box's host cores
+  breakdown_ms  per-step device time per kernel class (CUDA events inside the library)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+B_DEFAULT, T_DEFAULT = 256, 60
+METRIC = "denoising_steps_per_sec"
+UNIT = "steps/s (1 step = one p_sample over B=256 x T=60 poses per GPU, summed over GPUs)"
+
+
+def model_cfg():
+    import cases
+    return cases.MODELS["ntu"], cases.synth_kw("ntu")
+
+
+def flops_per_step(B, T, I=336, L=8):
+    """algorithmic FLOPs (2/MAC); GEMM part and attention part separately."""
+    gemm_tok = L * (2 * 512 * 1536 + 2 * 512 * 512 + 4 * 512 * 1024) + 2 * I * 512 + 2 * 512 * 512 + 2 * 512 * I
+    attn_tok = L * 4 * T * 512
+    per_sample = 2 * 2 * 512 * 512 + L * 2 * 2 * 512 * 512
+    return B * T * gemm_tok, B * T * attn_tok, B * per_sample
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def build_ours(device, B, T):
+    from regennet_b200 import gaussian_diffusion as gd
+    from regennet_b200 import respace, synthetic
+    from regennet_b200.cmdm import CMDM
+    mk, sk = model_cfg()
+    model = CMDM(**mk)
+    model.load_state_dict(synthetic.make_state_dict(seed=0, **sk), strict=False)
+    model = model.to(device).eval()
+    betas = gd.get_named_beta_schedule("cosine", 1000, 1.0)
+
+    def diffusion(respacing):
+        return respace.SpacedDiffusion(use_timesteps=respace.space_timesteps(1000, respacing), betas=betas,
+                                       model_mean_type=gd.ModelMeanType.START_X,
+                                       model_var_type=gd.ModelVarType.FIXED_SMALL, loss_type=gd.LossType.MSE)
+    return model, diffusion
+
+
+def run_ours(args):
+    from regennet_b200 import _lib, synthetic
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    B, T, K, W = args.batch, args.frames, args.steps, args.warmup
+    J, F = 56, 6
+    I = J * F
+    shape = (B, J, F, T)
+    model, mkdiff = build_ours(dev, B, T)
+    lib = _lib.lib()
+
+    # per-rank shard: independent samples, rank-offset seeds
+    _, y = synthetic.make_inputs(B, J, F, T, seed=10 + rank)
+    cm_host = y["cmotion"].pin_memory()
+    torch.manual_seed(10 + rank)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    # ------------------------------------------------------------------ value: device-resident K steps
+    full = mkdiff([1000])
+    yc = {"cmotion": cm_host.to(dev)}
+    img = torch.randn(*shape, device=dev)
+    sess = full._fast_session(model, shape, {"y": yc}, None, None, False, False, img)
+    assert sess is not None, "fast route not taken"
+    indices = list(range(full.num_timesteps))[::-1]
+    assert K + W <= len(indices)
+    gen = sess.run(full, "p", img, indices, False, 0.0)
+    for _ in range(W):
+        next(gen)
+    torch.cuda.synchronize()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    n0 = lib.regen_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(K):
+        next(gen)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(lib.regen_launch_count() - n0)
+    clk = clocks.stop()
+    gen.close()
+
+    # ------------------------------------------------------------------ per-class device time (profiling pass)
+    handle = model._handle
+    gen = sess.run(full, "p", img, indices, False, 0.0)
+    for _ in range(2):
+        next(gen)
+    torch.cuda.synchronize()
+    upd_events = []
+    orig_update = full._update
+
+    def timed_update(*a, **k):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        r = orig_update(*a, **k)
+        a1.record()
+        upd_events.append((a0, a1))
+        return r
+
+    full._update = timed_update
+    KP = min(K, 20)
+    _lib.check(lib.regen_profile_begin(handle.ptr), "profile_begin")
+    for _ in range(KP):
+        next(gen)
+    cls_ms = (_lib.c_float * 4)()
+    cls_n = (_lib.c_int * 4)()
+    _lib.check(lib.regen_profile_end(handle.ptr, cls_ms, cls_n), "profile_end")
+    full._update = orig_update
+    gen.close()
+    upd_ms = sum(a.elapsed_time(b) for a, b in upd_events[1:]) / max(1, len(upd_events) - 1)
+    gemm_ms, attn_ms, ln_ms, other_ms = [cls_ms[i] / KP for i in range(4)]
+
+    # ------------------------------------------------------------------ e2e: public API, host buffers in and out
+    e2e_diff = mkdiff([K])
+    out_host = torch.empty(shape, dtype=torch.float32).pin_memory()
+
+    def e2e_once():
+        ycm = {"cmotion": cm_host.to(dev, non_blocking=True)}
+        s = e2e_diff.p_sample_loop(model, shape, clip_denoised=False, model_kwargs={"y": ycm})
+        out_host.copy_(s, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_once()  # warm-up (allocator, handle)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_once()
+    e2e_s = time.perf_counter() - t0
+    h2d = cm_host.numel() * 4 / K
+    d2h = out_host.numel() * 4 / K
+
+    # ------------------------------------------------------------------ reduce over ranks (max time)
+    times = torch.tensor([ms, e2e_s * 1000.0], device=dev, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        # the one collective of the path: reassemble the generated batch
+        gathered = torch.empty((world * B, J, F, T), device=dev)
+        dist.all_gather_into_tensor(gathered, out_host.to(dev).contiguous())
+    ms_max, e2e_ms_max = times.tolist()
+
+    if rank == 0:
+        peaks = measured_peaks()
+        f_gemm, f_attn, f_small = flops_per_step(B, T, I)
+        steps_per_s = world * K / (ms_max / 1000.0)
+        gemm_tf = f_gemm / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
+        n_elem = B * I * T
+        upd_gbs = 16.0 * n_elem / (upd_ms / 1000.0) / 1e9 if upd_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 (3 bf16 tcgen05 MMAs per product, fp32 accumulate; fp32 residual/LN/softmax/update)",
+            "data": "synthetic (seeded random-init weights, random actor motion)",
+            "config": {"workload": "BASELINE configs[1]: NTU120-AS online unconstrained 8-layer CMDM, SMPL-X rot6d "
+                                   "56x6, T=%d, B=%d per GPU, 1000-step cosine DDPM p_sample_loop (steps %d..%d timed)"
+                                   % (T, B, 999 - W, 999 - W - K + 1),
+                       "batch_per_gpu": B, "frames": T, "layers": 8, "parallelism": "dp%d (independent shards)" % world,
+                       "l2": "working set per step (weights 107 MB + activations ~300 MB) exceeds the 126 MB L2"},
+            "poses_per_sec": steps_per_s * B * T,
+            "frames_per_sec_e2e_1000_steps": world * B * T / (1000.0 * (ms_max / K) / 1000.0),
+            "e2e": {"value": world * K / (e2e_ms_max / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h,
+                    "what": "SpacedDiffusion(%d steps).p_sample_loop(CMDM, ...) with pinned-host cmotion in and "
+                            "pinned-host samples out, wall clock incl. Python" % K},
+            "gpu_launches": launches,
+            "clocks": clk,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel<256,bf16x3> (all %d GEMM launches per step)" % (2 + 4 * 8),
+                         "achieved": gemm_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                         "frac": gemm_tf / peaks["tf_sust"], "traffic": None,
+                         "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % peaks["src"],
+                         "note": "achieved counts ALGORITHMIC flops (1 MAC per product); the bf16x3 parity mode "
+                                 "executes 3 MMAs per product, so frac is capped at 1/3"},
+            "roofline_hbm": {"bound": "hbm", "kernel": "p_sample_update_kernel", "achieved": upd_gbs,
+                             "peak": peaks["hbm"], "unit": "GB/s", "frac": upd_gbs / peaks["hbm"],
+                             "bytes_per_element": 16},
+            "breakdown_ms": {"gemm": gemm_ms, "attention": attn_ms, "layernorm": ln_ms, "split_cfg": other_ms,
+                             "posterior_update": upd_ms, "step_total": ms_max / K},
+            "algorithmic_gflop_per_step": (f_gemm + f_attn + f_small) / 1e9,
+            "tensor_frac_whole_step": (f_gemm + f_attn + f_small) / ((ms_max / K) / 1000.0) / 1e12 / peaks["tf_sust"],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(budget_s=15.0, T=T)
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_oracle_step_fn(Bs, T):
+    """One denoising step of the CPU oracle (port of the reference algorithm) at batch Bs."""
+    from oracle import cmdm_ref, sampler_ref
+    from regennet_b200 import synthetic
+    mk, sk = model_cfg()
+    sd = synthetic.make_state_dict(seed=0, **sk)
+    _, y = synthetic.make_inputs(Bs, 56, 6, T, seed=10)
+    smp = sampler_ref.Sampler()
+    kw = dict(num_layers=8, nhead=4, cond_mode="no_cond", cm_mode="concat")
+    state = {"x": torch.randn(Bs, 56, 6, T), "i": 999}
+
+    def step():
+        with torch.no_grad():
+            t = torch.tensor([state["i"]] * Bs)
+            state["x"], _ = smp.p_sample(lambda xx, tt: cmdm_ref.cmdm_forward(sd, xx, tt, y, **kw), state["x"], t,
+                                         torch.randn_like)
+            state["i"] -= 1
+    return step
+
+
+def cpu_baseline(budget_s, T, Bs=32):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_oracle_step_fn(Bs, T)
+    step()
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s or n < 2:
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    eq = (n / dt) * (Bs / float(B_DEFAULT))
+    return {"value": eq, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d p_sample steps of the CPU oracle (torch fp32, %d threads) at B=%d, T=%d in %.1f s; value is "
+                      "scaled by %d/%d to the B=256 step" % (n, cores, Bs, T, dt, Bs, B_DEFAULT)}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path.  The reference is a Python tree
+    that cannot travel to the GPU box, so this times the CPU oracle (oracle/, a restatement pinned to the
+    reference by tests/golden) with all host threads.  Each step is a bounded sample (B=32 of the 256)."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    K, W, T, Bs = args.steps, args.warmup, args.frames, 32
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_oracle_step_fn(Bs, T)
+    for _ in range(max(1, min(W, 3))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step()
+    dt = time.perf_counter() - t0
+    v = (K / dt) * (Bs / float(B_DEFAULT))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic (seeded random-init weights, random actor motion)",
+            "config": {"workload": "BASELINE configs[1] on host CPU: same model/config as the GPU arm; each step = one "
+                                   "p_sample at B=%d (bounded sample of B=256), value scaled by %d/256" % (Bs, Bs)},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d steps at B=%d, T=%d, %d threads, %.1f s" % (K, Bs, T, cores, dt)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=B_DEFAULT)
+    ap.add_argument("--frames", type=int, default=T_DEFAULT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

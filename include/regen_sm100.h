@@ -40,6 +40,8 @@ extern "C" {
 /* library / build info: "regen_sm100 <version> sm_100a" */
 const char* regen_version(void);
 const char* regen_last_error(void);
+/* kernels launched by this library in this process so far (evidence for bench.py's gpu_launches) */
+int64_t regen_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Handle-free elementwise operators (HBM-bound; coalesced, vectorised)
@@ -122,6 +124,10 @@ typedef struct {
   const float *pe;              /* sequence_pos_encoder.pe [pe_len, D] */
   int32_t pe_len;
   const float *out_w, *out_b;   /* output_process.poseFinal [I,D] */
+  const float *action_emb;      /* embed_action.action_embedding [num_actions, D] or NULL */
+  int32_t num_actions;
+  const float *text_w, *text_b; /* embed_text [D, clip_dim], [D] or NULL */
+  int32_t clip_dim;
   regen_layer_weights layers[REGEN_MAX_LAYERS];
 } regen_weight_ptrs;
 
@@ -135,18 +141,36 @@ void regen_destroy(regen_handle* h);
 int regen_load_weights(regen_handle* h, const regen_weight_ptrs* w, void* stream);
 
 /* Loop-invariant conditioning, once per sampling loop (or per forward in the generic route).
- * cmotion: actor motion, BJFT [B,J,F,T].  cond_emb: [B,D] action / text embedding already
- * masked for `uncond` (NULL = zeros).  guidance != 0 doubles the batch internally: rows [0,B)
- * conditional, rows [B,2B) unconditional (cond_emb treated as zero) -- model/cfg_sampler.py:24-31.
- * Replaces model/cmdm.py:181-187, :202 (cmo_process) and the cmotion half of :207-211, :218. */
-int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const float* cond_emb,
-                       int32_t B, int32_t T, int32_t guidance, void* stream);
+ * cmotion: actor motion, BJFT [B,J,F,T].  action: int64[B] class indices (EmbedAction row gather,
+ * model/cmdm.py:358-366) or NULL.  text_feat: [B, clip_dim] CLIP text features (embed_text Linear,
+ * model/cmdm.py:182-184) or NULL.  uncond != 0 zeroes both (mask_cond force_mask, :129-132).
+ * guidance != 0 doubles the batch internally: rows [0,B) conditional, rows [B,2B) unconditional
+ * -- model/cfg_sampler.py:24-31.  Replaces model/cmdm.py:181-187, :202 (cmo_process), the cmotion
+ * half of :207-211 and the positional-encoding add :218. */
+int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t* action,
+                       const float* text_feat, int32_t B, int32_t T, int32_t guidance,
+                       int32_t uncond, void* stream);
 
 /* CMDM.forward (model/cmdm.py:173-252) after regen_prepare_cond.  x_tbi [T,B,I]; t int64[B] device,
  * original (un-respaced) timesteps; x0_tbi [T,B,I] (with guidance: the guided combination
  * uncond + scale[b]*(cond-uncond), scale = cfg_scale[B] device). */
 int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const float* cfg_scale,
                   float* x0_tbi, int32_t B, int32_t T, void* stream);
+
+/* Measurement support: between begin and end every kernel the denoiser launches is bracketed by a
+ * CUDA event pair on its stream; end synchronises and returns the summed device time (ms) and the
+ * launch count per kernel class: [0] tcgen05 GEMMs, [1] attention, [2] LayerNorm, [3] other. */
+int regen_profile_begin(regen_handle* h);
+int regen_profile_end(regen_handle* h, float* ms, int32_t* launches);
+
+/* ------------------------------------------------------------------------------------------
+ * Kernel-level test hook (used by tests/ only): out[M,N] = act(A[M,K] . W[N,K]^T + bias + residual)
+ * through the same tcgen05/TMA GEMM kernel the denoiser uses (the arithmetic of every nn.Linear on
+ * the path, torch F.linear).  fp32 device buffers in and out; synchronises the stream.
+ * ---------------------------------------------------------------------------------------- */
+int regen_test_gemm(const float* A, const float* W, const float* bias, const float* residual,
+                    float* out, int32_t M, int32_t N, int32_t K, int32_t gelu, int32_t precision,
+                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -34,7 +34,8 @@ class LayerWeights(ctypes.Structure):
 class WeightPtrs(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in (
         "in_w", "in_b", "cmo_w", "cmo_b", "fuse_w", "fuse_b", "t0_w", "t0_b", "t2_w", "t2_b", "pe")] + \
-        [("pe_len", c_int)] + [(n, c_void_p) for n in ("out_w", "out_b")] + \
+        [("pe_len", c_int)] + [(n, c_void_p) for n in ("out_w", "out_b", "action_emb")] + \
+        [("num_actions", c_int), ("text_w", c_void_p), ("text_b", c_void_p), ("clip_dim", c_int)] + \
         [("layers", LayerWeights * REGEN_MAX_LAYERS)]
 
 
@@ -42,6 +43,9 @@ _SIGNATURES = {
     # name: (restype, argtypes)
     "regen_version": (ctypes.c_char_p, []),
     "regen_last_error": (ctypes.c_char_p, []),
+    "regen_launch_count": (c_i64, []),
+    "regen_profile_begin": (c_int, [c_void_p]),
+    "regen_profile_end": (c_int, [c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_int)]),
     "regen_p_sample_update": (c_int, [c_void_p] * 9 + [c_i64, c_i64, c_int, c_int, c_void_p]),
     "regen_ddim_update": (c_int, [c_void_p] * 10 + [c_float, c_i64, c_i64, c_int, c_int, c_void_p]),
     "regen_cfg_combine": (c_int, [c_void_p] * 4 + [c_i64, c_i64, c_int, c_void_p]),
@@ -51,8 +55,9 @@ _SIGNATURES = {
     "regen_create": (c_int, [ctypes.POINTER(c_void_p), c_int, ctypes.POINTER(ModelDesc)]),
     "regen_destroy": (None, [c_void_p]),
     "regen_load_weights": (c_int, [c_void_p, ctypes.POINTER(WeightPtrs), c_void_p]),
-    "regen_prepare_cond": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "regen_prepare_cond": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "regen_denoise": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "regen_test_gemm": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
 }
 
 _lib = None

@@ -43,7 +43,17 @@ void set_error(const char* fmt, ...);
 
 constexpr int kNumSMs = 148;  // B200
 
+// number of kernels this library has launched in this process (regen_launch_count)
+extern long long g_launches;
+inline void count_launch(int n = 1) { g_launches += n; }
+
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// grid size for a grid-stride kernel: enough blocks for the work, capped at 8 resident CTAs per SM
+inline int grid_cap(int64_t blocks) {
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
 
 // fp32 -> (hi, lo) bf16 pair with hi + lo ~= v to 16 significand bits (bf16x3 operand split)
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {

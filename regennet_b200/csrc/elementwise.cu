@@ -8,6 +8,7 @@
 
 namespace regen {
 
+long long g_launches = 0;
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -256,6 +257,7 @@ extern "C" {
 
 const char* regen_version(void) { return "regen_sm100 0.1.0 sm_100a"; }
 const char* regen_last_error(void) { return regen::g_err; }
+int64_t regen_launch_count(void) { return (int64_t)regen::g_launches; }
 
 int regen_p_sample_update(const float* x, const float* x0, const float* noise, float* out, float* pred_xstart,
                           const int64_t* t, const float* coef1, const float* coef2, const float* logvar,
@@ -278,6 +280,7 @@ int regen_p_sample_update(const float* x, const float* x0, const float* noise, f
                                                                         (uint32_t)B, clip_denoised);
   }
   REGEN_LAUNCH_CHECK();
+  count_launch();
   return REGEN_OK;
 }
 
@@ -304,6 +307,7 @@ int regen_ddim_update(const float* x, const float* x0, const float* noise, float
                                                                     (uint32_t)inner, (uint32_t)B, clip_denoised);
   }
   REGEN_LAUNCH_CHECK();
+  count_launch();
   return REGEN_OK;
 }
 
@@ -324,6 +328,7 @@ int regen_cfg_combine(const float* cond, const float* uncond, const float* scale
                                                                     (uint32_t)inner, (uint32_t)B);
   }
   REGEN_LAUNCH_CHECK();
+  count_launch();
   return REGEN_OK;
 }
 
@@ -337,6 +342,7 @@ int regen_rot6d_to_matrix(const float* d6, float* R, int64_t n, void* stream) {
   if (blocks > cap) blocks = cap;
   rot6d_kernel<<<(int)blocks, kRotPerBlock, 0, (cudaStream_t)stream>>>(d6, R, n);
   REGEN_LAUNCH_CHECK();
+  count_launch();
   return REGEN_OK;
 }
 
@@ -351,6 +357,7 @@ static int launch_transpose(bool to_tbi, const float* src, float* dst, int32_t B
   else
     transpose_kernel<false><<<grid, kTile * 8, 0, (cudaStream_t)stream>>>(src, dst, B, I, T);
   REGEN_LAUNCH_CHECK();
+  count_launch();
   return REGEN_OK;
 }
 

@@ -1,0 +1,528 @@
+// CMDM denoiser (arch='online') on sm_100a: handle, weight packing, loop-invariant conditioning and
+// the per-step forward.  See include/regen_sm100.h for the ABI and DESIGN.md for the data layout.
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_sm100.cuh"
+#include "layers.cuh"
+#include "tmap.cuh"
+
+using namespace regen;
+using layers::D;
+using layers::FF;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+struct SplitBuf {  // bf16 (hi, lo) operand pair + its TMA maps
+  bf16 *hi = nullptr, *lo = nullptr;
+  CUtensorMap tm_hi, tm_lo;
+};
+
+struct LayerDev {
+  SplitBuf wqkv, wo, w1, w2;
+  float *bqkv, *bo, *b1, *b2, *n1w, *n1b, *n2w, *n2b, *n3w, *n3b;
+};
+
+}  // namespace
+
+struct regen_handle {
+  regen_model_desc desc;
+  int device = 0;
+  int L = 0, I = 0, Kin = 0, Mmax = 0;
+  bool loaded = false, cond_ready = false;
+  // current problem (set by prepare_cond)
+  int B = 0, Beff = 0, T = 0, M = 0;
+  bool guidance = false, has_cond = false;
+
+  std::vector<void*> allocs;
+  // optional per-kernel-class CUDA-event profiling (regen_profile_begin / regen_profile_end)
+  bool prof_on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[4];
+  // weights
+  SplitBuf w_in, w_out;
+  float *b_out = nullptr, *w_c = nullptr, *b_c = nullptr, *P = nullptr, *qvec = nullptr, *ctab = nullptr, *pe = nullptr;
+  float *action_emb = nullptr, *text_w = nullptr, *text_b = nullptr, *cond_emb = nullptr;
+  int pe_len = 0, num_actions = 0, clip_dim = 0;
+  LayerDev layer[REGEN_MAX_LAYERS];
+  // activations
+  SplitBuf a_in, h_s, att, ffn;
+  float *h = nullptr, *qkv = nullptr, *tmp = nullptr, *x0e = nullptr, *condbias = nullptr, *cmo_tbi = nullptr,
+        *ccond = nullptr, *scratch = nullptr;
+
+  template <typename T>
+  int alloc(T** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+      return REGEN_ECUDA;
+    }
+    allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return REGEN_OK;
+  }
+};
+
+namespace {
+
+enum { CLS_GEMM = 0, CLS_ATTN = 1, CLS_LN = 2, CLS_OTHER = 3 };
+
+// RAII scope: records a CUDA event pair around the launches of one kernel class when profiling is on
+struct ProfScope {
+  regen_handle* h;
+  cudaStream_t s;
+  int cls;
+  cudaEvent_t e1 = nullptr;
+  ProfScope(regen_handle* h_, int cls_, cudaStream_t s_) : h(h_), s(s_), cls(cls_) {
+    if (h->prof_on) {
+      cudaEvent_t e0;
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, s);
+      h->prof_ev[cls].push_back({e0, e1});
+    }
+  }
+  ~ProfScope() {
+    if (e1) cudaEventRecord(e1, s);
+  }
+};
+
+#define TRY(expr)                \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != REGEN_OK) return _rc; \
+  } while (0)
+
+int alloc_split(regen_handle* h, SplitBuf* s, size_t rows, size_t cols, uint32_t box_rows) {
+  TRY(h->alloc(&s->hi, rows * cols));
+  TRY(h->alloc(&s->lo, rows * cols));
+  REGEN_CUDA(cudaMemset(s->hi, 0, rows * cols * sizeof(bf16)));
+  REGEN_CUDA(cudaMemset(s->lo, 0, rows * cols * sizeof(bf16)));
+  TRY(make_tmap_bf16_2d(&s->tm_hi, s->hi, rows, cols, cols, box_rows));
+  TRY(make_tmap_bf16_2d(&s->tm_lo, s->lo, rows, cols, cols, box_rows));
+  return REGEN_OK;
+}
+
+int copy_vec(regen_handle* h, float** dst, const float* src, size_t n, cudaStream_t s) {
+  TRY(h->alloc(dst, n));
+  REGEN_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return REGEN_OK;
+}
+
+int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, const gemm::Params& p, cudaStream_t s) {
+  ProfScope prof(h, CLS_GEMM, s);
+  cudaError_t e = h->desc.precision == 0 ? gemm::launch<256, true>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, p, s)
+                                         : gemm::launch<256, false>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, p, s);
+  if (e != cudaSuccess) {
+    set_error("gemm launch (M=%d N=%d K=%d) failed: %s", p.M, p.N, p.K, cudaGetErrorString(e));
+    return REGEN_ECUDA;
+  }
+  count_launch();
+  return REGEN_OK;
+}
+
+gemm::Params gp(int M, int N, int K) {
+  gemm::Params p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) {
+  REGEN_CHECK_ARG(out && d, "regen_create: null argument");
+  REGEN_CHECK_ARG(d->latent_dim == 512 && d->num_heads == 4 && d->ff_size == 1024,
+                  "regen_create: kernels are specialised for latent_dim=512, num_heads=4, ff_size=1024 "
+                  "(utils/model_util.py:69-70); got %d/%d/%d", d->latent_dim, d->num_heads, d->ff_size);
+  REGEN_CHECK_ARG(d->num_layers >= 1 && d->num_layers <= REGEN_MAX_LAYERS, "regen_create: bad num_layers %d",
+                  d->num_layers);
+  REGEN_CHECK_ARG(d->input_feats >= 1 && d->input_feats <= 4096, "regen_create: bad input_feats %d", d->input_feats);
+  REGEN_CHECK_ARG(d->cm_mode == 0 || d->cm_mode == 1, "regen_create: cm_mode must be 0 (add) or 1 (concat)");
+  REGEN_CHECK_ARG(d->precision == 0 || d->precision == 1, "regen_create: precision must be 0 (bf16x3) or 1 (bf16)");
+  REGEN_CHECK_ARG(d->max_batch >= 1 && d->max_frames >= 1 && d->num_table_steps >= 1, "regen_create: bad sizes");
+  REGEN_CHECK_ARG(layers::attention_smem_bytes(d->max_frames) <= 227 * 1024,
+                  "regen_create: max_frames=%d exceeds the attention kernel's shared-memory budget", d->max_frames);
+  REGEN_CHECK_ARG((int64_t)d->max_batch * d->max_frames < (1 << 24), "regen_create: max_batch*max_frames too large");
+  REGEN_CUDA(cudaSetDevice(device));
+  regen_handle* h = new regen_handle();
+  h->desc = *d;
+  h->device = device;
+  h->L = d->num_layers;
+  h->I = d->input_feats;
+  h->Kin = (int)ceil_div(h->I, 64) * 64;
+  h->Mmax = d->max_batch * d->max_frames;
+  const size_t Mx = (size_t)h->Mmax;
+  int rc = REGEN_OK;
+  do {
+    // packed weights
+    if ((rc = alloc_split(h, &h->w_in, D, h->Kin, 256))) break;
+    if ((rc = alloc_split(h, &h->w_out, h->I, D, 256))) break;
+    for (int l = 0; l < h->L && rc == REGEN_OK; ++l) {
+      LayerDev& ld = h->layer[l];
+      if ((rc = alloc_split(h, &ld.wqkv, 3 * D, D, 256))) break;
+      if ((rc = alloc_split(h, &ld.wo, D, D, 256))) break;
+      if ((rc = alloc_split(h, &ld.w1, FF, D, 256))) break;
+      if ((rc = alloc_split(h, &ld.w2, D, FF, 256))) break;
+    }
+    if (rc) break;
+    if ((rc = h->alloc(&h->w_c, (size_t)D * h->I))) break;
+    if ((rc = h->alloc(&h->b_c, D))) break;
+    if ((rc = h->alloc(&h->P, (size_t)h->L * D * D))) break;
+    if ((rc = h->alloc(&h->qvec, (size_t)h->L * D))) break;
+    if ((rc = h->alloc(&h->ctab, (size_t)d->num_table_steps * h->L * D))) break;
+    // activations
+    if ((rc = alloc_split(h, &h->a_in, Mx, h->Kin, 128))) break;
+    if ((rc = alloc_split(h, &h->h_s, Mx, D, 128))) break;
+    if ((rc = alloc_split(h, &h->att, Mx, D, 128))) break;
+    if ((rc = alloc_split(h, &h->ffn, Mx, FF, 128))) break;
+    if ((rc = h->alloc(&h->h, Mx * D))) break;
+    if ((rc = h->alloc(&h->qkv, Mx * 3 * D))) break;
+    if ((rc = h->alloc(&h->tmp, Mx * D))) break;
+    if ((rc = h->alloc(&h->x0e, Mx * h->I))) break;
+    if ((rc = h->alloc(&h->condbias, Mx * D))) break;
+    if ((rc = h->alloc(&h->cmo_tbi, Mx * h->I))) break;
+    if ((rc = h->alloc(&h->scratch, Mx * D))) break;
+    if ((rc = h->alloc(&h->ccond, (size_t)d->max_batch * h->L * D))) break;
+    if ((rc = h->alloc(&h->cond_emb, (size_t)d->max_batch * D))) break;
+    cudaError_t e = cudaFuncSetAttribute(layers::attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)layers::attention_smem_bytes(d->max_frames));
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(attention) failed: %s", cudaGetErrorString(e));
+      rc = REGEN_ECUDA;
+    }
+  } while (0);
+  if (rc != REGEN_OK) {
+    regen_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return REGEN_OK;
+}
+
+void regen_destroy(regen_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+int regen_load_weights(regen_handle* h, const regen_weight_ptrs* w, void* stream) {
+  REGEN_CHECK_ARG(h && w, "regen_load_weights: null argument");
+  REGEN_CHECK_ARG(!h->loaded, "regen_load_weights: weights already loaded (create a new handle to reload)");
+  REGEN_CHECK_ARG(w->in_w && w->in_b && w->cmo_w && w->cmo_b && w->t0_w && w->t0_b && w->t2_w && w->t2_b && w->pe &&
+                      w->out_w && w->out_b, "regen_load_weights: null weight pointer");
+  REGEN_CHECK_ARG(h->desc.cm_mode == 0 || (w->fuse_w && w->fuse_b), "regen_load_weights: cm_mode=concat needs fuse_process");
+  REGEN_CHECK_ARG(w->pe_len >= h->desc.num_table_steps && w->pe_len >= h->desc.max_frames,
+                  "regen_load_weights: positional table (%d rows) shorter than num_table_steps / max_frames", w->pe_len);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int I = h->I, L = h->L;
+  float* fold = nullptr;
+  TRY(h->alloc(&fold, (size_t)D * (I > D ? I : D)));
+  float* bvec = nullptr;
+  TRY(h->alloc(&bvec, D));
+
+  TRY(copy_vec(h, &h->pe, w->pe, (size_t)w->pe_len * D, s));
+  h->pe_len = w->pe_len;
+  TRY(copy_vec(h, &h->b_out, w->out_b, I, s));
+  if (w->action_emb) {
+    REGEN_CHECK_ARG(w->num_actions >= 1, "regen_load_weights: action_emb given but num_actions=%d", w->num_actions);
+    TRY(copy_vec(h, &h->action_emb, w->action_emb, (size_t)w->num_actions * D, s));
+    h->num_actions = w->num_actions;
+  }
+  if (w->text_w) {
+    REGEN_CHECK_ARG(w->text_b && w->clip_dim >= 1, "regen_load_weights: embed_text needs bias and clip_dim");
+    TRY(copy_vec(h, &h->text_w, w->text_w, (size_t)D * w->clip_dim, s));
+    TRY(copy_vec(h, &h->text_b, w->text_b, D, s));
+    h->clip_dim = w->clip_dim;
+  }
+
+  if (h->desc.cm_mode == 1) {
+    // h = W_f [hx ; hc] + b_f with hx = W_in x + b_in, hc = W_cmo c + b_cmo  (model/cmdm.py:201-211)
+    //   => h = (W_f1 W_in) x + (W_f2 W_cmo) c + (W_f1 b_in + W_f2 b_cmo + b_f)
+    // W_in' = W_f1 . W_in : [D, I];  A = W_f1 (row stride 2D), B = W_in [D(k), I(n)]
+    layers::launch_sgemm(w->fuse_w, 2 * D, 1, w->in_w, I, 1, nullptr, nullptr, fold, I, D, I, D, 0, s);
+    layers::launch_split_rows(fold, I, h->w_in.hi, h->w_in.lo, h->Kin, I, D, 1, 1, s);
+    // W_c = W_f2 . W_cmo
+    layers::launch_sgemm(w->fuse_w + D, 2 * D, 1, w->cmo_w, I, 1, nullptr, nullptr, h->w_c, I, D, I, D, 0, s);
+    // b_c = W_f1 b_in + (W_f2 b_cmo + b_f)
+    layers::launch_sgemm(w->fuse_w + D, 2 * D, 1, w->cmo_b, 1, 1, nullptr, w->fuse_b, bvec, 1, D, 1, D, 0, s);
+    layers::launch_sgemm(w->fuse_w, 2 * D, 1, w->in_b, 1, 1, nullptr, bvec, h->b_c, 1, D, 1, D, 0, s);
+  } else {
+    // 'add': h = W_in x + W_cmo c + (b_in + b_cmo)
+    layers::launch_split_rows(w->in_w, I, h->w_in.hi, h->w_in.lo, h->Kin, I, D, 1, 1, s);
+    REGEN_CUDA(cudaMemcpyAsync(h->w_c, w->cmo_w, (size_t)D * I * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    // b_c[m] = 1 * b_in[m] + b_cmo[m]   (K = 1 GEMM with A = b_in as a [D,1] matrix and B = [[1]])
+    float one = 1.f;
+    float* one_d = nullptr;
+    TRY(h->alloc(&one_d, 1));
+    REGEN_CUDA(cudaMemcpyAsync(one_d, &one, sizeof(float), cudaMemcpyHostToDevice, s));
+    layers::launch_sgemm(w->in_b, 1, 1, one_d, 1, 1, nullptr, w->cmo_b, h->b_c, 1, D, 1, 1, 0, s);
+  }
+  layers::launch_split_rows(w->out_w, D, h->w_out.hi, h->w_out.lo, D, D, I, 1, 1, s);
+
+  for (int l = 0; l < L; ++l) {
+    const regen_layer_weights& lw = w->layers[l];
+    REGEN_CHECK_ARG(lw.qkv_w && lw.qkv_b && lw.o_w && lw.o_b && lw.xv_w && lw.xv_b && lw.xo_w && lw.xo_b && lw.l1_w &&
+                        lw.l1_b && lw.l2_w && lw.l2_b && lw.n1_w && lw.n1_b && lw.n2_w && lw.n2_b && lw.n3_w && lw.n3_b,
+                    "regen_load_weights: null pointer in layer %d", l);
+    LayerDev& ld = h->layer[l];
+    layers::launch_split_rows(lw.qkv_w, D, ld.wqkv.hi, ld.wqkv.lo, D, D, 3 * D, 1, 1, s);
+    layers::launch_split_rows(lw.o_w, D, ld.wo.hi, ld.wo.lo, D, D, D, 1, 1, s);
+    layers::launch_split_rows(lw.l1_w, D, ld.w1.hi, ld.w1.lo, D, D, FF, 1, 1, s);
+    layers::launch_split_rows(lw.l2_w, FF, ld.w2.hi, ld.w2.lo, FF, FF, D, 1, 1, s);
+    TRY(copy_vec(h, &ld.bqkv, lw.qkv_b, 3 * D, s));
+    TRY(copy_vec(h, &ld.bo, lw.o_b, D, s));
+    TRY(copy_vec(h, &ld.b1, lw.l1_b, FF, s));
+    TRY(copy_vec(h, &ld.b2, lw.l2_b, D, s));
+    TRY(copy_vec(h, &ld.n1w, lw.n1_w, D, s));
+    TRY(copy_vec(h, &ld.n1b, lw.n1_b, D, s));
+    TRY(copy_vec(h, &ld.n2w, lw.n2_w, D, s));
+    TRY(copy_vec(h, &ld.n2b, lw.n2_b, D, s));
+    TRY(copy_vec(h, &ld.n3w, lw.n3_w, D, s));
+    TRY(copy_vec(h, &ld.n3b, lw.n3_b, D, s));
+    // 1-token cross-attention: c = W_xo (W_xv e + b_xv) + b_xo = P_l e + q_l
+    //   P_l = W_xo . W_xv : A = W_xo [D, D(k)], B = W_xv [D(k), D(n)]
+    layers::launch_sgemm(lw.xo_w, D, 1, lw.xv_w, D, 1, nullptr, nullptr, h->P + (size_t)l * D * D, D, D, D, D, 0, s);
+    //   q_l = W_xo b_xv + b_xo
+    layers::launch_sgemm(lw.xo_w, D, 1, lw.xv_b, 1, 1, nullptr, lw.xo_b, h->qvec + (size_t)l * D, 1, D, 1, D, 0, s);
+  }
+
+  // timestep table: ctab[t] = P (W_t2 silu(W_t0 pe[t] + b_t0) + b_t2) + q   for t < num_table_steps
+  // (model/cmdm.py:291-298 followed by the folded cross-attention of every layer)
+  {
+    const int nt = h->desc.num_table_steps;
+    float *e1 = nullptr, *e2 = nullptr;
+    TRY(h->alloc(&e1, (size_t)nt * D));
+    TRY(h->alloc(&e2, (size_t)nt * D));
+    // e1 = silu(pe[0:nt] . W_t0^T + b_t0):  B[k, n] = W_t0[n, k] -> sbk = 1, sbn = D
+    layers::launch_sgemm(h->pe, D, 1, w->t0_w, 1, D, w->t0_b, nullptr, e1, D, nt, D, D, 1, s);
+    layers::launch_sgemm(e1, D, 1, w->t2_w, 1, D, w->t2_b, nullptr, e2, D, nt, D, D, 0, s);
+    // ctab = e2 . P^T + q with P stacked [L*D, D]
+    layers::launch_sgemm(e2, D, 1, h->P, 1, D, h->qvec, nullptr, h->ctab, (int64_t)L * D, nt, L * D, D, 0, s);
+  }
+  REGEN_LAUNCH_CHECK();
+  h->loaded = true;
+  return REGEN_OK;
+}
+
+int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t* action, const float* text_feat,
+                       int32_t B, int32_t T, int32_t guidance, int32_t uncond, void* stream) {
+  REGEN_CHECK_ARG(h && cmotion_bjft, "regen_prepare_cond: null argument");
+  if (!h->loaded) {
+    set_error("regen_prepare_cond: weights not loaded");
+    return REGEN_ESTATE;
+  }
+  const int Beff = guidance ? 2 * B : B;
+  REGEN_CHECK_ARG(B >= 1 && T >= 1 && Beff <= h->desc.max_batch && T <= h->desc.max_frames &&
+                      (int64_t)Beff * T <= h->Mmax,
+                  "regen_prepare_cond: B=%d (effective %d) T=%d exceed the handle's max_batch=%d / max_frames=%d", B,
+                  Beff, T, h->desc.max_batch, h->desc.max_frames);
+  REGEN_CHECK_ARG(!action || h->action_emb, "regen_prepare_cond: action indices given but the model has no embed_action");
+  REGEN_CHECK_ARG(!text_feat || h->text_w, "regen_prepare_cond: text features given but the model has no embed_text");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int I = h->I, L = h->L;
+  h->B = B; h->Beff = Beff; h->T = T; h->M = T * Beff;
+  h->guidance = guidance != 0;
+  h->has_cond = !uncond && (action || text_feat);
+  // cmotion [B,I,T] -> [T,B,I]; hc' = cmotion . W_c^T + b_c; condbias = dup(hc') + pe[t]
+  TRY(regen_bjft_to_tbi(cmotion_bjft, h->cmo_tbi, B, I, T, stream));
+  layers::launch_sgemm(h->cmo_tbi, I, 1, h->w_c, 1, I, h->b_c, nullptr, h->scratch, D, T * B, D, I, 0, s);
+  {
+    int64_t total = (int64_t)h->M * (D / 4);
+    layers::finalize_condbias_kernel<<<grid_cap(ceil_div(total, 256)), 256, 0, s>>>(h->scratch, h->pe, h->condbias, T,
+                                                                                     B, guidance ? 2 : 1);
+    count_launch();
+  }
+  if (h->has_cond) {
+    // cond_emb[b] = embed_text(text_feat[b]) + action_embedding[action[b]]   (model/cmdm.py:182-187)
+    if (text_feat)
+      layers::launch_sgemm(text_feat, h->clip_dim, 1, h->text_w, 1, h->clip_dim, h->text_b, nullptr, h->cond_emb, D, B,
+                           D, h->clip_dim, 0, s);
+    if (action)
+    {
+      layers::gather_rows_kernel<<<B, 128, 0, s>>>(h->action_emb, action, h->cond_emb, h->num_actions,
+                                                   text_feat ? 1 : 0);
+      count_launch();
+    }
+    // ccond[b] = P . cond_emb[b]  (rows [B, 2B) stay zero: the unconditional half, mask_cond force_mask)
+    REGEN_CUDA(cudaMemsetAsync(h->ccond, 0, (size_t)Beff * L * D * sizeof(float), s));
+    layers::launch_sgemm(h->cond_emb, D, 1, h->P, 1, D, nullptr, nullptr, h->ccond, (int64_t)L * D, B, L * D, D, 0, s);
+  }
+  REGEN_LAUNCH_CHECK();
+  h->cond_ready = true;
+  return REGEN_OK;
+}
+
+int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const float* cfg_scale, float* x0_tbi,
+                  int32_t B, int32_t T, void* stream) {
+  REGEN_CHECK_ARG(h && x_tbi && t && x0_tbi, "regen_denoise: null argument");
+  if (!h->cond_ready) {
+    set_error("regen_denoise: regen_prepare_cond has not been called");
+    return REGEN_ESTATE;
+  }
+  REGEN_CHECK_ARG(B == h->B && T == h->T, "regen_denoise: B=%d T=%d differ from prepare_cond's B=%d T=%d", B, T, h->B,
+                  h->T);
+  REGEN_CHECK_ARG(!h->guidance || cfg_scale, "regen_denoise: guidance was requested but cfg_scale is null");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int M = h->M, I = h->I, L = h->L, Beff = h->Beff;
+
+  // A operand of the input projection: split x into bf16 (hi, lo), K padded to a multiple of 64,
+  // batch duplicated under guidance
+  {
+    ProfScope prof(h, CLS_OTHER, s);
+    layers::launch_split_rows(x_tbi, I, h->a_in.hi, h->a_in.lo, h->Kin, I, M, B, h->guidance ? 2 : 1, s);
+  }
+
+  // h = x . W_in'^T + condbias      (input_process + fuse_process + positional encoding, hoisted parts in condbias)
+  {
+    gemm::Params p = gp(M, D, h->Kin);
+    p.residual = h->condbias; p.ld_res = D;
+    p.out_f32 = h->h; p.ld_out = D;
+    p.out_hi = h->h_s.hi; p.out_lo = h->h_s.lo; p.ld_split = D;
+    TRY(run_gemm(h, h->a_in, h->w_in, p, s));
+  }
+  for (int l = 0; l < L; ++l) {
+    LayerDev& ld = h->layer[l];
+    {  // q | k | v
+      gemm::Params p = gp(M, 3 * D, D);
+      p.bias = ld.bqkv;
+      p.out_f32 = h->qkv; p.ld_out = 3 * D;
+      TRY(run_gemm(h, h->h_s, ld.wqkv, p, s));
+    }
+    {
+      ProfScope prof(h, CLS_ATTN, s);
+      layers::attention_simt_kernel<<<Beff * layers::H, layers::ATT_WARPS * 32, layers::attention_smem_bytes(T), s>>>(
+          h->qkv, h->att.hi, h->att.lo, T, Beff);
+      count_launch();
+    }
+    {  // tmp = h + attn . W_o^T + b_o
+      gemm::Params p = gp(M, D, D);
+      p.bias = ld.bo;
+      p.residual = h->h; p.ld_res = D;
+      p.out_f32 = h->tmp; p.ld_out = D;
+      TRY(run_gemm(h, h->att, ld.wo, p, s));
+    }
+    {  // h = LN2( LN1(tmp) + c_l[b] )
+      layers::LnParams q;
+      q.in = h->tmp; q.g1 = ld.n1w; q.b1 = ld.n1b; q.g2 = ld.n2w; q.b2 = ld.n2b;
+      q.ctab = h->ctab + (size_t)l * D;
+      q.ccond = h->has_cond ? h->ccond + (size_t)l * D : nullptr;
+      q.t = t; q.ld_c = L * D; q.B = B; q.Beff = Beff; q.n_table = h->desc.num_table_steps;
+      q.out_f32 = h->h; q.out_hi = h->h_s.hi; q.out_lo = h->h_s.lo; q.M = M;
+      ProfScope prof(h, CLS_LN, s);
+      layers::layernorm_kernel<true><<<(unsigned)ceil_div(M, 8), 256, 0, s>>>(q);
+      count_launch();
+    }
+    {  // ffn = gelu(h . W_1^T + b_1)
+      gemm::Params p = gp(M, FF, D);
+      p.bias = ld.b1; p.gelu = 1;
+      p.out_hi = h->ffn.hi; p.out_lo = h->ffn.lo; p.ld_split = FF;
+      TRY(run_gemm(h, h->h_s, ld.w1, p, s));
+    }
+    {  // tmp = h + ffn . W_2^T + b_2
+      gemm::Params p = gp(M, D, FF);
+      p.bias = ld.b2;
+      p.residual = h->h; p.ld_res = D;
+      p.out_f32 = h->tmp; p.ld_out = D;
+      TRY(run_gemm(h, h->ffn, ld.w2, p, s));
+    }
+    {  // h = LN3(tmp)
+      layers::LnParams q;
+      memset(&q, 0, sizeof(q));
+      q.in = h->tmp; q.g1 = ld.n3w; q.b1 = ld.n3b;
+      q.out_f32 = h->h; q.out_hi = h->h_s.hi; q.out_lo = h->h_s.lo; q.M = M;
+      q.B = B; q.Beff = Beff;
+      ProfScope prof(h, CLS_LN, s);
+      layers::layernorm_kernel<false><<<(unsigned)ceil_div(M, 8), 256, 0, s>>>(q);
+      count_launch();
+    }
+  }
+  {  // x0 = h . W_out^T + b_out   (output_process; rows already in [T,B,I] order)
+    gemm::Params p = gp(M, I, D);
+    p.bias = h->b_out;
+    p.out_f32 = h->guidance ? h->x0e : x0_tbi; p.ld_out = I;
+    TRY(run_gemm(h, h->h_s, h->w_out, p, s));
+  }
+  if (h->guidance) {
+    int64_t total = (int64_t)T * B * I;
+    int blocks = grid_cap(ceil_div(total, 256));
+    ProfScope prof(h, CLS_OTHER, s);
+    layers::cfg_rows_kernel<<<blocks, 256, 0, s>>>(h->x0e, cfg_scale, x0_tbi, T, B, I);
+    count_launch();
+  }
+  REGEN_LAUNCH_CHECK();
+  return REGEN_OK;
+}
+
+int regen_profile_begin(regen_handle* h) {
+  REGEN_CHECK_ARG(h, "regen_profile_begin: null handle");
+  for (auto& v : h->prof_ev) {
+    for (auto& p : v) {
+      cudaEventDestroy(p.first);
+      cudaEventDestroy(p.second);
+    }
+    v.clear();
+  }
+  h->prof_on = true;
+  return REGEN_OK;
+}
+
+int regen_profile_end(regen_handle* h, float* ms, int32_t* launches) {
+  REGEN_CHECK_ARG(h && ms && launches, "regen_profile_end: null argument");
+  h->prof_on = false;
+  REGEN_CUDA(cudaDeviceSynchronize());
+  for (int c = 0; c < 4; ++c) {
+    double tot = 0.0;
+    for (auto& p : h->prof_ev[c]) {
+      float t = 0.f;
+      REGEN_CUDA(cudaEventElapsedTime(&t, p.first, p.second));
+      tot += t;
+      cudaEventDestroy(p.first);
+      cudaEventDestroy(p.second);
+    }
+    ms[c] = (float)tot;
+    launches[c] = (int32_t)h->prof_ev[c].size();
+    h->prof_ev[c].clear();
+  }
+  return REGEN_OK;
+}
+
+// Kernel-level test hook: C = A . W^T (+bias)(+residual)(gelu) through the tcgen05 GEMM, fp32 in / out.
+int regen_test_gemm(const float* A, const float* W, const float* bias, const float* residual, float* out, int32_t M,
+                    int32_t N, int32_t K, int32_t gelu, int32_t precision, void* stream) {
+  REGEN_CHECK_ARG(A && W && out, "regen_test_gemm: null argument");
+  REGEN_CHECK_ARG(M >= 1 && N >= 1 && K >= 1, "regen_test_gemm: bad sizes");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Kp = (int)ceil_div(K, 64) * 64;
+  bf16 *ah, *al, *wh, *wl;
+  REGEN_CUDA(cudaMalloc(&ah, (size_t)M * Kp * 2));
+  REGEN_CUDA(cudaMalloc(&al, (size_t)M * Kp * 2));
+  REGEN_CUDA(cudaMalloc(&wh, (size_t)N * Kp * 2));
+  REGEN_CUDA(cudaMalloc(&wl, (size_t)N * Kp * 2));
+  layers::launch_split_rows(A, K, ah, al, Kp, K, M, 1, 1, s);
+  layers::launch_split_rows(W, K, wh, wl, Kp, K, N, 1, 1, s);
+  CUtensorMap ta_h, ta_l, tw_h, tw_l;
+  int rc = make_tmap_bf16_2d(&ta_h, ah, M, Kp, Kp, 128);
+  if (!rc) rc = make_tmap_bf16_2d(&ta_l, al, M, Kp, Kp, 128);
+  if (!rc) rc = make_tmap_bf16_2d(&tw_h, wh, N, Kp, Kp, 256);
+  if (!rc) rc = make_tmap_bf16_2d(&tw_l, wl, N, Kp, Kp, 256);
+  if (!rc) {
+    gemm::Params p = gp(M, N, Kp);
+    p.bias = bias; p.residual = residual; p.ld_res = N; p.out_f32 = out; p.ld_out = N; p.gelu = gelu;
+    cudaError_t e = precision == 0 ? gemm::launch<256, true>(ta_h, ta_l, tw_h, tw_l, p, s)
+                                   : gemm::launch<256, false>(ta_h, ta_l, tw_h, tw_l, p, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+      set_error("regen_test_gemm: %s", cudaGetErrorString(e));
+      rc = REGEN_ECUDA;
+    }
+  }
+  cudaFree(ah); cudaFree(al); cudaFree(wh); cudaFree(wl);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,52 @@
+// TMA tensor-map construction.  cuTensorMapEncodeTiled lives in the driver (libcuda); it is
+// resolved at run time through cudaGetDriverEntryPoint so the library links against cudart only
+// and still loads (for the symbol / argument-validation tests) on hosts without a GPU driver.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+namespace regen {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// bf16 matrix [rows, cols] (cols contiguous, row pitch in elements), box = box_rows x 64 columns,
+// 128-byte swizzle, out-of-bounds elements read as zero.
+inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                             uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    return REGEN_ECUDA;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu pitch=%llu box_rows=%u)", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_elems, box_rows);
+    return REGEN_ECUDA;
+  }
+  return REGEN_OK;
+}
+
+}  // namespace regen

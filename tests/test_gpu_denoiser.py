@@ -1,0 +1,140 @@
+"""GPU parity: CMDM.forward / ClassifierFreeSampleModel.forward (sm_100a kernels through the C ABI)
+vs the CPU oracle and vs the golden outputs of the imported reference.
+
+Tolerance: BASELINE.json's north star -- 1e-3 abs on the rot6d outputs.  The bf16x3 path is expected
+to sit around 3e-5; the test prints the measured error."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import cmdm_ref
+from regennet_b200 import synthetic
+from regennet_b200.cfg_sampler import ClassifierFreeSampleModel
+from regennet_b200.cmdm import CMDM
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-3          # north-star tolerance (rot6d abs)
+TOL_TIGHT = 2e-4    # what bf16x3 should comfortably achieve
+
+_models = {}
+
+
+def get_model(name, wseed):
+    key = (name, wseed)
+    if key not in _models:
+        m = CMDM(**cases.MODELS[name])
+        sd = synthetic.make_state_dict(seed=wseed, **cases.synth_kw(name))
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        assert not unexpected and all(k.startswith("clip_model.") for k in missing)
+        _models[key] = (m.cuda().eval(), sd)
+    return _models[key]
+
+
+def to_cuda(y):
+    return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in y.items()}
+
+
+def _kw(mk):
+    return dict(num_layers=mk["num_layers"], nhead=mk["num_heads"], cond_mode=mk["cond_mode"], cm_mode=mk["cm_mode"])
+
+
+@pytest.mark.parametrize("name", sorted(cases.FORWARD_CASES))
+def test_forward_matches_reference_golden(built_lib, name):
+    c = cases.FORWARD_CASES[name]
+    mk = cases.MODELS[c["model"]]
+    gold = torch.from_numpy(np.load(os.path.join(HERE, "forward.npz"))[name])
+    model, sd = get_model(c["model"], c["wseed"])
+    x, y = synthetic.make_inputs(c["B"], mk["njoints"], mk["nfeats"], c["T"], seed=c["xseed"],
+                                 cond_mode=mk["cond_mode"], num_actions=mk["num_actions"], scale=c.get("cfg_scale"))
+    if c.get("uncond"):
+        y["uncond"] = True
+    t = torch.tensor(c["t"], dtype=torch.long)
+    run = ClassifierFreeSampleModel(model) if "cfg_scale" in c else model
+    with torch.no_grad():
+        out = run(x.cuda(), t.cuda(), to_cuda(y))
+    assert out.shape == gold.shape
+    err = (out.cpu() - gold).abs().max().item()
+    print("%s: max abs err vs reference golden %.3e" % (name, err))
+    assert err < TOL
+    assert err < TOL_TIGHT
+
+
+def test_forward_output_is_permuted_view_like_reference(built_lib):
+    model, _ = get_model("ntu", 0)
+    x, y = synthetic.make_inputs(2, 56, 6, 60, seed=10)
+    out = model(x.cuda(), torch.tensor([5, 9]).cuda(), to_cuda(y))
+    assert out.shape == (2, 56, 6, 60)
+    assert out.permute(3, 0, 1, 2).is_contiguous()  # reference: output.permute(1, 2, 3, 0), model/cmdm.py:354
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (5, 3), (7, 64), (33, 60), (256, 60)])
+def test_forward_matches_oracle_various_sizes(built_lib, B, T):
+    """Ragged / tiny / full-size batches against the oracle run on the same seeded inputs.  At B=256
+    (BASELINE config 2) the oracle checks a strided subset of samples to stay within seconds."""
+    mk = cases.MODELS["ntu"]
+    model, sd = get_model("ntu", 0)
+    x, y = synthetic.make_inputs(B, 56, 6, T, seed=100 + B)
+    g = torch.Generator().manual_seed(B)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    with torch.no_grad():
+        out = model(x.cuda(), t.cuda(), to_cuda(y)).cpu()
+    sel = torch.arange(B) if B <= 33 else torch.tensor([0, 1, 63, 127, 128, 200, 255])
+    with torch.no_grad():
+        want = cmdm_ref.cmdm_forward(sd, x[sel], t[sel], {"cmotion": y["cmotion"][sel]}, **_kw(mk))
+    err = (out[sel] - want).abs().max().item()
+    print("B=%d T=%d: max abs err vs oracle %.3e" % (B, T, err))
+    assert err < TOL_TIGHT
+    # samples are independent: the full-batch result must equal a sub-batch result bit for bit
+    if B > 1:
+        with torch.no_grad():
+            sub = model(x[:1].cuda(), t[:1].cuda(), {"cmotion": y["cmotion"][:1].cuda()}).cpu()
+        assert torch.allclose(sub, out[:1], atol=1e-5)
+
+
+def test_causality_property(built_lib):
+    """arch='online': frame f of the output depends only on frames <= f of x and cmotion."""
+    model, _ = get_model("ntu", 0)
+    x, y = synthetic.make_inputs(2, 56, 6, 60, seed=3)
+    t = torch.tensor([400, 30]).cuda()
+    with torch.no_grad():
+        a = model(x.cuda(), t, to_cuda(y)).cpu()
+        x2, c2 = x.clone(), y["cmotion"].clone()
+        x2[..., 40:] += 1.0
+        c2[..., 40:] -= 2.0
+        b = model(x2.cuda(), t, {"cmotion": c2.cuda()}).cpu()
+    assert torch.equal(a[..., :40], b[..., :40])
+    assert not torch.allclose(a[..., 40:], b[..., 40:])
+
+
+def test_bf16_fast_mode_error_is_reported(built_lib):
+    """precision='bf16' (single MMA pass) is NOT parity-grade; record its error next to bf16x3."""
+    mk = cases.MODELS["ntu"]
+    m = CMDM(**dict(mk, precision="bf16"))
+    sd = synthetic.make_state_dict(seed=0, **cases.synth_kw("ntu"))
+    m.load_state_dict(sd, strict=False)
+    m = m.cuda().eval()
+    x, y = synthetic.make_inputs(2, 56, 6, 60, seed=10)
+    t = torch.tensor([999, 3])
+    gold = torch.from_numpy(np.load(os.path.join(HERE, "forward.npz"))["fwd_ntu"])
+    with torch.no_grad():
+        out = m(x.cuda(), t.cuda(), to_cuda(y)).cpu()
+    err = (out - gold).abs().max().item()
+    print("bf16 single-pass max abs err %.3e" % err)
+    assert err < 0.1
+
+
+def test_errors(built_lib):
+    model, _ = get_model("ntu", 0)
+    x, y = synthetic.make_inputs(2, 56, 6, 60, seed=10)
+    with pytest.raises(RuntimeError):
+        model(x, torch.tensor([1, 2]), y)                       # CPU tensors: no fallback
+    with pytest.raises(TypeError):
+        model(x.cuda(), torch.tensor([1, 2]).cuda(), None)      # the reference crashes on y=None as well
+    with pytest.raises(ValueError):
+        model(x[:, :10].cuda(), torch.tensor([1, 2]).cuda(), to_cuda(y))
+    with pytest.raises(NotImplementedError):
+        CMDM(**dict(cases.MODELS["ntu"], arch="trans_enc"))

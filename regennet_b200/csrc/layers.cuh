@@ -123,6 +123,12 @@ __global__ void __launch_bounds__(256) finalize_condbias_kernel(const float* __r
   }
 }
 
+// out[b, :] = vec[:]   (D = 512; one block of 128 threads per row)
+__global__ void __launch_bounds__(128) broadcast_rows_kernel(const float* __restrict__ vec, float* __restrict__ out) {
+  reinterpret_cast<float4*>(out + (size_t)blockIdx.x * D)[threadIdx.x] =
+      __ldg(reinterpret_cast<const float4*>(vec) + threadIdx.x);
+}
+
 // out[b, :] (+)= table[clamp(idx[b]), :]   -- EmbedAction row gather (model/cmdm.py:363-366), D = 512
 __global__ void __launch_bounds__(128) gather_rows_kernel(const float* __restrict__ table,
                                                           const int64_t* __restrict__ idx, float* __restrict__ out,

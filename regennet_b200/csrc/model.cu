@@ -188,8 +188,10 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
     if ((rc = h->alloc(&h->scratch, Mx * D))) break;
     if ((rc = h->alloc(&h->ccond, (size_t)d->max_batch * h->L * D))) break;
     if ((rc = h->alloc(&h->cond_emb, (size_t)d->max_batch * D))) break;
+    // the attribute is per function, not per handle: always allow the full 227 KB so that handles with
+    // different max_frames can coexist in one process
     cudaError_t e = cudaFuncSetAttribute(layers::attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)layers::attention_smem_bytes(d->max_frames));
+                                         227 * 1024);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(attention) failed: %s", cudaGetErrorString(e));
       rc = REGEN_ECUDA;
@@ -327,7 +329,11 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
   const int I = h->I, L = h->L;
   h->B = B; h->Beff = Beff; h->T = T; h->M = T * Beff;
   h->guidance = guidance != 0;
-  h->has_cond = !uncond && (action || text_feat);
+  // 'text' models keep a contribution even when unconditional: mask_cond zeroes the CLIP FEATURES, so
+  // embed_text still adds its bias (model/cmdm.py:182-184); 'action' embeddings are zeroed themselves (:185-187)
+  const bool text_model = h->text_w != nullptr;
+  REGEN_CHECK_ARG(!text_model || uncond || text_feat, "regen_prepare_cond: text-conditioned model needs text features");
+  h->has_cond = text_model || (action && !uncond);
   // cmotion [B,I,T] -> [T,B,I]; hc' = cmotion . W_c^T + b_c; condbias = dup(hc') + pe[t]
   TRY(regen_bjft_to_tbi(cmotion_bjft, h->cmo_tbi, B, I, T, stream));
   layers::launch_sgemm(h->cmo_tbi, I, 1, h->w_c, 1, I, h->b_c, nullptr, h->scratch, D, T * B, D, I, 0, s);
@@ -338,19 +344,23 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
     count_launch();
   }
   if (h->has_cond) {
-    // cond_emb[b] = embed_text(text_feat[b]) + action_embedding[action[b]]   (model/cmdm.py:182-187)
-    if (text_feat)
-      layers::launch_sgemm(text_feat, h->clip_dim, 1, h->text_w, 1, h->clip_dim, h->text_b, nullptr, h->cond_emb, D, B,
-                           D, h->clip_dim, 0, s);
-    if (action)
-    {
-      layers::gather_rows_kernel<<<B, 128, 0, s>>>(h->action_emb, action, h->cond_emb, h->num_actions,
-                                                   text_feat ? 1 : 0);
+    // cond_emb[b'] for b' in [0, Beff): conditional rows [0,B), unconditional rows [B,2B) under guidance
+    if (text_model) {
+      layers::broadcast_rows_kernel<<<Beff, 128, 0, s>>>(h->text_b, h->cond_emb);
+      count_launch();
+      if (!uncond)
+        layers::launch_sgemm(text_feat, h->clip_dim, 1, h->text_w, 1, h->clip_dim, h->text_b, nullptr, h->cond_emb, D,
+                             B, D, h->clip_dim, 0, s);
+    } else {
+      REGEN_CUDA(cudaMemsetAsync(h->cond_emb, 0, (size_t)Beff * D * sizeof(float), s));
+    }
+    if (action && !uncond) {
+      layers::gather_rows_kernel<<<B, 128, 0, s>>>(h->action_emb, action, h->cond_emb, h->num_actions, 1);
       count_launch();
     }
-    // ccond[b] = P . cond_emb[b]  (rows [B, 2B) stay zero: the unconditional half, mask_cond force_mask)
-    REGEN_CUDA(cudaMemsetAsync(h->ccond, 0, (size_t)Beff * L * D * sizeof(float), s));
-    layers::launch_sgemm(h->cond_emb, D, 1, h->P, 1, D, nullptr, nullptr, h->ccond, (int64_t)L * D, B, L * D, D, 0, s);
+    // ccond[b'] = P . cond_emb[b']   (folded 1-token cross-attention of every layer)
+    layers::launch_sgemm(h->cond_emb, D, 1, h->P, 1, D, nullptr, nullptr, h->ccond, (int64_t)L * D, Beff, L * D, D, 0,
+                         s);
   }
   REGEN_LAUNCH_CHECK();
   h->cond_ready = true;

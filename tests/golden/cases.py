@@ -39,6 +39,9 @@ FORWARD_CASES = {
     "fwd_chi3d_uncond": dict(model="chi3d", B=2, T=150, t=[640, 12], wseed=2, xseed=13, uncond=True),
     "fwd_chi3d_cfg": dict(model="chi3d", B=2, T=150, t=[640, 12], wseed=2, xseed=13, cfg_scale=2.5),
     "fwd_hml_text": dict(model="hml", B=2, T=196, t=[321, 900], wseed=3, xseed=14),
+    # unconditional text model: mask_cond zeroes the CLIP features, embed_text still adds its bias
+    "fwd_hml_uncond": dict(model="hml", B=2, T=196, t=[321, 900], wseed=3, xseed=14, uncond=True),
+    "fwd_hml_cfg": dict(model="hml", B=1, T=50, t=[77], wseed=3, xseed=15, cfg_scale=2.5),
 }
 
 LOOP_CASES = {

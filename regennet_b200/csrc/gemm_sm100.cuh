@@ -11,7 +11,9 @@
 //     (hi, lo) pair for the next GEMM's A operand.
 //
 // Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
-// One CTA per 128 x BN output tile.
+// Persistent: one CTA per SM loops over 128 x BN output tiles; the fp32 accumulator is double buffered in
+// TMEM so the epilogue of one tile overlaps the main loop of the next; epilogue traffic is staged
+// through shared memory so every global access is a full, coalesced 128-byte (fp32) / 64-byte (bf16) row segment.
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
@@ -30,11 +32,17 @@ struct Cfg {
   static constexpr int W_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + W_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;  // 2 for SPLIT @ BN=256, 4 for plain bf16
+  // epilogue staging: per epilogue warp 32 rows x 32 fp32 columns, row pitch padded to 36 words so that
+  // both the row-per-thread accesses and the coalesced 128-byte row segments are bank-conflict free
+  static constexpr int STG_PITCH = 36;
+  static constexpr int STG_WARP_BYTES = 32 * STG_PITCH * 4;
+  static constexpr int STG_BYTES = 4 * STG_WARP_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;                         // power of two for BN in {32..256}
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+  static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
   static_assert(STAGES >= 2, "need at least a double buffer");
-  static_assert((BN & (BN - 1)) == 0 && BN >= 32 && BN <= 256, "BN must be a power of two in [32,256]");
+  static_assert(BN == 128 || BN == 256, "BN must be 128 or 256 (TMEM_COLS a power of two <= 512)");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 struct Params {
@@ -52,6 +60,9 @@ struct Params {
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
+// Persistent kernel: grid = min(#tiles, #SMs); CTA c processes tiles c, c + grid, ... (n fastest, so
+// CTAs running concurrently share A tiles through L2).  The accumulator is double buffered in TMEM
+// (2 x BN columns): the epilogue of tile i overlaps the TMA/MMA main loop of tile i + 1.
 template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -60,16 +71,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   using C = Cfg<BN, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  float* staging = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::STG_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
   const int num_kb = p.K / BK;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int num_tiles = tiles_n * tiles_m;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a_hi);
@@ -82,7 +96,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&tmem_full_bar[b], 1);
+      ptx::mbar_init(&tmem_empty_bar[b], 4);  // one arrival per epilogue warp
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -99,19 +116,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* st = smem + stage * C::STAGE_BYTES;
-        ptx::mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-        ptx::tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * BK, m0);
-        ptx::tma_load_2d(st + C::A_BYTES, &tm_w_hi, &full_bar[stage], kb * BK, n0);
-        if (SPLIT) {
-          ptx::tma_load_2d(st + C::A_BYTES + C::W_BYTES, &tm_a_lo, &full_bar[stage], kb * BK, m0);
-          ptx::tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &tm_w_lo, &full_bar[stage], kb * BK, n0);
-        }
-        if (++stage == C::STAGES) {
-          stage = 0;
-          phase ^= 1;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * C::STAGE_BYTES;
+          ptx::mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          ptx::tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * BK, m0);
+          ptx::tma_load_2d(st + C::A_BYTES, &tm_w_hi, &full_bar[stage], kb * BK, n0);
+          if (SPLIT) {
+            ptx::tma_load_2d(st + C::A_BYTES + C::W_BYTES, &tm_a_lo, &full_bar[stage], kb * BK, m0);
+            ptx::tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &tm_w_lo, &full_bar[stage], kb * BK, n0);
+          }
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -121,95 +141,185 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        ptx::mbar_wait(&full_bar[stage], phase);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        ptx::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         ptx::tcgen05_fence_after();
-        const uint32_t st = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
-        const uint64_t a_hi = ptx::umma_desc_k_sw128(st);
-        const uint64_t w_hi = ptx::umma_desc_k_sw128(st + C::A_BYTES);
-        const uint64_t a_lo = ptx::umma_desc_k_sw128(st + C::A_BYTES + C::W_BYTES);
-        const uint64_t w_lo = ptx::umma_desc_k_sw128(st + 2 * C::A_BYTES + C::W_BYTES);
+        const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tcgen05_fence_after();
+          const uint32_t st = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint64_t a_hi = ptx::umma_desc_k_sw128(st);
+          const uint64_t w_hi = ptx::umma_desc_k_sw128(st + C::A_BYTES);
+          const uint64_t a_lo = ptx::umma_desc_k_sw128(st + C::A_BYTES + C::W_BYTES);
+          const uint64_t w_lo = ptx::umma_desc_k_sw128(st + 2 * C::A_BYTES + C::W_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-          const uint64_t adv = (uint64_t)(k * UMMA_K * 2 >> 4);
-          if (SPLIT) {
-            // small cross terms first, the dominant hi.hi product last
-            ptx::mma_f16_ss(tmem_base, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);
-            ptx::mma_f16_ss(tmem_base, a_hi + adv, w_lo + adv, idesc, 1);
-            ptx::mma_f16_ss(tmem_base, a_hi + adv, w_hi + adv, idesc, 1);
-          } else {
-            ptx::mma_f16_ss(tmem_base, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            const uint64_t adv = (uint64_t)(k * UMMA_K * 2 >> 4);
+            if (SPLIT) {
+              // small cross terms first, the dominant hi.hi product last
+              ptx::mma_f16_ss(acc, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);
+              ptx::mma_f16_ss(acc, a_hi + adv, w_lo + adv, idesc, 1);
+              ptx::mma_f16_ss(acc, a_hi + adv, w_hi + adv, idesc, 1);
+            } else {
+              ptx::mma_f16_ss(acc, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+            }
+          }
+          ptx::tcgen05_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
           }
         }
-        ptx::tcgen05_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
-        if (++stage == C::STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+        ptx::tcgen05_commit(&tmem_full_bar[buf]);  // accumulator complete
       }
-      ptx::tcgen05_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tcgen05_fence_after();
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.M;
+    float* stg = staging + q * (32 * C::STG_PITCH);
+    __nv_bfloat16* stg_h = reinterpret_cast<__nv_bfloat16*>(stg);  // bf16 staging: 32 rows x 40 halves (80 B pitch)
     const bool vec_ok = (p.N & 3) == 0;
-    const float* res_row = p.residual ? p.residual + (size_t)row * p.ld_res : nullptr;
-    float* out_row = p.out_f32 ? p.out_f32 + (size_t)row * p.ld_out : nullptr;
-    __nv_bfloat16* hi_row = p.out_hi ? p.out_hi + (size_t)row * p.ld_split : nullptr;
-    __nv_bfloat16* lo_row = p.out_hi ? p.out_lo + (size_t)row * p.ld_split : nullptr;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
-      ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      ptx::tmem_ld_wait();
-      if (row_ok && n0 + c0 < p.N) {
+    // coalesced mapping: lane -> (row i*4 + lane/8, 16-byte piece lane%8) for fp32,
+    //                            (row i*8 + lane/4, 16-byte piece lane%4) for bf16
+    const int cr = lane >> 3, cc = (lane & 7) * 4;
+    const int hr = lane >> 2, hc = (lane & 3) * 8;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const int buf = it & 1;
+      const int row0 = m0 + q * 32;   // first row of this warp
+      const int row = row0 + lane;    // this thread's accumulator row
+      const bool row_ok = row < p.M;
+      ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
+      ptx::tcgen05_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
+      if (vec_ok) {
+        float4 rpre[8];
+        auto prefetch_res = [&](int c0) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int n = n0 + c0 + j;
-        if (n >= p.N) break;
-        float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                      __uint_as_float(r[j + 3])};
-        if (vec_ok) {
-          if (p.bias) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+          for (int i = 0; i < 8; ++i) {
+            const int r = row0 + i * 4 + cr, n = n0 + c0 + cc;
+            rpre[i] = (r < p.M && n < p.N) ? *reinterpret_cast<const float4*>(p.residual + (size_t)r * p.ld_res + n)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          if (res_row) {
-            const float4 r4 = *reinterpret_cast<const float4*>(res_row + n);
-            v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+        };
+        if (p.residual) prefetch_res(0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (n0 + c0 >= p.N) break;  // warp-uniform
+          uint32_t r[32];
+          __syncwarp();
+          ptx::tmem_ld_32x32b_x32(acc + (uint32_t)c0, r);
+          if (p.residual) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(stg + (i * 4 + cr) * C::STG_PITCH + cc) = rpre[i];
+            __syncwarp();
+            if (c0 + 32 < BN && n0 + c0 + 32 < p.N) prefetch_res(c0 + 32);
+          }
+          ptx::tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int n = n0 + c0 + j;
+              if (n < p.N) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              }
+            }
+          }
+          if (p.residual) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 r4 = *reinterpret_cast<const float4*>(stg + lane * C::STG_PITCH + j);
+              v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+            }
+            __syncwarp();
           }
           if (p.gelu) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = gelu_erf(v[e]);
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
           }
-          if (out_row) *reinterpret_cast<float4*>(out_row + n) = make_float4(v[0], v[1], v[2], v[3]);
-          if (hi_row) {
-            __nv_bfloat16 h[4], l[4];
+          if (p.out_f32) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) split_bf16(v[e], h[e], l[e]);
-            *reinterpret_cast<uint2*>(hi_row + n) = *reinterpret_cast<uint2*>(h);
-            *reinterpret_cast<uint2*>(lo_row + n) = *reinterpret_cast<uint2*>(l);
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(stg + lane * C::STG_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = row0 + i * 4 + cr, n = n0 + c0 + cc;
+              if (rr < p.M && n < p.N)
+                *reinterpret_cast<float4*>(p.out_f32 + (size_t)rr * p.ld_out + n) =
+                    *reinterpret_cast<const float4*>(stg + (i * 4 + cr) * C::STG_PITCH + cc);
+            }
+            __syncwarp();
           }
-        } else {
+          if (p.out_hi) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (n + e >= p.N) break;
-            float w = v[e];
-            if (p.bias) w += __ldg(p.bias + n + e);
-            if (res_row) w += res_row[n + e];
-            if (p.gelu) w = gelu_erf(w);
-            if (out_row) out_row[n + e] = w;
-            if (hi_row) split_bf16(w, hi_row[n + e], lo_row[n + e]);
+            for (int pass = 0; pass < 2; ++pass) {
+              // pass 0: hi = bf16(v); pass 1: lo = bf16(v - hi)
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                __nv_bfloat16 h8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const __nv_bfloat16 hh = __float2bfloat16_rn(v[j + e]);
+                  h8[e] = pass == 0 ? hh : __float2bfloat16_rn(v[j + e] - __bfloat162float(hh));
+                }
+                *reinterpret_cast<uint4*>(stg_h + lane * 40 + j) = *reinterpret_cast<uint4*>(h8);
+              }
+              __syncwarp();
+              __nv_bfloat16* dst = pass == 0 ? p.out_hi : p.out_lo;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr = row0 + i * 8 + hr, n = n0 + c0 + hc;
+                if (rr < p.M && n < p.N)
+                  *reinterpret_cast<uint4*>(dst + (size_t)rr * p.ld_split + n) =
+                      *reinterpret_cast<const uint4*>(stg_h + (i * 8 + hr) * 40 + hc);
+              }
+              __syncwarp();
+            }
+          }
+        }
+      } else {
+        // N % 4 != 0 (hml_vec output projection, N = 263): scalar row-per-thread epilogue
+        const float* res_row = p.residual ? p.residual + (size_t)row * p.ld_res : nullptr;
+        float* out_row = p.out_f32 ? p.out_f32 + (size_t)row * p.ld_out : nullptr;
+        __nv_bfloat16* hi_row = p.out_hi ? p.out_hi + (size_t)row * p.ld_split : nullptr;
+        __nv_bfloat16* lo_row = p.out_hi ? p.out_lo + (size_t)row * p.ld_split : nullptr;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (n0 + c0 >= p.N) break;
+          uint32_t r[32];
+          __syncwarp();
+          ptx::tmem_ld_32x32b_x32(acc + (uint32_t)c0, r);
+          ptx::tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + c0 + j;
+              if (n < p.N) {
+                float w = __uint_as_float(r[j]);
+                if (p.bias) w += __ldg(p.bias + n);
+                if (res_row) w += res_row[n];
+                if (p.gelu) w = gelu_erf(w);
+                if (out_row) out_row[n] = w;
+                if (hi_row) split_bf16(w, hi_row[n], lo_row[n]);
+              }
+            }
           }
         }
       }
-      }
+      // release the accumulator buffer to the MMA warp
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[buf]);
     }
   }
 
@@ -234,7 +344,8 @@ inline cudaError_t launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, cons
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid((unsigned)ceil_div(p.N, BN), (unsigned)ceil_div(p.M, BM));
+  const int64_t tiles = ceil_div(p.N, BN) * ceil_div(p.M, BM);
+  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
   gemm_tn_kernel<BN, SPLIT><<<grid, kThreads, C::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
   return cudaGetLastError();
 }

@@ -172,6 +172,11 @@ int regen_test_gemm(const float* A, const float* W, const float* bias, const flo
                     float* out, int32_t M, int32_t N, int32_t K, int32_t gelu, int32_t precision,
                     void* stream);
 
+/* Kernel-level test hook (tests/ only): causal 4-head self-attention (head_dim 128) of a seq-first q|k|v
+ * tensor through the tcgen05 attention kernel -- the arithmetic of nn.MultiheadAttention with the causal
+ * mask of model/cmdm.py:168-171.  qkv fp32 [T*B, 1536] (row = t*B + b) -> out fp32 [T*B, 512].  dbg = 0. */
+int regen_test_attention(const float* qkv, float* out, int32_t B, int32_t T, int32_t dbg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -123,6 +123,14 @@ __global__ void __launch_bounds__(256) finalize_condbias_kernel(const float* __r
   }
 }
 
+// out = float(hi) + float(lo)   (test hooks: recombine a bf16 pair)
+__global__ void __launch_bounds__(256) merge_split_kernel(const __nv_bfloat16* __restrict__ hi,
+                                                          const __nv_bfloat16* __restrict__ lo,
+                                                          float* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+    out[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+}
+
 // out[b, :] = vec[:]   (D = 512; one block of 128 threads per row)
 __global__ void __launch_bounds__(128) broadcast_rows_kernel(const float* __restrict__ vec, float* __restrict__ out) {
   reinterpret_cast<float4*>(out + (size_t)blockIdx.x * D)[threadIdx.x] =

@@ -3,6 +3,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "attention_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "layers.cuh"
 #include "tmap.cuh"
@@ -46,7 +47,9 @@ struct regen_handle {
   int pe_len = 0, num_actions = 0, clip_dim = 0;
   LayerDev layer[REGEN_MAX_LAYERS];
   // activations
-  SplitBuf a_in, h_s, att, ffn;
+  SplitBuf a_in, h_s, att, ffn, qkv_s;
+  CUtensorMap tm_qkv_hi, tm_qkv_lo;  // 3-D [T, Beff, 1536] views of qkv_s for the attention kernel (per prepare_cond)
+  bool simt_attention = false;       // REGEN_DEBUG_SIMT_ATTENTION=1: fp32 CUDA-core attention for A/B debugging
   float *h = nullptr, *qkv = nullptr, *tmp = nullptr, *x0e = nullptr, *condbias = nullptr, *cmo_tbi = nullptr,
         *ccond = nullptr, *scratch = nullptr;
 
@@ -144,8 +147,8 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
   REGEN_CHECK_ARG(d->cm_mode == 0 || d->cm_mode == 1, "regen_create: cm_mode must be 0 (add) or 1 (concat)");
   REGEN_CHECK_ARG(d->precision == 0 || d->precision == 1, "regen_create: precision must be 0 (bf16x3) or 1 (bf16)");
   REGEN_CHECK_ARG(d->max_batch >= 1 && d->max_frames >= 1 && d->num_table_steps >= 1, "regen_create: bad sizes");
-  REGEN_CHECK_ARG(layers::attention_smem_bytes(d->max_frames) <= 227 * 1024,
-                  "regen_create: max_frames=%d exceeds the attention kernel's shared-memory budget", d->max_frames);
+  REGEN_CHECK_ARG(d->max_frames <= 256, "regen_create: max_frames=%d exceeds the attention kernel's limit of 256 "
+                  "(two key chunks of 128 resident in tensor memory)", d->max_frames);
   REGEN_CHECK_ARG((int64_t)d->max_batch * d->max_frames < (1 << 24), "regen_create: max_batch*max_frames too large");
   REGEN_CUDA(cudaSetDevice(device));
   regen_handle* h = new regen_handle();
@@ -155,6 +158,10 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
   h->I = d->input_feats;
   h->Kin = (int)ceil_div(h->I, 64) * 64;
   h->Mmax = d->max_batch * d->max_frames;
+  {
+    const char* e = getenv("REGEN_DEBUG_SIMT_ATTENTION");
+    h->simt_attention = e && e[0] == '1' && layers::attention_smem_bytes(d->max_frames) <= 227 * 1024;
+  }
   const size_t Mx = (size_t)h->Mmax;
   int rc = REGEN_OK;
   do {
@@ -179,6 +186,7 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
     if ((rc = alloc_split(h, &h->h_s, Mx, D, 128))) break;
     if ((rc = alloc_split(h, &h->att, Mx, D, 128))) break;
     if ((rc = alloc_split(h, &h->ffn, Mx, FF, 128))) break;
+    if ((rc = alloc_split(h, &h->qkv_s, Mx, 3 * D, 128))) break;
     if ((rc = h->alloc(&h->h, Mx * D))) break;
     if ((rc = h->alloc(&h->qkv, Mx * 3 * D))) break;
     if ((rc = h->alloc(&h->tmp, Mx * D))) break;
@@ -343,6 +351,8 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
                                                                                      B, guidance ? 2 : 1);
     count_launch();
   }
+  TRY(make_tmap_bf16_3d(&h->tm_qkv_hi, h->qkv_s.hi, 3 * D, Beff, T, T <= 64 ? 64 : 128));
+  TRY(make_tmap_bf16_3d(&h->tm_qkv_lo, h->qkv_s.lo, 3 * D, Beff, T, T <= 64 ? 64 : 128));
   if (h->has_cond) {
     // cond_emb[b'] for b' in [0, Beff): conditional rows [0,B), unconditional rows [B,2B) under guidance
     if (text_model) {
@@ -397,16 +407,28 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
   }
   for (int l = 0; l < L; ++l) {
     LayerDev& ld = h->layer[l];
-    {  // q | k | v
+    {  // q | k | v  -> bf16 (hi, lo) operands of the attention kernel
       gemm::Params p = gp(M, 3 * D, D);
       p.bias = ld.bqkv;
-      p.out_f32 = h->qkv; p.ld_out = 3 * D;
+      p.out_hi = h->qkv_s.hi; p.out_lo = h->qkv_s.lo; p.ld_split = 3 * D;
+      if (h->simt_attention) { p.out_f32 = h->qkv; p.ld_out = 3 * D; }
       TRY(run_gemm(h, h->h_s, ld.wqkv, p, s));
     }
     {
       ProfScope prof(h, CLS_ATTN, s);
-      layers::attention_simt_kernel<<<Beff * layers::H, layers::ATT_WARPS * 32, layers::attention_smem_bytes(T), s>>>(
-          h->qkv, h->att.hi, h->att.lo, T, Beff);
+      if (h->simt_attention) {
+        layers::attention_simt_kernel<<<Beff * layers::H, layers::ATT_WARPS * 32, layers::attention_smem_bytes(T), s>>>(
+            h->qkv, h->att.hi, h->att.lo, T, Beff);
+      } else {
+        attn::Params ap;
+        ap.out_hi = h->att.hi; ap.out_lo = h->att.lo; ap.T = T; ap.Beff = Beff; ap.dbg = 0;
+        cudaError_t e = T <= 64 ? attn::launch<64>(h->tm_qkv_hi, h->tm_qkv_lo, ap, s)
+                                : attn::launch<128>(h->tm_qkv_hi, h->tm_qkv_lo, ap, s);
+        if (e != cudaSuccess) {
+          set_error("attention launch (T=%d Beff=%d) failed: %s", T, Beff, cudaGetErrorString(e));
+          return REGEN_ECUDA;
+        }
+      }
       count_launch();
     }
     {  // tmp = h + attn . W_o^T + b_o
@@ -532,6 +554,38 @@ int regen_test_gemm(const float* A, const float* W, const float* bias, const flo
     }
   }
   cudaFree(ah); cudaFree(al); cudaFree(wh); cudaFree(wl);
+  return rc;
+}
+
+// Kernel-level test hook: causal multi-head self-attention on a seq-first q|k|v tensor through the tcgen05
+// attention kernel.  qkv fp32 [T*B, 1536] -> out fp32 [T*B, 512] (hi + lo recombined).  Synchronises.
+int regen_test_attention(const float* qkv, float* out, int32_t B, int32_t T, int32_t dbg, void* stream) {
+  REGEN_CHECK_ARG(qkv && out && B >= 1 && T >= 1 && T <= 256, "regen_test_attention: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t M = (size_t)B * T;
+  bf16 *qh, *ql, *oh, *ol;
+  REGEN_CUDA(cudaMalloc(&qh, M * 3 * D * 2));
+  REGEN_CUDA(cudaMalloc(&ql, M * 3 * D * 2));
+  REGEN_CUDA(cudaMalloc(&oh, M * D * 2));
+  REGEN_CUDA(cudaMalloc(&ol, M * D * 2));
+  layers::launch_split_rows(qkv, 3 * D, qh, ql, 3 * D, 3 * D, (int)M, 1, 1, s);
+  CUtensorMap th, tl;
+  int rc = make_tmap_bf16_3d(&th, qh, 3 * D, B, T, T <= 64 ? 64 : 128);
+  if (!rc) rc = make_tmap_bf16_3d(&tl, ql, 3 * D, B, T, T <= 64 ? 64 : 128);
+  if (!rc) {
+    attn::Params ap;
+    ap.out_hi = oh; ap.out_lo = ol; ap.T = T; ap.Beff = B; ap.dbg = dbg;
+    cudaError_t e = T <= 64 ? attn::launch<64>(th, tl, ap, s) : attn::launch<128>(th, tl, ap, s);
+    if (e == cudaSuccess) {
+      layers::merge_split_kernel<<<grid_cap(ceil_div((int64_t)M * D, 256)), 256, 0, s>>>(oh, ol, out, (int64_t)M * D);
+      e = cudaStreamSynchronize(s);
+    }
+    if (e != cudaSuccess) {
+      set_error("regen_test_attention: %s", cudaGetErrorString(e));
+      rc = REGEN_ECUDA;
+    }
+  }
+  cudaFree(qh); cudaFree(ql); cudaFree(oh); cudaFree(ol);
   return rc;
 }
 

@@ -60,6 +60,143 @@ struct Params {
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
+// Epilogue of one 32-row slice of an accumulator tile, executed by one warp (lane = TMEM lane = output row).
+//   acc   TMEM address of (first lane of this warp's quarter, first column of the tile)
+//   row0  global row of lane 0, n0 global column of the tile, ncols accumulator columns to process
+//   stg   this warp's private shared-memory staging area (32 x STG_PITCH floats)
+template <int STG_PITCH>
+__device__ __forceinline__ void epilogue_slice(const Params& p, float* stg, uint32_t acc, int row0, int n0, int ncols,
+                                               int lane) {
+  const int BN = ncols;
+  __nv_bfloat16* stg_h = reinterpret_cast<__nv_bfloat16*>(stg);  // bf16 staging: 32 rows x 40 halves (80 B pitch)
+  const bool vec_ok = (p.N & 3) == 0;
+  // coalesced mapping: lane -> (row i*4 + lane/8, 16-byte piece lane%8) for fp32,
+  //                            (row i*8 + lane/4, 16-byte piece lane%4) for bf16
+  const int cr = lane >> 3, cc = (lane & 7) * 4;
+  const int hr = lane >> 2, hc = (lane & 3) * 8;
+  const int row = row0 + lane;
+  const bool row_ok = row < p.M;
+  if (vec_ok) {
+    float4 rpre[8];
+    auto prefetch_res = [&](int c0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = row0 + i * 4 + cr, n = n0 + c0 + cc;
+        rpre[i] = (r < p.M && n < p.N) ? *reinterpret_cast<const float4*>(p.residual + (size_t)r * p.ld_res + n)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (p.residual) prefetch_res(0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= p.N) break;  // warp-uniform
+      uint32_t r[32];
+      __syncwarp();
+      ptx::tmem_ld_32x32b_x32(acc + (uint32_t)c0, r);
+      if (p.residual) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(stg + (i * 4 + cr) * STG_PITCH + cc) = rpre[i];
+        __syncwarp();
+        if (c0 + 32 < BN && n0 + c0 + 32 < p.N) prefetch_res(c0 + 32);
+      }
+      ptx::tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + c0 + j;
+          if (n < p.N) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+        }
+      }
+      if (p.residual) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 r4 = *reinterpret_cast<const float4*>(stg + lane * STG_PITCH + j);
+          v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+        }
+        __syncwarp();
+      }
+      if (p.gelu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      }
+      if (p.out_f32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = row0 + i * 4 + cr, n = n0 + c0 + cc;
+          if (rr < p.M && n < p.N)
+            *reinterpret_cast<float4*>(p.out_f32 + (size_t)rr * p.ld_out + n) =
+                *reinterpret_cast<const float4*>(stg + (i * 4 + cr) * STG_PITCH + cc);
+        }
+        __syncwarp();
+      }
+      if (p.out_hi) {
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          // pass 0: hi = bf16(v); pass 1: lo = bf16(v - hi)
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            __nv_bfloat16 h8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const __nv_bfloat16 hh = __float2bfloat16_rn(v[j + e]);
+              h8[e] = pass == 0 ? hh : __float2bfloat16_rn(v[j + e] - __bfloat162float(hh));
+            }
+            *reinterpret_cast<uint4*>(stg_h + lane * 40 + j) = *reinterpret_cast<uint4*>(h8);
+          }
+          __syncwarp();
+          __nv_bfloat16* dst = pass == 0 ? p.out_hi : p.out_lo;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = row0 + i * 8 + hr, n = n0 + c0 + hc;
+            if (rr < p.M && n < p.N)
+              *reinterpret_cast<uint4*>(dst + (size_t)rr * p.ld_split + n) =
+                  *reinterpret_cast<const uint4*>(stg_h + (i * 8 + hr) * 40 + hc);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // N % 4 != 0 (hml_vec output projection, N = 263): scalar row-per-thread epilogue
+    const float* res_row = p.residual ? p.residual + (size_t)row * p.ld_res : nullptr;
+    float* out_row = p.out_f32 ? p.out_f32 + (size_t)row * p.ld_out : nullptr;
+    __nv_bfloat16* hi_row = p.out_hi ? p.out_hi + (size_t)row * p.ld_split : nullptr;
+    __nv_bfloat16* lo_row = p.out_hi ? p.out_lo + (size_t)row * p.ld_split : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= p.N) break;
+      uint32_t r[32];
+      __syncwarp();
+      ptx::tmem_ld_32x32b_x32(acc + (uint32_t)c0, r);
+      ptx::tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c0 + j;
+          if (n < p.N) {
+            float w = __uint_as_float(r[j]);
+            if (p.bias) w += __ldg(p.bias + n);
+            if (res_row) w += res_row[n];
+            if (p.gelu) w = gelu_erf(w);
+            if (out_row) out_row[n] = w;
+            if (hi_row) split_bf16(w, hi_row[n], lo_row[n]);
+          }
+        }
+      }
+    }
+  }
+}
+
 // Persistent kernel: grid = min(#tiles, #SMs); CTA c processes tiles c, c + grid, ... (n fastest, so
 // CTAs running concurrently share A tiles through L2).  The accumulator is double buffered in TMEM
 // (2 x BN columns): the epilogue of tile i overlaps the TMA/MMA main loop of tile i + 1.
@@ -181,141 +318,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     float* stg = staging + q * (32 * C::STG_PITCH);
-    __nv_bfloat16* stg_h = reinterpret_cast<__nv_bfloat16*>(stg);  // bf16 staging: 32 rows x 40 halves (80 B pitch)
-    const bool vec_ok = (p.N & 3) == 0;
-    // coalesced mapping: lane -> (row i*4 + lane/8, 16-byte piece lane%8) for fp32,
-    //                            (row i*8 + lane/4, 16-byte piece lane%4) for bf16
-    const int cr = lane >> 3, cc = (lane & 7) * 4;
-    const int hr = lane >> 2, hc = (lane & 3) * 8;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
       const int buf = it & 1;
       const int row0 = m0 + q * 32;   // first row of this warp
-      const int row = row0 + lane;    // this thread's accumulator row
-      const bool row_ok = row < p.M;
       ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
       ptx::tcgen05_fence_after();
       const uint32_t acc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
-      if (vec_ok) {
-        float4 rpre[8];
-        auto prefetch_res = [&](int c0) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = row0 + i * 4 + cr, n = n0 + c0 + cc;
-            rpre[i] = (r < p.M && n < p.N) ? *reinterpret_cast<const float4*>(p.residual + (size_t)r * p.ld_res + n)
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        };
-        if (p.residual) prefetch_res(0);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          if (n0 + c0 >= p.N) break;  // warp-uniform
-          uint32_t r[32];
-          __syncwarp();
-          ptx::tmem_ld_32x32b_x32(acc + (uint32_t)c0, r);
-          if (p.residual) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(stg + (i * 4 + cr) * C::STG_PITCH + cc) = rpre[i];
-            __syncwarp();
-            if (c0 + 32 < BN && n0 + c0 + 32 < p.N) prefetch_res(c0 + 32);
-          }
-          ptx::tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const int n = n0 + c0 + j;
-              if (n < p.N) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-              }
-            }
-          }
-          if (p.residual) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 r4 = *reinterpret_cast<const float4*>(stg + lane * C::STG_PITCH + j);
-              v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
-            }
-            __syncwarp();
-          }
-          if (p.gelu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-          }
-          if (p.out_f32) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(stg + lane * C::STG_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = row0 + i * 4 + cr, n = n0 + c0 + cc;
-              if (rr < p.M && n < p.N)
-                *reinterpret_cast<float4*>(p.out_f32 + (size_t)rr * p.ld_out + n) =
-                    *reinterpret_cast<const float4*>(stg + (i * 4 + cr) * C::STG_PITCH + cc);
-            }
-            __syncwarp();
-          }
-          if (p.out_hi) {
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-              // pass 0: hi = bf16(v); pass 1: lo = bf16(v - hi)
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                __nv_bfloat16 h8[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const __nv_bfloat16 hh = __float2bfloat16_rn(v[j + e]);
-                  h8[e] = pass == 0 ? hh : __float2bfloat16_rn(v[j + e] - __bfloat162float(hh));
-                }
-                *reinterpret_cast<uint4*>(stg_h + lane * 40 + j) = *reinterpret_cast<uint4*>(h8);
-              }
-              __syncwarp();
-              __nv_bfloat16* dst = pass == 0 ? p.out_hi : p.out_lo;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int rr = row0 + i * 8 + hr, n = n0 + c0 + hc;
-                if (rr < p.M && n < p.N)
-                  *reinterpret_cast<uint4*>(dst + (size_t)rr * p.ld_split + n) =
-                      *reinterpret_cast<const uint4*>(stg_h + (i * 8 + hr) * 40 + hc);
-              }
-              __syncwarp();
-            }
-          }
-        }
-      } else {
-        // N % 4 != 0 (hml_vec output projection, N = 263): scalar row-per-thread epilogue
-        const float* res_row = p.residual ? p.residual + (size_t)row * p.ld_res : nullptr;
-        float* out_row = p.out_f32 ? p.out_f32 + (size_t)row * p.ld_out : nullptr;
-        __nv_bfloat16* hi_row = p.out_hi ? p.out_hi + (size_t)row * p.ld_split : nullptr;
-        __nv_bfloat16* lo_row = p.out_hi ? p.out_lo + (size_t)row * p.ld_split : nullptr;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          if (n0 + c0 >= p.N) break;
-          uint32_t r[32];
-          __syncwarp();
-          ptx::tmem_ld_32x32b_x32(acc + (uint32_t)c0, r);
-          ptx::tmem_ld_wait();
-          if (row_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = n0 + c0 + j;
-              if (n < p.N) {
-                float w = __uint_as_float(r[j]);
-                if (p.bias) w += __ldg(p.bias + n);
-                if (res_row) w += res_row[n];
-                if (p.gelu) w = gelu_erf(w);
-                if (out_row) out_row[n] = w;
-                if (hi_row) split_bf16(w, hi_row[n], lo_row[n]);
-              }
-            }
-          }
-        }
-      }
+      epilogue_slice<C::STG_PITCH>(p, stg, acc, row0, n0, BN, lane);
       // release the accumulator buffer to the MMA warp
       ptx::tcgen05_fence_before();
       __syncwarp();
@@ -347,6 +358,191 @@ inline cudaError_t launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, cons
   const int64_t tiles = ceil_div(p.N, BN) * ceil_div(p.M, BM);
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
   gemm_tn_kernel<BN, SPLIT><<<grid, kThreads, C::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// CTA-pair version (tcgen05 cta_group::2): two CTAs of a cluster -- two SMs of one TPC -- cooperate on a
+// 256 x BN tile.  CTA r owns accumulator rows [128 r, 128 r + 128) of the tile and loads its own A rows plus HALF of
+// the W tile (rows [BN/2 r, BN/2 (r+1))); the UMMA (M = 256) reads B from both CTAs' shared memory, so per SM the
+// TMA traffic drops from 96 KB to 64 KB per k-block and the tensor core's shared-memory operand reads from 12 KB to
+// 8 KB per instruction -- the single-CTA kernel is bound by exactly that bandwidth.  The leader CTA (rank 0)
+// issues all MMAs; full barriers live in the leader, empty / accumulator-full barriers are multicast to both CTAs.
+// =====================================================================================================
+template <int BN, bool SPLIT>
+struct Cfg2 {
+  static constexpr int A_BYTES = BM * BK * 2;          // this CTA's 128 A rows
+  static constexpr int W_BYTES = (BN / 2) * BK * 2;    // this CTA's half of the W tile
+  static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + W_BYTES);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;  // 3 for SPLIT @ BN=256
+  static constexpr int STG_PITCH = 36;
+  static constexpr int STG_WARP_BYTES = 32 * STG_PITCH * 4;
+  static constexpr int STG_BYTES = 4 * STG_WARP_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static_assert(BN == 256, "CTA-pair kernel is written for BN = 256");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <int BN, bool SPLIT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                const Params p) {
+  using C = Cfg2<BN, SPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* staging = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::STG_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2] (the leader's copy is the one in use)
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_kb = p.K / BK;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
+  const int num_tiles = tiles_n * tiles_m;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_a_hi);
+    ptx::prefetch_tmap(&tm_w_hi);
+    if (SPLIT) {
+      ptx::prefetch_tmap(&tm_a_lo);
+      ptx::prefetch_tmap(&tm_w_lo);
+    }
+    for (int s = 0; s < C::STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);   // leader's producer arrives (expect_tx for both CTAs' bytes)
+      ptx::mbar_init(&empty_bar[s], 1);  // one multicast tcgen05.commit
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&tmem_full_bar[b], 1);
+      ptx::mbar_init(&tmem_empty_bar[b], 8);  // 4 epilogue warps x 2 CTAs
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(tmem_base_smem, C::TMEM_COLS);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tcgen05_fence_before();
+  ptx::cluster_sync();  // barriers of both CTAs initialised before any remote arrive / multicast commit
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM;
+        const int nw = (tile % tiles_n) * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * C::STAGE_BYTES;
+          if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          ptx::tma_load_2d_2sm(st, &tm_a_hi, &full_bar[stage], kb * BK, m0);
+          ptx::tma_load_2d_2sm(st + C::A_BYTES, &tm_w_hi, &full_bar[stage], kb * BK, nw);
+          if (SPLIT) {
+            ptx::tma_load_2d_2sm(st + C::A_BYTES + C::W_BYTES, &tm_a_lo, &full_bar[stage], kb * BK, m0);
+            ptx::tma_load_2d_2sm(st + 2 * C::A_BYTES + C::W_BYTES, &tm_w_lo, &full_bar[stage], kb * BK, nw);
+          }
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int buf = it & 1;
+        ptx::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);  // both CTAs drained this accumulator
+        ptx::tcgen05_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tcgen05_fence_after();
+          const uint32_t st = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint64_t a_hi = ptx::umma_desc_k_sw128(st);
+          const uint64_t w_hi = ptx::umma_desc_k_sw128(st + C::A_BYTES);
+          const uint64_t a_lo = ptx::umma_desc_k_sw128(st + C::A_BYTES + C::W_BYTES);
+          const uint64_t w_lo = ptx::umma_desc_k_sw128(st + 2 * C::A_BYTES + C::W_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)(k * UMMA_K * 2 >> 4);
+            if (SPLIT) {
+              ptx::mma_f16_ss_2sm(acc, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);
+              ptx::mma_f16_ss_2sm(acc, a_hi + adv, w_lo + adv, idesc, 1);
+              ptx::mma_f16_ss_2sm(acc, a_hi + adv, w_hi + adv, idesc, 1);
+            } else {
+              ptx::mma_f16_ss_2sm(acc, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+            }
+          }
+          ptx::tcgen05_commit_2sm(&empty_bar[stage]);  // frees this stage in BOTH CTAs
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::tcgen05_commit_2sm(&tmem_full_bar[buf]);  // accumulator complete, signalled to both epilogues
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5 of both CTAs)
+    const int q = warp & 3;
+    float* stg = staging + q * (32 * C::STG_PITCH);
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM, n0 = (tile % tiles_n) * BN;
+      const int buf = it & 1;
+      ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
+      ptx::tcgen05_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
+      epilogue_slice<C::STG_PITCH>(p, stg, acc, m0 + q * 32, n0, BN, lane);
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_remote(&tmem_empty_bar[buf], 0);  // leader's barrier
+    }
+  }
+
+  // ------------------------------------------------------------------ teardown
+  ptx::tcgen05_fence_before();
+  ptx::cluster_sync();  // no CTA may exit (or free TMEM) while its peer can still touch its smem / barriers
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// W tensor maps for the pair kernel need box {64, BN/2}.
+template <int BN, bool SPLIT>
+inline cudaError_t launch2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                           const CUtensorMap& w_lo, const Params& p, cudaStream_t stream) {
+  using C = Cfg2<BN, SPLIT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_tn_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int64_t tiles = ceil_div(p.N, BN) * ceil_div(p.M, 2 * BM);
+  const int clusters = (int)(tiles < kNumSMs / 2 ? tiles : kNumSMs / 2);
+  gemm2_tn_kernel<BN, SPLIT><<<2 * clusters, kThreads, C::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
   return cudaGetLastError();
 }
 

@@ -17,7 +17,8 @@ namespace {
 
 struct SplitBuf {  // bf16 (hi, lo) operand pair + its TMA maps
   bf16 *hi = nullptr, *lo = nullptr;
-  CUtensorMap tm_hi, tm_lo;
+  CUtensorMap tm_hi, tm_lo;      // box rows: 128 for activations (A operand), 256 for weights (single-CTA kernel)
+  CUtensorMap tm_hi2, tm_lo2;    // weights only: box rows 128 = one CTA's half of the W tile in the CTA-pair kernel
 };
 
 struct LayerDev {
@@ -104,6 +105,8 @@ int alloc_split(regen_handle* h, SplitBuf* s, size_t rows, size_t cols, uint32_t
   REGEN_CUDA(cudaMemset(s->lo, 0, rows * cols * sizeof(bf16)));
   TRY(make_tmap_bf16_2d(&s->tm_hi, s->hi, rows, cols, cols, box_rows));
   TRY(make_tmap_bf16_2d(&s->tm_lo, s->lo, rows, cols, cols, box_rows));
+  TRY(make_tmap_bf16_2d(&s->tm_hi2, s->hi, rows, cols, cols, 128));
+  TRY(make_tmap_bf16_2d(&s->tm_lo2, s->lo, rows, cols, cols, 128));
   return REGEN_OK;
 }
 
@@ -113,10 +116,26 @@ int copy_vec(regen_handle* h, float** dst, const float* src, size_t n, cudaStrea
   return REGEN_OK;
 }
 
+// CTA-pair (cta_group::2, 256-row tiles) kernel for anything larger than one 128-row tile; the single-CTA kernel
+// serves tiny batches.  REGEN_DEBUG_GEMM_1CTA=1 forces the single-CTA kernel (A/B measurements).
+bool use_pair_kernel(int M) {
+  static int force1 = -1;
+  if (force1 < 0) {
+    const char* e = getenv("REGEN_DEBUG_GEMM_1CTA");
+    force1 = (e && e[0] == '1') ? 1 : 0;
+  }
+  return !force1 && M > 128;
+}
+
 int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, const gemm::Params& p, cudaStream_t s) {
   ProfScope prof(h, CLS_GEMM, s);
-  cudaError_t e = h->desc.precision == 0 ? gemm::launch<256, true>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, p, s)
-                                         : gemm::launch<256, false>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, p, s);
+  cudaError_t e;
+  if (use_pair_kernel(p.M))
+    e = h->desc.precision == 0 ? gemm::launch2<256, true>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, p, s)
+                               : gemm::launch2<256, false>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, p, s);
+  else
+    e = h->desc.precision == 0 ? gemm::launch<256, true>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, p, s)
+                               : gemm::launch<256, false>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, p, s);
   if (e != cudaSuccess) {
     set_error("gemm launch (M=%d N=%d K=%d) failed: %s", p.M, p.N, p.K, cudaGetErrorString(e));
     return REGEN_ECUDA;
@@ -538,15 +557,21 @@ int regen_test_gemm(const float* A, const float* W, const float* bias, const flo
   layers::launch_split_rows(A, K, ah, al, Kp, K, M, 1, 1, s);
   layers::launch_split_rows(W, K, wh, wl, Kp, K, N, 1, 1, s);
   CUtensorMap ta_h, ta_l, tw_h, tw_l;
+  const bool pair = use_pair_kernel(M);
   int rc = make_tmap_bf16_2d(&ta_h, ah, M, Kp, Kp, 128);
   if (!rc) rc = make_tmap_bf16_2d(&ta_l, al, M, Kp, Kp, 128);
-  if (!rc) rc = make_tmap_bf16_2d(&tw_h, wh, N, Kp, Kp, 256);
-  if (!rc) rc = make_tmap_bf16_2d(&tw_l, wl, N, Kp, Kp, 256);
+  if (!rc) rc = make_tmap_bf16_2d(&tw_h, wh, N, Kp, Kp, pair ? 128 : 256);
+  if (!rc) rc = make_tmap_bf16_2d(&tw_l, wl, N, Kp, Kp, pair ? 128 : 256);
   if (!rc) {
     gemm::Params p = gp(M, N, Kp);
     p.bias = bias; p.residual = residual; p.ld_res = N; p.out_f32 = out; p.ld_out = N; p.gelu = gelu;
-    cudaError_t e = precision == 0 ? gemm::launch<256, true>(ta_h, ta_l, tw_h, tw_l, p, s)
-                                   : gemm::launch<256, false>(ta_h, ta_l, tw_h, tw_l, p, s);
+    cudaError_t e;
+    if (pair)
+      e = precision == 0 ? gemm::launch2<256, true>(ta_h, ta_l, tw_h, tw_l, p, s)
+                         : gemm::launch2<256, false>(ta_h, ta_l, tw_h, tw_l, p, s);
+    else
+      e = precision == 0 ? gemm::launch<256, true>(ta_h, ta_l, tw_h, tw_l, p, s)
+                         : gemm::launch<256, false>(ta_h, ta_l, tw_h, tw_l, p, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) {
       set_error("regen_test_gemm: %s", cudaGetErrorString(e));

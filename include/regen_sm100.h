@@ -172,6 +172,10 @@ int regen_test_gemm(const float* A, const float* W, const float* bias, const flo
                     float* out, int32_t M, int32_t N, int32_t K, int32_t gelu, int32_t precision,
                     void* stream);
 
+/* Bring-up instrumentation for regen_test_gemm: when set to a device buffer of 128 uint64, CTA 0 of the next test
+ * GEMMs records SM clock values at pipeline events (see gemm_sm100.cuh Params::timeline).  NULL disables. */
+int regen_test_gemm_timeline(unsigned long long* device_buf128);
+
 /* Kernel-level test hook (tests/ only): causal 4-head self-attention (head_dim 128) of a seq-first q|k|v
  * tensor through the tcgen05 attention kernel -- the arithmetic of nn.MultiheadAttention with the causal
  * mask of model/cmdm.py:168-171.  qkv fp32 [T*B, 1536] (row = t*B + b) -> out fp32 [T*B, 512].  dbg = 0. */

@@ -58,6 +58,7 @@ _SIGNATURES = {
     "regen_prepare_cond": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "regen_denoise": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "regen_test_gemm": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
+    "regen_test_gemm_timeline": (c_int, [c_void_p]),
     "regen_test_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
 }
 

@@ -10,7 +10,7 @@
 //     row), add bias / residual, optionally apply exact-erf GELU, and store fp32 and/or a bf16
 //     (hi, lo) pair for the next GEMM's A operand.
 //
-// Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
 // Persistent: one CTA per SM loops over 128 x BN output tiles; the fp32 accumulator is double buffered in
 // TMEM so the epilogue of one tile overlaps the main loop of the next; epilogue traffic is staged
 // through shared memory so every global access is a full, coalesced 128-byte (fp32) / 64-byte (bf16) row segment.
@@ -24,7 +24,7 @@ namespace gemm {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
 
 template <int BN, bool SPLIT>
 struct Cfg {
@@ -32,11 +32,7 @@ struct Cfg {
   static constexpr int W_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + W_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;  // 2 for SPLIT @ BN=256, 4 for plain bf16
-  // epilogue staging: per epilogue warp 32 rows x 32 fp32 columns, row pitch padded to 36 words so that
-  // both the row-per-thread accesses and the coalesced 128-byte row segments are bank-conflict free
-  static constexpr int STG_PITCH = 36;
-  static constexpr int STG_WARP_BYTES = 32 * STG_PITCH * 4;
-  static constexpr int STG_BYTES = 4 * STG_WARP_BYTES;
+  static constexpr int STG_BYTES = 8 * 3072;  // kEpiWarps * STG_WARP_BYTES (epilogue staging, see epilogue_slice)
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
@@ -56,132 +52,173 @@ struct Params {
   __nv_bfloat16* out_lo;
   int ld_split;
   int gelu;                 // exact-erf GELU after bias/residual
+  // bring-up instrumentation (test hook only, null in production): CTA 0 records clock64() at pipeline events
+  //   [0] kernel entry  [1] setup done  [2] kernel exit  [8+2i] MMA of tile i: operands of first k-block landed
+  //   [9+2i] MMA of tile i: last instruction issued  [40+2i] epilogue of tile i: accumulator ready  [41+2i] done
+  //   [80..] fine-grained stamps inside the first epilogue sub-chunks of tile 0 (warp 2)
+  unsigned long long* timeline;
 };
+
+#define REGEN_TL(slot)                                                        \
+  do {                                                                        \
+    if (p.timeline && blockIdx.x == 0) p.timeline[(slot)] = (unsigned long long)clock64(); \
+  } while (0)
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
-// Epilogue of one 32-row slice of an accumulator tile, executed by one warp (lane = TMEM lane = output row).
-//   acc   TMEM address of (first lane of this warp's quarter, first column of the tile)
-//   row0  global row of lane 0, n0 global column of the tile, ncols accumulator columns to process
-//   stg   this warp's private shared-memory staging area (32 x STG_PITCH floats)
-template <int STG_PITCH>
-__device__ __forceinline__ void epilogue_slice(const Params& p, float* stg, uint32_t acc, int row0, int n0, int ncols,
-                                               int lane) {
-  const int BN = ncols;
-  __nv_bfloat16* stg_h = reinterpret_cast<__nv_bfloat16*>(stg);  // bf16 staging: 32 rows x 40 halves (80 B pitch)
+// Epilogue of a 32-row x ncols slice of an accumulator tile, executed by one warp (lane = TMEM lane = output row).
+//   acc   TMEM address of (first lane of this warp's quarter, first column of the slice)
+//   row0  global row of lane 0, n0 global column of the slice's first column
+//   stg   this warp's private shared-memory staging area (STG_WARP_BYTES)
+// The accumulator is consumed in 16-column sub-chunks.  Everything that touches global memory goes through the
+// staging area so that each warp-level access covers whole 32-byte sectors of consecutive rows:
+//   fp32: 4 lanes x 16 B per row (64 B), 8 rows per instruction; bf16: 2 lanes x 16 B per row, 16 rows per instruction.
+constexpr int STG_PITCH = 20;                      // floats per staged fp32 row (16 + 4 pad: conflict-free float4)
+constexpr int STG_HPITCH = 24;                     // halves per staged bf16 row (16 + 8 pad)
+constexpr int STG_WARP_BYTES = 3072;               // max(32*20*4, 2 * 32*24*2)
+constexpr int kEpiWarps = 8;                       // 2 warps per TMEM lane quarter, each takes half of the columns
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+#define REGEN_TLF(k)                                                                              \
+  do {                                                                                            \
+    if (trace && lane == 0 && c0 < 48) p.timeline[80 + (c0 / 16) * 8 + (k)] = (unsigned long long)clock64(); \
+  } while (0)
+
+__device__ __forceinline__ void epilogue_slice(const Params& p, uint8_t* stg_raw, uint32_t acc, int row0, int n0,
+                                               int ncols, int lane, bool trace_req = false) {
+  const bool trace = trace_req && p.timeline && blockIdx.x == 0;
+  float* stg = reinterpret_cast<float*>(stg_raw);
+  __nv_bfloat16* stg_hi = reinterpret_cast<__nv_bfloat16*>(stg_raw);
+  __nv_bfloat16* stg_lo = stg_hi + 32 * STG_HPITCH;
   const bool vec_ok = (p.N & 3) == 0;
-  // coalesced mapping: lane -> (row i*4 + lane/8, 16-byte piece lane%8) for fp32,
-  //                            (row i*8 + lane/4, 16-byte piece lane%4) for bf16
-  const int cr = lane >> 3, cc = (lane & 7) * 4;
-  const int hr = lane >> 2, hc = (lane & 3) * 8;
-  const int row = row0 + lane;
-  const bool row_ok = row < p.M;
+  const int fr = lane >> 2, fc = (lane & 3) * 4;   // fp32 coalesced mapping: row i*8 + fr, floats fc..fc+3
+  const int hr = lane >> 1, hc = (lane & 1) * 8;   // bf16 coalesced mapping: row i*16 + hr, halves hc..hc+7
   if (vec_ok) {
-    float4 rpre[8];
+    float4 rpre[4];
     auto prefetch_res = [&](int c0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = row0 + i * 4 + cr, n = n0 + c0 + cc;
+      for (int i = 0; i < 4; ++i) {
+        const int r = row0 + i * 8 + fr, n = n0 + c0 + fc;
         rpre[i] = (r < p.M && n < p.N) ? *reinterpret_cast<const float4*>(p.residual + (size_t)r * p.ld_res + n)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
+    // bias of the next sub-chunk is prefetched as well: with ~220 KB of the SM's unified L1/shared memory carved out
+    // as shared memory there is practically no L1, so every global load is an L2 round trip (~800 cycles under load)
+    float4 bpre[4];
+    auto prefetch_bias = [&](int c0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        bpre[j] = (n0 + c0 + 4 * j < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + 4 * j))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
     if (p.residual) prefetch_res(0);
+    if (p.bias) prefetch_bias(0);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
       if (n0 + c0 >= p.N) break;  // warp-uniform
-      uint32_t r[32];
+      uint32_t r[16];
       __syncwarp();
-      ptx::tmem_ld_32x32b_x32(acc + (uint32_t)c0, r);
+      REGEN_TLF(0);
+      ptx::tmem_ld_32x32b_x16(acc + (uint32_t)c0, r);
       if (p.residual) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(stg + (i * 4 + cr) * STG_PITCH + cc) = rpre[i];
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(stg + (i * 8 + fr) * STG_PITCH + fc) = rpre[i];
         __syncwarp();
-        if (c0 + 32 < BN && n0 + c0 + 32 < p.N) prefetch_res(c0 + 32);
+        REGEN_TLF(1);
+        if (c0 + 16 < ncols && n0 + c0 + 16 < p.N) prefetch_res(c0 + 16);
       }
       ptx::tmem_ld_wait();
-      float v[32];
+      REGEN_TLF(2);
+      float v[16];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
       if (p.bias) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + c0 + j;
-          if (n < p.N) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-          }
+        for (int j = 0; j < 4; ++j) {
+          v[4 * j] += bpre[j].x; v[4 * j + 1] += bpre[j].y; v[4 * j + 2] += bpre[j].z; v[4 * j + 3] += bpre[j].w;
         }
+        if (c0 + 16 < ncols && n0 + c0 + 16 < p.N) prefetch_bias(c0 + 16);
       }
       if (p.residual) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < 16; j += 4) {
           const float4 r4 = *reinterpret_cast<const float4*>(stg + lane * STG_PITCH + j);
           v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
         }
         __syncwarp();
       }
+      REGEN_TLF(3);
       if (p.gelu) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
       }
+      REGEN_TLF(4);
       if (p.out_f32) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
+        for (int j = 0; j < 16; j += 4)
           *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         __syncwarp();
+        REGEN_TLF(5);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = row0 + i * 4 + cr, n = n0 + c0 + cc;
+        for (int i = 0; i < 4; ++i) {
+          const int rr = row0 + i * 8 + fr, n = n0 + c0 + fc;
           if (rr < p.M && n < p.N)
             *reinterpret_cast<float4*>(p.out_f32 + (size_t)rr * p.ld_out + n) =
-                *reinterpret_cast<const float4*>(stg + (i * 4 + cr) * STG_PITCH + cc);
+                *reinterpret_cast<const float4*>(stg + (i * 8 + fr) * STG_PITCH + fc);
         }
         __syncwarp();
+        REGEN_TLF(6);
       }
       if (p.out_hi) {
+        uint32_t hw[8], lw[8];
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-          // pass 0: hi = bf16(v); pass 1: lo = bf16(v - hi)
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            __nv_bfloat16 h8[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const __nv_bfloat16 hh = __float2bfloat16_rn(v[j + e]);
-              h8[e] = pass == 0 ? hh : __float2bfloat16_rn(v[j + e] - __bfloat162float(hh));
-            }
-            *reinterpret_cast<uint4*>(stg_h + lane * 40 + j) = *reinterpret_cast<uint4*>(h8);
-          }
-          __syncwarp();
-          __nv_bfloat16* dst = pass == 0 ? p.out_hi : p.out_lo;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = row0 + i * 8 + hr, n = n0 + c0 + hc;
-            if (rr < p.M && n < p.N)
-              *reinterpret_cast<uint4*>(dst + (size_t)rr * p.ld_split + n) =
-                  *reinterpret_cast<const uint4*>(stg_h + (i * 8 + hr) * 40 + hc);
-          }
-          __syncwarp();
+        for (int j = 0; j < 8; ++j) {
+          const float a = v[2 * j], b = v[2 * j + 1];
+          hw[j] = pack_bf16x2(a, b);
+          // float(hi) is the bf16 bit pattern in the upper half of the word
+          lw[j] = pack_bf16x2(a - __uint_as_float(hw[j] << 16), b - __uint_as_float(hw[j] & 0xffff0000u));
         }
+        *reinterpret_cast<uint4*>(stg_hi + lane * STG_HPITCH) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(stg_hi + lane * STG_HPITCH + 8) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+        *reinterpret_cast<uint4*>(stg_lo + lane * STG_HPITCH) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        *reinterpret_cast<uint4*>(stg_lo + lane * STG_HPITCH + 8) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int rr = row0 + i * 16 + hr, n = n0 + c0 + hc;
+          if (rr < p.M && n < p.N) {
+            *reinterpret_cast<uint4*>(p.out_hi + (size_t)rr * p.ld_split + n) =
+                *reinterpret_cast<const uint4*>(stg_hi + (i * 16 + hr) * STG_HPITCH + hc);
+            *reinterpret_cast<uint4*>(p.out_lo + (size_t)rr * p.ld_split + n) =
+                *reinterpret_cast<const uint4*>(stg_lo + (i * 16 + hr) * STG_HPITCH + hc);
+          }
+        }
+        __syncwarp();
       }
     }
   } else {
     // N % 4 != 0 (hml_vec output projection, N = 263): scalar row-per-thread epilogue
+    const int row = row0 + lane;
+    const bool row_ok = row < p.M;
     const float* res_row = p.residual ? p.residual + (size_t)row * p.ld_res : nullptr;
     float* out_row = p.out_f32 ? p.out_f32 + (size_t)row * p.ld_out : nullptr;
     __nv_bfloat16* hi_row = p.out_hi ? p.out_hi + (size_t)row * p.ld_split : nullptr;
     __nv_bfloat16* lo_row = p.out_hi ? p.out_lo + (size_t)row * p.ld_split : nullptr;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
       if (n0 + c0 >= p.N) break;
-      uint32_t r[32];
+      uint32_t r[16];
       __syncwarp();
-      ptx::tmem_ld_32x32b_x32(acc + (uint32_t)c0, r);
+      ptx::tmem_ld_32x32b_x16(acc + (uint32_t)c0, r);
       ptx::tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 16; ++j) {
           const int n = n0 + c0 + j;
           if (n < p.N) {
             float w = __uint_as_float(r[j]);
@@ -208,7 +245,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   using C = Cfg<BN, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* staging = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::STG_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tmem_full_bar = empty_bar + C::STAGES;  // [2]
@@ -235,7 +272,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tmem_full_bar[b], 1);
-      ptx::mbar_init(&tmem_empty_bar[b], 4);  // one arrival per epilogue warp
+      ptx::mbar_init(&tmem_empty_bar[b], kEpiWarps);  // one arrival per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -315,18 +352,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* stg = staging + q * (32 * C::STG_PITCH);
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns
+    uint8_t* stg = staging + (warp - 2) * STG_WARP_BYTES;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
       const int buf = it & 1;
-      const int row0 = m0 + q * 32;   // first row of this warp
       ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
       ptx::tcgen05_fence_after();
-      const uint32_t acc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
-      epilogue_slice<C::STG_PITCH>(p, stg, acc, row0, n0, BN, lane);
+      const uint32_t acc = tmem_base + (uint32_t)(buf * BN + half * (BN / 2)) + ((uint32_t)(q * 32) << 16);
+      epilogue_slice(p, stg, acc, m0 + q * 32, n0 + half * (BN / 2), BN / 2, lane);
       // release the accumulator buffer to the MMA warp
       ptx::tcgen05_fence_before();
       __syncwarp();
@@ -375,9 +412,7 @@ struct Cfg2 {
   static constexpr int W_BYTES = (BN / 2) * BK * 2;    // this CTA's half of the W tile
   static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + W_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;  // 3 for SPLIT @ BN=256
-  static constexpr int STG_PITCH = 36;
-  static constexpr int STG_WARP_BYTES = 32 * STG_PITCH * 4;
-  static constexpr int STG_BYTES = 4 * STG_WARP_BYTES;
+  static constexpr int STG_BYTES = 8 * 3072;  // kEpiWarps * STG_WARP_BYTES
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
@@ -393,7 +428,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   using C = Cfg2<BN, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* staging = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::STG_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tmem_full_bar = empty_bar + C::STAGES;  // [2]
@@ -409,6 +444,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   const int tiles_n = (p.N + BN - 1) / BN;
   const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
   const int num_tiles = tiles_n * tiles_m;
+  if (threadIdx.x == 0) REGEN_TL(0);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_a_hi);
@@ -423,7 +459,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tmem_full_bar[b], 1);
-      ptx::mbar_init(&tmem_empty_bar[b], 8);  // 4 epilogue warps x 2 CTAs
+      ptx::mbar_init(&tmem_empty_bar[b], 2 * kEpiWarps);  // epilogue warps of both CTAs
     }
     ptx::fence_barrier_init();
   }
@@ -435,6 +471,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   ptx::cluster_sync();  // barriers of both CTAs initialised before any remote arrive / multicast commit
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  if (threadIdx.x == 0) REGEN_TL(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -475,6 +512,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
+          if (kb == 0 && it < 16) REGEN_TL(8 + 2 * it);
           ptx::tcgen05_fence_after();
           const uint32_t st = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t a_hi = ptx::umma_desc_k_sw128(st);
@@ -499,20 +537,24 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           }
         }
         ptx::tcgen05_commit_2sm(&tmem_full_bar[buf]);  // accumulator complete, signalled to both epilogues
+        if (it < 16) REGEN_TL(9 + 2 * it);
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5 of both CTAs)
+    // ------------------------------------------------------------------ epilogue (warps 2..9 of both CTAs)
     const int q = warp & 3;
-    float* stg = staging + q * (32 * C::STG_PITCH);
+    const int half = (warp - 2) >> 2;
+    uint8_t* stg = staging + (warp - 2) * STG_WARP_BYTES;
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM, n0 = (tile % tiles_n) * BN;
       const int buf = it & 1;
       ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
+      if (warp == 2 && lane == 0 && it < 16) REGEN_TL(40 + 2 * it);
       ptx::tcgen05_fence_after();
-      const uint32_t acc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
-      epilogue_slice<C::STG_PITCH>(p, stg, acc, m0 + q * 32, n0, BN, lane);
+      const uint32_t acc = tmem_base + (uint32_t)(buf * BN + half * (BN / 2)) + ((uint32_t)(q * 32) << 16);
+      epilogue_slice(p, stg, acc, m0 + q * 32, n0 + half * (BN / 2), BN / 2, lane, warp == 2 && it == 0);
+      if (warp == 2 && lane == 0 && it < 16) REGEN_TL(41 + 2 * it);
       ptx::tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_remote(&tmem_empty_bar[buf], 0);  // leader's barrier
@@ -522,6 +564,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   // ------------------------------------------------------------------ teardown
   ptx::tcgen05_fence_before();
   ptx::cluster_sync();  // no CTA may exit (or free TMEM) while its peer can still touch its smem / barriers
+  if (threadIdx.x == 0) REGEN_TL(2);
   if (warp == 1) {
     ptx::tcgen05_fence_after();
     ptx::tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);

@@ -543,6 +543,13 @@ int regen_profile_end(regen_handle* h, float* ms, int32_t* launches) {
 }
 
 // Kernel-level test hook: C = A . W^T (+bias)(+residual)(gelu) through the tcgen05 GEMM, fp32 in / out.
+static unsigned long long* g_test_timeline = nullptr;  // device buffer [128], set by regen_test_gemm_timeline
+
+int regen_test_gemm_timeline(unsigned long long* device_buf128) {
+  g_test_timeline = device_buf128;
+  return REGEN_OK;
+}
+
 int regen_test_gemm(const float* A, const float* W, const float* bias, const float* residual, float* out, int32_t M,
                     int32_t N, int32_t K, int32_t gelu, int32_t precision, void* stream) {
   REGEN_CHECK_ARG(A && W && out, "regen_test_gemm: null argument");
@@ -565,6 +572,7 @@ int regen_test_gemm(const float* A, const float* W, const float* bias, const flo
   if (!rc) {
     gemm::Params p = gp(M, N, Kp);
     p.bias = bias; p.residual = residual; p.ld_res = N; p.out_f32 = out; p.ld_out = N; p.gelu = gelu;
+    p.timeline = g_test_timeline;
     cudaError_t e;
     if (pair)
       e = precision == 0 ? gemm::launch2<256, true>(ta_h, ta_l, tw_h, tw_l, p, s)

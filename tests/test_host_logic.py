@@ -71,3 +71,74 @@ def test_unsupported_variants_raise():
     with pytest.raises(ValueError):
         gd.GaussianDiffusion(betas=betas, model_mean_type=gd.ModelMeanType.START_X,
                              model_var_type=gd.ModelVarType.FIXED_SMALL, loss_type=gd.LossType.MSE, lambda_pose=2.0)
+
+
+def test_cmdm_state_dict_keys_match_reference_layout():
+    """The parameter container must expose exactly the reference's state-dict keys so that
+    load_model_wo_clip(model, checkpoint) works: no unexpected keys, only clip_model.* may be missing."""
+    import torch
+    from regennet_b200 import synthetic
+    from regennet_b200.cmdm import CMDM
+    from regennet_b200.model_util import load_model_wo_clip
+    for name in ["ntu", "chi3d", "hml"]:
+        m = CMDM(**cases.MODELS[name])
+        sd = synthetic.make_state_dict(seed=0, **cases.synth_kw(name))
+        want = set(sd)
+        have = set(m.state_dict())
+        assert have == want, (sorted(want - have), sorted(have - want))
+        load_model_wo_clip(m, sd)
+        assert torch.equal(m.output_process.poseFinal.weight, sd["output_process.poseFinal.weight"])
+        assert m.njoints * m.nfeats == m.input_feats
+    assert abs(sum(p.numel() for p in CMDM(**cases.MODELS["ntu"]).parameters()) - 26.80e6) < 0.01e6
+
+
+def test_cmdm_rejects_out_of_scope_variants_and_cpu_forward():
+    import torch
+    from regennet_b200.cmdm import CMDM
+    with pytest.raises(NotImplementedError):
+        CMDM(**dict(cases.MODELS["ntu"], arch="trans_enc"))
+    with pytest.raises(NotImplementedError):
+        CMDM(**dict(cases.MODELS["ntu"], latent_dim=256))
+    m = CMDM(**cases.MODELS["ntu"])
+    x = torch.zeros(1, 56, 6, 60)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(x, torch.zeros(1, dtype=torch.long), {"cmotion": x})   # no CPU fallback
+
+
+def test_install_as_reference_modules_aliases():
+    import sys
+    import regennet_b200
+    saved = {k: sys.modules.get(k) for k in regennet_b200._ALIASES}
+    try:
+        regennet_b200.install_as_reference_modules()
+        from model.cmdm import CMDM as A            # noqa: the reference's import paths
+        from diffusion.respace import SpacedDiffusion as B
+        from utils.rotation_conversions import rotation_6d_to_matrix as C
+        from regennet_b200.cmdm import CMDM
+        from regennet_b200.respace import SpacedDiffusion
+        from regennet_b200.rotation_conversions import rotation_6d_to_matrix
+        assert A is CMDM and B is SpacedDiffusion and C is rotation_6d_to_matrix
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_model_util_factory_matches_reference_defaults():
+    from argparse import Namespace
+    from regennet_b200 import model_util
+    args = Namespace(unconstrained=True, dataset="ntu", pose_rep="rot6d", body_model="smplx", latent_dim=512, layers=8,
+                     cond_mask_prob=0.0, arch="online", cm_mode="concat", wo_pos_emb=False, emb_trans_dec=False,
+                     setting="cmdm", timestep_respacing="ddim5", noise_schedule="cosine", sigma_small=True,
+                     lambda_vel=0.0, lambda_rcxyz=0.0, lambda_fc=0.0, lambda_orient=0.0, lambda_body=0.0,
+                     lambda_transl=0.0, num_person=1, vel_threshold=0.01)
+
+    class D:
+        class dataset:
+            num_actions = 26
+    model, diffusion = model_util.create_model_and_diffusion(args, D)
+    assert (model.njoints, model.nfeats, model.cond_mode, model.num_frames) == (56, 6, "no_cond", 60)
+    assert diffusion.num_timesteps == 5 and diffusion.timestep_map == [0, 200, 400, 600, 800]
+    assert diffusion.model_var_type == gd.ModelVarType.FIXED_SMALL

@@ -32,7 +32,7 @@ struct Cfg {
   static constexpr int W_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + W_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;  // 2 for SPLIT @ BN=256, 4 for plain bf16
-  static constexpr int STG_BYTES = 8 * 3072;  // kEpiWarps * STG_WARP_BYTES (epilogue staging, see epilogue_slice)
+  static constexpr int STG_BYTES = 8 * 4096;  // kEpiWarps * STG_WARP_BYTES (epilogue staging, see epilogue_slice)
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
@@ -52,6 +52,7 @@ struct Params {
   __nv_bfloat16* out_lo;
   int ld_split;
   int gelu;                 // exact-erf GELU after bias/residual
+  int tma_store;            // 1: outputs are written with TMA stores through the tm_o* tensor maps (needs N % 4 == 0)
   // bring-up instrumentation (test hook only, null in production): CTA 0 records clock64() at pipeline events
   //   [0] kernel entry  [1] setup done  [2] kernel exit  [8+2i] MMA of tile i: operands of first k-block landed
   //   [9+2i] MMA of tile i: last instruction issued  [40+2i] epilogue of tile i: accumulator ready  [41+2i] done
@@ -64,45 +65,64 @@ struct Params {
     if (p.timeline && blockIdx.x == 0) p.timeline[(slot)] = (unsigned long long)clock64(); \
   } while (0)
 
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+// GELU(v) = v/2 (1 + erf(v/sqrt 2)), the exact-erf form torch's activation='gelu' uses.  erf is evaluated with the
+// Abramowitz-Stegun 7.1.26 rational/exponential form (|erf error| <= 5.5e-7 in fp32, |GELU error| <= 4.7e-7 measured
+// over [-8, 8]) instead of libdevice's erff: ~15 instructions instead of ~40, which matters because the FFN1
+// epilogue evaluates 15.7 M GELUs per layer on 8 warps per SM next to the tensor-core main loop.
+__device__ __forceinline__ float gelu_erf(float v) {
+  const float z = fabsf(v) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.0f - poly * t * __expf(-z * z);  // erf(|v|/sqrt 2)
+  return 0.5f * v + 0.5f * fabsf(v) * e;             // v/2 (1 + sign(v) e)
+}
 
 // Epilogue of a 32-row x ncols slice of an accumulator tile, executed by one warp (lane = TMEM lane = output row).
 //   acc   TMEM address of (first lane of this warp's quarter, first column of the slice)
 //   row0  global row of lane 0, n0 global column of the slice's first column
-//   stg   this warp's private shared-memory staging area (STG_WARP_BYTES)
-// The accumulator is consumed in 16-column sub-chunks.  Everything that touches global memory goes through the
-// staging area so that each warp-level access covers whole 32-byte sectors of consecutive rows:
-//   fp32: 4 lanes x 16 B per row (64 B), 8 rows per instruction; bf16: 2 lanes x 16 B per row, 16 rows per instruction.
-constexpr int STG_PITCH = 20;                      // floats per staged fp32 row (16 + 4 pad: conflict-free float4)
-constexpr int STG_HPITCH = 24;                     // halves per staged bf16 row (16 + 8 pad)
-constexpr int STG_WARP_BYTES = 3072;               // max(32*20*4, 2 * 32*24*2)
+//   stg   this warp's private shared-memory staging area (STG_WARP_BYTES = two 2 KB buffers, 1 KB aligned)
+// The accumulator is consumed in 16-column sub-chunks.  Each sub-chunk is staged in shared memory as a dense
+// 32-row tile in exactly the layout of a TMA box (fp32: 64-byte rows, SWIZZLE_64B; bf16: 32-byte rows,
+// SWIZZLE_32B), which makes the row-per-thread accesses bank-conflict free, and is then written by ONE
+// cp.async.bulk.tensor store (clipped at M / N by the tensor map) -- no LSU global stores on the path.  Without
+// output tensor maps (tma_store == 0) the staged tile is read back in a coalesced mapping and stored with st.global.
+constexpr int STG_WARP_BYTES = 4096;               // 2 buffers x 2 KB
 constexpr int kEpiWarps = 8;                       // 2 warps per TMEM lane quarter, each takes half of the columns
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// byte offset of 16-byte chunk `c` of row `r` inside a staged tile
+__device__ __forceinline__ int stg_off_f32(int r, int c) { return r * 64 + ((c ^ ((r >> 1) & 3)) << 4); }   // SWIZZLE_64B
+__device__ __forceinline__ int stg_off_bf16(int r, int c) { return r * 32 + ((c ^ ((r >> 2) & 1)) << 4); }  // SWIZZLE_32B
 
 #define REGEN_TLF(k)                                                                              \
   do {                                                                                            \
     if (trace && lane == 0 && c0 < 48) p.timeline[80 + (c0 / 16) * 8 + (k)] = (unsigned long long)clock64(); \
   } while (0)
 
-__device__ __forceinline__ void epilogue_slice(const Params& p, uint8_t* stg_raw, uint32_t acc, int row0, int n0,
-                                               int ncols, int lane, bool trace_req = false) {
+__device__ __forceinline__ void epilogue_slice(const Params& p, const CUtensorMap* tm_o32, const CUtensorMap* tm_ohi,
+                                               const CUtensorMap* tm_olo, uint8_t* stg_raw, uint32_t acc, int row0,
+                                               int n0, int ncols, int lane, bool trace_req = false) {
   const bool trace = trace_req && p.timeline && blockIdx.x == 0;
-  float* stg = reinterpret_cast<float*>(stg_raw);
-  __nv_bfloat16* stg_hi = reinterpret_cast<__nv_bfloat16*>(stg_raw);
-  __nv_bfloat16* stg_lo = stg_hi + 32 * STG_HPITCH;
   const bool vec_ok = (p.N & 3) == 0;
-  const int fr = lane >> 2, fc = (lane & 3) * 4;   // fp32 coalesced mapping: row i*8 + fr, floats fc..fc+3
-  const int hr = lane >> 1, hc = (lane & 1) * 8;   // bf16 coalesced mapping: row i*16 + hr, halves hc..hc+7
+  const int fr = lane >> 2, fch = lane & 3;        // fp32 coalesced mapping: row i*8 + fr, 16-byte chunk fch
+  const int hr = lane >> 1, hch = lane & 1;        // bf16 coalesced mapping: row i*16 + hr, 16-byte chunk hch
   if (vec_ok) {
+    // buffers may still be the source of bulk stores issued for the previous tile
+    if (p.tma_store) {
+      if (lane == 0) ptx::bulk_wait_read<0>();
+      __syncwarp();
+    }
     float4 rpre[4];
     auto prefetch_res = [&](int c0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int r = row0 + i * 8 + fr, n = n0 + c0 + fc;
+        const int r = row0 + i * 8 + fr, n = n0 + c0 + fch * 4;
         rpre[i] = (r < p.M && n < p.N) ? *reinterpret_cast<const float4*>(p.residual + (size_t)r * p.ld_res + n)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -118,16 +138,21 @@ __device__ __forceinline__ void epilogue_slice(const Params& p, uint8_t* stg_raw
     };
     if (p.residual) prefetch_res(0);
     if (p.bias) prefetch_bias(0);
+    int sc = 0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < ncols; c0 += 16) {
+    for (int c0 = 0; c0 < ncols; c0 += 16, ++sc) {
       if (n0 + c0 >= p.N) break;  // warp-uniform
+      uint8_t* buf = stg_raw + (sc & 1) * 2048;
+      if (p.tma_store && sc >= 2) {  // the store issued two sub-chunks ago has finished reading this buffer
+        if (lane == 0) ptx::bulk_wait_read<1>();
+      }
       uint32_t r[16];
       __syncwarp();
       REGEN_TLF(0);
       ptx::tmem_ld_32x32b_x16(acc + (uint32_t)c0, r);
       if (p.residual) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(stg + (i * 8 + fr) * STG_PITCH + fc) = rpre[i];
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(buf + stg_off_f32(i * 8 + fr, fch)) = rpre[i];
         __syncwarp();
         REGEN_TLF(1);
         if (c0 + 16 < ncols && n0 + c0 + 16 < p.N) prefetch_res(c0 + 16);
@@ -146,9 +171,9 @@ __device__ __forceinline__ void epilogue_slice(const Params& p, uint8_t* stg_raw
       }
       if (p.residual) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 r4 = *reinterpret_cast<const float4*>(stg + lane * STG_PITCH + j);
-          v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+        for (int j = 0; j < 4; ++j) {
+          const float4 r4 = *reinterpret_cast<const float4*>(buf + stg_off_f32(lane, j));
+          v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
         }
         __syncwarp();
       }
@@ -160,18 +185,30 @@ __device__ __forceinline__ void epilogue_slice(const Params& p, uint8_t* stg_raw
       REGEN_TLF(4);
       if (p.out_f32) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        __syncwarp();
-        REGEN_TLF(5);
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(buf + stg_off_f32(lane, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        if (p.tma_store) {
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          REGEN_TLF(5);
+          if (lane == 0) {
+            ptx::tma_store_2d(tm_o32, buf, n0 + c0, row0);
+            ptx::bulk_commit();
+            if (p.out_hi) ptx::bulk_wait_read<0>();  // the bf16 pair is staged in the same buffer next
+          }
+          __syncwarp();
+        } else {
+          __syncwarp();
+          REGEN_TLF(5);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = row0 + i * 8 + fr, n = n0 + c0 + fc;
-          if (rr < p.M && n < p.N)
-            *reinterpret_cast<float4*>(p.out_f32 + (size_t)rr * p.ld_out + n) =
-                *reinterpret_cast<const float4*>(stg + (i * 8 + fr) * STG_PITCH + fc);
+          for (int i = 0; i < 4; ++i) {
+            const int rr = row0 + i * 8 + fr, n = n0 + c0 + fch * 4;
+            if (rr < p.M && n < p.N)
+              *reinterpret_cast<float4*>(p.out_f32 + (size_t)rr * p.ld_out + n) =
+                  *reinterpret_cast<const float4*>(buf + stg_off_f32(i * 8 + fr, fch));
+          }
+          __syncwarp();
         }
-        __syncwarp();
         REGEN_TLF(6);
       }
       if (p.out_hi) {
@@ -183,22 +220,34 @@ __device__ __forceinline__ void epilogue_slice(const Params& p, uint8_t* stg_raw
           // float(hi) is the bf16 bit pattern in the upper half of the word
           lw[j] = pack_bf16x2(a - __uint_as_float(hw[j] << 16), b - __uint_as_float(hw[j] & 0xffff0000u));
         }
-        *reinterpret_cast<uint4*>(stg_hi + lane * STG_HPITCH) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(stg_hi + lane * STG_HPITCH + 8) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-        *reinterpret_cast<uint4*>(stg_lo + lane * STG_HPITCH) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        *reinterpret_cast<uint4*>(stg_lo + lane * STG_HPITCH + 8) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int rr = row0 + i * 16 + hr, n = n0 + c0 + hc;
-          if (rr < p.M && n < p.N) {
-            *reinterpret_cast<uint4*>(p.out_hi + (size_t)rr * p.ld_split + n) =
-                *reinterpret_cast<const uint4*>(stg_hi + (i * 16 + hr) * STG_HPITCH + hc);
-            *reinterpret_cast<uint4*>(p.out_lo + (size_t)rr * p.ld_split + n) =
-                *reinterpret_cast<const uint4*>(stg_lo + (i * 16 + hr) * STG_HPITCH + hc);
+        uint8_t* bh = buf;
+        uint8_t* bl = buf + 1024;
+        *reinterpret_cast<uint4*>(bh + stg_off_bf16(lane, 0)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(bh + stg_off_bf16(lane, 1)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+        *reinterpret_cast<uint4*>(bl + stg_off_bf16(lane, 0)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        *reinterpret_cast<uint4*>(bl + stg_off_bf16(lane, 1)) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+        if (p.tma_store) {
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(tm_ohi, bh, n0 + c0, row0);
+            ptx::tma_store_2d(tm_olo, bl, n0 + c0, row0);
+            ptx::bulk_commit();
           }
+        } else {
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int rr = row0 + i * 16 + hr, n = n0 + c0 + hch * 8;
+            if (rr < p.M && n < p.N) {
+              *reinterpret_cast<uint4*>(p.out_hi + (size_t)rr * p.ld_split + n) =
+                  *reinterpret_cast<const uint4*>(bh + stg_off_bf16(i * 16 + hr, hch));
+              *reinterpret_cast<uint4*>(p.out_lo + (size_t)rr * p.ld_split + n) =
+                  *reinterpret_cast<const uint4*>(bl + stg_off_bf16(i * 16 + hr, hch));
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else {
@@ -241,7 +290,8 @@ template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
-               const Params p) {
+               const __grid_constant__ CUtensorMap tm_o32, const __grid_constant__ CUtensorMap tm_ohi,
+               const __grid_constant__ CUtensorMap tm_olo, const Params p) {
   using C = Cfg<BN, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -363,7 +413,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
       ptx::tcgen05_fence_after();
       const uint32_t acc = tmem_base + (uint32_t)(buf * BN + half * (BN / 2)) + ((uint32_t)(q * 32) << 16);
-      epilogue_slice(p, stg, acc, m0 + q * 32, n0 + half * (BN / 2), BN / 2, lane);
+      epilogue_slice(p, &tm_o32, &tm_ohi, &tm_olo, stg, acc, m0 + q * 32, n0 + half * (BN / 2), BN / 2, lane);
       // release the accumulator buffer to the MMA warp
       ptx::tcgen05_fence_before();
       __syncwarp();
@@ -372,6 +422,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
 
   // ------------------------------------------------------------------ teardown
+  if (p.tma_store && warp >= 2 && lane == 0) ptx::bulk_wait<0>();  // all bulk stores of this thread complete
   ptx::tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -380,10 +431,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
 }
 
+struct OutMaps {  // store-side tensor maps (only read when Params::tma_store != 0)
+  CUtensorMap f32, hi, lo;
+};
+
 // Host launcher.  Tensor maps: A maps have box {64, 128}; W maps have box {64, BN}.
 template <int BN, bool SPLIT>
 inline cudaError_t launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
-                          const CUtensorMap& w_lo, const Params& p, cudaStream_t stream) {
+                          const CUtensorMap& w_lo, const OutMaps& o, const Params& p, cudaStream_t stream) {
   using C = Cfg<BN, SPLIT>;
   static bool configured = false;  // per template instantiation; attribute is per-function, set once
   if (!configured) {
@@ -394,7 +449,7 @@ inline cudaError_t launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, cons
   }
   const int64_t tiles = ceil_div(p.N, BN) * ceil_div(p.M, BM);
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  gemm_tn_kernel<BN, SPLIT><<<grid, kThreads, C::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
+  gemm_tn_kernel<BN, SPLIT><<<grid, kThreads, C::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, o.f32, o.hi, o.lo, p);
   return cudaGetLastError();
 }
 
@@ -412,7 +467,7 @@ struct Cfg2 {
   static constexpr int W_BYTES = (BN / 2) * BK * 2;    // this CTA's half of the W tile
   static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + W_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;  // 3 for SPLIT @ BN=256
-  static constexpr int STG_BYTES = 8 * 3072;  // kEpiWarps * STG_WARP_BYTES
+  static constexpr int STG_BYTES = 8 * 4096;  // kEpiWarps * STG_WARP_BYTES
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
@@ -424,7 +479,8 @@ template <int BN, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
-                const Params p) {
+                const __grid_constant__ CUtensorMap tm_o32, const __grid_constant__ CUtensorMap tm_ohi,
+                const __grid_constant__ CUtensorMap tm_olo, const Params p) {
   using C = Cfg2<BN, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -553,7 +609,8 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       if (warp == 2 && lane == 0 && it < 16) REGEN_TL(40 + 2 * it);
       ptx::tcgen05_fence_after();
       const uint32_t acc = tmem_base + (uint32_t)(buf * BN + half * (BN / 2)) + ((uint32_t)(q * 32) << 16);
-      epilogue_slice(p, stg, acc, m0 + q * 32, n0 + half * (BN / 2), BN / 2, lane, warp == 2 && it == 0);
+      epilogue_slice(p, &tm_o32, &tm_ohi, &tm_olo, stg, acc, m0 + q * 32, n0 + half * (BN / 2), BN / 2, lane,
+                     warp == 2 && it == 0);
       if (warp == 2 && lane == 0 && it < 16) REGEN_TL(41 + 2 * it);
       ptx::tcgen05_fence_before();
       __syncwarp();
@@ -562,6 +619,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   }
 
   // ------------------------------------------------------------------ teardown
+  if (p.tma_store && warp >= 2 && lane == 0) ptx::bulk_wait<0>();  // all bulk stores of this thread complete
   ptx::tcgen05_fence_before();
   ptx::cluster_sync();  // no CTA may exit (or free TMEM) while its peer can still touch its smem / barriers
   if (threadIdx.x == 0) REGEN_TL(2);
@@ -574,7 +632,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 // W tensor maps for the pair kernel need box {64, BN/2}.
 template <int BN, bool SPLIT>
 inline cudaError_t launch2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
-                           const CUtensorMap& w_lo, const Params& p, cudaStream_t stream) {
+                           const CUtensorMap& w_lo, const OutMaps& o, const Params& p, cudaStream_t stream) {
   using C = Cfg2<BN, SPLIT>;
   static bool configured = false;
   if (!configured) {
@@ -585,7 +643,8 @@ inline cudaError_t launch2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, con
   }
   const int64_t tiles = ceil_div(p.N, BN) * ceil_div(p.M, 2 * BM);
   const int clusters = (int)(tiles < kNumSMs / 2 ? tiles : kNumSMs / 2);
-  gemm2_tn_kernel<BN, SPLIT><<<2 * clusters, kThreads, C::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
+  gemm2_tn_kernel<BN, SPLIT><<<2 * clusters, kThreads, C::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, o.f32, o.hi, o.lo,
+                                                                                 p);
   return cudaGetLastError();
 }
 

@@ -19,6 +19,8 @@ struct SplitBuf {  // bf16 (hi, lo) operand pair + its TMA maps
   bf16 *hi = nullptr, *lo = nullptr;
   CUtensorMap tm_hi, tm_lo;      // box rows: 128 for activations (A operand), 256 for weights (single-CTA kernel)
   CUtensorMap tm_hi2, tm_lo2;    // weights only: box rows 128 = one CTA's half of the W tile in the CTA-pair kernel
+  CUtensorMap st_hi, st_lo;      // activations only: store-side maps (box 32 x 16), rebuilt per prepare_cond with rows = M
+  size_t cols = 0;
 };
 
 struct LayerDev {
@@ -50,6 +52,8 @@ struct regen_handle {
   // activations
   SplitBuf a_in, h_s, att, ffn, qkv_s;
   CUtensorMap tm_qkv_hi, tm_qkv_lo;  // 3-D [T, Beff, 1536] views of qkv_s for the attention kernel (per prepare_cond)
+  CUtensorMap st_h, st_tmp, st_x0e;  // store-side maps of the fp32 activation buffers (rows = M)
+  bool tma_store = true;             // REGEN_DEBUG_NO_TMA_STORE=1: st.global epilogue (A/B measurements)
   bool simt_attention = false;       // REGEN_DEBUG_SIMT_ATTENTION=1: fp32 CUDA-core attention for A/B debugging
   float *h = nullptr, *qkv = nullptr, *tmp = nullptr, *x0e = nullptr, *condbias = nullptr, *cmo_tbi = nullptr,
         *ccond = nullptr, *scratch = nullptr;
@@ -107,6 +111,7 @@ int alloc_split(regen_handle* h, SplitBuf* s, size_t rows, size_t cols, uint32_t
   TRY(make_tmap_bf16_2d(&s->tm_lo, s->lo, rows, cols, cols, box_rows));
   TRY(make_tmap_bf16_2d(&s->tm_hi2, s->hi, rows, cols, cols, 128));
   TRY(make_tmap_bf16_2d(&s->tm_lo2, s->lo, rows, cols, cols, 128));
+  s->cols = cols;
   return REGEN_OK;
 }
 
@@ -127,15 +132,27 @@ bool use_pair_kernel(int M) {
   return !force1 && M > 128;
 }
 
-int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, const gemm::Params& p, cudaStream_t s) {
+// o32 / osplit: store-side maps of the fp32 / bf16-pair outputs named in p (null -> st.global epilogue)
+int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, gemm::Params p, const CUtensorMap* o32,
+             const SplitBuf* osplit, cudaStream_t s) {
   ProfScope prof(h, CLS_GEMM, s);
+  gemm::OutMaps om;
+  p.tma_store = 0;
+  if (h->tma_store && (p.N & 3) == 0 && (!p.out_f32 || o32) && (!p.out_hi || osplit)) {
+    p.tma_store = 1;
+    if (o32) om.f32 = *o32;
+    if (osplit) {
+      om.hi = osplit->st_hi;
+      om.lo = osplit->st_lo;
+    }
+  }
   cudaError_t e;
   if (use_pair_kernel(p.M))
-    e = h->desc.precision == 0 ? gemm::launch2<256, true>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, p, s)
-                               : gemm::launch2<256, false>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, p, s);
+    e = h->desc.precision == 0 ? gemm::launch2<256, true>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, om, p, s)
+                               : gemm::launch2<256, false>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, om, p, s);
   else
-    e = h->desc.precision == 0 ? gemm::launch<256, true>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, p, s)
-                               : gemm::launch<256, false>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, p, s);
+    e = h->desc.precision == 0 ? gemm::launch<256, true>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, om, p, s)
+                               : gemm::launch<256, false>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, om, p, s);
   if (e != cudaSuccess) {
     set_error("gemm launch (M=%d N=%d K=%d) failed: %s", p.M, p.N, p.K, cudaGetErrorString(e));
     return REGEN_ECUDA;
@@ -180,6 +197,8 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
   {
     const char* e = getenv("REGEN_DEBUG_SIMT_ATTENTION");
     h->simt_attention = e && e[0] == '1' && layers::attention_smem_bytes(d->max_frames) <= 227 * 1024;
+    const char* e2 = getenv("REGEN_DEBUG_NO_TMA_STORE");
+    h->tma_store = !(e2 && e2[0] == '1');
   }
   const size_t Mx = (size_t)h->Mmax;
   int rc = REGEN_OK;
@@ -370,6 +389,14 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
                                                                                      B, guidance ? 2 : 1);
     count_launch();
   }
+  // store-side maps clip at the logical extents, so they are rebuilt for the current M = T * Beff
+  for (SplitBuf* sb : {&h->h_s, &h->ffn, &h->qkv_s}) {
+    TRY(make_tmap_store_2d(&sb->st_hi, sb->hi, true, h->M, sb->cols, sb->cols));
+    TRY(make_tmap_store_2d(&sb->st_lo, sb->lo, true, h->M, sb->cols, sb->cols));
+  }
+  TRY(make_tmap_store_2d(&h->st_h, h->h, false, h->M, D, D));
+  TRY(make_tmap_store_2d(&h->st_tmp, h->tmp, false, h->M, D, D));
+  if ((I & 3) == 0) TRY(make_tmap_store_2d(&h->st_x0e, h->x0e, false, h->M, I, I));
   TRY(make_tmap_bf16_3d(&h->tm_qkv_hi, h->qkv_s.hi, 3 * D, Beff, T, T <= 64 ? 64 : 128));
   TRY(make_tmap_bf16_3d(&h->tm_qkv_lo, h->qkv_s.lo, 3 * D, Beff, T, T <= 64 ? 64 : 128));
   if (h->has_cond) {
@@ -422,7 +449,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
     p.residual = h->condbias; p.ld_res = D;
     p.out_f32 = h->h; p.ld_out = D;
     p.out_hi = h->h_s.hi; p.out_lo = h->h_s.lo; p.ld_split = D;
-    TRY(run_gemm(h, h->a_in, h->w_in, p, s));
+    TRY(run_gemm(h, h->a_in, h->w_in, p, &h->st_h, &h->h_s, s));
   }
   for (int l = 0; l < L; ++l) {
     LayerDev& ld = h->layer[l];
@@ -431,7 +458,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       p.bias = ld.bqkv;
       p.out_hi = h->qkv_s.hi; p.out_lo = h->qkv_s.lo; p.ld_split = 3 * D;
       if (h->simt_attention) { p.out_f32 = h->qkv; p.ld_out = 3 * D; }
-      TRY(run_gemm(h, h->h_s, ld.wqkv, p, s));
+      TRY(run_gemm(h, h->h_s, ld.wqkv, p, nullptr, h->simt_attention ? nullptr : &h->qkv_s, s));
     }
     {
       ProfScope prof(h, CLS_ATTN, s);
@@ -455,7 +482,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       p.bias = ld.bo;
       p.residual = h->h; p.ld_res = D;
       p.out_f32 = h->tmp; p.ld_out = D;
-      TRY(run_gemm(h, h->att, ld.wo, p, s));
+      TRY(run_gemm(h, h->att, ld.wo, p, &h->st_tmp, nullptr, s));
     }
     {  // h = LN2( LN1(tmp) + c_l[b] )
       layers::LnParams q;
@@ -472,14 +499,14 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       gemm::Params p = gp(M, FF, D);
       p.bias = ld.b1; p.gelu = 1;
       p.out_hi = h->ffn.hi; p.out_lo = h->ffn.lo; p.ld_split = FF;
-      TRY(run_gemm(h, h->h_s, ld.w1, p, s));
+      TRY(run_gemm(h, h->h_s, ld.w1, p, nullptr, &h->ffn, s));
     }
     {  // tmp = h + ffn . W_2^T + b_2
       gemm::Params p = gp(M, D, FF);
       p.bias = ld.b2;
       p.residual = h->h; p.ld_res = D;
       p.out_f32 = h->tmp; p.ld_out = D;
-      TRY(run_gemm(h, h->ffn, ld.w2, p, s));
+      TRY(run_gemm(h, h->ffn, ld.w2, p, &h->st_tmp, nullptr, s));
     }
     {  // h = LN3(tmp)
       layers::LnParams q;
@@ -496,7 +523,17 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
     gemm::Params p = gp(M, I, D);
     p.bias = h->b_out;
     p.out_f32 = h->guidance ? h->x0e : x0_tbi; p.ld_out = I;
-    TRY(run_gemm(h, h->h_s, h->w_out, p, s));
+    CUtensorMap st_x0;
+    const CUtensorMap* om = nullptr;
+    if ((I & 3) == 0 && h->tma_store) {
+      if (h->guidance) {
+        om = &h->st_x0e;
+      } else {  // caller-owned output: the store map is encoded per call (host-side, ~1 us)
+        TRY(make_tmap_store_2d(&st_x0, x0_tbi, false, M, I, I));
+        om = &st_x0;
+      }
+    }
+    TRY(run_gemm(h, h->h_s, h->w_out, p, om, nullptr, s));
   }
   if (h->guidance) {
     int64_t total = (int64_t)T * B * I;
@@ -573,13 +610,17 @@ int regen_test_gemm(const float* A, const float* W, const float* bias, const flo
     gemm::Params p = gp(M, N, Kp);
     p.bias = bias; p.residual = residual; p.ld_res = N; p.out_f32 = out; p.ld_out = N; p.gelu = gelu;
     p.timeline = g_test_timeline;
+    gemm::OutMaps om;
+    const char* nt = getenv("REGEN_DEBUG_NO_TMA_STORE");
+    if ((N & 3) == 0 && !(nt && nt[0] == '1') && make_tmap_store_2d(&om.f32, out, false, M, N, N) == REGEN_OK)
+      p.tma_store = 1;
     cudaError_t e;
     if (pair)
-      e = precision == 0 ? gemm::launch2<256, true>(ta_h, ta_l, tw_h, tw_l, p, s)
-                         : gemm::launch2<256, false>(ta_h, ta_l, tw_h, tw_l, p, s);
+      e = precision == 0 ? gemm::launch2<256, true>(ta_h, ta_l, tw_h, tw_l, om, p, s)
+                         : gemm::launch2<256, false>(ta_h, ta_l, tw_h, tw_l, om, p, s);
     else
-      e = precision == 0 ? gemm::launch<256, true>(ta_h, ta_l, tw_h, tw_l, p, s)
-                         : gemm::launch<256, false>(ta_h, ta_l, tw_h, tw_l, p, s);
+      e = precision == 0 ? gemm::launch<256, true>(ta_h, ta_l, tw_h, tw_l, om, p, s)
+                         : gemm::launch<256, false>(ta_h, ta_l, tw_h, tw_l, om, p, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) {
       set_error("regen_test_gemm: %s", cudaGetErrorString(e));

@@ -49,6 +49,33 @@ inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, 
   return REGEN_OK;
 }
 
+// Store-side map for the GEMM epilogue: [rows, cols] matrix, box = 32 rows x 16 columns.
+//   fp32: 64-byte box rows, SWIZZLE_64B;  bf16: 32-byte box rows, SWIZZLE_32B.
+// TMA stores clip out-of-bounds rows / columns, so `rows` / `cols` must be the logical extents (M, N).
+inline int make_tmap_store_2d(CUtensorMap* out, const void* base, bool is_bf16, uint64_t rows, uint64_t cols,
+                              uint64_t pitch_elems) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    return REGEN_ECUDA;
+  }
+  const uint64_t esz = is_bf16 ? 2 : 4;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_elems * esz};
+  cuuint32_t box[2] = {16, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   is_bf16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(store) failed with CUresult %d (rows=%llu cols=%llu pitch=%llu bf16=%d)", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_elems, (int)is_bf16);
+    return REGEN_ECUDA;
+  }
+  return REGEN_OK;
+}
+
 // bf16 tensor [d2, d1, d0] (d0 contiguous), box = box2 x 1 x 64, 128-byte swizzle, zero fill out of bounds.
 // Used for q|k|v viewed as [T frames, Beff samples, 1536]: one box = one sample's frames x 64 head-dim columns.
 inline int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,

@@ -153,6 +153,24 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const float* __restric
   *o = v;
 }
 
+// cyc[l][r][:] = ctab[t[(r % Beff) % B]][l][:] (+ ccond[r % Beff][l][:])  for r in [0, Beff + 32):
+// the folded cross-attention constant of every layer as a row-cyclic table, so that the 32 consecutive token rows
+// (t, b0 .. b0+31 wrapping into t+1) of an epilogue slice are ONE 2-D TMA box starting at row (row0 % Beff).
+__global__ void __launch_bounds__(128) build_cyc_kernel(const float* __restrict__ ctab, const float* __restrict__ ccond,
+                                                        const int64_t* __restrict__ t, float* __restrict__ cyc, int L,
+                                                        int B, int Beff, int n_table) {
+  const int r = blockIdx.x, l = blockIdx.y;
+  const int be = r % Beff;
+  int64_t tb = t[be % B];
+  tb = tb < 0 ? 0 : (tb >= n_table ? n_table - 1 : tb);
+  float4 v = __ldg(reinterpret_cast<const float4*>(ctab + ((size_t)tb * L + l) * D) + threadIdx.x);
+  if (ccond) {
+    const float4 c = __ldg(reinterpret_cast<const float4*>(ccond + ((size_t)be * L + l) * D) + threadIdx.x);
+    v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+  }
+  reinterpret_cast<float4*>(cyc + ((size_t)l * (Beff + 32) + r) * D)[threadIdx.x] = v;
+}
+
 // ------------------------------------------------------------------------------------------
 // LayerNorm over D=512, one warp per token row.
 //   CHAIN = false:  y = LN(in; g1, b1)                                      (norm3)

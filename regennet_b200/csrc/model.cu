@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "attention_sm100.cuh"
 #include "gemm_sm100.cuh"
+#include "gemm_ln_sm100.cuh"
 #include "layers.cuh"
 #include "tmap.cuh"
 
@@ -54,6 +55,9 @@ struct regen_handle {
   CUtensorMap tm_qkv_hi, tm_qkv_lo;  // 3-D [T, Beff, 1536] views of qkv_s for the attention kernel (per prepare_cond)
   CUtensorMap st_h, st_tmp, st_x0e;  // store-side maps of the fp32 activation buffers (rows = M)
   bool tma_store = true;             // REGEN_DEBUG_NO_TMA_STORE=1: st.global epilogue (A/B measurements)
+  bool fused_ln = true;              // REGEN_DEBUG_NO_FUSED_LN=1: GEMM -> tmp -> LayerNorm kernels
+  float* cyc = nullptr;              // [L][max_batch + 32][512] row-cyclic cross-attention constants (per denoise)
+  CUtensorMap tm_cyc[REGEN_MAX_LAYERS];
   bool simt_attention = false;       // REGEN_DEBUG_SIMT_ATTENTION=1: fp32 CUDA-core attention for A/B debugging
   float *h = nullptr, *qkv = nullptr, *tmp = nullptr, *x0e = nullptr, *condbias = nullptr, *cmo_tbi = nullptr,
         *ccond = nullptr, *scratch = nullptr;
@@ -199,6 +203,8 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
     h->simt_attention = e && e[0] == '1' && layers::attention_smem_bytes(d->max_frames) <= 227 * 1024;
     const char* e2 = getenv("REGEN_DEBUG_NO_TMA_STORE");
     h->tma_store = !(e2 && e2[0] == '1');
+    const char* e3 = getenv("REGEN_DEBUG_NO_FUSED_LN");
+    h->fused_ln = h->tma_store && !(e3 && e3[0] == '1');
   }
   const size_t Mx = (size_t)h->Mmax;
   int rc = REGEN_OK;
@@ -234,6 +240,7 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
     if ((rc = h->alloc(&h->scratch, Mx * D))) break;
     if ((rc = h->alloc(&h->ccond, (size_t)d->max_batch * h->L * D))) break;
     if ((rc = h->alloc(&h->cond_emb, (size_t)d->max_batch * D))) break;
+    if ((rc = h->alloc(&h->cyc, (size_t)h->L * (d->max_batch + 32) * D))) break;
     // the attribute is per function, not per handle: always allow the full 227 KB so that handles with
     // different max_frames can coexist in one process
     cudaError_t e = cudaFuncSetAttribute(layers::attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -394,6 +401,8 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
     TRY(make_tmap_store_2d(&sb->st_hi, sb->hi, true, h->M, sb->cols, sb->cols));
     TRY(make_tmap_store_2d(&sb->st_lo, sb->lo, true, h->M, sb->cols, sb->cols));
   }
+  for (int l = 0; l < L; ++l)
+    TRY(make_tmap_store_2d(&h->tm_cyc[l], h->cyc + (size_t)l * (Beff + 32) * D, false, Beff + 32, D, D));
   TRY(make_tmap_store_2d(&h->st_h, h->h, false, h->M, D, D));
   TRY(make_tmap_store_2d(&h->st_tmp, h->tmp, false, h->M, D, D));
   if ((I & 3) == 0) TRY(make_tmap_store_2d(&h->st_x0e, h->x0e, false, h->M, I, I));
@@ -451,6 +460,12 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
     p.out_hi = h->h_s.hi; p.out_lo = h->h_s.lo; p.ld_split = D;
     TRY(run_gemm(h, h->a_in, h->w_in, p, &h->st_h, &h->h_s, s));
   }
+  if (h->fused_ln) {
+    ProfScope prof(h, CLS_OTHER, s);
+    layers::build_cyc_kernel<<<dim3(Beff + 32, L), 128, 0, s>>>(h->ctab, h->has_cond ? h->ccond : nullptr, t, h->cyc, L, B,
+                                                                Beff, h->desc.num_table_steps);
+    count_launch();
+  }
   for (int l = 0; l < L; ++l) {
     LayerDev& ld = h->layer[l];
     {  // q | k | v  -> bf16 (hi, lo) operands of the attention kernel
@@ -477,6 +492,22 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       }
       count_launch();
     }
+    if (h->fused_ln) {  // h = LN2( LN1(h + attn . W_o^T + b_o) + c_l[b] )   -- one kernel
+      ProfScope prof(h, CLS_GEMM, s);
+      gemmln::Params q;
+      q.M = M; q.K = D; q.Beff = Beff; q.bias = ld.bo; q.g1 = ld.n1w; q.b1 = ld.n1b; q.g2 = ld.n2w; q.b2 = ld.n2b;
+      q.ln_eps = layers::LN_EPS;
+      cudaError_t e = h->desc.precision == 0
+          ? gemmln::launch<true, true>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st_h, h->tm_cyc[l],
+                                       h->h_s.st_hi, h->h_s.st_lo, q, s)
+          : gemmln::launch<false, true>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st_h, h->tm_cyc[l],
+                                        h->h_s.st_hi, h->h_s.st_lo, q, s);
+      if (e != cudaSuccess) {
+        set_error("fused out_proj+LayerNorm launch failed: %s", cudaGetErrorString(e));
+        return REGEN_ECUDA;
+      }
+      count_launch();
+    } else {
     {  // tmp = h + attn . W_o^T + b_o
       gemm::Params p = gp(M, D, D);
       p.bias = ld.bo;
@@ -495,12 +526,29 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       layers::layernorm_kernel<true><<<(unsigned)ceil_div(M, 8), 256, 0, s>>>(q);
       count_launch();
     }
+    }
     {  // ffn = gelu(h . W_1^T + b_1)
       gemm::Params p = gp(M, FF, D);
       p.bias = ld.b1; p.gelu = 1;
       p.out_hi = h->ffn.hi; p.out_lo = h->ffn.lo; p.ld_split = FF;
       TRY(run_gemm(h, h->h_s, ld.w1, p, nullptr, &h->ffn, s));
     }
+    if (h->fused_ln) {  // h = LN3(h + ffn . W_2^T + b_2)   -- one kernel
+      ProfScope prof(h, CLS_GEMM, s);
+      gemmln::Params q;
+      q.M = M; q.K = FF; q.Beff = Beff; q.bias = ld.b2; q.g1 = ld.n3w; q.b1 = ld.n3b; q.g2 = nullptr; q.b2 = nullptr;
+      q.ln_eps = layers::LN_EPS;
+      cudaError_t e = h->desc.precision == 0
+          ? gemmln::launch<true, false>(h->ffn.tm_hi, h->ffn.tm_lo, ld.w2.tm_hi2, ld.w2.tm_lo2, h->st_h, h->st_h,
+                                        h->h_s.st_hi, h->h_s.st_lo, q, s)
+          : gemmln::launch<false, false>(h->ffn.tm_hi, h->ffn.tm_lo, ld.w2.tm_hi2, ld.w2.tm_lo2, h->st_h, h->st_h,
+                                         h->h_s.st_hi, h->h_s.st_lo, q, s);
+      if (e != cudaSuccess) {
+        set_error("fused linear2+LayerNorm launch failed: %s", cudaGetErrorString(e));
+        return REGEN_ECUDA;
+      }
+      count_launch();
+    } else {
     {  // tmp = h + ffn . W_2^T + b_2
       gemm::Params p = gp(M, D, FF);
       p.bias = ld.b2;
@@ -517,6 +565,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       ProfScope prof(h, CLS_LN, s);
       layers::layernorm_kernel<false><<<(unsigned)ceil_div(M, 8), 256, 0, s>>>(q);
       count_launch();
+    }
     }
   }
   {  // x0 = h . W_out^T + b_out   (output_process; rows already in [T,B,I] order)

@@ -26,7 +26,11 @@ constexpr int BM = 128, BK = 64, UMMA_K = 16, ND = 512;
 constexpr int kThreads = 320;
 constexpr int STAGE_BYTES = 6 * 16384;  // A_hi | A_lo | W_hi[0] | W_hi[1] | W_lo[0] | W_lo[1]
 constexpr int STAGES = 2;
-constexpr int EPI_WARP_BYTES = 24576;   // res ring 4 x 2 KB | c ring 4 x 2 KB | 2 x (fp32 2 KB + hi 1 KB + lo 1 KB)
+constexpr int EPI_WARP_BYTES = 24576;   // res ring 3 x 4 KB | c ring 3 x 4 KB; the 2 x 8 KB output buffers alias [0, 16 KB)
+constexpr int SC = 32;                  // columns per epilogue sub-chunk (one tcgen05.ld/st x32, one TMA box)
+constexpr int NSC = 256 / SC;           // sub-chunks per warp (each warp owns 32 rows x 256 columns)
+constexpr int RING = 3;                 // TMA ring depth of the residual / c tiles
+constexpr int SLOT = 32 * SC * 4;       // 4 KB: 32 rows x 32 fp32, 128-byte rows (SWIZZLE_128B)
 constexpr int PARAM_BYTES = 5 * ND * 4; // bias, g1, b1, g2, b2
 constexpr int STATS_BYTES = 2 * 128 * 2 * 8;
 constexpr int BAR_BYTES = 1024;
@@ -38,22 +42,23 @@ struct Params {
   int M, K, Beff;
   const float *bias, *g1, *b1, *g2, *b2;  // [512] each (g2/b2 unused without CHAIN)
   float ln_eps;
+  unsigned long long* timeline;  // bring-up instrumentation (null in production), see tools/ln_timeline.py
 };
 
-__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#define REGEN_LTL(k)                                                                                   \
+  do {                                                                                                 \
+    if (p.timeline && blockIdx.x == 0) p.timeline[(CHAIN ? 0 : 20) + (k)] = (unsigned long long)clock64(); \
+  } while (0)
+
+// byte offset of 16-byte chunk c of row r in a staged tile: fp32 32 x 32 (128-byte rows, SWIZZLE_128B) and
+// bf16 32 x 32 (64-byte rows, SWIZZLE_64B)
+__device__ __forceinline__ int off_f32(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
+__device__ __forceinline__ int off_bf16(int r, int c) { return r * 64 + ((c ^ ((r >> 1) & 3)) << 4); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// tm_res: fp32 [M, 512] residual stream h (box 32 x 16, SWIZZLE_64B) -- used for the residual LOAD and the h STORE
+// tm_res: fp32 [M, 512] residual stream h (box 32 x 32, SWIZZLE_128B) -- used for the residual LOAD and the h STORE
 // tm_c  : fp32 [Beff + 32, 512] cyclic per-sample constant (row r = c[r % Beff]); only read with CHAIN
 // tm_ohi / tm_olo: bf16 [M, 512] split of h (store)
 template <bool SPLIT, bool CHAIN>
@@ -80,27 +85,23 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int num_kb = p.K / BK;
   const int num_tiles = (p.M + 2 * BM - 1) / (2 * BM);
+  if (threadIdx.x == 0) REGEN_LTL(0);
 
-  // LayerNorm / bias vectors -> shared memory (global loads are L2 round trips here: there is no L1 left)
-  for (int i = threadIdx.x; i < 5 * ND / 4; i += kThreads) {
-    const int which = i / (ND / 4), j = i % (ND / 4);
-    const float* src = which == 0 ? p.bias : which == 1 ? p.g1 : which == 2 ? p.b1 : which == 3 ? p.g2 : p.b2;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (src) v = __ldg(reinterpret_cast<const float4*>(src) + j);
-    reinterpret_cast<float4*>(s_par)[i] = v;
-  }
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tm_a_hi);
-    ptx::prefetch_tmap(&tm_w_hi);
-    ptx::prefetch_tmap(&tm_res);
-    for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tm_a_hi);
+      ptx::prefetch_tmap(&tm_w_hi);
+      ptx::prefetch_tmap(&tm_res);
+      for (int s = 0; s < STAGES; ++s) {
+        ptx::mbar_init(&full_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], 1);
+      }
+      ptx::mbar_init(tmem_full_bar, 1);
+      ptx::mbar_init(tmem_empty_bar, 16);
+      ptx::mbar_init(epi_done_bar, 8);
     }
-    ptx::mbar_init(tmem_full_bar, 1);
-    ptx::mbar_init(tmem_empty_bar, 16);
-    ptx::mbar_init(epi_done_bar, 8);
-    for (int i = 0; i < 64; ++i) ptx::mbar_init(&ring_bar[i], 1);
+    ptx::mbar_init(&ring_bar[lane], 1);
+    ptx::mbar_init(&ring_bar[32 + lane], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -151,6 +152,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         ptx::tcgen05_fence_after();
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
+          if (kb == 0 && it == 0) REGEN_LTL(1);
           ptx::tcgen05_fence_after();
           const uint32_t st = ptx::smem_u32(smem + stage * STAGE_BYTES);
 #pragma unroll
@@ -179,6 +181,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           }
         }
         ptx::tcgen05_commit_2sm(tmem_full_bar);
+        if (it == 0) REGEN_LTL(2);
       }
     }
   } else {
@@ -186,11 +189,20 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     const int ew = warp - 2;
     const int q = warp & 3, hf = ew >> 2;
     const int r_local = q * 32 + lane;                 // row inside this CTA's 128 rows == TMEM lane
+    // LayerNorm / bias vectors -> shared memory while the main loop runs (global loads are L2 round trips here)
+    for (int i = threadIdx.x - 64; i < 5 * ND / 4; i += 256) {
+      const int which = i / (ND / 4), j = i % (ND / 4);
+      const float* src = which == 0 ? p.bias : which == 1 ? p.g1 : which == 2 ? p.b1 : which == 3 ? p.g2 : p.b2;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src) v = __ldg(reinterpret_cast<const float4*>(src) + j);
+      reinterpret_cast<float4*>(s_par)[i] = v;
+    }
+    named_bar_sync(5, 256);
     uint8_t* my = smem + ew * EPI_WARP_BYTES;
     uint8_t* res_ring = my;
-    uint8_t* c_ring = my + 8192;
-    uint8_t* out_buf = my + 16384;
-    uint64_t* rbar = ring_bar + ew * 8;
+    uint8_t* c_ring = my + RING * SLOT;
+    uint8_t* out_buf = my;                             // 2 x 8 KB, used after both rings are drained
+    uint64_t* rbar = ring_bar + ew * 8;                // [0..2] residual slots, [4..6] c slots
     const float* s_bias = s_par + hf * 256;
     const float* s_g1 = s_par + ND + hf * 256;
     const float* s_b1 = s_par + 2 * ND + hf * 256;
@@ -203,42 +215,44 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       const int row0 = tile * (2 * BM) + (int)rank * BM + q * 32;  // global row of lane 0
       const int n_base = hf * 256;
       const int crow0 = row0 % p.Beff;                              // first row in the cyclic c table
-      const uint32_t ring_phase0 = (uint32_t)(it * 4);              // each slot is filled 4 times per tile per ring
       ptx::mbar_wait(tmem_full_bar, it & 1);                        // accumulator complete => operand ring is idle
+      const bool tr = warp == 2 && lane == 0 && it == 0;
+      if (tr) REGEN_LTL(3);
       ptx::tcgen05_fence_after();
-      // prime the residual (and c) rings: 4 sub-chunks each
+      // prime the residual (and c) rings
       if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          ptx::mbar_expect_tx(&rbar[s], 2048);
-          ptx::tma_load_2d(res_ring + s * 2048, &tm_res, &rbar[s], n_base + 16 * s, row0);
+        for (int s = 0; s < RING; ++s) {
+          ptx::mbar_expect_tx(&rbar[s], SLOT);
+          ptx::tma_load_2d(res_ring + s * SLOT, &tm_res, &rbar[s], n_base + SC * s, row0);
           if (CHAIN) {
-            ptx::mbar_expect_tx(&rbar[4 + s], 2048);
-            ptx::tma_load_2d(c_ring + s * 2048, &tm_c, &rbar[4 + s], n_base + 16 * s, crow0);
+            ptx::mbar_expect_tx(&rbar[4 + s], SLOT);
+            ptx::tma_load_2d(c_ring + s * SLOT, &tm_c, &rbar[4 + s], n_base + SC * s, crow0);
           }
         }
       }
       // ---- pass 1: v = acc + bias + residual, row statistics, v -> TMEM
       float sum = 0.f, sq = 0.f;
 #pragma unroll 1
-      for (int sc = 0; sc < 16; ++sc) {
-        const int slot = sc & 3;
-        uint32_t r[16];
+      for (int sc = 0; sc < NSC; ++sc) {
+        const int slot = sc % RING;
+        uint32_t r[32];
         __syncwarp();
-        ptx::tmem_ld_32x32b_x16(lane_addr + (uint32_t)(sc * 16), r);
-        ptx::mbar_wait(&rbar[slot], (ring_phase0 + (uint32_t)(sc >> 2)) & 1);
-        float4 rr[4];
+        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(sc * SC), r);
+        // slot `slot` is filled ceil((NSC - slot) / RING) times per tile; this is fill number sc / RING of this tile
+        ptx::mbar_wait(&rbar[slot], (uint32_t)(it * ((NSC - slot + RING - 1) / RING) + sc / RING) & 1);
+        float4 rr[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const float4*>(res_ring + slot * 2048 + gemm::stg_off_f32(lane, j));
+        for (int j = 0; j < 8; ++j) rr[j] = *reinterpret_cast<const float4*>(res_ring + slot * SLOT + off_f32(lane, j));
         ptx::tmem_ld_wait();
         __syncwarp();  // every lane has read the slot
-        if (lane == 0 && sc + 4 < 16) {
-          ptx::mbar_expect_tx(&rbar[slot], 2048);
-          ptx::tma_load_2d(res_ring + slot * 2048, &tm_res, &rbar[slot], n_base + 16 * (sc + 4), row0);
+        if (lane == 0 && sc + RING < NSC) {
+          ptx::mbar_expect_tx(&rbar[slot], SLOT);
+          ptx::tma_load_2d(res_ring + slot * SLOT, &tm_res, &rbar[slot], n_base + SC * (sc + RING), row0);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + sc * 16 + 4 * j);
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + sc * SC + 4 * j);
           float v0 = __uint_as_float(r[4 * j]) + b4.x + rr[j].x, v1 = __uint_as_float(r[4 * j + 1]) + b4.y + rr[j].y;
           float v2 = __uint_as_float(r[4 * j + 2]) + b4.z + rr[j].z, v3 = __uint_as_float(r[4 * j + 3]) + b4.w + rr[j].w;
           sum += (v0 + v1) + (v2 + v3);
@@ -246,12 +260,14 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           r[4 * j] = __float_as_uint(v0); r[4 * j + 1] = __float_as_uint(v1);
           r[4 * j + 2] = __float_as_uint(v2); r[4 * j + 3] = __float_as_uint(v3);
         }
-        tmem_st_32x32b_x16(lane_addr + (uint32_t)(sc * 16), r);
+        ptx::tmem_st_32x32b_x32(lane_addr + (uint32_t)(sc * SC), r);
       }
-      tmem_st_wait();
+      ptx::tmem_st_wait();
+      if (tr) REGEN_LTL(4);
       // exchange the half-row statistics with the warp that owns the other 256 columns of the same rows
       s_stats[r_local * 2 + hf] = make_float2(sum, sq);
       named_bar_sync(1 + q, 64);
+      if (tr) REGEN_LTL(5);
       {
         const float2 o = s_stats[r_local * 2 + (hf ^ 1)];
         sum += o.x;
@@ -264,25 +280,25 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         // ---- pass 2: y = LN1(v) + c, statistics of y, y -> TMEM
         float sum2 = 0.f, sq2 = 0.f;
 #pragma unroll 1
-        for (int sc = 0; sc < 16; ++sc) {
-          const int slot = sc & 3;
-          uint32_t r[16];
+        for (int sc = 0; sc < NSC; ++sc) {
+          const int slot = sc % RING;
+          uint32_t r[32];
           __syncwarp();
-          ptx::tmem_ld_32x32b_x16(lane_addr + (uint32_t)(sc * 16), r);
-          ptx::mbar_wait(&rbar[4 + slot], (ring_phase0 + (uint32_t)(sc >> 2)) & 1);
-          float4 cc[4];
+          ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(sc * SC), r);
+          ptx::mbar_wait(&rbar[4 + slot], (uint32_t)(it * ((NSC - slot + RING - 1) / RING) + sc / RING) & 1);
+          float4 cc[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) cc[j] = *reinterpret_cast<const float4*>(c_ring + slot * 2048 + gemm::stg_off_f32(lane, j));
+          for (int j = 0; j < 8; ++j) cc[j] = *reinterpret_cast<const float4*>(c_ring + slot * SLOT + off_f32(lane, j));
           ptx::tmem_ld_wait();
           __syncwarp();
-          if (lane == 0 && sc + 4 < 16) {
-            ptx::mbar_expect_tx(&rbar[4 + slot], 2048);
-            ptx::tma_load_2d(c_ring + slot * 2048, &tm_c, &rbar[4 + slot], n_base + 16 * (sc + 4), crow0);
+          if (lane == 0 && sc + RING < NSC) {
+            ptx::mbar_expect_tx(&rbar[4 + slot], SLOT);
+            ptx::tma_load_2d(c_ring + slot * SLOT, &tm_c, &rbar[4 + slot], n_base + SC * (sc + RING), crow0);
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 g4 = *reinterpret_cast<const float4*>(s_g1 + sc * 16 + 4 * j);
-            const float4 b4 = *reinterpret_cast<const float4*>(s_b1 + sc * 16 + 4 * j);
+          for (int j = 0; j < 8; ++j) {
+            const float4 g4 = *reinterpret_cast<const float4*>(s_g1 + sc * SC + 4 * j);
+            const float4 b4 = *reinterpret_cast<const float4*>(s_b1 + sc * SC + 4 * j);
             float y0 = (__uint_as_float(r[4 * j]) - mean) * rstd * g4.x + b4.x + cc[j].x;
             float y1 = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * g4.y + b4.y + cc[j].y;
             float y2 = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * g4.z + b4.z + cc[j].z;
@@ -292,11 +308,13 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             r[4 * j] = __float_as_uint(y0); r[4 * j + 1] = __float_as_uint(y1);
             r[4 * j + 2] = __float_as_uint(y2); r[4 * j + 3] = __float_as_uint(y3);
           }
-          tmem_st_32x32b_x16(lane_addr + (uint32_t)(sc * 16), r);
+          ptx::tmem_st_32x32b_x32(lane_addr + (uint32_t)(sc * SC), r);
         }
-        tmem_st_wait();
+        ptx::tmem_st_wait();
+        if (tr) REGEN_LTL(6);
         s_stats[256 + r_local * 2 + hf] = make_float2(sum2, sq2);
         named_bar_sync(1 + q, 64);
+        if (tr) REGEN_LTL(7);
         {
           const float2 o = s_stats[256 + r_local * 2 + (hf ^ 1)];
           sum2 += o.x;
@@ -306,50 +324,52 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         rstd = 1.0f / sqrtf(fmaxf(sq2 * inv_n - mean * mean, 0.f) + p.ln_eps);
       }
 
-      // ---- final pass: z = LN(.), fp32 + bf16 (hi, lo) out through TMA stores
+      // ---- final pass: z = LN(.), fp32 + bf16 (hi, lo) out through TMA stores (8 KB per sub-chunk, double buffered)
       const float* gg = CHAIN ? s_g2 : s_g1;
       const float* bb = CHAIN ? s_b2 : s_b1;
-      if (lane == 0) ptx::bulk_wait_read<0>();  // output buffers of the previous tile
+      __syncwarp();  // both rings fully consumed by every lane: their memory becomes the output buffers
 #pragma unroll 1
-      for (int sc = 0; sc < 16; ++sc) {
-        uint8_t* ob = out_buf + (sc & 1) * 4096;
+      for (int sc = 0; sc < NSC; ++sc) {
+        uint8_t* ob = out_buf + (sc & 1) * 8192;
         if (sc >= 2 && lane == 0) ptx::bulk_wait_read<1>();
-        uint32_t r[16];
+        uint32_t r[32];
         __syncwarp();
-        ptx::tmem_ld_32x32b_x16(lane_addr + (uint32_t)(sc * 16), r);
+        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(sc * SC), r);
         ptx::tmem_ld_wait();
-        float z[16];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 g4 = *reinterpret_cast<const float4*>(gg + sc * 16 + 4 * j);
-          const float4 b4 = *reinterpret_cast<const float4*>(bb + sc * 16 + 4 * j);
-          z[4 * j] = (__uint_as_float(r[4 * j]) - mean) * rstd * g4.x + b4.x;
-          z[4 * j + 1] = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * g4.y + b4.y;
-          z[4 * j + 2] = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * g4.z + b4.z;
-          z[4 * j + 3] = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * g4.w + b4.w;
-          *reinterpret_cast<float4*>(ob + gemm::stg_off_f32(lane, j)) = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
-        }
-        uint32_t hw[8], lw[8];
+        uint32_t hw[16], lw[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          hw[j] = gemm::pack_bf16x2(z[2 * j], z[2 * j + 1]);
-          lw[j] = gemm::pack_bf16x2(z[2 * j] - __uint_as_float(hw[j] << 16), z[2 * j + 1] - __uint_as_float(hw[j] & 0xffff0000u));
+          const float4 g4 = *reinterpret_cast<const float4*>(gg + sc * SC + 4 * j);
+          const float4 b4 = *reinterpret_cast<const float4*>(bb + sc * SC + 4 * j);
+          const float z0 = (__uint_as_float(r[4 * j]) - mean) * rstd * g4.x + b4.x;
+          const float z1 = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * g4.y + b4.y;
+          const float z2 = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * g4.z + b4.z;
+          const float z3 = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * g4.w + b4.w;
+          *reinterpret_cast<float4*>(ob + off_f32(lane, j)) = make_float4(z0, z1, z2, z3);
+          const uint32_t h0 = gemm::pack_bf16x2(z0, z1), h1 = gemm::pack_bf16x2(z2, z3);
+          hw[2 * j] = h0;
+          hw[2 * j + 1] = h1;
+          lw[2 * j] = gemm::pack_bf16x2(z0 - __uint_as_float(h0 << 16), z1 - __uint_as_float(h0 & 0xffff0000u));
+          lw[2 * j + 1] = gemm::pack_bf16x2(z2 - __uint_as_float(h1 << 16), z3 - __uint_as_float(h1 & 0xffff0000u));
         }
-        *reinterpret_cast<uint4*>(ob + 2048 + gemm::stg_off_bf16(lane, 0)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(ob + 2048 + gemm::stg_off_bf16(lane, 1)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-        *reinterpret_cast<uint4*>(ob + 3072 + gemm::stg_off_bf16(lane, 0)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        *reinterpret_cast<uint4*>(ob + 3072 + gemm::stg_off_bf16(lane, 1)) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          *reinterpret_cast<uint4*>(ob + 4096 + off_bf16(lane, c)) = make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]);
+          *reinterpret_cast<uint4*>(ob + 6144 + off_bf16(lane, c)) = make_uint4(lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]);
+        }
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          ptx::tma_store_2d(&tm_res, ob, n_base + 16 * sc, row0);
-          ptx::tma_store_2d(&tm_ohi, ob + 2048, n_base + 16 * sc, row0);
-          ptx::tma_store_2d(&tm_olo, ob + 3072, n_base + 16 * sc, row0);
+          ptx::tma_store_2d(&tm_res, ob, n_base + SC * sc, row0);
+          ptx::tma_store_2d(&tm_ohi, ob + 4096, n_base + SC * sc, row0);
+          ptx::tma_store_2d(&tm_olo, ob + 6144, n_base + SC * sc, row0);
           ptx::bulk_commit();
         }
       }
       // accumulator and operand ring are free again
+      if (tr) REGEN_LTL(8);
       if (lane == 0) ptx::bulk_wait_read<0>();
+      if (tr) REGEN_LTL(9);
       ptx::tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -363,6 +383,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 
   ptx::tcgen05_fence_before();
   ptx::cluster_sync();
+  if (threadIdx.x == 0) REGEN_LTL(10);
   if (warp == 1) {
     ptx::tcgen05_fence_after();
     ptx::tmem_dealloc_2sm(tmem_base, 512);

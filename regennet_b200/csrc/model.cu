@@ -21,6 +21,7 @@ struct SplitBuf {  // bf16 (hi, lo) operand pair + its TMA maps
   CUtensorMap tm_hi, tm_lo;      // box rows: 128 for activations (A operand), 256 for weights (single-CTA kernel)
   CUtensorMap tm_hi2, tm_lo2;    // weights only: box rows 128 = one CTA's half of the W tile in the CTA-pair kernel
   CUtensorMap st_hi, st_lo;      // activations only: store-side maps (box 32 x 16), rebuilt per prepare_cond with rows = M
+  CUtensorMap st32_hi, st32_lo;  // same with box 32 x 32 (fused GEMM+LayerNorm epilogue)
   size_t cols = 0;
 };
 
@@ -54,6 +55,7 @@ struct regen_handle {
   SplitBuf a_in, h_s, att, ffn, qkv_s;
   CUtensorMap tm_qkv_hi, tm_qkv_lo;  // 3-D [T, Beff, 1536] views of qkv_s for the attention kernel (per prepare_cond)
   CUtensorMap st_h, st_tmp, st_x0e;  // store-side maps of the fp32 activation buffers (rows = M)
+  CUtensorMap st32_h;                // h with box 32 x 32: residual load + store of the fused GEMM+LayerNorm kernel
   bool tma_store = true;             // REGEN_DEBUG_NO_TMA_STORE=1: st.global epilogue (A/B measurements)
   bool fused_ln = true;              // REGEN_DEBUG_NO_FUSED_LN=1: GEMM -> tmp -> LayerNorm kernels
   float* cyc = nullptr;              // [L][max_batch + 32][512] row-cyclic cross-attention constants (per denoise)
@@ -75,6 +77,8 @@ struct regen_handle {
     return REGEN_OK;
   }
 };
+
+static unsigned long long* g_test_timeline = nullptr;  // device buffer [128], set by regen_test_gemm_timeline
 
 namespace {
 
@@ -400,9 +404,12 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
   for (SplitBuf* sb : {&h->h_s, &h->ffn, &h->qkv_s}) {
     TRY(make_tmap_store_2d(&sb->st_hi, sb->hi, true, h->M, sb->cols, sb->cols));
     TRY(make_tmap_store_2d(&sb->st_lo, sb->lo, true, h->M, sb->cols, sb->cols));
+    TRY(make_tmap_store_2d(&sb->st32_hi, sb->hi, true, h->M, sb->cols, sb->cols, 32));
+    TRY(make_tmap_store_2d(&sb->st32_lo, sb->lo, true, h->M, sb->cols, sb->cols, 32));
   }
+  TRY(make_tmap_store_2d(&h->st32_h, h->h, false, h->M, D, D, 32));
   for (int l = 0; l < L; ++l)
-    TRY(make_tmap_store_2d(&h->tm_cyc[l], h->cyc + (size_t)l * (Beff + 32) * D, false, Beff + 32, D, D));
+    TRY(make_tmap_store_2d(&h->tm_cyc[l], h->cyc + (size_t)l * (Beff + 32) * D, false, Beff + 32, D, D, 32));
   TRY(make_tmap_store_2d(&h->st_h, h->h, false, h->M, D, D));
   TRY(make_tmap_store_2d(&h->st_tmp, h->tmp, false, h->M, D, D));
   if ((I & 3) == 0) TRY(make_tmap_store_2d(&h->st_x0e, h->x0e, false, h->M, I, I));
@@ -497,11 +504,12 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       gemmln::Params q;
       q.M = M; q.K = D; q.Beff = Beff; q.bias = ld.bo; q.g1 = ld.n1w; q.b1 = ld.n1b; q.g2 = ld.n2w; q.b2 = ld.n2b;
       q.ln_eps = layers::LN_EPS;
+      q.timeline = g_test_timeline;
       cudaError_t e = h->desc.precision == 0
-          ? gemmln::launch<true, true>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st_h, h->tm_cyc[l],
-                                       h->h_s.st_hi, h->h_s.st_lo, q, s)
-          : gemmln::launch<false, true>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st_h, h->tm_cyc[l],
-                                        h->h_s.st_hi, h->h_s.st_lo, q, s);
+          ? gemmln::launch<true, true>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->tm_cyc[l],
+                                       h->h_s.st32_hi, h->h_s.st32_lo, q, s)
+          : gemmln::launch<false, true>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->tm_cyc[l],
+                                        h->h_s.st32_hi, h->h_s.st32_lo, q, s);
       if (e != cudaSuccess) {
         set_error("fused out_proj+LayerNorm launch failed: %s", cudaGetErrorString(e));
         return REGEN_ECUDA;
@@ -538,11 +546,12 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       gemmln::Params q;
       q.M = M; q.K = FF; q.Beff = Beff; q.bias = ld.b2; q.g1 = ld.n3w; q.b1 = ld.n3b; q.g2 = nullptr; q.b2 = nullptr;
       q.ln_eps = layers::LN_EPS;
+      q.timeline = g_test_timeline;
       cudaError_t e = h->desc.precision == 0
-          ? gemmln::launch<true, false>(h->ffn.tm_hi, h->ffn.tm_lo, ld.w2.tm_hi2, ld.w2.tm_lo2, h->st_h, h->st_h,
-                                        h->h_s.st_hi, h->h_s.st_lo, q, s)
-          : gemmln::launch<false, false>(h->ffn.tm_hi, h->ffn.tm_lo, ld.w2.tm_hi2, ld.w2.tm_lo2, h->st_h, h->st_h,
-                                         h->h_s.st_hi, h->h_s.st_lo, q, s);
+          ? gemmln::launch<true, false>(h->ffn.tm_hi, h->ffn.tm_lo, ld.w2.tm_hi2, ld.w2.tm_lo2, h->st32_h, h->st32_h,
+                                        h->h_s.st32_hi, h->h_s.st32_lo, q, s)
+          : gemmln::launch<false, false>(h->ffn.tm_hi, h->ffn.tm_lo, ld.w2.tm_hi2, ld.w2.tm_lo2, h->st32_h, h->st32_h,
+                                         h->h_s.st32_hi, h->h_s.st32_lo, q, s);
       if (e != cudaSuccess) {
         set_error("fused linear2+LayerNorm launch failed: %s", cudaGetErrorString(e));
         return REGEN_ECUDA;
@@ -629,7 +638,6 @@ int regen_profile_end(regen_handle* h, float* ms, int32_t* launches) {
 }
 
 // Kernel-level test hook: C = A . W^T (+bias)(+residual)(gelu) through the tcgen05 GEMM, fp32 in / out.
-static unsigned long long* g_test_timeline = nullptr;  // device buffer [128], set by regen_test_gemm_timeline
 
 int regen_test_gemm_timeline(unsigned long long* device_buf128) {
   g_test_timeline = device_buf128;

@@ -49,28 +49,31 @@ inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, 
   return REGEN_OK;
 }
 
-// Store-side map for the GEMM epilogue: [rows, cols] matrix, box = 32 rows x 16 columns.
-//   fp32: 64-byte box rows, SWIZZLE_64B;  bf16: 32-byte box rows, SWIZZLE_32B.
+// Epilogue-side map (TMA store, and TMA load of residual tiles): [rows, cols] matrix, box = 32 rows x box_cols
+// columns (16 or 32).  The swizzle equals the box row size: 32 B -> SWIZZLE_32B, 64 B -> SWIZZLE_64B, 128 B -> SWIZZLE_128B.
 // TMA stores clip out-of-bounds rows / columns, so `rows` / `cols` must be the logical extents (M, N).
 inline int make_tmap_store_2d(CUtensorMap* out, const void* base, bool is_bf16, uint64_t rows, uint64_t cols,
-                              uint64_t pitch_elems) {
+                              uint64_t pitch_elems, uint32_t box_cols = 16) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
     return REGEN_ECUDA;
   }
   const uint64_t esz = is_bf16 ? 2 : 4;
+  const uint64_t row_bytes = box_cols * esz;
+  const CUtensorMapSwizzle sw = row_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {pitch_elems * esz};
-  cuuint32_t box[2] = {16, 32};
+  cuuint32_t box[2] = {box_cols, 32};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   is_bf16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(store) failed with CUresult %d (rows=%llu cols=%llu pitch=%llu bf16=%d)", (int)r,
-              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_elems, (int)is_bf16);
+    set_error("cuTensorMapEncodeTiled(store) failed with CUresult %d (rows=%llu cols=%llu pitch=%llu bf16=%d box=%u)",
+              (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_elems, (int)is_bf16,
+              box_cols);
     return REGEN_ECUDA;
   }
   return REGEN_OK;

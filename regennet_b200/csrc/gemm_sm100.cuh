@@ -105,6 +105,7 @@ __device__ __forceinline__ int stg_off_bf16(int r, int c) { return r * 32 + ((c 
     if (trace && lane == 0 && c0 < 48) p.timeline[80 + (c0 / 16) * 8 + (k)] = (unsigned long long)clock64(); \
   } while (0)
 
+template <bool RES = true, bool DBUF = true>
 __device__ __forceinline__ void epilogue_slice(const Params& p, const CUtensorMap* tm_o32, const CUtensorMap* tm_ohi,
                                                const CUtensorMap* tm_olo, uint8_t* stg_raw, uint32_t acc, int row0,
                                                int n0, int ncols, int lane, bool trace_req = false) {
@@ -136,21 +137,24 @@ __device__ __forceinline__ void epilogue_slice(const Params& p, const CUtensorMa
         bpre[j] = (n0 + c0 + 4 * j < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + 4 * j))
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    if (p.residual) prefetch_res(0);
+    const bool has_res = RES && p.residual != nullptr;
+    if (has_res) prefetch_res(0);
     if (p.bias) prefetch_bias(0);
     int sc = 0;
 #pragma unroll 1
     for (int c0 = 0; c0 < ncols; c0 += 16, ++sc) {
       if (n0 + c0 >= p.N) break;  // warp-uniform
-      uint8_t* buf = stg_raw + (sc & 1) * 2048;
-      if (p.tma_store && sc >= 2) {  // the store issued two sub-chunks ago has finished reading this buffer
-        if (lane == 0) ptx::bulk_wait_read<1>();
+      uint8_t* buf = stg_raw + (DBUF ? (sc & 1) * 2048 : 0);
+      if (p.tma_store && sc >= (DBUF ? 2 : 1)) {  // the previous store from this buffer has finished reading it
+        if (lane == 0) {
+          if (DBUF) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
+        }
       }
       uint32_t r[16];
       __syncwarp();
       REGEN_TLF(0);
       ptx::tmem_ld_32x32b_x16(acc + (uint32_t)c0, r);
-      if (p.residual) {
+      if (has_res) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(buf + stg_off_f32(i * 8 + fr, fch)) = rpre[i];
         __syncwarp();
@@ -169,7 +173,7 @@ __device__ __forceinline__ void epilogue_slice(const Params& p, const CUtensorMa
         }
         if (c0 + 16 < ncols && n0 + c0 + 16 < p.N) prefetch_bias(c0 + 16);
       }
-      if (p.residual) {
+      if (has_res) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 r4 = *reinterpret_cast<const float4*>(buf + stg_off_f32(lane, j));
@@ -475,8 +479,11 @@ struct Cfg2 {
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN, bool SPLIT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+// EW = 8: general epilogue (residual, fp32 and/or bf16-pair outputs), double-buffered staging.
+// EW = 16 (RES = false): 4 epilogue warps per scheduler for the bias/GELU/bf16-split epilogues, which are bound by
+// instruction issue and latency, not bandwidth; 576 threads -> at most 112 registers, so the residual path is compiled out.
+template <int BN, bool SPLIT, int EW, bool RES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                 const __grid_constant__ CUtensorMap tm_o32, const __grid_constant__ CUtensorMap tm_ohi,
@@ -515,7 +522,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tmem_full_bar[b], 1);
-      ptx::mbar_init(&tmem_empty_bar[b], 2 * kEpiWarps);  // epilogue warps of both CTAs
+      ptx::mbar_init(&tmem_empty_bar[b], 2 * EW);  // epilogue warps of both CTAs
     }
     ptx::fence_barrier_init();
   }
@@ -597,10 +604,12 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..9 of both CTAs)
+    // ------------------------------------------------------------------ epilogue (warps 2..EW+1 of both CTAs)
+    constexpr int PARTS = EW / 4;          // warps per TMEM lane quarter; each takes BN / PARTS columns
+    constexpr int PCOLS = BN / PARTS;
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    uint8_t* stg = staging + (warp - 2) * STG_WARP_BYTES;
+    const int part = (warp - 2) >> 2;
+    uint8_t* stg = staging + (warp - 2) * (C::STG_BYTES / EW);
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM, n0 = (tile % tiles_n) * BN;
@@ -608,9 +617,9 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
       if (warp == 2 && lane == 0 && it < 16) REGEN_TL(40 + 2 * it);
       ptx::tcgen05_fence_after();
-      const uint32_t acc = tmem_base + (uint32_t)(buf * BN + half * (BN / 2)) + ((uint32_t)(q * 32) << 16);
-      epilogue_slice(p, &tm_o32, &tm_ohi, &tm_olo, stg, acc, m0 + q * 32, n0 + half * (BN / 2), BN / 2, lane,
-                     warp == 2 && it == 0);
+      const uint32_t acc = tmem_base + (uint32_t)(buf * BN + part * PCOLS) + ((uint32_t)(q * 32) << 16);
+      epilogue_slice<RES, EW == 8>(p, &tm_o32, &tm_ohi, &tm_olo, stg, acc, m0 + q * 32, n0 + part * PCOLS, PCOLS, lane,
+                                   warp == 2 && it == 0);
       if (warp == 2 && lane == 0 && it < 16) REGEN_TL(41 + 2 * it);
       ptx::tcgen05_fence_before();
       __syncwarp();
@@ -630,22 +639,31 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 }
 
 // W tensor maps for the pair kernel need box {64, BN/2}.
-template <int BN, bool SPLIT>
-inline cudaError_t launch2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
-                           const CUtensorMap& w_lo, const OutMaps& o, const Params& p, cudaStream_t stream) {
+template <int BN, bool SPLIT, int EW, bool RES>
+inline cudaError_t launch2_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                                const CUtensorMap& w_lo, const OutMaps& o, const Params& p, cudaStream_t stream) {
   using C = Cfg2<BN, SPLIT>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_tn_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm2_tn_kernel<BN, SPLIT, EW, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int64_t tiles = ceil_div(p.N, BN) * ceil_div(p.M, 2 * BM);
   const int clusters = (int)(tiles < kNumSMs / 2 ? tiles : kNumSMs / 2);
-  gemm2_tn_kernel<BN, SPLIT><<<2 * clusters, kThreads, C::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, o.f32, o.hi, o.lo,
-                                                                                 p);
+  gemm2_tn_kernel<BN, SPLIT, EW, RES><<<2 * clusters, 64 + 32 * EW, C::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, o.f32,
+                                                                                             o.hi, o.lo, p);
   return cudaGetLastError();
+}
+
+template <int BN, bool SPLIT>
+inline cudaError_t launch2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                           const CUtensorMap& w_lo, const OutMaps& o, const Params& p, cudaStream_t stream) {
+  // 16 epilogue warps whenever no residual is added and the outputs leave through TMA stores
+  if (!p.residual && p.tma_store && !(p.out_f32 && p.out_hi))
+    return launch2_impl<BN, SPLIT, 16, false>(a_hi, a_lo, w_hi, w_lo, o, p, stream);
+  return launch2_impl<BN, SPLIT, 8, true>(a_hi, a_lo, w_hi, w_lo, o, p, stream);
 }
 
 }  // namespace gemm

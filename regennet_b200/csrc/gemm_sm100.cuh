@@ -287,6 +287,91 @@ __device__ __forceinline__ void epilogue_slice(const Params& p, const CUtensorMa
   }
 }
 
+// Epilogue variant of the 16-warp kernels (no residual): 32-column TMEM loads; the bf16 outputs leave as 32-column
+// TMA boxes (64-byte rows, SWIZZLE_64B: half as many row requests for the TMA unit as 16-column boxes), hi then lo
+// through the warp's single 2 KB staging tile; fp32 outputs as two 16-column boxes.  The warp's 64-column bias slice
+// lives in registers (one float2 per lane, one L2 round trip per tile) and is broadcast with shuffles.
+template <int PCOLS>
+__device__ __forceinline__ void epilogue_slice32(const Params& p, const CUtensorMap* tm_o32, const CUtensorMap* tm_ohi,
+                                                 const CUtensorMap* tm_olo, uint8_t* stg, uint32_t acc, int row0, int n0,
+                                                 int lane) {
+  static_assert(PCOLS == 64, "one float2 of bias per lane");
+  if (n0 >= p.N) return;  // warp-uniform
+  float2 b2 = make_float2(0.f, 0.f);
+  if (p.bias && n0 + 2 * lane < p.N) b2 = __ldg(reinterpret_cast<const float2*>(p.bias + n0) + lane);
+#pragma unroll 1
+  for (int c0 = 0; c0 < PCOLS; c0 += 32) {
+    if (n0 + c0 >= p.N) break;
+    uint32_t r[32];
+    __syncwarp();
+    ptx::tmem_ld_32x32b_x32(acc + (uint32_t)c0, r);
+    ptx::tmem_ld_wait();
+    // + bias (lane (c0 + j) / 2 holds columns c0 + j - (j & 1) .. + 1), optional GELU
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const int src = (c0 >> 1) + (j >> 1);
+      float v0 = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, b2.x, src);
+      float v1 = __uint_as_float(r[j + 1]) + __shfl_sync(0xffffffffu, b2.y, src);
+      if (p.gelu) {
+        v0 = gelu_erf(v0);
+        v1 = gelu_erf(v1);
+      }
+      r[j] = __float_as_uint(v0);
+      r[j + 1] = __float_as_uint(v1);
+    }
+    if (p.out_hi) {
+      uint32_t lw[16];
+      if (lane == 0) ptx::bulk_wait_read<0>();  // previous store from the staging tile has been read
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t hw[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a = __uint_as_float(r[8 * c + 2 * k]), b = __uint_as_float(r[8 * c + 2 * k + 1]);
+          hw[k] = pack_bf16x2(a, b);
+          lw[4 * c + k] = pack_bf16x2(a - __uint_as_float(hw[k] << 16), b - __uint_as_float(hw[k] & 0xffff0000u));
+        }
+        *reinterpret_cast<uint4*>(stg + stg_off_f32(lane, c)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);  // SWIZZLE_64B
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_store_2d(tm_ohi, stg, n0 + c0, row0);
+        ptx::bulk_commit();
+        ptx::bulk_wait_read<0>();
+      }
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(stg + stg_off_f32(lane, c)) = make_uint4(lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_store_2d(tm_olo, stg, n0 + c0, row0);
+        ptx::bulk_commit();
+      }
+    } else {
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {  // two 16-column fp32 boxes (64-byte rows, SWIZZLE_64B)
+        if (n0 + c0 + 16 * hlf >= p.N) break;
+        if (lane == 0) ptx::bulk_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(stg + stg_off_f32(lane, c)) =
+              make_uint4(r[16 * hlf + 4 * c], r[16 * hlf + 4 * c + 1], r[16 * hlf + 4 * c + 2], r[16 * hlf + 4 * c + 3]);
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_2d(tm_o32, stg, n0 + c0 + 16 * hlf, row0);
+          ptx::bulk_commit();
+        }
+      }
+    }
+  }
+}
+
 // Persistent kernel: grid = min(#tiles, #SMs); CTA c processes tiles c, c + grid, ... (n fastest, so
 // CTAs running concurrently share A tiles through L2).  The accumulator is double buffered in TMEM
 // (2 x BN columns): the epilogue of tile i overlaps the TMA/MMA main loop of tile i + 1.
@@ -465,13 +550,14 @@ inline cudaError_t launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, cons
 // 8 KB per instruction -- the single-CTA kernel is bound by exactly that bandwidth.  The leader CTA (rank 0)
 // issues all MMAs; full barriers live in the leader, empty / accumulator-full barriers are multicast to both CTAs.
 // =====================================================================================================
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, int EW>
 struct Cfg2 {
   static constexpr int A_BYTES = BM * BK * 2;          // this CTA's 128 A rows
   static constexpr int W_BYTES = (BN / 2) * BK * 2;    // this CTA's half of the W tile
   static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + W_BYTES);
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;  // 3 for SPLIT @ BN=256
-  static constexpr int STG_BYTES = 8 * 4096;  // kEpiWarps * STG_WARP_BYTES
+  // staging: 8 epilogue warps x 4 KB (double buffered) or 16 x 2 KB
+  static constexpr int STG_BYTES = 32768;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;  // 3 for SPLIT @ BN=256 (2 stages starve the MMA)
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
@@ -488,7 +574,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                 const __grid_constant__ CUtensorMap tm_o32, const __grid_constant__ CUtensorMap tm_ohi,
                 const __grid_constant__ CUtensorMap tm_olo, const Params p) {
-  using C = Cfg2<BN, SPLIT>;
+  using C = Cfg2<BN, SPLIT, EW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;
@@ -618,8 +704,11 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       if (warp == 2 && lane == 0 && it < 16) REGEN_TL(40 + 2 * it);
       ptx::tcgen05_fence_after();
       const uint32_t acc = tmem_base + (uint32_t)(buf * BN + part * PCOLS) + ((uint32_t)(q * 32) << 16);
-      epilogue_slice<RES, EW == 8>(p, &tm_o32, &tm_ohi, &tm_olo, stg, acc, m0 + q * 32, n0 + part * PCOLS, PCOLS, lane,
-                                   warp == 2 && it == 0);
+      if constexpr (EW == 16)
+        epilogue_slice32<PCOLS>(p, &tm_o32, &tm_ohi, &tm_olo, stg, acc, m0 + q * 32, n0 + part * PCOLS, lane);
+      else
+        epilogue_slice<RES, true>(p, &tm_o32, &tm_ohi, &tm_olo, stg, acc, m0 + q * 32, n0 + part * PCOLS, PCOLS, lane,
+                                  warp == 2 && it == 0);
       if (warp == 2 && lane == 0 && it < 16) REGEN_TL(41 + 2 * it);
       ptx::tcgen05_fence_before();
       __syncwarp();
@@ -642,7 +731,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 template <int BN, bool SPLIT, int EW, bool RES>
 inline cudaError_t launch2_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                 const CUtensorMap& w_lo, const OutMaps& o, const Params& p, cudaStream_t stream) {
-  using C = Cfg2<BN, SPLIT>;
+  using C = Cfg2<BN, SPLIT, EW>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm2_tn_kernel<BN, SPLIT, EW, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,

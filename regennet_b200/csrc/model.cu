@@ -140,7 +140,8 @@ bool use_pair_kernel(int M) {
   return !force1 && M > 128;
 }
 
-// o32 / osplit: store-side maps of the fp32 / bf16-pair outputs named in p (null -> st.global epilogue)
+// o32: store-side maps {box 16, box 32} of the fp32 output named in p; osplit: the bf16-pair output buffer
+// (null -> st.global epilogue)
 int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, gemm::Params p, const CUtensorMap* o32,
              const SplitBuf* osplit, cudaStream_t s) {
   ProfScope prof(h, CLS_GEMM, s);
@@ -148,10 +149,12 @@ int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, gemm::Params
   p.tma_store = 0;
   if (h->tma_store && (p.N & 3) == 0 && (!p.out_f32 || o32) && (!p.out_hi || osplit)) {
     p.tma_store = 1;
-    if (o32) om.f32 = *o32;
+    // the 16-epilogue-warp pair kernel (no residual, one kind of output) stores 32-column boxes, everything else 16
+    const bool wide = use_pair_kernel(p.M) && !p.residual && !(p.out_f32 && p.out_hi);
+    if (o32) om.f32 = o32[0];  // fp32 outputs always use 16-column boxes
     if (osplit) {
-      om.hi = osplit->st_hi;
-      om.lo = osplit->st_lo;
+      om.hi = wide ? osplit->st32_hi : osplit->st_hi;
+      om.lo = wide ? osplit->st32_lo : osplit->st_lo;
     }
   }
   cudaError_t e;
@@ -465,7 +468,8 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
     p.residual = h->condbias; p.ld_res = D;
     p.out_f32 = h->h; p.ld_out = D;
     p.out_hi = h->h_s.hi; p.out_lo = h->h_s.lo; p.ld_split = D;
-    TRY(run_gemm(h, h->a_in, h->w_in, p, &h->st_h, &h->h_s, s));
+    const CUtensorMap hmaps[2] = {h->st_h, h->st32_h};
+    TRY(run_gemm(h, h->a_in, h->w_in, p, hmaps, &h->h_s, s));
   }
   if (h->fused_ln) {
     ProfScope prof(h, CLS_OTHER, s);
@@ -521,7 +525,8 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       p.bias = ld.bo;
       p.residual = h->h; p.ld_res = D;
       p.out_f32 = h->tmp; p.ld_out = D;
-      TRY(run_gemm(h, h->att, ld.wo, p, &h->st_tmp, nullptr, s));
+      const CUtensorMap tmaps[2] = {h->st_tmp, h->st_tmp};
+      TRY(run_gemm(h, h->att, ld.wo, p, tmaps, nullptr, s));
     }
     {  // h = LN2( LN1(tmp) + c_l[b] )
       layers::LnParams q;
@@ -563,7 +568,8 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       p.bias = ld.b2;
       p.residual = h->h; p.ld_res = D;
       p.out_f32 = h->tmp; p.ld_out = D;
-      TRY(run_gemm(h, h->ffn, ld.w2, p, &h->st_tmp, nullptr, s));
+      const CUtensorMap tmaps[2] = {h->st_tmp, h->st_tmp};
+      TRY(run_gemm(h, h->ffn, ld.w2, p, tmaps, nullptr, s));
     }
     {  // h = LN3(tmp)
       layers::LnParams q;
@@ -581,15 +587,14 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
     gemm::Params p = gp(M, I, D);
     p.bias = h->b_out;
     p.out_f32 = h->guidance ? h->x0e : x0_tbi; p.ld_out = I;
-    CUtensorMap st_x0;
+    CUtensorMap st_x0[2];
     const CUtensorMap* om = nullptr;
     if ((I & 3) == 0 && h->tma_store) {
-      if (h->guidance) {
-        om = &h->st_x0e;
-      } else {  // caller-owned output: the store map is encoded per call (host-side, ~1 us)
-        TRY(make_tmap_store_2d(&st_x0, x0_tbi, false, M, I, I));
-        om = &st_x0;
-      }
+      // store maps (box 16 and box 32) of the output buffer; a caller-owned output is encoded per call (~1 us each)
+      float* dst = h->guidance ? h->x0e : x0_tbi;
+      TRY(make_tmap_store_2d(&st_x0[0], dst, false, M, I, I, 16));
+      TRY(make_tmap_store_2d(&st_x0[1], dst, false, M, I, I, 32));
+      om = st_x0;
     }
     TRY(run_gemm(h, h->h_s, h->w_out, p, om, nullptr, s));
   }
@@ -669,7 +674,8 @@ int regen_test_gemm(const float* A, const float* W, const float* bias, const flo
     p.timeline = g_test_timeline;
     gemm::OutMaps om;
     const char* nt = getenv("REGEN_DEBUG_NO_TMA_STORE");
-    if ((N & 3) == 0 && !(nt && nt[0] == '1') && make_tmap_store_2d(&om.f32, out, false, M, N, N) == REGEN_OK)
+    if ((N & 3) == 0 && !(nt && nt[0] == '1') &&
+        make_tmap_store_2d(&om.f32, out, false, M, N, N, 16) == REGEN_OK)
       p.tma_store = 1;
     cudaError_t e;
     if (pair)

@@ -57,7 +57,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks + throttle reasons sampled every 50 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -66,7 +66,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -237,6 +237,10 @@ def run_ours(args):
         gemm_tf = f_gemm / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
         n_elem = B * I * T
         upd_gbs = 16.0 * n_elem / (upd_ms / 1000.0) / 1e9 if upd_ms > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("_gemm_class_avg_dram_bytes_per_launch")
         line = {
             "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -255,9 +259,12 @@ def run_ours(args):
                             "pinned-host samples out, wall clock incl. Python" % K},
             "gpu_launches": launches,
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel<256,bf16x3> (all %d GEMM launches per step)" % (2 + 4 * 8),
+            "roofline": {"bound": "tensor", "kernel": "tcgen05 GEMM class: gemm2_tn_kernel<256,bf16x3> (QKV, FFN1, in/out projections) + "
+                                   "gemm_ln_kernel (out_proj+LN1+LN2, linear2+LN3 fused), %d launches per step" % (2 + 4 * 8),
                          "achieved": gemm_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                         "frac": gemm_tf / peaks["tf_sust"], "traffic": None,
+                         "frac": gemm_tf / peaks["tf_sust"], "traffic": traffic,
+                         "traffic_note": "DRAM bytes per GEMM-class launch (ncu dram__bytes_read+write, profiles/r01_traffic.json); "
+                                         "algorithmic operand+result bytes per launch: QKV 129 MB, FFN1 100 MB, fused N=512 GEMMs 96-128 MB",
                          "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % peaks["src"],
                          "note": "achieved counts ALGORITHMIC flops (1 MAC per product); the bf16x3 parity mode "
                                  "executes 3 MMAs per product, so frac is capped at 1/3"},

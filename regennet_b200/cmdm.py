@@ -301,16 +301,19 @@ class CMDM(nn.Module):
                 text = self.encode_text(y['text'])
             text = _lib.require_cuda_f32(text, "text features").contiguous()
         handle = self._get_handle(2 * B if guidance else B, T, device)
-        key = (cmotion.data_ptr(), cmotion._version, B, T, bool(guidance), uncond,
-               None if action is None else tuple(y['action'].shape) + (y['action'].data_ptr(), y['action']._version),
-               None if text is None else (text.data_ptr(), text._version))
+        # Cache on the IDENTITY of the conditioning tensors (kept alive below, so an id cannot be recycled) plus their
+        # in-place version counters.  Keying on data_ptr() would be wrong: the caching allocator hands the address
+        # of a freed tensor to the next one of the same size.
+        srcs = (y['cmotion'], y.get('action') if action is not None else None,
+                (y.get('text_embed') if 'text_embed' in y else text) if text is not None else None)
+        key = (B, T, bool(guidance), uncond) + tuple((id(t), t._version) if t is not None else None for t in srcs)
         if self._cond_key != key:
             cm = cmotion.contiguous()
             rc = _lib.lib().regen_prepare_cond(handle.ptr, _lib.ptr(cm), _lib.ptr(action), _lib.ptr(text), B, T,
                                                int(bool(guidance)), int(uncond), _lib.stream_ptr(device))
             _lib.check(rc, "regen_prepare_cond")
             self._cond_key = key
-            self._cond_keepalive = (cm, action, text)
+            self._cond_keepalive = (srcs, cm, action, text)
         return handle
 
     def _denoise_tbi(self, handle, x_tbi, t, scale, B, T):

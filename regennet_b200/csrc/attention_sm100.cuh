@@ -11,7 +11,7 @@
 //   O[128 x 128] += P[128 x TB] . V_chunk[TB x 128]        (B operand MN-major: V tiles are used as loaded)
 //   out          = O / rowsum  -> bf16 (hi, lo) [T*Beff, 512], the A operand of the output projection.
 //
-// TB = 64 (T <= 64: ~96 KB of shared memory, two CTAs per SM) or 128 (longer sequences, key chunks of 128 with the
+// TB = 64 (T <= 64: ~100 KB of shared memory, two CTAs per SM) or 128 (longer sequences, key chunks of 128 with the
 // scores of all chunks resident in TMEM so the row max is exact before any exponential is taken).
 // Reference semantics: nn.MultiheadAttention with the additive causal mask of model/cmdm.py:168-171, 220-227.
 #pragma once
@@ -23,7 +23,7 @@ namespace attn {
 
 constexpr int HD = 128;
 constexpr int DM = 512;
-constexpr int kThreads = 160;  // warp 0: TMA + MMA control, warps 1..4: softmax / epilogue
+constexpr int kThreads = 288;  // warp 0: TMA + MMA control, warps 1..8: softmax / epilogue (2 per TMEM lane quarter)
 
 template <int TB>
 struct Cfg {
@@ -32,7 +32,7 @@ struct Cfg {
   static constexpr int P_TILE = 128 * 128;         // 128 query rows x 64 keys
   static constexpr int P_BYTES = 2 * (TB / 64) * P_TILE;
   static_assert(P_BYTES == OPERAND, "P aliases the Q operand region");
-  static constexpr int SMEM_BYTES = 3 * OPERAND + 256 + 1024;
+  static constexpr int SMEM_BYTES = 3 * OPERAND + 4096 + 1024;  // + barriers / row statistics exchange
 };
 
 // UMMA smem descriptor, MN-major operand, 128-byte swizzle: 64 contiguous MN elements per 128-byte row, rows
@@ -49,15 +49,22 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
 }
 
 struct Params {
-  __nv_bfloat16* out_hi;  // [T*Beff, 512]
+  __nv_bfloat16* out_hi;  // [T*Beff, 512] (the kernel stores through tm_ohi / tm_olo)
   __nv_bfloat16* out_lo;
   int T, Beff;
   int dbg;  // test-hook only: bit 0 swaps the LBO / SBO fields of the V descriptor (bring-up A/B switch)
+  unsigned long long* timeline;  // bring-up instrumentation (null in production): CTA 0 stamps clock64() at events
 };
+
+#define REGEN_ATL(k)                                                                      \
+  do {                                                                                    \
+    if (p.timeline && blockIdx.x == 0) p.timeline[(k)] = (unsigned long long)clock64();   \
+  } while (0)
 
 template <int TB>
 __global__ void __launch_bounds__(kThreads, TB == 64 ? 2 : 1)
-attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const Params p) {
+attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                 const __grid_constant__ CUtensorMap tm_ohi, const __grid_constant__ CUtensorMap tm_olo, const Params p) {
   using C = Cfg<TB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -73,6 +80,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   uint64_t* barP = bars + 5;   // P chunk written by the 128 softmax threads
   uint64_t* barO = bars + 6;   // P.V chunk complete (tcgen05.commit)
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 7);
+  float* s_max = reinterpret_cast<float*>(smem + 3 * C::OPERAND + 1024);   // [128 rows][2 key halves]
+  float* s_sum = s_max + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qblocks = (p.T + 127) / 128;
@@ -84,6 +93,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   const int nkc = (kv_len + TB - 1) / TB;                    // key chunks
   constexpr uint32_t TMEM_COLS = TB == 64 ? 256 : 512;       // O: 128 cols, S: up to 256 cols
   constexpr uint32_t O_COL = 0, S_COL = 128;
+  if (threadIdx.x == 0) REGEN_ATL(0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -94,7 +104,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       ptx::mbar_init(barV, 1);
       ptx::mbar_init(&barS[0], 1);
       ptx::mbar_init(&barS[1], 1);
-      ptx::mbar_init(barP, 128);
+      ptx::mbar_init(barP, 256);
       ptx::mbar_init(barO, 1);
       ptx::fence_barrier_init();
     }
@@ -106,6 +116,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  if (threadIdx.x == 0) REGEN_ATL(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -130,6 +141,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       ptx::mbar_wait(barQ, 0);
       for (int kc = 0; kc < nkc; ++kc) {
         ptx::mbar_wait(barK, kc & 1);
+        if (kc == 0) REGEN_ATL(2);
         ptx::tcgen05_fence_after();
         const uint32_t accS = tmem_base + S_COL + (uint32_t)(kc * TB);
 #pragma unroll
@@ -146,12 +158,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         }
         ptx::tcgen05_commit(&barS[kc]);
         ptx::mbar_wait(&barS[kc], 0);  // K buffer (and finally Q) free again
+        if (kc == 0) REGEN_ATL(3);
         if (kc + 1 < nkc) load_operand(sK, barK, DM + h * HD, (kc + 1) * TB);
       }
       // ---- O += P_kc . V_kc
       for (int kc = 0; kc < nkc; ++kc) {
         ptx::mbar_wait(barP, kc & 1);  // P chunk is in shared memory (written through the generic proxy + fence)
         ptx::mbar_wait(barV, kc & 1);
+        if (kc == 0) REGEN_ATL(6);
         ptx::tcgen05_fence_after();
         const uint32_t accO = tmem_base + O_COL;
 #pragma unroll
@@ -176,84 +190,123 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       }
     }
   } else {
-    // ------------------------------------------------------------------ softmax + epilogue: one thread per query row
-    const int q = warp & 3;
+    // ------------------------------------------------------------------ softmax + epilogue
+    // warps 1..8: TMEM lane quarter q = warp & 3, two warps per quarter; warp `half` owns key columns
+    // [half*KH, half*KH + KH) of every chunk (softmax) and head-dim columns [half*64, half*64 + 64) (epilogue).
+    constexpr int KH = TB / 2;
+    const int q = warp & 3, half = (warp - 1) >> 2;
     const int r = q * 32 + lane;           // row in the 128-row tile == TMEM lane
     const int i = q0 + r;                  // query frame
     const bool row_ok = i < p.T && r < (TB == 64 ? 64 : 128);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float sc = 0.08838834764831845f * 1.4426950408889634f;  // 1/sqrt(128) * log2(e)
 
-    // all score chunks complete
-    for (int kc = 0; kc < nkc; ++kc) ptx::mbar_wait(&barS[kc], 0);
+    for (int kc = 0; kc < nkc; ++kc) ptx::mbar_wait(&barS[kc], 0);  // all score chunks complete
     ptx::tcgen05_fence_after();
-    // pass 1: exact row maximum over the causal window
+    // pass 1: exact row maximum over the causal window (this warp's key half of every chunk, then exchange)
     float mx = -INFINITY;
-    for (int c0 = 0; c0 < nkc * TB; c0 += 32) {
-      uint32_t v[32];
-      __syncwarp();
-      ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + (uint32_t)c0, v);
-      ptx::tmem_ld_wait();
+    for (int kc = 0; kc < nkc; ++kc) {
+#pragma unroll 1
+      for (int c0 = half * KH; c0 < half * KH + KH; c0 += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + (uint32_t)(kc * TB + c0), v);
+        ptx::tmem_ld_wait();
+        const int j0 = kc * TB + c0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c0 + j <= i && c0 + j < p.T) mx = fmaxf(mx, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; ++j)
+          if (j0 + j <= i && j0 + j < p.T) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
     }
+    s_max[r * 2 + half] = mx;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+    mx = fmaxf(mx, s_max[r * 2 + (half ^ 1)]);
     if (!row_ok) mx = 0.f;
+    if (warp == 1 && lane == 0) REGEN_ATL(4);
     float sum = 0.f;
     for (int kc = 0; kc < nkc; ++kc) {
       if (kc > 0) ptx::mbar_wait(barO, (kc - 1) & 1);  // previous P chunk consumed by the tensor core
-      for (int c0 = 0; c0 < TB; c0 += 32) {
+#pragma unroll 1
+      for (int c0 = half * KH; c0 < half * KH + KH; c0 += 32) {
         uint32_t v[32];
         __syncwarp();
         ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + (uint32_t)(kc * TB + c0), v);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j8 = 0; j8 < 32; j8 += 8) {
-          __nv_bfloat16 hi8[8], lo8[8];
+          uint32_t hw[4], lw[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int j = kc * TB + c0 + j8 + e;
-            float pv = 0.f;
-            if (row_ok && j <= i) pv = exp2f((__uint_as_float(v[j8 + e]) - mx) * sc);
-            sum += pv;
-            split_bf16(pv, hi8[e], lo8[e]);
+          for (int e = 0; e < 4; ++e) {
+            const int j = kc * TB + c0 + j8 + 2 * e;
+            float p0 = 0.f, p1 = 0.f;
+            if (row_ok && j <= i) p0 = exp2f((__uint_as_float(v[j8 + 2 * e]) - mx) * sc);
+            if (row_ok && j + 1 <= i) p1 = exp2f((__uint_as_float(v[j8 + 2 * e + 1]) - mx) * sc);
+            sum += p0 + p1;
+            __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+            hw[e] = *reinterpret_cast<uint32_t*>(&hh);
+            __nv_bfloat162 ll = __floats2bfloat162_rn(p0 - __uint_as_float(hw[e] << 16), p1 - __uint_as_float(hw[e] & 0xffff0000u));
+            lw[e] = *reinterpret_cast<uint32_t*>(&ll);
           }
           // K-major SW128 A-operand layout: 16-byte chunk index XOR (row & 7)
           const int jj = c0 + j8;  // key offset inside the chunk
           const uint32_t off = (uint32_t)(jj >> 6) * C::P_TILE + (uint32_t)r * 128 +
                                ((((uint32_t)(jj & 63) >> 3) ^ ((uint32_t)r & 7)) << 4);
-          *reinterpret_cast<uint4*>(sQ + off) = *reinterpret_cast<uint4*>(hi8);
-          *reinterpret_cast<uint4*>(sQ + (TB / 64) * C::P_TILE + off) = *reinterpret_cast<uint4*>(lo8);
+          *reinterpret_cast<uint4*>(sQ + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(sQ + (TB / 64) * C::P_TILE + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
       }
       ptx::fence_proxy_async_smem();  // make the generic-proxy stores visible to the tensor core (async proxy)
       ptx::mbar_arrive(barP);
+      if (warp == 1 && lane == 0 && kc == 0) REGEN_ATL(5);
     }
-    // epilogue: O / rowsum -> bf16 (hi, lo)
+    s_sum[r * 2 + half] = sum;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+    sum += s_sum[r * 2 + (half ^ 1)];
+    // epilogue: O / rowsum -> bf16 (hi, lo), staged as [32 rows x 64 d] tiles (128-byte rows, SWIZZLE_128B) in the
+    // dead K / V operand buffers and written with TMA stores (3-D box {64 d, 1 sample, 32 frames}; frames >= T clipped)
     ptx::mbar_wait(barO, (nkc - 1) & 1);
+    if (warp == 1 && lane == 0) REGEN_ATL(7);
     ptx::tcgen05_fence_after();
     const float inv = 1.f / sum;
-    const size_t grow = ((size_t)i * p.Beff + b) * DM + (size_t)h * HD;
-    for (int c0 = 0; c0 < HD; c0 += 32) {
+    uint8_t* st_hi = sK + (warp - 1) * 8192;   // K and V buffers are contiguous: 8 warps x 8 KB <= 2 * OPERAND
+    uint8_t* st_lo = st_hi + 4096;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 32) {
       uint32_t v[32];
       __syncwarp();
-      ptx::tmem_ld_32x32b_x32(lane_addr + O_COL + (uint32_t)c0, v);
+      ptx::tmem_ld_32x32b_x32(lane_addr + O_COL + (uint32_t)(half * 64 + c0), v);
       ptx::tmem_ld_wait();
-      if (row_ok) {
 #pragma unroll
-        for (int j8 = 0; j8 < 32; j8 += 8) {
-          __nv_bfloat16 hi8[8], lo8[8];
+      for (int j8 = 0; j8 < 32; j8 += 8) {
+        uint32_t hw[4], lw[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) split_bf16(__uint_as_float(v[j8 + e]) * inv, hi8[e], lo8[e]);
-          *reinterpret_cast<uint4*>(p.out_hi + grow + c0 + j8) = *reinterpret_cast<uint4*>(hi8);
-          *reinterpret_cast<uint4*>(p.out_lo + grow + c0 + j8) = *reinterpret_cast<uint4*>(lo8);
+        for (int e = 0; e < 4; ++e) {
+          const float a = __uint_as_float(v[j8 + 2 * e]) * inv, b2 = __uint_as_float(v[j8 + 2 * e + 1]) * inv;
+          __nv_bfloat162 hh = __floats2bfloat162_rn(a, b2);
+          hw[e] = *reinterpret_cast<uint32_t*>(&hh);
+          __nv_bfloat162 ll = __floats2bfloat162_rn(a - __uint_as_float(hw[e] << 16), b2 - __uint_as_float(hw[e] & 0xffff0000u));
+          lw[e] = *reinterpret_cast<uint32_t*>(&ll);
         }
+        const int chunk = (c0 + j8) >> 3;  // 16-byte chunk of the 128-byte row
+        const uint32_t off = (uint32_t)lane * 128 + (((uint32_t)chunk ^ ((uint32_t)lane & 7)) << 4);
+        *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(st_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
       }
+    }
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && q0 + q * 32 < p.T) {
+      ptx::tma_store_3d(&tm_ohi, st_hi, h * HD + half * 64, b, q0 + q * 32);
+      ptx::tma_store_3d(&tm_olo, st_lo, h * HD + half * 64, b, q0 + q * 32);
+      ptx::bulk_commit();
+      ptx::bulk_wait<0>();
     }
   }
 
+  if (warp == 1 && lane == 0) REGEN_ATL(8);
   ptx::tcgen05_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) REGEN_ATL(9);
   if (warp == 0) {
     ptx::tcgen05_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -261,7 +314,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
 }
 
 template <int TB>
-inline cudaError_t launch(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const Params& p, cudaStream_t s) {
+inline cudaError_t launch(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const CUtensorMap& tm_ohi,
+                          const CUtensorMap& tm_olo, const Params& p, cudaStream_t s) {
   using C = Cfg<TB>;
   static bool configured = false;
   if (!configured) {
@@ -271,7 +325,7 @@ inline cudaError_t launch(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, co
   }
   if (p.T > (TB == 64 ? 64 : 256)) return cudaErrorInvalidValue;  // at most two key chunks of 128
   const int qblocks = (p.T + 127) / 128;
-  attention_kernel<TB><<<p.Beff * 4 * qblocks, kThreads, C::SMEM_BYTES, s>>>(tm_hi, tm_lo, p);
+  attention_kernel<TB><<<p.Beff * 4 * qblocks, kThreads, C::SMEM_BYTES, s>>>(tm_hi, tm_lo, tm_ohi, tm_olo, p);
   return cudaGetLastError();
 }
 

@@ -54,6 +54,7 @@ struct regen_handle {
   // activations
   SplitBuf a_in, h_s, att, ffn, qkv_s;
   CUtensorMap tm_qkv_hi, tm_qkv_lo;  // 3-D [T, Beff, 1536] views of qkv_s for the attention kernel (per prepare_cond)
+  CUtensorMap tm_att_hi, tm_att_lo;  // 3-D [T, Beff, 512] store views of the attention output (box 32 frames x 64 d)
   CUtensorMap st_h, st_tmp, st_x0e;  // store-side maps of the fp32 activation buffers (rows = M)
   CUtensorMap st32_h;                // h with box 32 x 32: residual load + store of the fused GEMM+LayerNorm kernel
   bool tma_store = true;             // REGEN_DEBUG_NO_TMA_STORE=1: st.global epilogue (A/B measurements)
@@ -418,6 +419,8 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
   if ((I & 3) == 0) TRY(make_tmap_store_2d(&h->st_x0e, h->x0e, false, h->M, I, I));
   TRY(make_tmap_bf16_3d(&h->tm_qkv_hi, h->qkv_s.hi, 3 * D, Beff, T, T <= 64 ? 64 : 128));
   TRY(make_tmap_bf16_3d(&h->tm_qkv_lo, h->qkv_s.lo, 3 * D, Beff, T, T <= 64 ? 64 : 128));
+  TRY(make_tmap_bf16_3d(&h->tm_att_hi, h->att.hi, D, Beff, T, 32));
+  TRY(make_tmap_bf16_3d(&h->tm_att_lo, h->att.lo, D, Beff, T, 32));
   if (h->has_cond) {
     // cond_emb[b'] for b' in [0, Beff): conditional rows [0,B), unconditional rows [B,2B) under guidance
     if (text_model) {
@@ -493,9 +496,9 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
             h->qkv, h->att.hi, h->att.lo, T, Beff);
       } else {
         attn::Params ap;
-        ap.out_hi = h->att.hi; ap.out_lo = h->att.lo; ap.T = T; ap.Beff = Beff; ap.dbg = 0;
-        cudaError_t e = T <= 64 ? attn::launch<64>(h->tm_qkv_hi, h->tm_qkv_lo, ap, s)
-                                : attn::launch<128>(h->tm_qkv_hi, h->tm_qkv_lo, ap, s);
+        ap.out_hi = h->att.hi; ap.out_lo = h->att.lo; ap.T = T; ap.Beff = Beff; ap.dbg = 0; ap.timeline = nullptr;
+        cudaError_t e = T <= 64 ? attn::launch<64>(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s)
+                                : attn::launch<128>(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s);
         if (e != cudaSuccess) {
           set_error("attention launch (T=%d Beff=%d) failed: %s", T, Beff, cudaGetErrorString(e));
           return REGEN_ECUDA;
@@ -706,13 +709,15 @@ int regen_test_attention(const float* qkv, float* out, int32_t B, int32_t T, int
   REGEN_CUDA(cudaMalloc(&oh, M * D * 2));
   REGEN_CUDA(cudaMalloc(&ol, M * D * 2));
   layers::launch_split_rows(qkv, 3 * D, qh, ql, 3 * D, 3 * D, (int)M, 1, 1, s);
-  CUtensorMap th, tl;
+  CUtensorMap th, tl, toh, tol;
   int rc = make_tmap_bf16_3d(&th, qh, 3 * D, B, T, T <= 64 ? 64 : 128);
   if (!rc) rc = make_tmap_bf16_3d(&tl, ql, 3 * D, B, T, T <= 64 ? 64 : 128);
+  if (!rc) rc = make_tmap_bf16_3d(&toh, oh, D, B, T, 32);
+  if (!rc) rc = make_tmap_bf16_3d(&tol, ol, D, B, T, 32);
   if (!rc) {
     attn::Params ap;
-    ap.out_hi = oh; ap.out_lo = ol; ap.T = T; ap.Beff = B; ap.dbg = dbg;
-    cudaError_t e = T <= 64 ? attn::launch<64>(th, tl, ap, s) : attn::launch<128>(th, tl, ap, s);
+    ap.out_hi = oh; ap.out_lo = ol; ap.T = T; ap.Beff = B; ap.dbg = dbg; ap.timeline = g_test_timeline;
+    cudaError_t e = T <= 64 ? attn::launch<64>(th, tl, toh, tol, ap, s) : attn::launch<128>(th, tl, toh, tol, ap, s);
     if (e == cudaSuccess) {
       layers::merge_split_kernel<<<grid_cap(ceil_div((int64_t)M * D, 256)), 256, 0, s>>>(oh, ol, out, (int64_t)M * D);
       e = cudaStreamSynchronize(s);

@@ -82,7 +82,7 @@ inline int make_tmap_store_2d(CUtensorMap* out, const void* base, bool is_bf16, 
 // bf16 tensor [d2, d1, d0] (d0 contiguous), box = box2 x 1 x 64, 128-byte swizzle, zero fill out of bounds.
 // Used for q|k|v viewed as [T frames, Beff samples, 1536]: one box = one sample's frames x 64 head-dim columns.
 inline int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
-                             uint32_t box2) {
+                             uint32_t box2, uint32_t box0 = 64) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
@@ -90,7 +90,7 @@ inline int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, ui
   }
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
-  cuuint32_t box[3] = {64, 1, box2};
+  cuuint32_t box[3] = {box0, 1, box2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

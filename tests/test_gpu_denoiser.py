@@ -138,3 +138,25 @@ def test_errors(built_lib):
         model(x[:, :10].cuda(), torch.tensor([1, 2]).cuda(), to_cuda(y))
     with pytest.raises(NotImplementedError):
         CMDM(**dict(cases.MODELS["ntu"], arch="trans_enc"))
+
+
+def test_conditioning_cache_is_not_fooled_by_allocator_address_reuse(built_lib):
+    """The hoisted conditioning is cached per conditioning-tensor identity; a NEW cmotion tensor that happens to get
+    the freed tensor's device address (caching allocator) must not hit the cache."""
+    model, _ = get_model("ntu", 0)
+    x, y = synthetic.make_inputs(2, 56, 6, 60, seed=31)
+    t = torch.tensor([100, 200]).cuda()
+    xc = x.cuda()
+    ptrs = set()
+    for k in range(6):
+        g = torch.Generator().manual_seed(1000 + k)
+        cm = torch.randn(2, 56, 6, 60, generator=g).cuda()
+        ptrs.add(cm.data_ptr())
+        with torch.no_grad():
+            a = model(xc, t, {"cmotion": cm}).clone()
+            model._cond_key = None  # force a fresh prepare_cond for the reference result
+            b = model(xc, t, {"cmotion": cm}).clone()
+        assert torch.equal(a, b), "stale conditioning reused at iteration %d" % k
+        del cm
+    # (the allocator normally reuses one or two addresses here, which is what makes the scenario real)
+    assert len(ptrs) <= 6

@@ -23,7 +23,6 @@ namespace attn {
 
 constexpr int HD = 128;
 constexpr int DM = 512;
-constexpr int kThreads = 288;  // warp 0: TMA + MMA control, warps 1..8: softmax / epilogue (2 per TMEM lane quarter)
 
 template <int TB>
 struct Cfg {
@@ -32,7 +31,12 @@ struct Cfg {
   static constexpr int P_TILE = 128 * 128;         // 128 query rows x 64 keys
   static constexpr int P_BYTES = 2 * (TB / 64) * P_TILE;
   static_assert(P_BYTES == OPERAND, "P aliases the Q operand region");
-  static constexpr int SMEM_BYTES = 3 * OPERAND + 4096 + 1024;  // + barriers / row statistics exchange
+  // TB = 64 ("compact"): K and V share one buffer (V is fetched while the softmax runs) and O reuses the TMEM columns
+  // of S, so a CTA needs ~69 KB of shared memory, 128 TMEM columns and 160 threads: three CTAs per SM.
+  static constexpr bool COMPACT = TB == 64;
+  static constexpr int SW = COMPACT ? 4 : 8;                 // softmax / epilogue warps
+  static constexpr int THREADS = 32 + 32 * SW;               // + warp 0: TMA + MMA control
+  static constexpr int SMEM_BYTES = (COMPACT ? 2 : 3) * OPERAND + 4096 + 1024;  // + barriers / row statistics
 };
 
 // UMMA smem descriptor, MN-major operand, 128-byte swizzle: 64 contiguous MN elements per 128-byte row, rows
@@ -62,16 +66,17 @@ struct Params {
   } while (0)
 
 template <int TB>
-__global__ void __launch_bounds__(kThreads, TB == 64 ? 2 : 1)
+__global__ void __launch_bounds__(Cfg<TB>::THREADS, TB == 64 ? 3 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                  const __grid_constant__ CUtensorMap tm_ohi, const __grid_constant__ CUtensorMap tm_olo, const Params p) {
   using C = Cfg<TB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                  // later: P
+  constexpr int NBUF = C::COMPACT ? 2 : 3;
   uint8_t* sK = smem + C::OPERAND;
-  uint8_t* sV = smem + 2 * C::OPERAND;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * C::OPERAND);
+  uint8_t* sV = C::COMPACT ? sK : smem + 2 * C::OPERAND;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NBUF * C::OPERAND);
   uint64_t* barQ = bars + 0;
   uint64_t* barK = bars + 1;
   uint64_t* barV = bars + 2;
@@ -80,7 +85,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   uint64_t* barP = bars + 5;   // P chunk written by the 128 softmax threads
   uint64_t* barO = bars + 6;   // P.V chunk complete (tcgen05.commit)
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 7);
-  float* s_max = reinterpret_cast<float*>(smem + 3 * C::OPERAND + 1024);   // [128 rows][2 key halves]
+  float* s_max = reinterpret_cast<float*>(smem + NBUF * C::OPERAND + 1024);   // [128 rows][2 key halves]
   float* s_sum = s_max + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -91,8 +96,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   const int q0 = qb * 128;                                   // first query frame of this CTA
   const int kv_len = min(p.T, q0 + 128);                     // causal: keys [0, kv_len)
   const int nkc = (kv_len + TB - 1) / TB;                    // key chunks
-  constexpr uint32_t TMEM_COLS = TB == 64 ? 256 : 512;       // O: 128 cols, S: up to 256 cols
-  constexpr uint32_t O_COL = 0, S_COL = 128;
+  // O: 128 columns, S: TB columns per chunk.  Compact: O overwrites S (S is dead once P has been written).
+  constexpr uint32_t TMEM_COLS = C::COMPACT ? 128 : 512;
+  constexpr uint32_t O_COL = 0, S_COL = C::COMPACT ? 0 : 128;
   if (threadIdx.x == 0) REGEN_ATL(0);
 
   if (warp == 0) {
@@ -104,7 +110,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       ptx::mbar_init(barV, 1);
       ptx::mbar_init(&barS[0], 1);
       ptx::mbar_init(&barS[1], 1);
-      ptx::mbar_init(barP, 256);
+      ptx::mbar_init(barP, 32 * C::SW);
       ptx::mbar_init(barO, 1);
       ptx::fence_barrier_init();
     }
@@ -130,7 +136,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       };
       load_operand(sQ, barQ, h * HD, q0);
       load_operand(sK, barK, DM + h * HD, 0);
-      load_operand(sV, barV, 2 * DM + h * HD, 0);
+      if (!C::COMPACT) load_operand(sV, barV, 2 * DM + h * HD, 0);
 
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16_f32(128, TB);
       // P.V: B operand (V) is MN-major -> b_major bit 16
@@ -161,6 +167,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         if (kc == 0) REGEN_ATL(3);
         if (kc + 1 < nkc) load_operand(sK, barK, DM + h * HD, (kc + 1) * TB);
       }
+      if (C::COMPACT) load_operand(sV, barV, 2 * DM + h * HD, 0);  // K is dead: V takes its buffer during the softmax
       // ---- O += P_kc . V_kc
       for (int kc = 0; kc < nkc; ++kc) {
         ptx::mbar_wait(barP, kc & 1);  // P chunk is in shared memory (written through the generic proxy + fence)
@@ -193,7 +200,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     // ------------------------------------------------------------------ softmax + epilogue
     // warps 1..8: TMEM lane quarter q = warp & 3, two warps per quarter; warp `half` owns key columns
     // [half*KH, half*KH + KH) of every chunk (softmax) and head-dim columns [half*64, half*64 + 64) (epilogue).
-    constexpr int KH = TB / 2;
+    constexpr int NH = C::SW / 4;          // warps per TMEM lane quarter
+    constexpr int KH = TB / NH;            // keys per warp per chunk
+    constexpr int DW = HD / NH;            // head-dim columns per warp in the epilogue
     const int q = warp & 3, half = (warp - 1) >> 2;
     const int r = q * 32 + lane;           // row in the 128-row tile == TMEM lane
     const int i = q0 + r;                  // query frame
@@ -218,9 +227,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
           if (j0 + j <= i && j0 + j < p.T) mx = fmaxf(mx, __uint_as_float(v[j]));
       }
     }
-    s_max[r * 2 + half] = mx;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-    mx = fmaxf(mx, s_max[r * 2 + (half ^ 1)]);
+    if (NH == 2) {
+      s_max[r * 2 + half] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      mx = fmaxf(mx, s_max[r * 2 + (half ^ 1)]);
+    }
     if (!row_ok) mx = 0.f;
     if (warp == 1 && lane == 0) REGEN_ATL(4);
     float sum = 0.f;
@@ -259,23 +270,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       ptx::mbar_arrive(barP);
       if (warp == 1 && lane == 0 && kc == 0) REGEN_ATL(5);
     }
-    s_sum[r * 2 + half] = sum;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-    sum += s_sum[r * 2 + (half ^ 1)];
+    if (NH == 2) {
+      s_sum[r * 2 + half] = sum;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      sum += s_sum[r * 2 + (half ^ 1)];
+    }
     // epilogue: O / rowsum -> bf16 (hi, lo), staged as [32 rows x 64 d] tiles (128-byte rows, SWIZZLE_128B) in the
     // dead K / V operand buffers and written with TMA stores (3-D box {64 d, 1 sample, 32 frames}; frames >= T clipped)
     ptx::mbar_wait(barO, (nkc - 1) & 1);
     if (warp == 1 && lane == 0) REGEN_ATL(7);
     ptx::tcgen05_fence_after();
     const float inv = 1.f / sum;
-    uint8_t* st_hi = sK + (warp - 1) * 8192;   // K and V buffers are contiguous: 8 warps x 8 KB <= 2 * OPERAND
-    uint8_t* st_lo = st_hi + 4096;
+    // staging: (DW / 64) hi tiles + as many lo tiles of 4 KB per warp, 64 KB per CTA: the dead K/V buffers, or in
+    // compact mode the dead P (= Q) and K/V buffers, which are contiguous
+    uint8_t* st = (C::COMPACT ? sQ : sK) + (warp - 1) * (DW / 64) * 8192;
 #pragma unroll 1
-    for (int c0 = 0; c0 < 64; c0 += 32) {
+    for (int c0 = 0; c0 < DW; c0 += 32) {
       uint32_t v[32];
       __syncwarp();
-      ptx::tmem_ld_32x32b_x32(lane_addr + O_COL + (uint32_t)(half * 64 + c0), v);
+      ptx::tmem_ld_32x32b_x32(lane_addr + O_COL + (uint32_t)(half * DW + c0), v);
       ptx::tmem_ld_wait();
+      uint8_t* st_hi = st + (c0 >> 6) * 8192;
+      uint8_t* st_lo = st_hi + 4096;
 #pragma unroll
       for (int j8 = 0; j8 < 32; j8 += 8) {
         uint32_t hw[4], lw[4];
@@ -287,7 +303,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
           __nv_bfloat162 ll = __floats2bfloat162_rn(a - __uint_as_float(hw[e] << 16), b2 - __uint_as_float(hw[e] & 0xffff0000u));
           lw[e] = *reinterpret_cast<uint32_t*>(&ll);
         }
-        const int chunk = (c0 + j8) >> 3;  // 16-byte chunk of the 128-byte row
+        const int chunk = ((c0 & 63) + j8) >> 3;  // 16-byte chunk of the 128-byte row
         const uint32_t off = (uint32_t)lane * 128 + (((uint32_t)chunk ^ ((uint32_t)lane & 7)) << 4);
         *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         *reinterpret_cast<uint4*>(st_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -296,8 +312,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     ptx::fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0 && q0 + q * 32 < p.T) {
-      ptx::tma_store_3d(&tm_ohi, st_hi, h * HD + half * 64, b, q0 + q * 32);
-      ptx::tma_store_3d(&tm_olo, st_lo, h * HD + half * 64, b, q0 + q * 32);
+#pragma unroll
+      for (int tile = 0; tile < DW / 64; ++tile) {
+        ptx::tma_store_3d(&tm_ohi, st + tile * 8192, h * HD + half * DW + tile * 64, b, q0 + q * 32);
+        ptx::tma_store_3d(&tm_olo, st + tile * 8192 + 4096, h * HD + half * DW + tile * 64, b, q0 + q * 32);
+      }
       ptx::bulk_commit();
       ptx::bulk_wait<0>();
     }
@@ -325,7 +344,7 @@ inline cudaError_t launch(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, co
   }
   if (p.T > (TB == 64 ? 64 : 256)) return cudaErrorInvalidValue;  // at most two key chunks of 128
   const int qblocks = (p.T + 127) / 128;
-  attention_kernel<TB><<<p.Beff * 4 * qblocks, kThreads, C::SMEM_BYTES, s>>>(tm_hi, tm_lo, tm_ohi, tm_olo, p);
+  attention_kernel<TB><<<p.Beff * 4 * qblocks, C::THREADS, C::SMEM_BYTES, s>>>(tm_hi, tm_lo, tm_ohi, tm_olo, p);
   return cudaGetLastError();
 }
 

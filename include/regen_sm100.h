@@ -81,6 +81,17 @@ int regen_cfg_combine(const float* cond, const float* uncond, const float* scale
  * d6 [n,6] contiguous -> R [n,3,3] contiguous, rows (b1,b2,b3).                         */
 int regen_rot6d_to_matrix(const float* d6, float* R, int64_t n, void* stream);
 
+/* Post-sampling tail.  Temporal Gaussian smoothing = scipy.ndimage.gaussian_filter1d(x, sigma,
+ * axis=-1, mode='reflect', truncate) as called at sample/cgenerate.py:142 (sigma 1) and render/crendermotion.py:79
+ * (sigma 3), double accumulation like scipy.  layout 0: BJFT ([n_cols, T], T contiguous), 1: TBI ([T, n_cols]). */
+int regen_gaussian_filter1d_time(const float* src, float* dst, int64_t n_cols, int32_t T, int32_t layout,
+                                 double sigma, double truncate, void* stream);
+/* Fused tail on the sampler's native layout: x TBI [T,B,J,6] -> Gaussian filter along T -> drop the last
+ * drop_joints joints (translation row, model/rotation2xyz.py:253-255) -> rotation_6d_to_matrix ->
+ * R [B,T,J-drop_joints,3,3] (the tensor model/rotation2xyz.py:270 hands to the body model). */
+int regen_smooth_rot6d_to_matrix(const float* x_tbi, float* R, int32_t T, int32_t B, int32_t J,
+                                 int32_t drop_joints, double sigma, double truncate, void* stream);
+
 /* Layout conversion between the user-facing BJFT and the internal TBI layout.  Replaces the
  * permute/reshape of model/cmdm.py:312-313 (InputProcess) and :353-354 (OutputProcess). */
 int regen_bjft_to_tbi(const float* src, float* dst, int32_t B, int32_t I, int32_t T, void* stream);

@@ -50,6 +50,10 @@ _SIGNATURES = {
     "regen_ddim_update": (c_int, [c_void_p] * 10 + [c_float, c_i64, c_i64, c_int, c_int, c_void_p]),
     "regen_cfg_combine": (c_int, [c_void_p] * 4 + [c_i64, c_i64, c_int, c_void_p]),
     "regen_rot6d_to_matrix": (c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
+    "regen_gaussian_filter1d_time": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, ctypes.c_double,
+                                             ctypes.c_double, c_void_p]),
+    "regen_smooth_rot6d_to_matrix": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.c_double,
+                                             ctypes.c_double, c_void_p]),
     "regen_bjft_to_tbi": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "regen_tbi_to_bjft": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "regen_create": (c_int, [ctypes.POINTER(c_void_p), c_int, ctypes.POINTER(ModelDesc)]),

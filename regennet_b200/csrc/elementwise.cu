@@ -246,6 +246,88 @@ __global__ void __launch_bounds__(kTile * 8) transpose_kernel(const float* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Temporal Gaussian smoothing of generated motions -- scipy.ndimage.gaussian_filter1d(x, sigma, axis=-1) as called at
+// sample/cgenerate.py:142 (sigma=1) and render/crendermotion.py:79 (sigma=3): weights exp(-k^2 / 2 sigma^2) / sum over
+// |k| <= radius = int(truncate*sigma + 0.5), 'reflect' boundary (d c b a | a b c d | d c b a), double accumulation.
+// Element (col, t) lives at col_base(col) + t*t_stride: BJFT: col*T + t;  TBI: col + t*n_cols.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kMaxRadius = 64;
+__device__ __forceinline__ int reflect_index(int i, int n) {
+  // scipy 'reflect' (half-sample symmetric), valid for any offset
+  const int period = 2 * n;
+  i %= period;
+  if (i < 0) i += period;
+  return i < n ? i : period - 1 - i;
+}
+
+__device__ __forceinline__ void gaussian_weights(double* sw, int radius, double sigma) {
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int k = -radius; k <= radius; ++k) {
+      const double w = exp(-0.5 * (double)(k * k) / (sigma * sigma));
+      sw[k + radius] = w;
+      tot += w;
+    }
+    for (int k = 0; k <= 2 * radius; ++k) sw[k] /= tot;
+  }
+  __syncthreads();
+}
+
+template <bool TBI>
+__global__ void __launch_bounds__(256) gaussian_filter_time_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                   int64_t n_cols, int T, int radius, double sigma) {
+  __shared__ double sw[2 * kMaxRadius + 1];
+  gaussian_weights(sw, radius, sigma);
+  const int64_t total = n_cols * T;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+    // consecutive threads walk the contiguous dimension: t for BJFT, col for TBI
+    const int64_t col = TBI ? e % n_cols : e / T;
+    const int t = (int)(TBI ? e / n_cols : e % T);
+    const int64_t base = TBI ? col : col * T;
+    const int64_t ts = TBI ? n_cols : 1;
+    double acc = 0.0;
+    for (int k = -radius; k <= radius; ++k) acc += sw[k + radius] * (double)src[base + (int64_t)reflect_index(t + k, T) * ts];
+    dst[e] = (float)acc;
+  }
+}
+
+// Fused tail of sample/cgenerate.py:142-156 + model/rotation2xyz.py:253-270 on the sampler's native layout:
+// x [T, B, J, 6] (TBI) -> temporal Gaussian filter -> drop the last `drop` joints (the translation row) ->
+// rotation_6d_to_matrix -> R [B, T, J - drop, 3, 3].  One thread per (b, t, joint).
+__global__ void __launch_bounds__(256) smooth_rot6d_kernel(const float* __restrict__ x, float* __restrict__ R, int T, int B,
+                                                           int J, int drop, int radius, double sigma) {
+  __shared__ double sw[2 * kMaxRadius + 1];
+  gaussian_weights(sw, radius, sigma);
+  const int Jr = J - drop;
+  const int64_t total = (int64_t)B * T * Jr;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+    const int j = (int)(e % Jr);
+    const int t = (int)((e / Jr) % T);
+    const int b = (int)(e / ((int64_t)Jr * T));
+    double a[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = -radius; k <= radius; ++k) {
+      const float* p = x + (((int64_t)reflect_index(t + k, T) * B + b) * J + j) * 6;
+      const double w = sw[k + radius];
+#pragma unroll
+      for (int f = 0; f < 6; ++f) a[f] += w * (double)p[f];
+    }
+    const float a1x = (float)a[0], a1y = (float)a[1], a1z = (float)a[2], a2x = (float)a[3], a2y = (float)a[4], a2z = (float)a[5];
+    float n1 = fmaxf(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(a1x, a1x), __fmul_rn(a1y, a1y)), __fmul_rn(a1z, a1z))), 1e-12f);
+    float b1x = __fdiv_rn(a1x, n1), b1y = __fdiv_rn(a1y, n1), b1z = __fdiv_rn(a1z, n1);
+    float d = __fadd_rn(__fadd_rn(__fmul_rn(b1x, a2x), __fmul_rn(b1y, a2y)), __fmul_rn(b1z, a2z));
+    float b2x = __fsub_rn(a2x, __fmul_rn(d, b1x)), b2y = __fsub_rn(a2y, __fmul_rn(d, b1y)), b2z = __fsub_rn(a2z, __fmul_rn(d, b1z));
+    float n2 = fmaxf(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(b2x, b2x), __fmul_rn(b2y, b2y)), __fmul_rn(b2z, b2z))), 1e-12f);
+    b2x = __fdiv_rn(b2x, n2); b2y = __fdiv_rn(b2y, n2); b2z = __fdiv_rn(b2z, n2);
+    float* o = R + e * 9;  // e enumerates (b, t, j) in output order
+    o[0] = b1x; o[1] = b1y; o[2] = b1z;
+    o[3] = b2x; o[4] = b2y; o[5] = b2z;
+    o[6] = __fsub_rn(__fmul_rn(b1y, b2z), __fmul_rn(b1z, b2y));
+    o[7] = __fsub_rn(__fmul_rn(b1z, b2x), __fmul_rn(b1x, b2z));
+    o[8] = __fsub_rn(__fmul_rn(b1x, b2y), __fmul_rn(b1y, b2x));
+  }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -366,6 +448,42 @@ int regen_bjft_to_tbi(const float* src, float* dst, int32_t B, int32_t I, int32_
 }
 int regen_tbi_to_bjft(const float* src, float* dst, int32_t B, int32_t I, int32_t T, void* stream) {
   return launch_transpose(false, src, dst, B, I, T, stream);
+}
+
+static int gaussian_radius(double sigma, double truncate) { return (int)(truncate * sigma + 0.5); }
+
+int regen_gaussian_filter1d_time(const float* src, float* dst, int64_t n_cols, int32_t T, int32_t layout, double sigma,
+                                 double truncate, void* stream) {
+  REGEN_CHECK_ARG(n_cols >= 0 && T >= 0, "gaussian_filter1d_time: negative size");
+  if (n_cols == 0 || T == 0) return REGEN_OK;
+  REGEN_CHECK_ARG(src && dst && src != dst, "gaussian_filter1d_time: null or aliased pointers");
+  REGEN_CHECK_ARG(sigma > 0.0 && truncate > 0.0, "gaussian_filter1d_time: sigma and truncate must be positive");
+  const int radius = gaussian_radius(sigma, truncate);
+  REGEN_CHECK_ARG(radius <= kMaxRadius, "gaussian_filter1d_time: radius %d exceeds %d", radius, kMaxRadius);
+  REGEN_CHECK_ARG(layout == 0 || layout == 1, "gaussian_filter1d_time: layout must be 0 (BJFT) or 1 (TBI)");
+  const int blocks = grid_for(n_cols * T);
+  if (layout == 1)
+    gaussian_filter_time_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n_cols, T, radius, sigma);
+  else
+    gaussian_filter_time_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n_cols, T, radius, sigma);
+  REGEN_LAUNCH_CHECK();
+  count_launch();
+  return REGEN_OK;
+}
+
+int regen_smooth_rot6d_to_matrix(const float* x_tbi, float* R, int32_t T, int32_t B, int32_t J, int32_t drop_joints,
+                                 double sigma, double truncate, void* stream) {
+  REGEN_CHECK_ARG(T >= 0 && B >= 0 && J >= 0 && drop_joints >= 0 && drop_joints <= J, "smooth_rot6d: bad sizes");
+  if (T == 0 || B == 0 || J == drop_joints) return REGEN_OK;
+  REGEN_CHECK_ARG(x_tbi && R, "smooth_rot6d: null pointer");
+  REGEN_CHECK_ARG(sigma > 0.0 && truncate > 0.0, "smooth_rot6d: sigma and truncate must be positive");
+  const int radius = gaussian_radius(sigma, truncate);
+  REGEN_CHECK_ARG(radius <= kMaxRadius, "smooth_rot6d: radius %d exceeds %d", radius, kMaxRadius);
+  const int blocks = grid_for((int64_t)B * T * (J - drop_joints));
+  smooth_rot6d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x_tbi, R, T, B, J, drop_joints, radius, sigma);
+  REGEN_LAUNCH_CHECK();
+  count_launch();
+  return REGEN_OK;
 }
 
 }  // extern "C"

@@ -23,19 +23,30 @@ namespace regen {
 namespace gemmln {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16, ND = 512;
-constexpr int kThreads = 320;
 constexpr int STAGE_BYTES = 6 * 16384;  // A_hi | A_lo | W_hi[0] | W_hi[1] | W_lo[0] | W_lo[1]
 constexpr int STAGES = 2;
-constexpr int EPI_WARP_BYTES = 24576;   // res ring 3 x 4 KB | c ring 3 x 4 KB; the 2 x 8 KB output buffers alias [0, 16 KB)
 constexpr int SC = 32;                  // columns per epilogue sub-chunk (one tcgen05.ld/st x32, one TMA box)
-constexpr int NSC = 256 / SC;           // sub-chunks per warp (each warp owns 32 rows x 256 columns)
-constexpr int RING = 3;                 // TMA ring depth of the residual / c tiles
 constexpr int SLOT = 32 * SC * 4;       // 4 KB: 32 rows x 32 fp32, 128-byte rows (SWIZZLE_128B)
+// Epilogue geometry for EW epilogue warps per CTA (EW / 4 warps share a TMEM lane quarter and split the 512 columns).
+// The operand ring (192 KB) is re-used as staging: per warp  res ring | c ring ; the 8 KB output buffers alias offset 0.
+//   EW =  8: 24 KB per warp: res 3 x 4 KB, c 3 x 4 KB, 2 output buffers
+//   EW = 16: 12 KB per warp: res 2 x 4 KB, c 1 x 4 KB, 1 output buffer   (4 warps per scheduler hide the exposed latency)
+template <int EW>
+struct Epi {
+  static constexpr int PARTS = EW / 4;
+  static constexpr int WCOLS = ND / PARTS;      // columns per warp
+  static constexpr int NSC = WCOLS / SC;        // sub-chunks per warp
+  static constexpr int RING_R = EW == 16 ? 2 : 3;
+  static constexpr int RING_C = EW == 16 ? 1 : 3;
+  static constexpr int NOB = EW == 16 ? 1 : 2;
+  static constexpr int WARP_BYTES = (STAGES * STAGE_BYTES) / EW;
+  static constexpr int THREADS = 64 + 32 * EW;
+  static_assert((RING_R + RING_C) * SLOT <= WARP_BYTES && NOB * 8192 <= WARP_BYTES, "epilogue staging budget");
+};
 constexpr int PARAM_BYTES = 5 * ND * 4; // bias, g1, b1, g2, b2
-constexpr int STATS_BYTES = 2 * 128 * 2 * 8;
-constexpr int BAR_BYTES = 1024;
+constexpr int STATS_BYTES = 2 * 128 * 4 * 8;   // [2 exchanges][128 rows][<= 4 column parts] float2
+constexpr int BAR_BYTES = 2048;                // 8 pipeline barriers + 16 warps x 8 ring barriers
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PARAM_BYTES + STATS_BYTES + BAR_BYTES + 1024;
-static_assert(8 * EPI_WARP_BYTES <= STAGES * STAGE_BYTES, "epilogue staging lives in the operand ring");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct Params {
@@ -61,8 +72,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // tm_res: fp32 [M, 512] residual stream h (box 32 x 32, SWIZZLE_128B) -- used for the residual LOAD and the h STORE
 // tm_c  : fp32 [Beff + 32, 512] cyclic per-sample constant (row r = c[r % Beff]); only read with CHAIN
 // tm_ohi / tm_olo: bf16 [M, 512] split of h (store)
-template <bool SPLIT, bool CHAIN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+template <bool SPLIT, bool CHAIN, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Epi<EW>::THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_c,
@@ -77,8 +88,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   uint64_t* tmem_full_bar = bars + 4;
   uint64_t* tmem_empty_bar = bars + 5;   // leader's copy: 16 arrivals (epilogue warps of both CTAs)
   uint64_t* epi_done_bar = bars + 6;     // local: 8 arrivals, operand ring free again for the producer
-  uint64_t* ring_bar = bars + 8;         // [8 warps][8]: res slots 0..3, c slots 4..7
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 8 + 64);
+  using E = Epi<EW>;
+  uint64_t* ring_bar = bars + 8;         // [EW warps][8]: res slots 0..3, c slots 4..7
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 8 + 8 * EW);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -97,11 +109,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         ptx::mbar_init(&empty_bar[s], 1);
       }
       ptx::mbar_init(tmem_full_bar, 1);
-      ptx::mbar_init(tmem_empty_bar, 16);
-      ptx::mbar_init(epi_done_bar, 8);
+      ptx::mbar_init(tmem_empty_bar, 2 * EW);
+      ptx::mbar_init(epi_done_bar, EW);
     }
-    ptx::mbar_init(&ring_bar[lane], 1);
-    ptx::mbar_init(&ring_bar[32 + lane], 1);
+    for (int i = lane; i < 8 * EW; i += 32) ptx::mbar_init(&ring_bar[i], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -187,33 +198,33 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   } else {
     // ------------------------------------------------------------------ epilogue: warps 2..9, one thread = one row
     const int ew = warp - 2;
-    const int q = warp & 3, hf = ew >> 2;
+    const int q = warp & 3, hf = ew >> 2;  // hf: which WCOLS-wide column part of the 512 this warp owns
     const int r_local = q * 32 + lane;                 // row inside this CTA's 128 rows == TMEM lane
     // LayerNorm / bias vectors -> shared memory while the main loop runs (global loads are L2 round trips here)
-    for (int i = threadIdx.x - 64; i < 5 * ND / 4; i += 256) {
+    for (int i = threadIdx.x - 64; i < 5 * ND / 4; i += 32 * EW) {
       const int which = i / (ND / 4), j = i % (ND / 4);
       const float* src = which == 0 ? p.bias : which == 1 ? p.g1 : which == 2 ? p.b1 : which == 3 ? p.g2 : p.b2;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (src) v = __ldg(reinterpret_cast<const float4*>(src) + j);
       reinterpret_cast<float4*>(s_par)[i] = v;
     }
-    named_bar_sync(5, 256);
-    uint8_t* my = smem + ew * EPI_WARP_BYTES;
+    named_bar_sync(5, 32 * EW);
+    uint8_t* my = smem + ew * E::WARP_BYTES;
     uint8_t* res_ring = my;
-    uint8_t* c_ring = my + RING * SLOT;
-    uint8_t* out_buf = my;                             // 2 x 8 KB, used after both rings are drained
+    uint8_t* c_ring = my + E::RING_R * SLOT;
+    uint8_t* out_buf = my;                             // NOB x 8 KB, used after both rings are drained
     uint64_t* rbar = ring_bar + ew * 8;                // [0..2] residual slots, [4..6] c slots
-    const float* s_bias = s_par + hf * 256;
-    const float* s_g1 = s_par + ND + hf * 256;
-    const float* s_b1 = s_par + 2 * ND + hf * 256;
-    const float* s_g2 = s_par + 3 * ND + hf * 256;
-    const float* s_b2 = s_par + 4 * ND + hf * 256;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 256);
+    const float* s_bias = s_par + hf * E::WCOLS;
+    const float* s_g1 = s_par + ND + hf * E::WCOLS;
+    const float* s_b1 = s_par + 2 * ND + hf * E::WCOLS;
+    const float* s_g2 = s_par + 3 * ND + hf * E::WCOLS;
+    const float* s_b2 = s_par + 4 * ND + hf * E::WCOLS;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * E::WCOLS);
     const float inv_n = 1.0f / ND;
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int row0 = tile * (2 * BM) + (int)rank * BM + q * 32;  // global row of lane 0
-      const int n_base = hf * 256;
+      const int n_base = hf * E::WCOLS;
       const int crow0 = row0 % p.Beff;                              // first row in the cyclic c table
       ptx::mbar_wait(tmem_full_bar, it & 1);                        // accumulator complete => operand ring is idle
       const bool tr = warp == 2 && lane == 0 && it == 0;
@@ -222,10 +233,13 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       // prime the residual (and c) rings
       if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < RING; ++s) {
+        for (int s = 0; s < E::RING_R; ++s) {
           ptx::mbar_expect_tx(&rbar[s], SLOT);
           ptx::tma_load_2d(res_ring + s * SLOT, &tm_res, &rbar[s], n_base + SC * s, row0);
-          if (CHAIN) {
+        }
+        if (CHAIN) {
+#pragma unroll
+          for (int s = 0; s < E::RING_C; ++s) {
             ptx::mbar_expect_tx(&rbar[4 + s], SLOT);
             ptx::tma_load_2d(c_ring + s * SLOT, &tm_c, &rbar[4 + s], n_base + SC * s, crow0);
           }
@@ -234,42 +248,44 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       // ---- pass 1: v = acc + bias + residual, row statistics, v -> TMEM
       float sum = 0.f, sq = 0.f;
 #pragma unroll 1
-      for (int sc = 0; sc < NSC; ++sc) {
+      for (int sc = 0; sc < E::NSC; ++sc) {
+        constexpr int RING = E::RING_R;
         const int slot = sc % RING;
         uint32_t r[32];
         __syncwarp();
         ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(sc * SC), r);
         // slot `slot` is filled ceil((NSC - slot) / RING) times per tile; this is fill number sc / RING of this tile
-        ptx::mbar_wait(&rbar[slot], (uint32_t)(it * ((NSC - slot + RING - 1) / RING) + sc / RING) & 1);
-        float4 rr[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) rr[j] = *reinterpret_cast<const float4*>(res_ring + slot * SLOT + off_f32(lane, j));
+        ptx::mbar_wait(&rbar[slot], (uint32_t)(it * ((E::NSC - slot + RING - 1) / RING) + sc / RING) & 1);
         ptx::tmem_ld_wait();
-        __syncwarp();  // every lane has read the slot
-        if (lane == 0 && sc + RING < NSC) {
-          ptx::mbar_expect_tx(&rbar[slot], SLOT);
-          ptx::tma_load_2d(res_ring + slot * SLOT, &tm_res, &rbar[slot], n_base + SC * (sc + RING), row0);
-        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 b4 = *reinterpret_cast<const float4*>(s_bias + sc * SC + 4 * j);
-          float v0 = __uint_as_float(r[4 * j]) + b4.x + rr[j].x, v1 = __uint_as_float(r[4 * j + 1]) + b4.y + rr[j].y;
-          float v2 = __uint_as_float(r[4 * j + 2]) + b4.z + rr[j].z, v3 = __uint_as_float(r[4 * j + 3]) + b4.w + rr[j].w;
+          const float4 rj = *reinterpret_cast<const float4*>(res_ring + slot * SLOT + off_f32(lane, j));
+          float v0 = __uint_as_float(r[4 * j]) + b4.x + rj.x, v1 = __uint_as_float(r[4 * j + 1]) + b4.y + rj.y;
+          float v2 = __uint_as_float(r[4 * j + 2]) + b4.z + rj.z, v3 = __uint_as_float(r[4 * j + 3]) + b4.w + rj.w;
           sum += (v0 + v1) + (v2 + v3);
           sq = fmaf(v0, v0, sq); sq = fmaf(v1, v1, sq); sq = fmaf(v2, v2, sq); sq = fmaf(v3, v3, sq);
           r[4 * j] = __float_as_uint(v0); r[4 * j + 1] = __float_as_uint(v1);
           r[4 * j + 2] = __float_as_uint(v2); r[4 * j + 3] = __float_as_uint(v3);
         }
         ptx::tmem_st_32x32b_x32(lane_addr + (uint32_t)(sc * SC), r);
+        __syncwarp();  // every lane has read the slot
+        if (lane == 0 && sc + RING < E::NSC) {
+          ptx::mbar_expect_tx(&rbar[slot], SLOT);
+          ptx::tma_load_2d(res_ring + slot * SLOT, &tm_res, &rbar[slot], n_base + SC * (sc + RING), row0);
+        }
       }
       ptx::tmem_st_wait();
       if (tr) REGEN_LTL(4);
       // exchange the half-row statistics with the warp that owns the other 256 columns of the same rows
-      s_stats[r_local * 2 + hf] = make_float2(sum, sq);
-      named_bar_sync(1 + q, 64);
+      s_stats[r_local * 4 + hf] = make_float2(sum, sq);
+      named_bar_sync(1 + q, 32 * E::PARTS);
       if (tr) REGEN_LTL(5);
-      {
-        const float2 o = s_stats[r_local * 2 + (hf ^ 1)];
+      sum = 0.f;
+      sq = 0.f;
+#pragma unroll
+      for (int pp = 0; pp < E::PARTS; ++pp) {  // same order in every warp: bit-identical statistics across the row
+        const float2 o = s_stats[r_local * 4 + pp];
         sum += o.x;
         sq += o.y;
       }
@@ -280,43 +296,45 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         // ---- pass 2: y = LN1(v) + c, statistics of y, y -> TMEM
         float sum2 = 0.f, sq2 = 0.f;
 #pragma unroll 1
-        for (int sc = 0; sc < NSC; ++sc) {
+        for (int sc = 0; sc < E::NSC; ++sc) {
+          constexpr int RING = E::RING_C;
           const int slot = sc % RING;
           uint32_t r[32];
           __syncwarp();
           ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(sc * SC), r);
-          ptx::mbar_wait(&rbar[4 + slot], (uint32_t)(it * ((NSC - slot + RING - 1) / RING) + sc / RING) & 1);
-          float4 cc[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) cc[j] = *reinterpret_cast<const float4*>(c_ring + slot * SLOT + off_f32(lane, j));
+          ptx::mbar_wait(&rbar[4 + slot], (uint32_t)(it * ((E::NSC - slot + RING - 1) / RING) + sc / RING) & 1);
           ptx::tmem_ld_wait();
-          __syncwarp();
-          if (lane == 0 && sc + RING < NSC) {
-            ptx::mbar_expect_tx(&rbar[4 + slot], SLOT);
-            ptx::tma_load_2d(c_ring + slot * SLOT, &tm_c, &rbar[4 + slot], n_base + SC * (sc + RING), crow0);
-          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 g4 = *reinterpret_cast<const float4*>(s_g1 + sc * SC + 4 * j);
             const float4 b4 = *reinterpret_cast<const float4*>(s_b1 + sc * SC + 4 * j);
-            float y0 = (__uint_as_float(r[4 * j]) - mean) * rstd * g4.x + b4.x + cc[j].x;
-            float y1 = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * g4.y + b4.y + cc[j].y;
-            float y2 = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * g4.z + b4.z + cc[j].z;
-            float y3 = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * g4.w + b4.w + cc[j].w;
+            const float4 cj = *reinterpret_cast<const float4*>(c_ring + slot * SLOT + off_f32(lane, j));
+            float y0 = (__uint_as_float(r[4 * j]) - mean) * rstd * g4.x + b4.x + cj.x;
+            float y1 = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * g4.y + b4.y + cj.y;
+            float y2 = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * g4.z + b4.z + cj.z;
+            float y3 = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * g4.w + b4.w + cj.w;
             sum2 += (y0 + y1) + (y2 + y3);
             sq2 = fmaf(y0, y0, sq2); sq2 = fmaf(y1, y1, sq2); sq2 = fmaf(y2, y2, sq2); sq2 = fmaf(y3, y3, sq2);
             r[4 * j] = __float_as_uint(y0); r[4 * j + 1] = __float_as_uint(y1);
             r[4 * j + 2] = __float_as_uint(y2); r[4 * j + 3] = __float_as_uint(y3);
           }
           ptx::tmem_st_32x32b_x32(lane_addr + (uint32_t)(sc * SC), r);
+          __syncwarp();  // every lane has read the slot
+          if (lane == 0 && sc + RING < E::NSC) {
+            ptx::mbar_expect_tx(&rbar[4 + slot], SLOT);
+            ptx::tma_load_2d(c_ring + slot * SLOT, &tm_c, &rbar[4 + slot], n_base + SC * (sc + RING), crow0);
+          }
         }
         ptx::tmem_st_wait();
         if (tr) REGEN_LTL(6);
-        s_stats[256 + r_local * 2 + hf] = make_float2(sum2, sq2);
-        named_bar_sync(1 + q, 64);
+        s_stats[512 + r_local * 4 + hf] = make_float2(sum2, sq2);
+        named_bar_sync(1 + q, 32 * E::PARTS);
         if (tr) REGEN_LTL(7);
-        {
-          const float2 o = s_stats[256 + r_local * 2 + (hf ^ 1)];
+        sum2 = 0.f;
+        sq2 = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < E::PARTS; ++pp) {
+          const float2 o = s_stats[512 + r_local * 4 + pp];
           sum2 += o.x;
           sq2 += o.y;
         }
@@ -329,33 +347,36 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       const float* bb = CHAIN ? s_b2 : s_b1;
       __syncwarp();  // both rings fully consumed by every lane: their memory becomes the output buffers
 #pragma unroll 1
-      for (int sc = 0; sc < NSC; ++sc) {
-        uint8_t* ob = out_buf + (sc & 1) * 8192;
-        if (sc >= 2 && lane == 0) ptx::bulk_wait_read<1>();
+      for (int sc = 0; sc < E::NSC; ++sc) {
+        uint8_t* ob = out_buf + (E::NOB == 2 ? (sc & 1) * 8192 : 0);
+        if (sc >= E::NOB && lane == 0) {
+          if (E::NOB == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
+        }
         uint32_t r[32];
         __syncwarp();
         ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(sc * SC), r);
         ptx::tmem_ld_wait();
-        uint32_t hw[16], lw[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 g4 = *reinterpret_cast<const float4*>(gg + sc * SC + 4 * j);
-          const float4 b4 = *reinterpret_cast<const float4*>(bb + sc * SC + 4 * j);
-          const float z0 = (__uint_as_float(r[4 * j]) - mean) * rstd * g4.x + b4.x;
-          const float z1 = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * g4.y + b4.y;
-          const float z2 = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * g4.z + b4.z;
-          const float z3 = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * g4.w + b4.w;
-          *reinterpret_cast<float4*>(ob + off_f32(lane, j)) = make_float4(z0, z1, z2, z3);
-          const uint32_t h0 = gemm::pack_bf16x2(z0, z1), h1 = gemm::pack_bf16x2(z2, z3);
-          hw[2 * j] = h0;
-          hw[2 * j + 1] = h1;
-          lw[2 * j] = gemm::pack_bf16x2(z0 - __uint_as_float(h0 << 16), z1 - __uint_as_float(h0 & 0xffff0000u));
-          lw[2 * j + 1] = gemm::pack_bf16x2(z2 - __uint_as_float(h1 << 16), z3 - __uint_as_float(h1 & 0xffff0000u));
-        }
+        for (int c = 0; c < 4; ++c) {  // 8 columns = two fp32 chunks, one bf16 hi chunk, one bf16 lo chunk
+          uint32_t hw[4], lw[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          *reinterpret_cast<uint4*>(ob + 4096 + off_bf16(lane, c)) = make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]);
-          *reinterpret_cast<uint4*>(ob + 6144 + off_bf16(lane, c)) = make_uint4(lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]);
+          for (int jj = 0; jj < 2; ++jj) {
+            const int j = 2 * c + jj;
+            const float4 g4 = *reinterpret_cast<const float4*>(gg + sc * SC + 4 * j);
+            const float4 b4 = *reinterpret_cast<const float4*>(bb + sc * SC + 4 * j);
+            const float z0 = (__uint_as_float(r[4 * j]) - mean) * rstd * g4.x + b4.x;
+            const float z1 = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * g4.y + b4.y;
+            const float z2 = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * g4.z + b4.z;
+            const float z3 = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * g4.w + b4.w;
+            *reinterpret_cast<float4*>(ob + off_f32(lane, j)) = make_float4(z0, z1, z2, z3);
+            const uint32_t h0 = gemm::pack_bf16x2(z0, z1), h1 = gemm::pack_bf16x2(z2, z3);
+            hw[2 * jj] = h0;
+            hw[2 * jj + 1] = h1;
+            lw[2 * jj] = gemm::pack_bf16x2(z0 - __uint_as_float(h0 << 16), z1 - __uint_as_float(h0 & 0xffff0000u));
+            lw[2 * jj + 1] = gemm::pack_bf16x2(z2 - __uint_as_float(h1 << 16), z3 - __uint_as_float(h1 & 0xffff0000u));
+          }
+          *reinterpret_cast<uint4*>(ob + 4096 + off_bf16(lane, c)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(ob + 6144 + off_bf16(lane, c)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
@@ -376,7 +397,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         ptx::mbar_arrive_remote(tmem_empty_bar, 0);
         ptx::mbar_arrive(epi_done_bar);
       }
-      named_bar_sync(1 + q, 64);  // the statistics slots are rewritten by the next tile
+      named_bar_sync(1 + q, 32 * E::PARTS);  // the statistics slots are rewritten by the next tile
     }
     if (lane == 0) ptx::bulk_wait<0>();
   }
@@ -390,20 +411,39 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
 }
 
-template <bool SPLIT, bool CHAIN>
-inline cudaError_t launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
-                          const CUtensorMap& w_lo, const CUtensorMap& res, const CUtensorMap& c, const CUtensorMap& ohi,
-                          const CUtensorMap& olo, const Params& p, cudaStream_t stream) {
+template <bool SPLIT, bool CHAIN, int EW>
+inline cudaError_t launch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                               const CUtensorMap& w_lo, const CUtensorMap& res, const CUtensorMap& c,
+                               const CUtensorMap& ohi, const CUtensorMap& olo, const Params& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_ln_kernel<SPLIT, CHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_ln_kernel<SPLIT, CHAIN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int64_t tiles = ceil_div(p.M, 2 * BM);
   const int clusters = (int)(tiles < kNumSMs / 2 ? tiles : kNumSMs / 2);
-  gemm_ln_kernel<SPLIT, CHAIN><<<2 * clusters, kThreads, SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, res, c, ohi, olo, p);
+  gemm_ln_kernel<SPLIT, CHAIN, EW><<<2 * clusters, Epi<EW>::THREADS, SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, res, c,
+                                                                                           ohi, olo, p);
   return cudaGetLastError();
+}
+
+// 8 epilogue warps per CTA by default.  Measured on B200 (round 1): 16 warps change the three epilogue passes by < 10 %
+// (10.2k/8.9k/16.8k vs 11.2k/9.8k/18.6k cycles) -- the passes are bound by TMEM and shared-memory traffic (256 KB read +
+// 256 KB written per pass per CTA), not by per-warp latency -- and cost register spills at the 96-register cap of 576
+// threads, so 16 stays an A/B switch (REGEN_DEBUG_LN_EW=16).
+template <bool SPLIT, bool CHAIN>
+inline cudaError_t launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                          const CUtensorMap& w_lo, const CUtensorMap& res, const CUtensorMap& c, const CUtensorMap& ohi,
+                          const CUtensorMap& olo, const Params& p, cudaStream_t stream) {
+  static int ew = 0;
+  if (!ew) {
+    const char* e = getenv("REGEN_DEBUG_LN_EW");
+    ew = (e && atoi(e) == 16) ? 16 : 8;
+  }
+  return ew == 16 ? launch_impl<SPLIT, CHAIN, 16>(a_hi, a_lo, w_hi, w_lo, res, c, ohi, olo, p, stream)
+                  : launch_impl<SPLIT, CHAIN, 8>(a_hi, a_lo, w_hi, w_lo, res, c, ohi, olo, p, stream);
 }
 
 }  // namespace gemmln

@@ -42,6 +42,17 @@ const char* regen_version(void);
 const char* regen_last_error(void);
 /* kernels launched by this library in this process so far (evidence for bench.py's gpu_launches) */
 int64_t regen_launch_count(void);
+/* credit n kernel launches executed by a CUDA-graph replay (the counter above only sees the launches
+ * made while the graph was captured); called by the host layer after cudaGraphLaunch */
+void regen_launch_count_add(int64_t n);
+
+/* Step bookkeeping for a CUDA-graph-captured sampling loop.  Replaces the per-step host code of
+ * diffusion/gaussian_diffusion.py:726-728 (`t = th.tensor([i] * shape[0])`) and the integer remap of
+ * diffusion/respace.py:125-126 (`map_tensor[ts]`), bit-exact: with p = pos[0] (clamped to
+ * [0, n_seq)), t_idx[0..B) = seq_idx[p], t_model[0..B) = seq_model[p], then pos[0] = p + 1.
+ * All pointers are device int64; one launch, capturable. */
+int regen_step_tables(const int64_t* seq_idx, const int64_t* seq_model, int64_t* pos, int64_t* t_idx,
+                      int64_t* t_model, int32_t B, int32_t n_seq, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Handle-free elementwise operators (HBM-bound; coalesced, vectorised)

@@ -44,6 +44,8 @@ _SIGNATURES = {
     "regen_version": (ctypes.c_char_p, []),
     "regen_last_error": (ctypes.c_char_p, []),
     "regen_launch_count": (c_i64, []),
+    "regen_launch_count_add": (None, [c_i64]),
+    "regen_step_tables": (c_int, [c_void_p] * 5 + [c_int, c_int, c_void_p]),
     "regen_profile_begin": (c_int, [c_void_p]),
     "regen_profile_end": (c_int, [c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_int)]),
     "regen_p_sample_update": (c_int, [c_void_p] * 9 + [c_i64, c_i64, c_int, c_int, c_void_p]),

@@ -215,6 +215,7 @@ class CMDM(nn.Module):
     def _invalidate(self):
         self._handle = None
         self._cond_key = None
+        self.__dict__.pop("_graph_cache", None)   # captured graphs hold the old handle's buffers
 
     # --------------------------------------------------------------------------- library plumbing
     def _get_handle(self, batch_eff, frames, device):
@@ -224,8 +225,7 @@ class CMDM(nn.Module):
         if (h is not None and h.device == device and h.max_batch >= batch_eff and h.max_frames >= frames
                 and h.key == (wkey, self.precision)):
             return h
-        self._handle = None
-        self._cond_key = None
+        self._invalidate()
         if device.type != 'cuda':
             raise RuntimeError("regennet_b200.CMDM runs on CUDA (sm_100a) only; move the model and inputs to a GPU "
                                "-- there is no CPU fallback for the sampling hot path")
@@ -350,15 +350,58 @@ class CMDM(nn.Module):
         return SamplingSession(self, shape, y, timestep_map, scale)
 
 
+_ORIG_RANDN_LIKE = torch.randn_like   # a replaced torch.randn_like (noise-recording test hooks) disables graph replay
+_GRAPH_CACHE_MAX = 4
+_SEQ_CAP = 4096                       # capacity of the per-graph step sequences (loop length - 1)
+
+
+def _graph_unroll(n_after_first):
+    """Steps per captured graph: REGEN_CUDA_GRAPH=0 disables graphs, =U forces U; default = the U in [6, 12]
+    leaving the fewest trailing (step-by-step) steps, larger U on ties."""
+    import os
+    env = os.environ.get("REGEN_CUDA_GRAPH", "")
+    if env == "0":
+        return 0
+    if env.isdigit() and int(env) > 0:
+        return int(env)
+    best = None
+    for u in range(12, 5, -1):
+        rem = n_after_first % u
+        if best is None or rem < best[0]:
+            best = (rem, u)
+    return best[1]
+
+
+class _StepGraph:
+    """A captured CUDA graph of `unroll` consecutive sampling steps on static buffers."""
+
+    def __init__(self):
+        self.graph = None
+        self.launches = 0
+
+
 class SamplingSession:
     """Fused sampling loop state: token-major x, hoisted conditioning, one denoise + one update
-    kernel sequence per step.  Created by GaussianDiffusion._fast_session."""
+    kernel sequence per step.  Created by GaussianDiffusion._fast_session.
+
+    Two drivers over the same kernels:
+      * step-by-step: the host enqueues every step (the progressive generators, short loops, dump_steps);
+      * graph replay (``graph=True``, only from the non-progressive loops, which consume just the final
+        sample): after the first step, `unroll` consecutive steps -- device-side timestep bookkeeping
+        (regen_step_tables), denoiser, ``torch.randn_like`` noise, posterior update -- are captured once into
+        a CUDA graph on static buffers and replayed; this removes the host launch path and most of the
+        kernel-to-kernel gaps.  The noise stream is the one the step-by-step driver draws (torch's
+        graph-safe Philox offsets), so both drivers return bit-identical samples for a given seed.
+    """
 
     def __init__(self, model, shape, y, timestep_map, scale):
         self.model, self.shape, self.y, self.scale = model, tuple(shape), y, scale
         self.timestep_map = timestep_map
 
-    def run(self, diffusion, kind, img, indices, clip_denoised, eta):
+    # ------------------------------------------------------------------------------------------------
+    def run(self, diffusion, kind, img, indices, clip_denoised, eta, graph=False, progress=False, unroll=None):
+        """Generator over the loop.  Step-by-step it yields once per step; with graph replay it yields once
+        per replayed graph (dict key "steps" = steps advanced by that yield)."""
         from .gaussian_diffusion import _to_layout
         m = self.model
         B, J, F, T = self.shape
@@ -369,19 +412,123 @@ class SamplingSession:
         scale = None
         if guidance:
             scale = _lib.require_cuda_f32(self.scale.to(dev), "y['scale']").reshape(-1).contiguous()
+        idx = [int(i) for i in indices]
+        n = len(idx)
+        bar = None
+        if progress:
+            from tqdm.auto import tqdm
+            bar = tqdm(total=n)
         x = _to_layout(img, "tbi")                                  # logical [B,J,F,T], memory [T,B,J,F]
         t_model = torch.empty(B, dtype=torch.long, device=dev)
         t_idx = torch.empty(B, dtype=torch.long, device=dev)
-        first = True
+
+        def eager_step(x, i, first):
+            t_idx.fill_(i)
+            t_model.fill_(int(self.timestep_map[i]))                # respace.py:125-126 (integer remap)
+            x0 = m._denoise_tbi(handle, x.permute(3, 0, 1, 2), t_model, scale, B, T).view(T, B, J, F).permute(1, 2, 3, 0)
+            # the reference draws randn_like(x) AFTER the model call, in x's memory layout: contiguous
+            # [B,J,F,T] at the first step, the permuted model-output layout from then on
+            noise = torch.randn_like(img if first else x)
+            return diffusion._update("p" if kind == "p" else "ddim", x, x0, noise, t_idx, clip_denoised, eta=eta)
+
         with torch.no_grad():
-            for i in indices:
-                t_idx.fill_(int(i))
-                t_model.fill_(int(self.timestep_map[int(i)]))           # respace.py:125-126 (integer remap)
-                x_tbi = x.permute(3, 0, 1, 2)
-                x0 = m._denoise_tbi(handle, x_tbi, t_model, scale, B, T).view(T, B, J, F).permute(1, 2, 3, 0)
-                # the reference draws randn_like(x) AFTER the model call, in x's memory layout: contiguous
-                # [B,J,F,T] at the first step, the permuted model-output layout from then on
-                noise = torch.randn_like(img if first else x)
-                first = False
-                x, pred = diffusion._update("p" if kind == "p" else "ddim", x, x0, noise, t_idx, clip_denoised, eta=eta)
-                yield {"sample": x, "pred_xstart": pred}
+            U = 0
+            if graph and n >= 2 and torch.randn_like is _ORIG_RANDN_LIKE and n - 1 <= _SEQ_CAP:
+                U = unroll if unroll is not None else _graph_unroll(n - 1)
+                if U and (n - 1) // U < 2:
+                    U = 0                                           # not worth a capture
+            k = 0
+            if n:
+                x, pred = eager_step(x, idx[0], True)
+                k = 1
+                if bar is not None:
+                    bar.update(1)
+                yield {"sample": x, "pred_xstart": pred, "steps": 1}
+            if U:
+                st = self._graph_state(diffusion, kind, handle, scale, clip_denoised, eta, U, dev)
+                st["x"].copy_(x)
+                rest = idx[1:]
+                st["seq_idx"][:len(rest)].copy_(torch.tensor(rest, dtype=torch.long), non_blocking=False)
+                st["seq_model"][:len(rest)].copy_(torch.tensor([int(self.timestep_map[i]) for i in rest],
+                                                               dtype=torch.long))
+                st["pos"].zero_()
+                if scale is not None:
+                    st["scale"].copy_(scale)
+                sg = st["graph"]
+                if sg.graph is None:
+                    self._capture(st, diffusion, kind, handle, clip_denoised, eta, U)
+                L = _lib.lib()
+                for _ in range((n - 1) // U):
+                    sg.graph.replay()
+                    L.regen_launch_count_add(sg.launches)
+                    k += U
+                    if bar is not None:
+                        bar.update(U)
+                    yield {"sample": st["x"], "pred_xstart": st["pred"], "steps": U}
+                # detach the result from the static buffers (the next loop on this model reuses them)
+                x, pred = st["x"].clone(), st["pred"].clone()
+                if k == n:
+                    yield {"sample": x, "pred_xstart": pred, "steps": 0}
+            while k < n:
+                x, pred = eager_step(x, idx[k], False)
+                k += 1
+                if bar is not None:
+                    bar.update(1)
+                yield {"sample": x, "pred_xstart": pred, "steps": 1}
+        if bar is not None:
+            bar.close()
+
+    # ------------------------------------------------------------------------------------------------
+    def _graph_state(self, diffusion, kind, handle, scale, clip_denoised, eta, U, dev):
+        """Static buffers + graph for this (handle, problem, sampler) combination, cached on the model."""
+        m = self.model
+        B, J, F, T = self.shape
+        key = (id(handle), id(diffusion), B, T, kind, bool(clip_denoised), float(eta), U, scale is not None,
+               m._cond_key[:4] if m._cond_key else None, handle.ptr.value)
+        cache = m.__dict__.setdefault("_graph_cache", {})
+        st = cache.get(key)
+        if st is not None and st["handle"] is handle and st["diffusion"] is diffusion:
+            cache[key] = cache.pop(key)                              # most recently used last
+            return st
+        while len(cache) >= _GRAPH_CACHE_MAX:
+            cache.pop(next(iter(cache)))
+        st = {
+            "handle": handle, "diffusion": diffusion, "graph": _StepGraph(),
+            "x": torch.empty((T, B, J, F), device=dev, dtype=torch.float32).permute(1, 2, 3, 0),
+            "pred": None,
+            "seq_idx": torch.zeros(_SEQ_CAP, dtype=torch.long, device=dev),
+            "seq_model": torch.zeros(_SEQ_CAP, dtype=torch.long, device=dev),
+            "pos": torch.zeros(1, dtype=torch.long, device=dev),
+            "t_idx": torch.empty(B, dtype=torch.long, device=dev),
+            "t_model": torch.empty(B, dtype=torch.long, device=dev),
+            "scale": torch.empty_like(scale) if scale is not None else None,
+        }
+        cache[key] = st
+        return st
+
+    def _capture(self, st, diffusion, kind, handle, clip_denoised, eta, U):
+        m = self.model
+        B, J, F, T = self.shape
+        L = _lib.lib()
+        dev = st["x"].device
+        diffusion._tables(dev)                                       # device tables exist before capture
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        n0 = L.regen_launch_count()
+        with torch.cuda.graph(g):
+            xs = st["x"]
+            pred = None
+            for u in range(U):
+                _lib.check(L.regen_step_tables(_lib.ptr(st["seq_idx"]), _lib.ptr(st["seq_model"]), _lib.ptr(st["pos"]),
+                                               _lib.ptr(st["t_idx"]), _lib.ptr(st["t_model"]), B, _SEQ_CAP,
+                                               _lib.stream_ptr(dev)), "regen_step_tables")
+                x0 = m._denoise_tbi(handle, xs.permute(3, 0, 1, 2), st["t_model"], st["scale"], B, T)
+                x0 = x0.view(T, B, J, F).permute(1, 2, 3, 0)
+                noise = torch.randn_like(xs)
+                xs, pred = diffusion._update("p" if kind == "p" else "ddim", xs, x0, noise, st["t_idx"], clip_denoised,
+                                             eta=eta, out=st["x"] if u == U - 1 else None)
+            st["pred"] = pred
+        st["graph"].graph = g
+        st["graph"].launches = int(L.regen_launch_count() - n0)
+        # the capture pass enqueued nothing: undo its contribution to the executed-launch counter
+        L.regen_launch_count_add(-st["graph"].launches)

@@ -122,6 +122,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  ptx::griddep_wait();    // PDL: q | k | v come from the preceding QKV GEMM
+  ptx::griddep_launch();  // the successor launches once every CTA of this grid has started
   if (threadIdx.x == 0) REGEN_ATL(1);
 
   if (warp == 0) {
@@ -344,8 +346,8 @@ inline cudaError_t launch(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, co
   }
   if (p.T > (TB == 64 ? 64 : 256)) return cudaErrorInvalidValue;  // at most two key chunks of 128
   const int qblocks = (p.T + 127) / 128;
-  attention_kernel<TB><<<p.Beff * 4 * qblocks, C::THREADS, C::SMEM_BYTES, s>>>(tm_hi, tm_lo, tm_ohi, tm_olo, p);
-  return cudaGetLastError();
+  return launch_pdl(attention_kernel<TB>, dim3(p.Beff * 4 * qblocks), dim3(C::THREADS), C::SMEM_BYTES, s, tm_hi, tm_lo,
+                    tm_ohi, tm_olo, p);
 }
 
 }  // namespace attn

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/regen_sm100.h"
 
@@ -46,6 +47,35 @@ constexpr int kNumSMs = 148;  // B200
 // number of kernels this library has launched in this process (regen_launch_count)
 extern long long g_launches;
 inline void count_launch(int n = 1) { g_launches += n; }
+
+// Launch with programmatic stream serialization (PDL): the kernel's CTAs may be scheduled while the preceding kernel of
+// the stream is still draining, so its prologue (barrier init, TMEM allocation, tensor-map prefetch) and the launch
+// latency overlap that tail.  EVERY kernel launched through here executes ptx::griddep_wait() before its first global
+// memory access.  REGEN_DEBUG_NO_PDL=1 turns the attribute off (A/B measurements).
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("REGEN_DEBUG_NO_PDL");
+    on = (e && e[0] == '1') ? 0 : 1;
+  }
+  return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

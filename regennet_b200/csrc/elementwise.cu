@@ -5,6 +5,7 @@
 // round-to-nearest intrinsics (no FMA contraction), so the update is bit-comparable with the
 // eager PyTorch sequence it replaces.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace regen {
 
@@ -328,6 +329,26 @@ __global__ void __launch_bounds__(256) smooth_rot6d_kernel(const float* __restri
   }
 }
 
+// Device-side step bookkeeping of a CUDA-graph-captured sampling loop: step number pos[0] selects the loop index
+// (table index of the update) and the model timestep (respace.py:125-126) from per-loop sequences, broadcasts both to
+// the int64[B] vectors the denoiser / update kernels read, and advances pos -- one launch per step, no host values.
+__global__ void step_tables_kernel(const int64_t* __restrict__ seq_idx, const int64_t* __restrict__ seq_model,
+                                   int64_t* pos, int64_t* __restrict__ t_idx, int64_t* __restrict__ t_model, int B,
+                                   int n_seq) {
+  ptx::griddep_wait();  // PDL: the previous step's update kernel still reads t_idx
+  ptx::griddep_launch();
+  int64_t p = pos[0];
+  if (p < 0) p = 0;
+  if (p >= n_seq) p = n_seq - 1;
+  const int64_t a = seq_idx[p], b = seq_model[p];
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    t_idx[i] = a;
+    t_model[i] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) pos[0] = p + 1;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -340,6 +361,17 @@ extern "C" {
 const char* regen_version(void) { return "regen_sm100 0.1.0 sm_100a"; }
 const char* regen_last_error(void) { return regen::g_err; }
 int64_t regen_launch_count(void) { return (int64_t)regen::g_launches; }
+void regen_launch_count_add(int64_t n) { regen::g_launches += n; }
+
+int regen_step_tables(const int64_t* seq_idx, const int64_t* seq_model, int64_t* pos, int64_t* t_idx, int64_t* t_model,
+                      int32_t B, int32_t n_seq, void* stream) {
+  REGEN_CHECK_ARG(seq_idx && seq_model && pos && t_idx && t_model, "step_tables: null pointer");
+  REGEN_CHECK_ARG(B >= 1 && n_seq >= 1, "step_tables: bad sizes");
+  REGEN_CUDA(launch_pdl(step_tables_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, seq_idx, seq_model, pos, t_idx,
+                        t_model, B, n_seq));
+  count_launch();
+  return REGEN_OK;
+}
 
 int regen_p_sample_update(const float* x, const float* x0, const float* noise, float* out, float* pred_xstart,
                           const int64_t* t, const float* coef1, const float* coef2, const float* logvar,

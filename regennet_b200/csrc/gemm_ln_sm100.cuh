@@ -124,6 +124,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   ptx::cluster_sync();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  ptx::griddep_wait();    // PDL: the setup above overlapped the previous kernel's tail
+  ptx::griddep_launch();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -424,9 +426,8 @@ inline cudaError_t launch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo,
   }
   const int64_t tiles = ceil_div(p.M, 2 * BM);
   const int clusters = (int)(tiles < kNumSMs / 2 ? tiles : kNumSMs / 2);
-  gemm_ln_kernel<SPLIT, CHAIN, EW><<<2 * clusters, Epi<EW>::THREADS, SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, res, c,
-                                                                                           ohi, olo, p);
-  return cudaGetLastError();
+  return launch_pdl(gemm_ln_kernel<SPLIT, CHAIN, EW>, dim3(2 * clusters), dim3(Epi<EW>::THREADS), SMEM_BYTES, stream, a_hi,
+                    a_lo, w_hi, w_lo, res, c, ohi, olo, p);
 }
 
 // 8 epilogue warps per CTA by default.  Measured on B200 (round 1): 16 warps change the three epilogue passes by < 10 %

@@ -423,6 +423,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  // PDL: everything above overlapped the previous kernel's tail; its results are needed from here on
+  ptx::griddep_wait();
+  ptx::griddep_launch();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -538,8 +541,8 @@ inline cudaError_t launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, cons
   }
   const int64_t tiles = ceil_div(p.N, BN) * ceil_div(p.M, BM);
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  gemm_tn_kernel<BN, SPLIT><<<grid, kThreads, C::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, o.f32, o.hi, o.lo, p);
-  return cudaGetLastError();
+  return launch_pdl(gemm_tn_kernel<BN, SPLIT>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream, a_hi, a_lo, w_hi, w_lo,
+                    o.f32, o.hi, o.lo, p);
 }
 
 // =====================================================================================================
@@ -620,6 +623,8 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   ptx::cluster_sync();  // barriers of both CTAs initialised before any remote arrive / multicast commit
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  ptx::griddep_wait();    // PDL: the setup above overlapped the previous kernel's tail
+  ptx::griddep_launch();  // the next kernel's CTAs may take over each SM as soon as this CTA exits
   if (threadIdx.x == 0) REGEN_TL(1);
 
   if (warp == 0) {
@@ -741,9 +746,8 @@ inline cudaError_t launch2_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo
   }
   const int64_t tiles = ceil_div(p.N, BN) * ceil_div(p.M, 2 * BM);
   const int clusters = (int)(tiles < kNumSMs / 2 ? tiles : kNumSMs / 2);
-  gemm2_tn_kernel<BN, SPLIT, EW, RES><<<2 * clusters, 64 + 32 * EW, C::SMEM_BYTES, stream>>>(a_hi, a_lo, w_hi, w_lo, o.f32,
-                                                                                             o.hi, o.lo, p);
-  return cudaGetLastError();
+  return launch_pdl(gemm2_tn_kernel<BN, SPLIT, EW, RES>, dim3(2 * clusters), dim3(64 + 32 * EW), C::SMEM_BYTES, stream, a_hi,
+                    a_lo, w_hi, w_lo, o.f32, o.hi, o.lo, p);
 }
 
 template <int BN, bool SPLIT>

@@ -3,6 +3,7 @@
 // Token rows are seq-first: row = t * B + b (the reference's [T, B, D] layout, model/cmdm.py:312-313).
 #pragma once
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace regen {
 namespace layers {
@@ -21,6 +22,8 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
                                                          __nv_bfloat16* __restrict__ hi,
                                                          __nv_bfloat16* __restrict__ lo, int Cpad, int C, int R_out,
                                                          int B, int dup) {
+  ptx::griddep_wait();  // PDL (launch_pdl below): src may be the previous kernel's output
+  ptx::griddep_launch();
   const int c4n = Cpad / 4;
   const int64_t total = (int64_t)R_out * c4n;
   const int Beff = B * dup;
@@ -48,7 +51,7 @@ inline void launch_split_rows(const float* src, int ld_src, __nv_bfloat16* hi, _
                               int R_out, int B, int dup, cudaStream_t s) {
   int64_t total = (int64_t)R_out * (Cpad / 4);
   int blocks = grid_cap(ceil_div(total, 256));
-  split_rows_kernel<<<blocks, 256, 0, s>>>(src, ld_src, hi, lo, Cpad, C, R_out, B, dup);
+  launch_pdl(split_rows_kernel, dim3(blocks), dim3(256), 0, s, src, ld_src, hi, lo, Cpad, C, R_out, B, dup);
   count_launch();
 }
 
@@ -159,6 +162,8 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const float* __restric
 __global__ void __launch_bounds__(128) build_cyc_kernel(const float* __restrict__ ctab, const float* __restrict__ ccond,
                                                         const int64_t* __restrict__ t, float* __restrict__ cyc, int L,
                                                         int B, int Beff, int n_table) {
+  ptx::griddep_wait();  // PDL: t is written by the step-bookkeeping kernel, cyc is read by the previous step's GEMMs
+  ptx::griddep_launch();
   const int r = blockIdx.x, l = blockIdx.y;
   const int be = r % Beff;
   int64_t tb = t[be % B];
@@ -353,6 +358,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_simt_kernel(const fl
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cfg_rows_kernel(const float* __restrict__ x0e, const float* __restrict__ scale,
                                                        float* __restrict__ out, int T, int B, int I) {
+  ptx::griddep_wait();  // PDL: x0e comes from the output-projection GEMM
+  ptx::griddep_launch();
   const int64_t total = (int64_t)T * B * I;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
     int c = (int)(i % I);

@@ -476,8 +476,9 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
   }
   if (h->fused_ln) {
     ProfScope prof(h, CLS_OTHER, s);
-    layers::build_cyc_kernel<<<dim3(Beff + 32, L), 128, 0, s>>>(h->ctab, h->has_cond ? h->ccond : nullptr, t, h->cyc, L, B,
-                                                                Beff, h->desc.num_table_steps);
+    launch_pdl(layers::build_cyc_kernel, dim3(Beff + 32, L), dim3(128), 0, s, h->ctab,
+               h->has_cond ? (const float*)h->ccond : (const float*)nullptr, t, h->cyc, L, B, Beff,
+               h->desc.num_table_steps);
     count_launch();
   }
   for (int l = 0; l < L; ++l) {
@@ -605,7 +606,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
     int64_t total = (int64_t)T * B * I;
     int blocks = grid_cap(ceil_div(total, 256));
     ProfScope prof(h, CLS_OTHER, s);
-    layers::cfg_rows_kernel<<<blocks, 256, 0, s>>>(h->x0e, cfg_scale, x0_tbi, T, B, I);
+    launch_pdl(layers::cfg_rows_kernel, dim3(blocks), dim3(256), 0, s, h->x0e, cfg_scale, x0_tbi, T, B, I);
     count_launch();
   }
   REGEN_LAUNCH_CHECK();

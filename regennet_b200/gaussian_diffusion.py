@@ -241,8 +241,9 @@ class GaussianDiffusion:
         assert model_output.shape == x.shape
         return model_output
 
-    def _update(self, kind, x, x0, noise, t, clip_denoised, eta=0.0):
-        """One fused update kernel over (x, x0, noise) -> (sample, pred_xstart).
+    def _update(self, kind, x, x0, noise, t, clip_denoised, eta=0.0, out=None):
+        """One fused update kernel over (x, x0, noise) -> (sample, pred_xstart).  `out` (optional, fast route
+        only) receives the sample instead of a fresh tensor; it must have x0's memory layout and may alias x.
 
         Memory layout follows the reference's TensorIterator rule: the result takes the layout of
         the model output (first operand of ``coef1*x0 + coef2*x``), x / noise are re-laid-out if
@@ -256,7 +257,10 @@ class GaussianDiffusion:
                 lay = "bjft"
             x_l = _to_layout(x, lay)
             n_l = _to_layout(noise, lay) if noise is not None else None
-            out = _empty_in_layout(x.shape, lay, x.device)
+            if out is None:
+                out = _empty_in_layout(x.shape, lay, x.device)
+            else:
+                assert _layout_of(out) == lay and out.shape == x.shape
             pred = _empty_in_layout(x.shape, lay, x.device) if clip_denoised else None
             B = x.shape[0]
             inner = x[0].numel() if lay == "bjft" else x.shape[1] * x.shape[2]
@@ -351,11 +355,13 @@ class GaussianDiffusion:
         final = None
         if dump_steps is not None:
             dump = []
-        for i, sample in enumerate(self.p_sample_loop_progressive(
-                model, shape, noise=noise, clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn,
-                model_kwargs=model_kwargs, device=device, progress=progress, skip_timesteps=skip_timesteps,
-                init_image=init_image, randomize_class=randomize_class, cond_fn_with_grad=cond_fn_with_grad,
-                const_noise=const_noise)):
+        if cond_fn_with_grad:
+            raise NotImplementedError("p_sample_with_grad is off the sampling hot path")
+        # only the final sample is consumed here, so the fast route may replay CUDA graphs of several steps at a
+        # time (the progressive generator below hands out every intermediate tensor and stays step-by-step)
+        for i, sample in enumerate(self._loop(
+                "p", model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device, progress,
+                skip_timesteps, init_image, randomize_class, const_noise, 0.0, graph_ok=dump_steps is None)):
             if dump_steps is not None and i in dump_steps:
                 dump.append(deepcopy(sample["sample"]))
             final = sample
@@ -382,10 +388,10 @@ class GaussianDiffusion:
         if const_noise == True:  # noqa: E712  (mirrors the reference check)
             raise NotImplementedError()
         final = None
-        for sample in self.ddim_sample_loop_progressive(
-                model, shape, noise=noise, clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn,
-                model_kwargs=model_kwargs, device=device, progress=progress, eta=eta, skip_timesteps=skip_timesteps,
-                init_image=init_image, randomize_class=randomize_class, cond_fn_with_grad=cond_fn_with_grad):
+        if cond_fn_with_grad:
+            raise NotImplementedError("ddim_sample_with_grad is off the sampling hot path")
+        for sample in self._loop("ddim", model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device,
+                                 progress, skip_timesteps, init_image, randomize_class, False, eta, graph_ok=True):
             final = sample
         return final["sample"]
 
@@ -400,7 +406,7 @@ class GaussianDiffusion:
                               progress, skip_timesteps, init_image, randomize_class, False, eta)
 
     def _loop(self, kind, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device, progress,
-              skip_timesteps, init_image, randomize_class, const_noise, eta):
+              skip_timesteps, init_image, randomize_class, const_noise, eta, graph_ok=False):
         self._check_supported()
         if device is None:
             device = next(model.parameters()).device
@@ -418,13 +424,15 @@ class GaussianDiffusion:
 
         fast = self._fast_session(model, shape, model_kwargs, denoised_fn, cond_fn, randomize_class, const_noise,
                                   img)
+        if fast is not None:
+            for out in fast.run(self, kind, img, indices, clip_denoised, eta, graph=graph_ok, progress=progress):
+                out.pop("steps", None)   # the session's own bookkeeping; callers see the reference's two keys
+                yield out
+            return
+
         if progress:
             from tqdm.auto import tqdm
             indices = tqdm(indices)
-
-        if fast is not None:
-            yield from fast.run(self, kind, img, indices, clip_denoised, eta)
-            return
 
         for i in indices:
             t = th.tensor([i] * shape[0], device=device)

@@ -138,3 +138,54 @@ def test_seeded_gpu_loop_vs_oracle_with_recorded_noise(built_lib):
     err = (out.cpu() - want).abs().max().item()
     print("20-step loop max abs err vs oracle %.3e" % err)
     assert err < TOL
+
+
+def _loop_eager_and_graph(monkeypatch, d, run, shape, yc, seed, ddim=False, unroll=None, clip=False):
+    """Same seed through the step-by-step driver (REGEN_CUDA_GRAPH=0) and the graph-replay driver."""
+    fn = d.ddim_sample_loop if ddim else d.p_sample_loop
+    monkeypatch.setenv("REGEN_CUDA_GRAPH", "0")
+    torch.manual_seed(seed)
+    a = fn(run, shape, clip_denoised=clip, model_kwargs={"y": yc})
+    monkeypatch.setenv("REGEN_CUDA_GRAPH", str(unroll) if unroll else "")
+    torch.manual_seed(seed)
+    b = fn(run, shape, clip_denoised=clip, model_kwargs={"y": yc})
+    return a, b
+
+
+@pytest.mark.parametrize("steps,unroll", [(25, 4), (27, 4), (30, None), (13, 6)])
+def test_graph_replay_is_bit_identical_to_step_by_step(built_lib, monkeypatch, steps, unroll):
+    """CUDA-graph replay of the loop (regen_step_tables + denoiser + randn_like + update captured once) must give
+    exactly the samples of the host-enqueued loop: same kernels, same Philox noise stream, integer timestep
+    bookkeeping on the device (respace.py:125-126) bit-exact.  Covers trailing step-by-step steps (27 = 1 + 6*4 + 2)."""
+    from regennet_b200 import _lib
+    model, sd = get_model("ntu", 0)
+    _, y = synthetic.make_inputs(3, 56, 6, 60, seed=31)
+    d = _diffusion("ddim%d" % steps)
+    n0 = _lib.lib().regen_launch_count()
+    a, b = _loop_eager_and_graph(monkeypatch, d, model, (3, 56, 6, 60), to_cuda(y), seed=5, unroll=unroll)
+    assert torch.equal(a, b)
+    assert b.permute(3, 0, 1, 2).is_contiguous()
+    assert model.__dict__.get("_graph_cache"), "graph driver was not used"
+    # replayed launches are credited to the library's counter: both drivers launch ~the same number of kernels
+    assert _lib.lib().regen_launch_count() - n0 > 2 * steps * 40
+
+
+def test_graph_replay_cfg_ddim_clip_and_cache_reuse(built_lib, monkeypatch):
+    mk = cases.MODELS["chi3d"]
+    model, sd = get_model("chi3d", 2)
+    run = ClassifierFreeSampleModel(model)
+    shape = (2, 56, 6, 60)
+    d = _diffusion("ddim20")
+    _, y1 = synthetic.make_inputs(2, 56, 6, 60, seed=41, cond_mode="action", num_actions=mk["num_actions"], scale=2.5)
+    _, y2 = synthetic.make_inputs(2, 56, 6, 60, seed=42, cond_mode="action", num_actions=mk["num_actions"], scale=1.5)
+    for ddim, clip in [(True, False), (False, True)]:
+        a1, b1 = _loop_eager_and_graph(monkeypatch, d, run, shape, to_cuda(y1), seed=7, ddim=ddim, unroll=5, clip=clip)
+        assert torch.equal(a1, b1)
+        n_graphs = len(model.__dict__["_graph_cache"])
+        # second loop, new conditioning + guidance scale: the cached graph is reused on its static buffers
+        a2, b2 = _loop_eager_and_graph(monkeypatch, d, run, shape, to_cuda(y2), seed=8, ddim=ddim, unroll=5, clip=clip)
+        assert torch.equal(a2, b2)
+        assert len(model.__dict__["_graph_cache"]) == n_graphs
+        assert not torch.equal(a1, a2)
+        # results are detached from the static buffers
+        assert torch.equal(a1, b1)

@@ -96,3 +96,17 @@ def rotation_6d_to_matrix(d6):
     b2 = b2 / b2.norm(dim=-1, keepdim=True).clamp_min(1e-12)
     b3 = torch.cross(b1, b2, dim=-1)
     return torch.stack((b1, b2, b3), dim=-2)
+
+
+def auto_regressive(loop_fn, cmotion_bak, setting='cmdm'):
+    """eval/a2m/stgcn_eval.py:50-67 restated.  loop_fn(f, cmotion) -> sample [B,V,C,T] is one full sampling loop with
+    the actor motion revealed up to frame f (zeros afterwards); frame f of its result is kept."""
+    B, V, C, T = cmotion_bak.shape
+    cmotion = torch.zeros_like(cmotion_bak)
+    output = torch.zeros((B, V, C * 2, T)) if setting == 'cmdm' else torch.zeros((B, V, C, T))
+    for f in range(T):
+        cmotion[:, :, :, f] = cmotion_bak[:, :, :, f]
+        sample = loop_fn(f, cmotion)
+        tmp = torch.cat((cmotion, sample), dim=2) if setting == 'cmdm' else sample
+        output[:, :, :, f] = tmp[:, :, :, f]
+    return output

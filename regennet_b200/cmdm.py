@@ -529,6 +529,11 @@ class SamplingSession:
                                              eta=eta, out=st["x"] if u == U - 1 else None)
             st["pred"] = pred
         st["graph"].graph = g
+        import os
+        if os.environ.get("REGEN_DEBUG_GRAPH"):
+            import sys
+            print("[regen] captured %d-step graph (B=%d T=%d, %d kernels)" % (U, B, T, L.regen_launch_count() - n0),
+                  file=sys.stderr)
         st["graph"].launches = int(L.regen_launch_count() - n0)
         # the capture pass enqueued nothing: undo its contribution to the executed-launch counter
         L.regen_launch_count_add(-st["graph"].launches)

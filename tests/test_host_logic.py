@@ -142,3 +142,41 @@ def test_model_util_factory_matches_reference_defaults():
     assert (model.njoints, model.nfeats, model.cond_mode, model.num_frames) == (56, 6, "no_cond", 60)
     assert diffusion.num_timesteps == 5 and diffusion.timestep_map == [0, 200, 400, 600, 800]
     assert diffusion.model_var_type == gd.ModelVarType.FIXED_SMALL
+
+
+def test_auto_regressive_driver_indexing():
+    """Host logic of regennet_b200.autoregressive (eval/a2m/stgcn_eval.py:50-67): with a deterministic causal
+    stand-in for the sampling loop, the literal, truncated and batch-stacked drivers all equal the oracle's loop."""
+    import torch
+    from oracle import sampler_ref
+    from regennet_b200.autoregressive import auto_regressive_sample
+    B, V, C, T = 3, 4, 2, 9
+    g = torch.Generator().manual_seed(0)
+    cm = torch.randn(B, V, C, T, generator=g)
+    action = torch.arange(B).view(B, 1)
+    calls = []
+
+    def fake_loop(model, shape, clip_denoised, model_kwargs):
+        y = model_kwargs["y"]
+        assert tuple(y["cmotion"].shape) == tuple(shape) and y["action"].shape[0] == shape[0]
+        assert len(y["action_text"]) == shape[0] and y["tag"] == "kept"
+        calls.append(tuple(shape))
+        # causal in time, independent across samples, conditioned on the per-sample action
+        return torch.cumsum(y["cmotion"], dim=-1) * (1.0 + y["action"].view(-1, 1, 1, 1).float())
+
+    def oracle_loop(f, cmotion):
+        return torch.cumsum(cmotion, dim=-1) * (1.0 + action.view(-1, 1, 1, 1).float())
+
+    for setting in ("cmdm", "sample"):
+        want = sampler_ref.auto_regressive(oracle_loop, cm, setting=setting)
+        for G, trunc in [(1, False), (1, True), (4, True), (4, False), (9, True), (20, True)]:
+            calls.clear()
+            y = {"cmotion": cm.clone(), "action": action, "action_text": ["a"] * B, "tag": "kept"}
+            got = auto_regressive_sample(fake_loop, None, (B, V, C, T), {"y": y}, setting=setting, truncate=trunc,
+                                         frames_per_call=G)
+            assert torch.equal(got, want), (setting, G, trunc)
+            assert torch.equal(y["cmotion"], cm)
+            Ge = min(G, T)
+            assert len(calls) == (T + Ge - 1) // Ge
+            if trunc:
+                assert [c[-1] for c in calls] == [min(k * Ge + Ge, T) for k in range(len(calls))]

@@ -71,7 +71,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
                  const __grid_constant__ CUtensorMap tm_ohi, const __grid_constant__ CUtensorMap tm_olo, const Params p) {
   using C = Cfg<TB>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1 KB alignment by pointer arithmetic on the __shared__ array (NOT an integer round trip): the compiler keeps the
+  // shared address space and emits LDS / STS instead of generic LD / ST for every staging access below
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                  // later: P
   constexpr int NBUF = C::COMPACT ? 2 : 3;
   uint8_t* sK = smem + C::OPERAND;

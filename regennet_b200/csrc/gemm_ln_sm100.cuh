@@ -28,20 +28,26 @@ constexpr int STAGES = 2;
 constexpr int SC = 32;                  // columns per epilogue sub-chunk (one tcgen05.ld/st x32, one TMA box)
 constexpr int SLOT = 32 * SC * 4;       // 4 KB: 32 rows x 32 fp32, 128-byte rows (SWIZZLE_128B)
 // Epilogue geometry for EW epilogue warps per CTA (EW / 4 warps share a TMEM lane quarter and split the 512 columns).
-// The operand ring (192 KB) is re-used as staging: per warp  res ring | c ring ; the 8 KB output buffers alias offset 0.
-//   EW =  8: 24 KB per warp: res 3 x 4 KB, c 3 x 4 KB, 2 output buffers
-//   EW = 16: 12 KB per warp: res 2 x 4 KB, c 1 x 4 KB, 1 output buffer   (4 warps per scheduler hide the exposed latency)
-template <int EW>
+// The operand ring (192 KB) is re-used as staging, WARP_BYTES per warp: residual ring | c ring during passes 1 / 2, and
+// the output staging of the final pass aliases the same bytes (both rings are drained by then):
+//   EW =  8: 24 KB per warp: res 3 x 4 KB + c 3 x 4 KB (res 6 x 4 KB without CHAIN);
+//            output: fp32 ring 2 x 4 KB | bf16 hi 2 x 4 KB | bf16 lo 2 x 4 KB  (bf16 tiles are 32 rows x 64 columns)
+//   EW = 16: 12 KB per warp: res 2 x 4 KB, c 1 x 4 KB; output: fp32 1 x 4 KB | hi 4 KB | lo 4 KB  (A/B variant only)
+template <int EW, bool CHAIN = true>
 struct Epi {
   static constexpr int PARTS = EW / 4;
   static constexpr int WCOLS = ND / PARTS;      // columns per warp
   static constexpr int NSC = WCOLS / SC;        // sub-chunks per warp
-  static constexpr int RING_R = EW == 16 ? 2 : 3;
+  // without CHAIN there is no c ring: its slots deepen the residual ring (more TMA loads in flight per warp)
+  static constexpr int RING_R = CHAIN ? (EW == 16 ? 2 : 3) : (EW == 16 ? 3 : 6);
   static constexpr int RING_C = EW == 16 ? 1 : 3;
-  static constexpr int NOB = EW == 16 ? 1 : 2;
+  static constexpr int NOB = EW == 16 ? 1 : 2;  // output staging depth (fp32 slots, and bf16 hi / lo tile pairs)
   static constexpr int WARP_BYTES = (STAGES * STAGE_BYTES) / EW;
   static constexpr int THREADS = 64 + 32 * EW;
-  static_assert((RING_R + RING_C) * SLOT <= WARP_BYTES && NOB * 8192 <= WARP_BYTES, "epilogue staging budget");
+  static_assert((RING_R + (CHAIN ? RING_C : 0)) * SLOT <= WARP_BYTES && 3 * NOB * SLOT <= WARP_BYTES,
+                "epilogue staging budget");
+  static_assert(RING_R <= 8 && (!CHAIN || RING_R <= 4), "ring barriers: residual slots 0.., c slots 4..");
+  static_assert(NSC % 2 == 0, "sub-chunks are processed in pairs (register double buffer, 64-column bf16 tiles)");
 };
 constexpr int PARAM_BYTES = 5 * ND * 4; // bias, g1, b1, g2, b2
 constexpr int STATS_BYTES = 2 * 128 * 4 * 8;   // [2 exchanges][128 rows][<= 4 column parts] float2
@@ -53,6 +59,7 @@ struct Params {
   int M, K, Beff;
   const float *bias, *g1, *b1, *g2, *b2;  // [512] each (g2/b2 unused without CHAIN)
   float ln_eps;
+  int prefetch_res;              // 1: L2-prefetch the residual tile during the main loop (REGEN_DEBUG_NO_RES_PREFETCH=1 -> 0)
   unsigned long long* timeline;  // bring-up instrumentation (null in production), see tools/ln_timeline.py
 };
 
@@ -71,15 +78,17 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // tm_res: fp32 [M, 512] residual stream h (box 32 x 32, SWIZZLE_128B) -- used for the residual LOAD and the h STORE
 // tm_c  : fp32 [Beff + 32, 512] cyclic per-sample constant (row r = c[r % Beff]); only read with CHAIN
-// tm_ohi / tm_olo: bf16 [M, 512] split of h (store)
+// tm_ohi / tm_olo: bf16 [M, 512] split of h (store, box 32 rows x 64 columns, SWIZZLE_128B)
 template <bool SPLIT, bool CHAIN, int EW>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Epi<EW>::THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Epi<EW, CHAIN>::THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_c,
                const __grid_constant__ CUtensorMap tm_ohi, const __grid_constant__ CUtensorMap tm_olo, const Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1 KB alignment by pointer arithmetic on the __shared__ array (NOT an integer round trip): the compiler keeps the
+  // shared address space and emits LDS / STS instead of generic LD / ST for every staging access below
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   float* s_par = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);             // bias | g1 | b1 | g2 | b2
   float2* s_stats = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + PARAM_BYTES);  // [2 exchanges][128 rows][2 halves]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + PARAM_BYTES + STATS_BYTES);
@@ -88,7 +97,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   uint64_t* tmem_full_bar = bars + 4;
   uint64_t* tmem_empty_bar = bars + 5;   // leader's copy: 16 arrivals (epilogue warps of both CTAs)
   uint64_t* epi_done_bar = bars + 6;     // local: 8 arrivals, operand ring free again for the producer
-  using E = Epi<EW>;
+  using E = Epi<EW, CHAIN>;
   uint64_t* ring_bar = bars + 8;         // [EW warps][8]: res slots 0..3, c slots 4..7
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 8 + 8 * EW);
 
@@ -146,6 +155,14 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             ptx::tma_load_2d_2sm(st + 16384, &tm_a_lo, &full_bar[stage], kb * BK, m0);
             ptx::tma_load_2d_2sm(st + 4 * 16384, &tm_w_lo, &full_bar[stage], kb * BK, (int)rank * 128);
             ptx::tma_load_2d_2sm(st + 5 * 16384, &tm_w_lo, &full_bar[stage], kb * BK, 256 + (int)rank * 128);
+          }
+          // The epilogue's first pass reads this CTA's 128 x 512 fp32 residual tile in one burst; by then h has been
+          // evicted from L2 by the operand stream (ncu: the whole tile came from DRAM, pass 1 was HBM-bound).  Pull it
+          // into L2 during the main loop, which leaves DRAM bandwidth unused: 64 boxes of 32 x 32 spread over the k-blocks.
+          if (p.prefetch_res) {
+            const int per_kb = (64 + num_kb - 1) / num_kb;
+            for (int i = kb * per_kb; i < (kb + 1) * per_kb && i < 64; ++i)
+              ptx::tma_prefetch_l2_2d(&tm_res, (i & 15) * SC, m0 + (i >> 4) * 32);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -214,7 +231,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     uint8_t* my = smem + ew * E::WARP_BYTES;
     uint8_t* res_ring = my;
     uint8_t* c_ring = my + E::RING_R * SLOT;
-    uint8_t* out_buf = my;                             // NOB x 8 KB, used after both rings are drained
+    uint8_t* out_buf = my;                             // 3 x NOB x 4 KB, used after both rings are drained
     uint64_t* rbar = ring_bar + ew * 8;                // [0..2] residual slots, [4..6] c slots
     const float* s_bias = s_par + hf * E::WCOLS;
     const float* s_g1 = s_par + ND + hf * E::WCOLS;
@@ -247,18 +264,17 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           }
         }
       }
+      // The three passes are software pipelined over the 32-column sub-chunks: the tcgen05.ld of sub-chunk sc + 1 is in
+      // flight (second register buffer) while sub-chunk sc is processed, so the TMEM read latency (~500 cycles with
+      // 8 warps sharing the 64 B/clk read port) is off each warp's critical path.
+      uint32_t ra[32], rb[32];
       // ---- pass 1: v = acc + bias + residual, row statistics, v -> TMEM
       float sum = 0.f, sq = 0.f;
-#pragma unroll 1
-      for (int sc = 0; sc < E::NSC; ++sc) {
+      auto pass1 = [&](uint32_t (&r)[32], int sc) {
         constexpr int RING = E::RING_R;
         const int slot = sc % RING;
-        uint32_t r[32];
-        __syncwarp();
-        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(sc * SC), r);
         // slot `slot` is filled ceil((NSC - slot) / RING) times per tile; this is fill number sc / RING of this tile
         ptx::mbar_wait(&rbar[slot], (uint32_t)(it * ((E::NSC - slot + RING - 1) / RING) + sc / RING) & 1);
-        ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 b4 = *reinterpret_cast<const float4*>(s_bias + sc * SC + 4 * j);
@@ -276,6 +292,17 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           ptx::mbar_expect_tx(&rbar[slot], SLOT);
           ptx::tma_load_2d(res_ring + slot * SLOT, &tm_res, &rbar[slot], n_base + SC * (sc + RING), row0);
         }
+      };
+      __syncwarp();
+      ptx::tmem_ld_32x32b_x32(lane_addr, ra);
+#pragma unroll 1
+      for (int sc = 0; sc < E::NSC; sc += 2) {
+        ptx::tmem_ld_wait(ra);
+        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)((sc + 1) * SC), rb);
+        pass1(ra, sc);
+        ptx::tmem_ld_wait(rb);
+        if (sc + 2 < E::NSC) ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)((sc + 2) * SC), ra);
+        pass1(rb, sc + 1);
       }
       ptx::tmem_st_wait();
       if (tr) REGEN_LTL(4);
@@ -297,15 +324,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       if (CHAIN) {
         // ---- pass 2: y = LN1(v) + c, statistics of y, y -> TMEM
         float sum2 = 0.f, sq2 = 0.f;
-#pragma unroll 1
-        for (int sc = 0; sc < E::NSC; ++sc) {
+        auto pass2 = [&](uint32_t (&r)[32], int sc) {
           constexpr int RING = E::RING_C;
           const int slot = sc % RING;
-          uint32_t r[32];
-          __syncwarp();
-          ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(sc * SC), r);
           ptx::mbar_wait(&rbar[4 + slot], (uint32_t)(it * ((E::NSC - slot + RING - 1) / RING) + sc / RING) & 1);
-          ptx::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 g4 = *reinterpret_cast<const float4*>(s_g1 + sc * SC + 4 * j);
@@ -326,6 +348,17 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             ptx::mbar_expect_tx(&rbar[4 + slot], SLOT);
             ptx::tma_load_2d(c_ring + slot * SLOT, &tm_c, &rbar[4 + slot], n_base + SC * (sc + RING), crow0);
           }
+        };
+        __syncwarp();
+        ptx::tmem_ld_32x32b_x32(lane_addr, ra);
+#pragma unroll 1
+        for (int sc = 0; sc < E::NSC; sc += 2) {
+          ptx::tmem_ld_wait(ra);
+          ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)((sc + 1) * SC), rb);
+          pass2(ra, sc);
+          ptx::tmem_ld_wait(rb);
+          if (sc + 2 < E::NSC) ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)((sc + 2) * SC), ra);
+          pass2(rb, sc + 1);
         }
         ptx::tmem_st_wait();
         if (tr) REGEN_LTL(6);
@@ -344,20 +377,25 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         rstd = 1.0f / sqrtf(fmaxf(sq2 * inv_n - mean * mean, 0.f) + p.ln_eps);
       }
 
-      // ---- final pass: z = LN(.), fp32 + bf16 (hi, lo) out through TMA stores (8 KB per sub-chunk, double buffered)
+      // ---- final pass: z = LN(.), fp32 + bf16 (hi, lo) out through TMA stores.  Measured on B200: the TMA unit retires
+      // about one box row per 2.6 cycles whatever its length (<= 128 B), and that row rate -- not shared-memory or TMEM
+      // bandwidth -- bounds this pass, so the bf16 halves are staged as 32 x 64 tiles (128-byte rows, one store per
+      // PAIR of sub-chunks): 128 instead of 192 row requests per 64 columns.  Staging per warp: fp32 slots F[NOB],
+      // hi tiles H[NOB], lo tiles L[NOB] (4 KB each); every sub-chunk commits one bulk group (the odd ones carry the
+      // bf16 tiles of their pair).
       const float* gg = CHAIN ? s_g2 : s_g1;
       const float* bb = CHAIN ? s_b2 : s_b1;
-      __syncwarp();  // both rings fully consumed by every lane: their memory becomes the output buffers
-#pragma unroll 1
-      for (int sc = 0; sc < E::NSC; ++sc) {
-        uint8_t* ob = out_buf + (E::NOB == 2 ? (sc & 1) * 8192 : 0);
-        if (sc >= E::NOB && lane == 0) {
-          if (E::NOB == 2) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
-        }
-        uint32_t r[32];
+      auto pass3 = [&](uint32_t (&r)[32], int sc) {
+        const int u = sc >> 1, half = sc & 1;
+        uint8_t* fb = out_buf + (sc % E::NOB) * SLOT;
+        uint8_t* hb = out_buf + (E::NOB + (u % E::NOB)) * SLOT;
+        uint8_t* lb = out_buf + (2 * E::NOB + (u % E::NOB)) * SLOT;
+        if (tr && sc == 2) REGEN_LTL(11);
+        // F[sc % NOB] was last stored by group sc - NOB; H/L[u % NOB] by group 2 (u - NOB) + 1 = sc - 2 NOB + 1 (sc even):
+        // both are complete once at most NOB - 1 groups are pending
+        if (sc >= E::NOB && lane == 0) ptx::bulk_wait_read<E::NOB - 1>();
         __syncwarp();
-        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(sc * SC), r);
-        ptx::tmem_ld_wait();
+        if (tr && sc == 2) REGEN_LTL(12);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {  // 8 columns = two fp32 chunks, one bf16 hi chunk, one bf16 lo chunk
           uint32_t hw[4], lw[4];
@@ -370,24 +408,42 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const float z1 = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * g4.y + b4.y;
             const float z2 = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * g4.z + b4.z;
             const float z3 = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * g4.w + b4.w;
-            *reinterpret_cast<float4*>(ob + off_f32(lane, j)) = make_float4(z0, z1, z2, z3);
+            *reinterpret_cast<float4*>(fb + off_f32(lane, j)) = make_float4(z0, z1, z2, z3);
             const uint32_t h0 = gemm::pack_bf16x2(z0, z1), h1 = gemm::pack_bf16x2(z2, z3);
             hw[2 * jj] = h0;
             hw[2 * jj + 1] = h1;
             lw[2 * jj] = gemm::pack_bf16x2(z0 - __uint_as_float(h0 << 16), z1 - __uint_as_float(h0 & 0xffff0000u));
             lw[2 * jj + 1] = gemm::pack_bf16x2(z2 - __uint_as_float(h1 << 16), z3 - __uint_as_float(h1 & 0xffff0000u));
           }
-          *reinterpret_cast<uint4*>(ob + 4096 + off_bf16(lane, c)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          *reinterpret_cast<uint4*>(ob + 6144 + off_bf16(lane, c)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          // 16-byte chunk (half * 4 + c) of this row's 128-byte bf16 row (same SWIZZLE_128B pattern as the fp32 tile)
+          *reinterpret_cast<uint4*>(hb + off_f32(lane, half * 4 + c)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(lb + off_f32(lane, half * 4 + c)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
+        if (tr && sc == 2) REGEN_LTL(13);
         ptx::fence_proxy_async_smem();
         __syncwarp();
+        if (tr && sc == 2) REGEN_LTL(14);
         if (lane == 0) {
-          ptx::tma_store_2d(&tm_res, ob, n_base + SC * sc, row0);
-          ptx::tma_store_2d(&tm_ohi, ob + 4096, n_base + SC * sc, row0);
-          ptx::tma_store_2d(&tm_olo, ob + 6144, n_base + SC * sc, row0);
+          ptx::tma_store_2d(&tm_res, fb, n_base + SC * sc, row0);
+          if (half) {
+            ptx::tma_store_2d(&tm_ohi, hb, n_base + 2 * SC * u, row0);
+            ptx::tma_store_2d(&tm_olo, lb, n_base + 2 * SC * u, row0);
+          }
           ptx::bulk_commit();
         }
+      };
+      __syncwarp();  // both rings fully consumed by every lane: their memory becomes the output buffers
+      ptx::tmem_ld_32x32b_x32(lane_addr, ra);
+#pragma unroll 1
+      for (int sc = 0; sc < E::NSC; sc += 2) {
+        ptx::tmem_ld_wait(ra);
+        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)((sc + 1) * SC), rb);
+        pass3(ra, sc);
+        if (tr && sc == 2) REGEN_LTL(15);
+        ptx::tmem_ld_wait(rb);
+        if (tr && sc == 2) REGEN_LTL(16);
+        if (sc + 2 < E::NSC) ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)((sc + 2) * SC), ra);
+        pass3(rb, sc + 1);
       }
       // accumulator and operand ring are free again
       if (tr) REGEN_LTL(8);
@@ -426,7 +482,7 @@ inline cudaError_t launch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo,
   }
   const int64_t tiles = ceil_div(p.M, 2 * BM);
   const int clusters = (int)(tiles < kNumSMs / 2 ? tiles : kNumSMs / 2);
-  return launch_pdl(gemm_ln_kernel<SPLIT, CHAIN, EW>, dim3(2 * clusters), dim3(Epi<EW>::THREADS), SMEM_BYTES, stream, a_hi,
+  return launch_pdl(gemm_ln_kernel<SPLIT, CHAIN, EW>, dim3(2 * clusters), dim3(Epi<EW, CHAIN>::THREADS), SMEM_BYTES, stream, a_hi,
                     a_lo, w_hi, w_lo, res, c, ohi, olo, p);
 }
 

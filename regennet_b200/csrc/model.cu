@@ -21,7 +21,8 @@ struct SplitBuf {  // bf16 (hi, lo) operand pair + its TMA maps
   CUtensorMap tm_hi, tm_lo;      // box rows: 128 for activations (A operand), 256 for weights (single-CTA kernel)
   CUtensorMap tm_hi2, tm_lo2;    // weights only: box rows 128 = one CTA's half of the W tile in the CTA-pair kernel
   CUtensorMap st_hi, st_lo;      // activations only: store-side maps (box 32 x 16), rebuilt per prepare_cond with rows = M
-  CUtensorMap st32_hi, st32_lo;  // same with box 32 x 32 (fused GEMM+LayerNorm epilogue)
+  CUtensorMap st32_hi, st32_lo;  // same with box 32 x 32 (16-warp GEMM epilogue)
+  CUtensorMap st64_hi, st64_lo;  // same with box 32 x 64, 128-byte rows (fused GEMM+LayerNorm epilogue)
   size_t cols = 0;
 };
 
@@ -59,6 +60,7 @@ struct regen_handle {
   CUtensorMap st32_h;                // h with box 32 x 32: residual load + store of the fused GEMM+LayerNorm kernel
   bool tma_store = true;             // REGEN_DEBUG_NO_TMA_STORE=1: st.global epilogue (A/B measurements)
   bool fused_ln = true;              // REGEN_DEBUG_NO_FUSED_LN=1: GEMM -> tmp -> LayerNorm kernels
+  bool prefetch_res = true;          // REGEN_DEBUG_NO_RES_PREFETCH=1: no L2 prefetch of the residual tile (A/B)
   float* cyc = nullptr;              // [L][max_batch + 32][512] row-cyclic cross-attention constants (per denoise)
   CUtensorMap tm_cyc[REGEN_MAX_LAYERS];
   bool simt_attention = false;       // REGEN_DEBUG_SIMT_ATTENTION=1: fp32 CUDA-core attention for A/B debugging
@@ -213,6 +215,8 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
     h->tma_store = !(e2 && e2[0] == '1');
     const char* e3 = getenv("REGEN_DEBUG_NO_FUSED_LN");
     h->fused_ln = h->tma_store && !(e3 && e3[0] == '1');
+    const char* e4 = getenv("REGEN_DEBUG_NO_RES_PREFETCH");
+    h->prefetch_res = !(e4 && e4[0] == '1');
   }
   const size_t Mx = (size_t)h->Mmax;
   int rc = REGEN_OK;
@@ -410,6 +414,8 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
     TRY(make_tmap_store_2d(&sb->st_lo, sb->lo, true, h->M, sb->cols, sb->cols));
     TRY(make_tmap_store_2d(&sb->st32_hi, sb->hi, true, h->M, sb->cols, sb->cols, 32));
     TRY(make_tmap_store_2d(&sb->st32_lo, sb->lo, true, h->M, sb->cols, sb->cols, 32));
+    TRY(make_tmap_store_2d(&sb->st64_hi, sb->hi, true, h->M, sb->cols, sb->cols, 64));
+    TRY(make_tmap_store_2d(&sb->st64_lo, sb->lo, true, h->M, sb->cols, sb->cols, 64));
   }
   TRY(make_tmap_store_2d(&h->st32_h, h->h, false, h->M, D, D, 32));
   for (int l = 0; l < L; ++l)
@@ -512,12 +518,13 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       gemmln::Params q;
       q.M = M; q.K = D; q.Beff = Beff; q.bias = ld.bo; q.g1 = ld.n1w; q.b1 = ld.n1b; q.g2 = ld.n2w; q.b2 = ld.n2b;
       q.ln_eps = layers::LN_EPS;
+      q.prefetch_res = h->prefetch_res ? 1 : 0;
       q.timeline = g_test_timeline;
       cudaError_t e = h->desc.precision == 0
           ? gemmln::launch<true, true>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->tm_cyc[l],
-                                       h->h_s.st32_hi, h->h_s.st32_lo, q, s)
+                                       h->h_s.st64_hi, h->h_s.st64_lo, q, s)
           : gemmln::launch<false, true>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->tm_cyc[l],
-                                        h->h_s.st32_hi, h->h_s.st32_lo, q, s);
+                                        h->h_s.st64_hi, h->h_s.st64_lo, q, s);
       if (e != cudaSuccess) {
         set_error("fused out_proj+LayerNorm launch failed: %s", cudaGetErrorString(e));
         return REGEN_ECUDA;
@@ -555,12 +562,13 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       gemmln::Params q;
       q.M = M; q.K = FF; q.Beff = Beff; q.bias = ld.b2; q.g1 = ld.n3w; q.b1 = ld.n3b; q.g2 = nullptr; q.b2 = nullptr;
       q.ln_eps = layers::LN_EPS;
+      q.prefetch_res = h->prefetch_res ? 1 : 0;
       q.timeline = g_test_timeline;
       cudaError_t e = h->desc.precision == 0
           ? gemmln::launch<true, false>(h->ffn.tm_hi, h->ffn.tm_lo, ld.w2.tm_hi2, ld.w2.tm_lo2, h->st32_h, h->st32_h,
-                                        h->h_s.st32_hi, h->h_s.st32_lo, q, s)
+                                        h->h_s.st64_hi, h->h_s.st64_lo, q, s)
           : gemmln::launch<false, false>(h->ffn.tm_hi, h->ffn.tm_lo, ld.w2.tm_hi2, ld.w2.tm_lo2, h->st32_h, h->st32_h,
-                                         h->h_s.st32_hi, h->h_s.st32_lo, q, s);
+                                         h->h_s.st64_hi, h->h_s.st64_lo, q, s);
       if (e != cudaSuccess) {
         set_error("fused linear2+LayerNorm launch failed: %s", cudaGetErrorString(e));
         return REGEN_ECUDA;

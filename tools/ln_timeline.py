@@ -25,7 +25,9 @@ for rep in range(3):
 lib.regen_test_gemm_timeline(None)
 v = tl.cpu().tolist()
 names = ["entry", "mma first operands", "mma issue end", "epi: acc ready", "pass1 done", "exchange1 done",
-         "pass2 done", "exchange2 done", "final pass done", "stores drained", "exit"]
+         "pass2 done", "exchange2 done", "final pass done", "stores drained", "exit",
+         "p3 sc2: enter", "p3 sc2: buffer free", "p3 sc2: computed+staged", "p3 sc2: fenced", "p3 sc2: stores issued",
+         "p3 sc3: tmem ready"]
 for base, label in [(0, "out_proj + LN1 + c + LN2 (K=512)"), (20, "linear2 + LN3 (K=1024)")]:
     print("==", label)
     t0 = v[base]

@@ -2,6 +2,7 @@
 
     python profiles/summarize.py launches gpurun_out/launches.csv profiles/r01_launches_<tag>.txt
     python profiles/summarize.py full gpurun_out/prof_gemm.ncu-rep profiles/r01_ncu_<tag>.txt
+    python profiles/summarize.py traffic gpurun_out/prof_gemm.ncu-rep profiles/r01_traffic.json
 """
 import collections
 import csv
@@ -56,5 +57,28 @@ def full(src, dst):
                     f.write("  %-78s %s %s\n" % (m, r[idx[m]], units[idx[m]]))
 
 
+def traffic(src, dst):
+    """Per-kernel DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) -> JSON read by bench.py.
+    ncu flushes the caches before every replay, so these are COLD-cache figures (upper bounds for the in-pipeline run)."""
+    import json
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    agg = collections.OrderedDict()
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]].split("(")[0]
+        b = sum(float(r[idx[m]].replace(",", "")) * scale[units[idx[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += b
+    res = {k: {"launches": v[0], "dram_bytes_per_launch": v[1] / v[0]} for k, v in agg.items()}
+    gem = [v for k, v in agg.items() if "gemm" in k]
+    res["_gemm_class_avg_dram_bytes_per_launch"] = sum(v[1] for v in gem) / max(1, sum(v[0] for v in gem))
+    res["_source"] = "%s (ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum; cold cache)" % src
+    json.dump(res, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])

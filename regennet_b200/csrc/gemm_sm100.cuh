@@ -749,7 +749,15 @@ inline cudaError_t launch2_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo
     configured = true;
   }
   const int64_t tiles = ceil_div(p.N, BN) * ceil_div(p.M, 2 * BM);
-  const int clusters = (int)(tiles < kNumSMs / 2 ? tiles : kNumSMs / 2);
+  int clusters = (int)(tiles < kNumSMs / 2 ? tiles : kNumSMs / 2);
+  {
+    static int cap = -1;  // REGEN_DEBUG_GEMM_MAXCLUSTERS: bring-up only (L2-bandwidth experiments)
+    if (cap < 0) {
+      const char* e = getenv("REGEN_DEBUG_GEMM_MAXCLUSTERS");
+      cap = e ? atoi(e) : 0;
+    }
+    if (cap > 0 && clusters > cap) clusters = cap;
+  }
   return launch_pdl(gemm2_tn_kernel<BN, SPLIT, EW, RES>, dim3(2 * clusters), dim3(64 + 32 * EW), C::SMEM_BYTES, stream, a_hi,
                     a_lo, w_hi, w_lo, o.f32, o.hi, o.lo, p);
 }

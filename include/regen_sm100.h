@@ -90,6 +90,11 @@ int regen_cfg_combine(const float* cond, const float* uncond, const float* scale
 
 /* rot6d -> rotation matrix (Gram-Schmidt).  Replaces utils/rotation_conversions.py:513-534.
  * d6 [n,6] contiguous -> R [n,3,3] contiguous, rows (b1,b2,b3).                         */
+/* Inpainting blend of the model output (motion editing, sample/edit.py:75-90).  Replaces
+ * diffusion/gaussian_diffusion.py:319-323:  x0 = x0 * ~mask + motion * mask, in place, torch's operation order.
+ * mask01 holds 0.0f / 1.0f; all three arrays share one memory layout (the sampler uses [T,B,I]). */
+int regen_inpaint_blend(float* x0, const float* motion, const float* mask01, int64_t n_elem, void* stream);
+
 int regen_rot6d_to_matrix(const float* d6, float* R, int64_t n, void* stream);
 
 /* Post-sampling tail.  Temporal Gaussian smoothing = scipy.ndimage.gaussian_filter1d(x, sigma,

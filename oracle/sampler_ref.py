@@ -26,7 +26,10 @@ def _extract(arr, t, ndim):
 class Sampler:
     """SpacedDiffusion restated: START_X mean, fixed variance, clip_denoised off by default."""
 
-    def __init__(self, noise_schedule="cosine", steps=1000, timestep_respacing="", sigma_small=True):
+    def __init__(self, noise_schedule="cosine", steps=1000, timestep_respacing="", sigma_small=True, inpaint=None):
+        # inpaint = (mask bool, motion): diffusion/gaussian_diffusion.py:319-323, the model output is overwritten
+        # where the mask is set (y['inpainting_mask'], y['inpainted_motion']; sample/edit.py:75-90)
+        self.inpaint = inpaint
         base = schedule.named_beta_schedule(noise_schedule, steps)
         use = schedule.space_timesteps(steps, timestep_respacing if timestep_respacing else [steps])
         self.tab, self.timestep_map = schedule.spaced_tables(base, use)
@@ -40,6 +43,9 @@ class Sampler:
     def p_mean_variance(self, model, x, t, clip_denoised=False):
         tab = self.tab
         x0 = model(x, self.remap(t))
+        if self.inpaint is not None:
+            mask, motion = self.inpaint
+            x0 = (x0 * ~mask) + (motion * mask)
         if self.sigma_small:
             logvar = tab.posterior_log_variance_clipped
         else:  # FIXED_LARGE, gaussian_diffusion.py:345-350

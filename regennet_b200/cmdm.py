@@ -421,11 +421,24 @@ class SamplingSession:
         x = _to_layout(img, "tbi")                                  # logical [B,J,F,T], memory [T,B,J,F]
         t_model = torch.empty(B, dtype=torch.long, device=dev)
         t_idx = torch.empty(B, dtype=torch.long, device=dev)
+        # motion editing (gaussian_diffusion.py:319-323): mask / motion re-laid-out once to the model-output layout
+        inpaint = None
+        if 'inpainting_mask' in self.y:
+            inpaint = (_to_layout(self.y['inpainting_mask'].to(device=dev, dtype=torch.float32), "tbi"),
+                       _to_layout(_lib.require_cuda_f32(self.y['inpainted_motion'].to(dev), "y['inpainted_motion']"), "tbi"))
+
+        def blend(x0_tbi, mask_tbi, motion_tbi):
+            _lib.check(_lib.lib().regen_inpaint_blend(_lib.ptr(x0_tbi), _lib.ptr(motion_tbi), _lib.ptr(mask_tbi),
+                                                      x0_tbi.numel(), _lib.stream_ptr(dev)), "regen_inpaint_blend")
+        self._blend = blend
 
         def eager_step(x, i, first):
             t_idx.fill_(i)
             t_model.fill_(int(self.timestep_map[i]))                # respace.py:125-126 (integer remap)
-            x0 = m._denoise_tbi(handle, x.permute(3, 0, 1, 2), t_model, scale, B, T).view(T, B, J, F).permute(1, 2, 3, 0)
+            x0 = m._denoise_tbi(handle, x.permute(3, 0, 1, 2), t_model, scale, B, T)
+            if inpaint is not None:
+                blend(x0, inpaint[0], inpaint[1])
+            x0 = x0.view(T, B, J, F).permute(1, 2, 3, 0)
             # the reference draws randn_like(x) AFTER the model call, in x's memory layout: contiguous
             # [B,J,F,T] at the first step, the permuted model-output layout from then on
             noise = torch.randn_like(img if first else x)
@@ -445,8 +458,11 @@ class SamplingSession:
                     bar.update(1)
                 yield {"sample": x, "pred_xstart": pred, "steps": 1}
             if U:
-                st = self._graph_state(diffusion, kind, handle, scale, clip_denoised, eta, U, dev)
+                st = self._graph_state(diffusion, kind, handle, scale, clip_denoised, eta, U, dev, inpaint is not None)
                 st["x"].copy_(x)
+                if inpaint is not None:
+                    st["inp_mask"].copy_(inpaint[0])
+                    st["inp_motion"].copy_(inpaint[1])
                 rest = idx[1:]
                 st["seq_idx"][:len(rest)].copy_(torch.tensor(rest, dtype=torch.long), non_blocking=False)
                 st["seq_model"][:len(rest)].copy_(torch.tensor([int(self.timestep_map[i]) for i in rest],
@@ -479,12 +495,12 @@ class SamplingSession:
             bar.close()
 
     # ------------------------------------------------------------------------------------------------
-    def _graph_state(self, diffusion, kind, handle, scale, clip_denoised, eta, U, dev):
+    def _graph_state(self, diffusion, kind, handle, scale, clip_denoised, eta, U, dev, inpainting=False):
         """Static buffers + graph for this (handle, problem, sampler) combination, cached on the model."""
         m = self.model
         B, J, F, T = self.shape
         key = (id(handle), id(diffusion), B, T, kind, bool(clip_denoised), float(eta), U, scale is not None,
-               m._cond_key[:4] if m._cond_key else None, handle.ptr.value)
+               m._cond_key[:4] if m._cond_key else None, handle.ptr.value, bool(inpainting))
         cache = m.__dict__.setdefault("_graph_cache", {})
         st = cache.get(key)
         if st is not None and st["handle"] is handle and st["diffusion"] is diffusion:
@@ -502,6 +518,8 @@ class SamplingSession:
             "t_idx": torch.empty(B, dtype=torch.long, device=dev),
             "t_model": torch.empty(B, dtype=torch.long, device=dev),
             "scale": torch.empty_like(scale) if scale is not None else None,
+            "inp_mask": torch.empty((T, B, J, F), device=dev).permute(1, 2, 3, 0) if inpainting else None,
+            "inp_motion": torch.empty((T, B, J, F), device=dev).permute(1, 2, 3, 0) if inpainting else None,
         }
         cache[key] = st
         return st
@@ -523,6 +541,8 @@ class SamplingSession:
                                                _lib.ptr(st["t_idx"]), _lib.ptr(st["t_model"]), B, _SEQ_CAP,
                                                _lib.stream_ptr(dev)), "regen_step_tables")
                 x0 = m._denoise_tbi(handle, xs.permute(3, 0, 1, 2), st["t_model"], st["scale"], B, T)
+                if st["inp_mask"] is not None:
+                    self._blend(x0, st["inp_mask"], st["inp_motion"])
                 x0 = x0.view(T, B, J, F).permute(1, 2, 3, 0)
                 noise = torch.randn_like(xs)
                 xs, pred = diffusion._update("p" if kind == "p" else "ddim", xs, x0, noise, st["t_idx"], clip_denoised,

@@ -164,6 +164,29 @@ __global__ void __launch_bounds__(kThreads) cfg_combine_kernel(const float* __re
   }
 }
 
+// diffusion/gaussian_diffusion.py:319-323 (motion editing / in-betweening): the model output is overwritten where the
+// mask is set,  out = x0 * ~mask + motion * mask, with torch's operation order (two products, one sum).  mask holds 0.0 / 1.0.
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) inpaint_blend_kernel(float* __restrict__ x0, const float* __restrict__ motion,
+                                                                 const float* __restrict__ mask, uint32_t n_items) {
+  ptx::griddep_wait();  // PDL: x0 is the output projection's (or the guidance combine's) result
+  ptx::griddep_launch();
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n_items; i += gridDim.x * kThreads) {
+    if (VEC) {
+      float4 v = reinterpret_cast<float4*>(x0)[i];
+      const float4 m = reinterpret_cast<const float4*>(mask)[i];
+      const float4 w = reinterpret_cast<const float4*>(motion)[i];
+      v.x = __fadd_rn(__fmul_rn(v.x, 1.f - m.x), __fmul_rn(w.x, m.x));
+      v.y = __fadd_rn(__fmul_rn(v.y, 1.f - m.y), __fmul_rn(w.y, m.y));
+      v.z = __fadd_rn(__fmul_rn(v.z, 1.f - m.z), __fmul_rn(w.z, m.z));
+      v.w = __fadd_rn(__fmul_rn(v.w, 1.f - m.w), __fmul_rn(w.w, m.w));
+      reinterpret_cast<float4*>(x0)[i] = v;
+    } else {
+      x0[i] = __fadd_rn(__fmul_rn(x0[i], 1.f - mask[i]), __fmul_rn(motion[i], mask[i]));
+    }
+  }
+}
+
 // utils/rotation_conversions.py:529-534.  One rotation per thread; the block's 6-float inputs and
 // 9-float outputs are staged through shared memory so global traffic is float4-coalesced.
 constexpr int kRotPerBlock = 256;
@@ -442,6 +465,22 @@ int regen_cfg_combine(const float* cond, const float* uncond, const float* scale
                                                                     (uint32_t)inner, (uint32_t)B);
   }
   REGEN_LAUNCH_CHECK();
+  count_launch();
+  return REGEN_OK;
+}
+
+int regen_inpaint_blend(float* x0, const float* motion, const float* mask01, int64_t n_elem, void* stream) {
+  REGEN_CHECK_ARG(n_elem >= 0 && n_elem < (int64_t)1 << 32, "inpaint_blend: bad n_elem");
+  if (n_elem == 0) return REGEN_OK;
+  REGEN_CHECK_ARG(x0 && motion && mask01, "inpaint_blend: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((n_elem % 4 == 0) && aligned16(x0) && aligned16(motion) && aligned16(mask01)) {
+    const uint32_t items = (uint32_t)(n_elem / 4);
+    REGEN_CUDA(launch_pdl(inpaint_blend_kernel<true>, dim3(grid_for(items)), dim3(kThreads), 0, s, x0, motion, mask01, items));
+  } else {
+    REGEN_CUDA(launch_pdl(inpaint_blend_kernel<false>, dim3(grid_for(n_elem)), dim3(kThreads), 0, s, x0, motion, mask01,
+                          (uint32_t)n_elem));
+  }
   count_launch();
   return REGEN_OK;
 }

@@ -458,8 +458,15 @@ class GaussianDiffusion:
         if self.rescale_timesteps or len(shape) != 4 or not img.is_cuda:
             return None
         y = (model_kwargs or {}).get('y', None)
-        if not isinstance(y, dict) or 'inpainting_mask' in y or 'inpainted_motion' in y:
+        if not isinstance(y, dict):
             return None
+        if ('inpainting_mask' in y) != ('inpainted_motion' in y):
+            return None      # the reference blends only when both keys are present (:319); leave odd inputs to the generic route
+        if 'inpainting_mask' in y:
+            m, w = y['inpainting_mask'], y['inpainted_motion']
+            if not (th.is_tensor(m) and th.is_tensor(w) and m.dtype == th.bool and tuple(m.shape) == tuple(shape)
+                    and tuple(w.shape) == tuple(shape) and w.dtype == th.float32):
+                return None
         return maker(shape, y, self._timestep_map_for_model())
 
     def _timestep_map_for_model(self):

@@ -189,3 +189,69 @@ def test_graph_replay_cfg_ddim_clip_and_cache_reuse(built_lib, monkeypatch):
         assert not torch.equal(a1, a2)
         # results are detached from the static buffers
         assert torch.equal(a1, b1)
+
+
+def _edit_inputs(B, T, seed):
+    """sample/edit.py:75-90 'in_between': keep a prefix and a suffix of the input motion, generate the middle."""
+    g = torch.Generator().manual_seed(seed)
+    motion = torch.randn(B, 56, 6, T, generator=g)
+    mask = torch.ones(B, 56, 6, T, dtype=torch.bool)
+    mask[:, :, :, int(0.25 * T):int(0.75 * T)] = False
+    mask[1, :10] = True      # ragged: sample 1 also keeps some joints everywhere
+    return mask, motion
+
+
+def test_inpainting_fast_route_matches_generic_route_and_oracle(built_lib, monkeypatch):
+    """Motion editing (gaussian_diffusion.py:319-323): x0 <- x0 * ~mask + motion * mask every step.  The fused route
+    (regen_inpaint_blend, also inside the captured graph) must equal the generic route bit for bit and the oracle to 1e-3."""
+    mk = cases.MODELS["ntu"]
+    model, sd = get_model("ntu", 0)
+    B, T = 2, 60
+    shape = (B, 56, 6, T)
+    _, y = synthetic.make_inputs(B, 56, 6, T, seed=61)
+    mask, motion = _edit_inputs(B, T, 62)
+    yc = to_cuda(dict(y, inpainting_mask=mask, inpainted_motion=motion))
+    d = _diffusion("ddim16")
+    assert d._fast_session(model, shape, {"y": yc}, None, None, False, False, torch.zeros(1, device="cuda")) is not None
+
+    class Wrap(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, x, t, y=None):
+            return self.m(x, t, y)
+
+    outs = {}
+    for name, run, graph in [("generic", Wrap(model), "0"), ("fast", model, "0"), ("graph", model, "5")]:
+        monkeypatch.setenv("REGEN_CUDA_GRAPH", graph)
+        torch.manual_seed(3)
+        outs[name] = d.p_sample_loop(run, shape, clip_denoised=False, model_kwargs={"y": yc})
+    assert torch.equal(outs["generic"], outs["fast"])
+    assert torch.equal(outs["fast"], outs["graph"])
+    # last step (t = 0): sample == blended prediction, so the kept region is the input motion exactly
+    assert torch.equal(outs["fast"].cpu()[mask], motion[mask])
+
+    # oracle on the recorded noise
+    noises = []
+    orig = torch.randn_like
+
+    def rec(x, **kw):
+        n = orig(x, **kw)
+        noises.append(n.cpu())
+        return n
+
+    torch.manual_seed(10)
+    init = torch.randn(*shape, device="cuda")
+    torch.randn_like = rec
+    try:
+        out = d.p_sample_loop(model, shape, noise=init, clip_denoised=False, model_kwargs={"y": yc})
+    finally:
+        torch.randn_like = orig
+    it = iter(noises)
+    smp = sampler_ref.Sampler(timestep_respacing="ddim16", inpaint=(mask, motion))
+    want, _ = smp.loop(lambda xx, tt: cmdm_ref.cmdm_forward(sd, xx, tt, y, **_kw(mk)), shape,
+                       noise_fn=lambda x: next(it), init_noise=init.cpu())
+    err = (out.cpu() - want).abs().max().item()
+    print("16-step in-betweening loop max abs err vs oracle %.3e" % err)
+    assert err < TOL

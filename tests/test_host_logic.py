@@ -180,3 +180,20 @@ def test_auto_regressive_driver_indexing():
             assert len(calls) == (T + Ge - 1) // Ge
             if trunc:
                 assert [c[-1] for c in calls] == [min(k * Ge + Ge, T) for k in range(len(calls))]
+
+
+def test_oracle_inpainting_blend_matches_reference_expression():
+    """oracle Sampler(inpaint=...) restates gaussian_diffusion.py:319-323: where the mask is set the prediction is the
+    input motion, elsewhere the model output, and the last step (t=0) returns exactly that blend."""
+    import torch
+    from oracle import sampler_ref
+    g = torch.Generator().manual_seed(1)
+    shape = (2, 3, 2, 5)
+    motion = torch.randn(*shape, generator=g)
+    mask = torch.rand(*shape, generator=g) > 0.5
+    model = lambda x, t: 0.5 * x + 1.0
+    smp = sampler_ref.Sampler(timestep_respacing="ddim4", inpaint=(mask, motion))
+    torch.manual_seed(0)
+    out, x0 = smp.loop(model, shape)
+    assert torch.equal(out[mask], motion[mask]) and torch.equal(x0[mask], motion[mask])
+    assert not torch.equal(out[~mask], motion[~mask])

@@ -114,7 +114,7 @@ int regen_bjft_to_tbi(const float* src, float* dst, int32_t B, int32_t I, int32_
 int regen_tbi_to_bjft(const float* src, float* dst, int32_t B, int32_t I, int32_t T, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * The denoiser: CMDM.forward, arch='online'  (model/cmdm.py:173-252)
+ * The denoiser: CMDM.forward, arch='online' / 'offline'  (model/cmdm.py:173-252)
  * ---------------------------------------------------------------------------------------- */
 
 typedef struct regen_handle regen_handle;
@@ -130,16 +130,18 @@ typedef struct {
   int32_t max_frames;      /* largest T */
   int32_t num_table_steps; /* size of the timestep-embedding table; timesteps must be < this */
   int32_t precision;       /* 0 = bf16x3 split (parity mode), 1 = single-pass bf16 (fast) */
+  int32_t arch;            /* 0 = 'online': causal nn.TransformerDecoder, 1-token memory (model/cmdm.py:75-81, 203-227);
+                              1 = 'offline': nn.TransformerEncoder over [condition token | frames], no mask (:63-71, 228-238) */
 } regen_model_desc;
 
 typedef struct {
   const float *qkv_w, *qkv_b;   /* self_attn.in_proj_{weight[3D,D],bias[3D]} */
   const float *o_w, *o_b;       /* self_attn.out_proj */
-  const float *xv_w, *xv_b;     /* multihead_attn.in_proj_weight[2D:3D], in_proj_bias[2D:3D] */
-  const float *xo_w, *xo_b;     /* multihead_attn.out_proj */
+  const float *xv_w, *xv_b;     /* multihead_attn.in_proj_weight[2D:3D], in_proj_bias[2D:3D]  (arch 0 only) */
+  const float *xo_w, *xo_b;     /* multihead_attn.out_proj                                    (arch 0 only) */
   const float *l1_w, *l1_b;     /* linear1 [F,D] */
   const float *l2_w, *l2_b;     /* linear2 [D,F] */
-  const float *n1_w, *n1_b, *n2_w, *n2_b, *n3_w, *n3_b; /* norm1..3 */
+  const float *n1_w, *n1_b, *n2_w, *n2_b, *n3_w, *n3_b; /* norm1..3 (arch 1: norm1, norm2 only) */
 } regen_layer_weights;
 
 typedef struct {

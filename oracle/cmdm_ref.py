@@ -1,4 +1,4 @@
-"""Oracle (test infrastructure): CMDM.forward, arch='online', restated on CPU fp32.
+"""Oracle (test infrastructure): CMDM.forward, arch='online' and arch='offline', restated on CPU fp32.
 
 Follows model/cmdm.py:173-252 (forward), :265-281 (PositionalEncoding),
 :284-298 (TimestepEmbedder), :301-317 (InputProcess), :329-355 (OutputProcess),
@@ -89,7 +89,7 @@ def embed(sd, timesteps, y, cond_mode):
     return e
 
 
-def cmdm_forward(sd, x, timesteps, y, *, num_layers=8, nhead=4, cond_mode="no_cond", cm_mode="concat"):
+def cmdm_forward(sd, x, timesteps, y, *, num_layers=8, nhead=4, cond_mode="no_cond", cm_mode="concat", arch="online"):
     """x [B,J,F,T], timesteps int64 [B] -> x0_hat [B,J,F,T].  model/cmdm.py:173-252."""
     B, J, F, T = x.shape
     emb = embed(sd, timesteps, y, cond_mode)
@@ -101,6 +101,20 @@ def cmdm_forward(sd, x, timesteps, y, *, num_layers=8, nhead=4, cond_mode="no_co
         h = hx + hc
     else:
         h = _lin(torch.cat((hx, hc), -1), sd["fuse_process.weight"], sd["fuse_process.bias"])
+    if arch == "offline":
+        # model/cmdm.py:228-238: the condition embedding is token 0, positions 0..T, nn.TransformerEncoder
+        # (post-norm encoder layers, no mask: every frame attends to every frame), token 0 dropped at the end
+        h = torch.cat((emb, h), 0) + sd["sequence_pos_encoder.pe"][:T + 1]
+        for l in range(num_layers):
+            p = "seqTransEncoder.layers.%d." % l
+            sa = _mha(h, h, sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"],
+                      sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"], nhead, None)
+            h = _layer_norm(h + sa, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+            ff = _lin(_gelu(_lin(h, sd[p + "linear1.weight"], sd[p + "linear1.bias"])),
+                      sd[p + "linear2.weight"], sd[p + "linear2.bias"])
+            h = _layer_norm(h + ff, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+        out = _lin(h[1:], sd["output_process.poseFinal.weight"], sd["output_process.poseFinal.bias"])
+        return out.reshape(T, B, J, F).permute(1, 2, 3, 0)
     h = h + sd["sequence_pos_encoder.pe"][:T]
     mask = causal_mask(T)
     for l in range(num_layers):

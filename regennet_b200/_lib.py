@@ -22,7 +22,7 @@ REGEN_MAX_LAYERS = 16
 class ModelDesc(ctypes.Structure):
     _fields_ = [(n, c_int) for n in (
         "latent_dim", "num_heads", "ff_size", "num_layers", "input_feats", "cm_mode", "max_batch",
-        "max_frames", "num_table_steps", "precision")]
+        "max_frames", "num_table_steps", "precision", "arch")]
 
 
 class LayerWeights(ctypes.Structure):

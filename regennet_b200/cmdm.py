@@ -1,5 +1,6 @@
 """Conditional motion diffusion model -- host-side mirror of the reference's ``model/cmdm.py``
-for ``arch='online'`` (causal decoder, cm_mode 'concat' or 'add'), backed by libregen_sm100.
+for ``arch='online'`` (causal decoder) and ``arch='offline'`` (encoder with the condition as first token), cm_mode
+'concat' or 'add', backed by libregen_sm100.
 
 The class keeps the reference constructor signature, attribute names and state-dict keys
 (model/cmdm.py:13-111), so ``utils/model_util.create_model_and_diffusion`` + ``load_model_wo_clip``
@@ -125,9 +126,10 @@ class CMDM(nn.Module):
         self.precision = kargs.get('precision', 'bf16x3')
 
         # --- scope of the B200 path: everything else in the reference is a different model
-        if arch != 'online':
-            raise NotImplementedError("regennet_b200.CMDM implements arch='online' only (got %r); the other "
-                                      "architectures of model/cmdm.py:63-89 are outside the sampling hot path" % arch)
+        if arch not in ('online', 'offline'):
+            raise NotImplementedError("regennet_b200.CMDM implements arch='online' and arch='offline' (got %r); the "
+                                      "trans_enc / trans_dec / gru / mlp variants of model/cmdm.py:63-89 are outside "
+                                      "the sampling hot path" % arch)
         if cm_mode not in ('concat', 'add'):
             raise ValueError("cm_mode must be 'concat' or 'add'")
         if emb_trans_dec or wo_pos_emb:
@@ -144,10 +146,16 @@ class CMDM(nn.Module):
         self.sequence_pos_encoder = PositionalEncoding(self.latent_dim, self.dropout)
         if self.cm_mode == 'concat':
             self.fuse_process = nn.Linear(self.latent_dim * 2, self.latent_dim)
-        layer = nn.TransformerDecoderLayer(d_model=self.latent_dim, nhead=self.num_heads,
-                                           dim_feedforward=self.ff_size, dropout=self.dropout,
-                                           activation=activation)
-        self.seqTransDecoder = nn.TransformerDecoder(layer, num_layers=self.num_layers)
+        if arch == 'offline':   # model/cmdm.py:63-71: encoder over [condition token | frames], no mask
+            layer = nn.TransformerEncoderLayer(d_model=self.latent_dim, nhead=self.num_heads,
+                                               dim_feedforward=self.ff_size, dropout=self.dropout,
+                                               activation=activation)
+            self.seqTransEncoder = nn.TransformerEncoder(layer, num_layers=self.num_layers, enable_nested_tensor=False)
+        else:                   # model/cmdm.py:75-81: causal decoder, the condition is a 1-token memory
+            layer = nn.TransformerDecoderLayer(d_model=self.latent_dim, nhead=self.num_heads,
+                                               dim_feedforward=self.ff_size, dropout=self.dropout,
+                                               activation=activation)
+            self.seqTransDecoder = nn.TransformerDecoder(layer, num_layers=self.num_layers)
         self.embed_timestep = TimestepEmbedder(self.latent_dim, self.sequence_pos_encoder)
         if self.cond_mode != 'no_cond':
             if 'text' in self.cond_mode:
@@ -236,7 +244,8 @@ class CMDM(nn.Module):
                               cm_mode=1 if self.cm_mode == 'concat' else 0,
                               max_batch=max(batch_eff, h.max_batch if h else 0),
                               max_frames=max(frames, h.max_frames if h else 0, min(self.num_frames, 196)),
-                              num_table_steps=table_steps, precision=0 if self.precision == 'bf16x3' else 1)
+                              num_table_steps=table_steps, precision=0 if self.precision == 'bf16x3' else 1,
+                              arch=1 if self.arch == 'offline' else 0)
         hp = ctypes.c_void_p()
         dev_index = device.index if device.index is not None else torch.cuda.current_device()
         _lib.check(L.regen_create(ctypes.byref(hp), dev_index, ctypes.byref(desc)), "regen_create")
@@ -264,18 +273,21 @@ class CMDM(nn.Module):
         if 'text' in self.cond_mode:
             w.text_w, w.text_b, w.clip_dim = P(self.embed_text.weight), P(self.embed_text.bias), self.clip_dim
         esz = 4
-        for l, layer in enumerate(self.seqTransDecoder.layers):
+        offline = self.arch == 'offline'
+        for l, layer in enumerate((self.seqTransEncoder if offline else self.seqTransDecoder).layers):
             lw = w.layers[l]
             lw.qkv_w, lw.qkv_b = P(layer.self_attn.in_proj_weight), P(layer.self_attn.in_proj_bias)
             lw.o_w, lw.o_b = P(layer.self_attn.out_proj.weight), P(layer.self_attn.out_proj.bias)
-            # 1-token memory: only the value rows [2D:3D] of the cross-attention in-projection matter
-            lw.xv_w = P(layer.multihead_attn.in_proj_weight) + 2 * D * D * esz
-            lw.xv_b = P(layer.multihead_attn.in_proj_bias) + 2 * D * esz
-            lw.xo_w, lw.xo_b = P(layer.multihead_attn.out_proj.weight), P(layer.multihead_attn.out_proj.bias)
             lw.l1_w, lw.l1_b = P(layer.linear1.weight), P(layer.linear1.bias)
             lw.l2_w, lw.l2_b = P(layer.linear2.weight), P(layer.linear2.bias)
             lw.n1_w, lw.n1_b = P(layer.norm1.weight), P(layer.norm1.bias)
             lw.n2_w, lw.n2_b = P(layer.norm2.weight), P(layer.norm2.bias)
+            if offline:
+                continue
+            # 1-token memory: only the value rows [2D:3D] of the cross-attention in-projection matter
+            lw.xv_w = P(layer.multihead_attn.in_proj_weight) + 2 * D * D * esz
+            lw.xv_b = P(layer.multihead_attn.in_proj_bias) + 2 * D * esz
+            lw.xo_w, lw.xo_b = P(layer.multihead_attn.out_proj.weight), P(layer.multihead_attn.out_proj.bias)
             lw.n3_w, lw.n3_b = P(layer.norm3.weight), P(layer.norm3.bias)
         _lib.check(L.regen_load_weights(hp, ctypes.byref(w), _lib.stream_ptr(device)), "regen_load_weights")
         self._handle = handle

@@ -56,6 +56,7 @@ struct Params {
   __nv_bfloat16* out_hi;  // [T*Beff, 512] (the kernel stores through tm_ohi / tm_olo)
   __nv_bfloat16* out_lo;
   int T, Beff;
+  int causal;  // 1: additive causal mask of model/cmdm.py:168-171 (arch 'online'); 0: no mask (arch 'offline')
   int dbg;  // test-hook only: bit 0 swaps the LBO / SBO fields of the V descriptor (bring-up A/B switch)
   unsigned long long* timeline;  // bring-up instrumentation (null in production): CTA 0 stamps clock64() at events
 };
@@ -96,7 +97,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   const int bh = blockIdx.x / qblocks;
   const int h = bh & 3, b = bh >> 2;
   const int q0 = qb * 128;                                   // first query frame of this CTA
-  const int kv_len = min(p.T, q0 + 128);                     // causal: keys [0, kv_len)
+  const int kv_len = p.causal ? min(p.T, q0 + 128) : p.T;    // causal: keys [0, kv_len)
   const int nkc = (kv_len + TB - 1) / TB;                    // key chunks
   // O: 128 columns, S: TB columns per chunk.  Compact: O overwrites S (S is dead once P has been written).
   constexpr uint32_t TMEM_COLS = C::COMPACT ? 128 : 512;
@@ -211,6 +212,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const int r = q * 32 + lane;           // row in the 128-row tile == TMEM lane
     const int i = q0 + r;                  // query frame
     const bool row_ok = i < p.T && r < (TB == 64 ? 64 : 128);
+    const int jmax = p.causal ? i : p.T - 1;  // last key this query attends to
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float sc = 0.08838834764831845f * 1.4426950408889634f;  // 1/sqrt(128) * log2(e)
 
@@ -228,7 +230,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         const int j0 = kc * TB + c0;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j0 + j <= i && j0 + j < p.T) mx = fmaxf(mx, __uint_as_float(v[j]));
+          if (j0 + j <= jmax && j0 + j < p.T) mx = fmaxf(mx, __uint_as_float(v[j]));
       }
     }
     if (NH == 2) {
@@ -254,8 +256,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
           for (int e = 0; e < 4; ++e) {
             const int j = kc * TB + c0 + j8 + 2 * e;
             float p0 = 0.f, p1 = 0.f;
-            if (row_ok && j <= i) p0 = exp2f((__uint_as_float(v[j8 + 2 * e]) - mx) * sc);
-            if (row_ok && j + 1 <= i) p1 = exp2f((__uint_as_float(v[j8 + 2 * e + 1]) - mx) * sc);
+            if (row_ok && j <= jmax) p0 = exp2f((__uint_as_float(v[j8 + 2 * e]) - mx) * sc);
+            if (row_ok && j + 1 <= jmax) p1 = exp2f((__uint_as_float(v[j8 + 2 * e + 1]) - mx) * sc);
             sum += p0 + p1;
             __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
             hw[e] = *reinterpret_cast<uint32_t*>(&hh);

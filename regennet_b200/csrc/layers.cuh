@@ -156,6 +156,32 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const float* __restric
   *o = v;
 }
 
+// arch 'offline' (model/cmdm.py:234-235): token 0 of sample b' is the condition embedding,
+//   h[b', :] = (e2tab[t[b' % B]] + cond_emb[b']) + pe[0]     -> fp32 row + bf16 (hi, lo) split, rows [0, Beff)
+__global__ void __launch_bounds__(128) build_emb_rows_kernel(const float* __restrict__ e2tab,
+                                                             const float* __restrict__ cond_emb,
+                                                             const float* __restrict__ pe0, const int64_t* __restrict__ t,
+                                                             float* __restrict__ h, __nv_bfloat16* __restrict__ hi,
+                                                             __nv_bfloat16* __restrict__ lo, int B, int n_table) {
+  ptx::griddep_wait();  // PDL: t comes from the step-bookkeeping kernel; h rows are read by the previous step's GEMMs
+  ptx::griddep_launch();
+  const int be = blockIdx.x;
+  int64_t tb = t[be % B];
+  tb = tb < 0 ? 0 : (tb >= n_table ? n_table - 1 : tb);
+  float4 v = __ldg(reinterpret_cast<const float4*>(e2tab + (size_t)tb * D) + threadIdx.x);
+  if (cond_emb) {
+    const float4 c = __ldg(reinterpret_cast<const float4*>(cond_emb + (size_t)be * D) + threadIdx.x);
+    v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+  }
+  const float4 p = __ldg(reinterpret_cast<const float4*>(pe0) + threadIdx.x);
+  v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+  reinterpret_cast<float4*>(h + (size_t)be * D)[threadIdx.x] = v;
+  __nv_bfloat16 hh[4], ll[4];
+  split_bf16(v.x, hh[0], ll[0]); split_bf16(v.y, hh[1], ll[1]); split_bf16(v.z, hh[2], ll[2]); split_bf16(v.w, hh[3], ll[3]);
+  *reinterpret_cast<uint2*>(hi + (size_t)be * D + 4 * threadIdx.x) = *reinterpret_cast<uint2*>(hh);
+  *reinterpret_cast<uint2*>(lo + (size_t)be * D + 4 * threadIdx.x) = *reinterpret_cast<uint2*>(ll);
+}
+
 // cyc[l][r][:] = ctab[t[(r % Beff) % B]][l][:] (+ ccond[r % Beff][l][:])  for r in [0, Beff + 32):
 // the folded cross-attention constant of every layer as a row-cyclic table, so that the 32 consecutive token rows
 // (t, b0 .. b0+31 wrapping into t+1) of an epilogue slice are ONE 2-D TMA box starting at row (row0 % Beff).

@@ -38,8 +38,9 @@ struct regen_handle {
   int device = 0;
   int L = 0, I = 0, Kin = 0, Mmax = 0;
   bool loaded = false, cond_ready = false;
-  // current problem (set by prepare_cond)
-  int B = 0, Beff = 0, T = 0, M = 0;
+  bool offline = false;  // arch 1: encoder over S = T + 1 tokens (condition token first)
+  // current problem (set by prepare_cond): S tokens per sample (T, or T + 1 offline), M = S * Beff token rows
+  int B = 0, Beff = 0, T = 0, S = 0, M = 0;
   bool guidance = false, has_cond = false;
 
   std::vector<void*> allocs;
@@ -54,6 +55,10 @@ struct regen_handle {
   LayerDev layer[REGEN_MAX_LAYERS];
   // activations
   SplitBuf a_in, h_s, att, ffn, qkv_s;
+  SplitBuf h_fr;                     // offline: view of h_s without the condition-token rows (A operand of the output
+                                     // projection, bf16 outputs of the input projection); maps rebuilt per prepare_cond
+  CUtensorMap st_h_fr, st32_h_fr;    // offline: fp32 h without the condition-token rows (stores of the input projection)
+  float* e2tab = nullptr;            // offline: timestep-embedding table [num_table_steps, 512] (model/cmdm.py:291-298)
   CUtensorMap tm_qkv_hi, tm_qkv_lo;  // 3-D [T, Beff, 1536] views of qkv_s for the attention kernel (per prepare_cond)
   CUtensorMap tm_att_hi, tm_att_lo;  // 3-D [T, Beff, 512] store views of the attention output (box 32 frames x 64 d)
   CUtensorMap st_h, st_tmp, st_x0e;  // store-side maps of the fp32 activation buffers (rows = M)
@@ -196,9 +201,10 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
   REGEN_CHECK_ARG(d->input_feats >= 1 && d->input_feats <= 4096, "regen_create: bad input_feats %d", d->input_feats);
   REGEN_CHECK_ARG(d->cm_mode == 0 || d->cm_mode == 1, "regen_create: cm_mode must be 0 (add) or 1 (concat)");
   REGEN_CHECK_ARG(d->precision == 0 || d->precision == 1, "regen_create: precision must be 0 (bf16x3) or 1 (bf16)");
+  REGEN_CHECK_ARG(d->arch == 0 || d->arch == 1, "regen_create: arch must be 0 ('online') or 1 ('offline')");
   REGEN_CHECK_ARG(d->max_batch >= 1 && d->max_frames >= 1 && d->num_table_steps >= 1, "regen_create: bad sizes");
-  REGEN_CHECK_ARG(d->max_frames <= 256, "regen_create: max_frames=%d exceeds the attention kernel's limit of 256 "
-                  "(two key chunks of 128 resident in tensor memory)", d->max_frames);
+  REGEN_CHECK_ARG(d->max_frames + d->arch <= 256, "regen_create: max_frames=%d exceeds the attention kernel's limit of "
+                  "256 tokens (two key chunks of 128 resident in tensor memory)", d->max_frames);
   REGEN_CHECK_ARG((int64_t)d->max_batch * d->max_frames < (1 << 24), "regen_create: max_batch*max_frames too large");
   REGEN_CUDA(cudaSetDevice(device));
   regen_handle* h = new regen_handle();
@@ -207,7 +213,8 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
   h->L = d->num_layers;
   h->I = d->input_feats;
   h->Kin = (int)ceil_div(h->I, 64) * 64;
-  h->Mmax = d->max_batch * d->max_frames;
+  h->offline = d->arch == 1;
+  h->Mmax = d->max_batch * (d->max_frames + d->arch);
   {
     const char* e = getenv("REGEN_DEBUG_SIMT_ATTENTION");
     h->simt_attention = e && e[0] == '1' && layers::attention_smem_bytes(d->max_frames) <= 227 * 1024;
@@ -236,7 +243,8 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
     if ((rc = h->alloc(&h->b_c, D))) break;
     if ((rc = h->alloc(&h->P, (size_t)h->L * D * D))) break;
     if ((rc = h->alloc(&h->qvec, (size_t)h->L * D))) break;
-    if ((rc = h->alloc(&h->ctab, (size_t)d->num_table_steps * h->L * D))) break;
+    if (!h->offline && (rc = h->alloc(&h->ctab, (size_t)d->num_table_steps * h->L * D))) break;
+    if (h->offline && (rc = h->alloc(&h->e2tab, (size_t)d->num_table_steps * D))) break;
     // activations
     if ((rc = alloc_split(h, &h->a_in, Mx, h->Kin, 128))) break;
     if ((rc = alloc_split(h, &h->h_s, Mx, D, 128))) break;
@@ -333,9 +341,11 @@ int regen_load_weights(regen_handle* h, const regen_weight_ptrs* w, void* stream
 
   for (int l = 0; l < L; ++l) {
     const regen_layer_weights& lw = w->layers[l];
-    REGEN_CHECK_ARG(lw.qkv_w && lw.qkv_b && lw.o_w && lw.o_b && lw.xv_w && lw.xv_b && lw.xo_w && lw.xo_b && lw.l1_w &&
-                        lw.l1_b && lw.l2_w && lw.l2_b && lw.n1_w && lw.n1_b && lw.n2_w && lw.n2_b && lw.n3_w && lw.n3_b,
+    REGEN_CHECK_ARG(lw.qkv_w && lw.qkv_b && lw.o_w && lw.o_b && lw.l1_w && lw.l1_b && lw.l2_w && lw.l2_b && lw.n1_w &&
+                        lw.n1_b && lw.n2_w && lw.n2_b,
                     "regen_load_weights: null pointer in layer %d", l);
+    REGEN_CHECK_ARG(h->offline || (lw.xv_w && lw.xv_b && lw.xo_w && lw.xo_b && lw.n3_w && lw.n3_b),
+                    "regen_load_weights: null cross-attention / norm3 pointer in decoder layer %d", l);
     LayerDev& ld = h->layer[l];
     layers::launch_split_rows(lw.qkv_w, D, ld.wqkv.hi, ld.wqkv.lo, D, D, 3 * D, 1, 1, s);
     layers::launch_split_rows(lw.o_w, D, ld.wo.hi, ld.wo.lo, D, D, D, 1, 1, s);
@@ -349,6 +359,7 @@ int regen_load_weights(regen_handle* h, const regen_weight_ptrs* w, void* stream
     TRY(copy_vec(h, &ld.n1b, lw.n1_b, D, s));
     TRY(copy_vec(h, &ld.n2w, lw.n2_w, D, s));
     TRY(copy_vec(h, &ld.n2b, lw.n2_b, D, s));
+    if (h->offline) continue;  // encoder layer: no cross-attention, no norm3
     TRY(copy_vec(h, &ld.n3w, lw.n3_w, D, s));
     TRY(copy_vec(h, &ld.n3b, lw.n3_b, D, s));
     // 1-token cross-attention: c = W_xo (W_xv e + b_xv) + b_xo = P_l e + q_l
@@ -367,9 +378,10 @@ int regen_load_weights(regen_handle* h, const regen_weight_ptrs* w, void* stream
     TRY(h->alloc(&e2, (size_t)nt * D));
     // e1 = silu(pe[0:nt] . W_t0^T + b_t0):  B[k, n] = W_t0[n, k] -> sbk = 1, sbn = D
     layers::launch_sgemm(h->pe, D, 1, w->t0_w, 1, D, w->t0_b, nullptr, e1, D, nt, D, D, 1, s);
-    layers::launch_sgemm(e1, D, 1, w->t2_w, 1, D, w->t2_b, nullptr, e2, D, nt, D, D, 0, s);
-    // ctab = e2 . P^T + q with P stacked [L*D, D]
-    layers::launch_sgemm(e2, D, 1, h->P, 1, D, h->qvec, nullptr, h->ctab, (int64_t)L * D, nt, L * D, D, 0, s);
+    layers::launch_sgemm(e1, D, 1, w->t2_w, 1, D, w->t2_b, nullptr, h->offline ? h->e2tab : e2, D, nt, D, D, 0, s);
+    // ctab = e2 . P^T + q with P stacked [L*D, D]   (online; the offline model uses e2 itself as token 0)
+    if (!h->offline)
+      layers::launch_sgemm(e2, D, 1, h->P, 1, D, h->qvec, nullptr, h->ctab, (int64_t)L * D, nt, L * D, D, 0, s);
   }
   REGEN_LAUNCH_CHECK();
   h->loaded = true;
@@ -384,15 +396,17 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
     return REGEN_ESTATE;
   }
   const int Beff = guidance ? 2 * B : B;
+  const int S = T + (h->offline ? 1 : 0);  // tokens per sample
   REGEN_CHECK_ARG(B >= 1 && T >= 1 && Beff <= h->desc.max_batch && T <= h->desc.max_frames &&
-                      (int64_t)Beff * T <= h->Mmax,
+                      (int64_t)Beff * S <= h->Mmax,
                   "regen_prepare_cond: B=%d (effective %d) T=%d exceed the handle's max_batch=%d / max_frames=%d", B,
                   Beff, T, h->desc.max_batch, h->desc.max_frames);
   REGEN_CHECK_ARG(!action || h->action_emb, "regen_prepare_cond: action indices given but the model has no embed_action");
   REGEN_CHECK_ARG(!text_feat || h->text_w, "regen_prepare_cond: text features given but the model has no embed_text");
   cudaStream_t s = (cudaStream_t)stream;
   const int I = h->I, L = h->L;
-  h->B = B; h->Beff = Beff; h->T = T; h->M = T * Beff;
+  h->B = B; h->Beff = Beff; h->T = T; h->S = S; h->M = S * Beff;
+  const int Mf = T * Beff;  // frame rows (the input / output projections never see the condition token)
   h->guidance = guidance != 0;
   // 'text' models keep a contribution even when unconditional: mask_cond zeroes the CLIP FEATURES, so
   // embed_text still adds its bias (model/cmdm.py:182-184); 'action' embeddings are zeroed themselves (:185-187)
@@ -403,9 +417,10 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
   TRY(regen_bjft_to_tbi(cmotion_bjft, h->cmo_tbi, B, I, T, stream));
   layers::launch_sgemm(h->cmo_tbi, I, 1, h->w_c, 1, I, h->b_c, nullptr, h->scratch, D, T * B, D, I, 0, s);
   {
-    int64_t total = (int64_t)h->M * (D / 4);
-    layers::finalize_condbias_kernel<<<grid_cap(ceil_div(total, 256)), 256, 0, s>>>(h->scratch, h->pe, h->condbias, T,
-                                                                                     B, guidance ? 2 : 1);
+    int64_t total = (int64_t)Mf * (D / 4);
+    // offline: frame f is token f + 1 and gets pe[f + 1] (model/cmdm.py:234-236)
+    layers::finalize_condbias_kernel<<<grid_cap(ceil_div(total, 256)), 256, 0, s>>>(
+        h->scratch, h->pe + (h->offline ? D : 0), h->condbias, T, B, guidance ? 2 : 1);
     count_launch();
   }
   // store-side maps clip at the logical extents, so they are rebuilt for the current M = T * Beff
@@ -418,15 +433,29 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
     TRY(make_tmap_store_2d(&sb->st64_lo, sb->lo, true, h->M, sb->cols, sb->cols, 64));
   }
   TRY(make_tmap_store_2d(&h->st32_h, h->h, false, h->M, D, D, 32));
-  for (int l = 0; l < L; ++l)
+  if (h->offline) {
+    // views without the Beff condition-token rows: outputs of the input projection, A operand of the output projection
+    const size_t off = (size_t)Beff * D;
+    SplitBuf& v = h->h_fr;
+    v.hi = h->h_s.hi + off; v.lo = h->h_s.lo + off; v.cols = D;
+    TRY(make_tmap_bf16_2d(&v.tm_hi, v.hi, Mf, D, D, 128));
+    TRY(make_tmap_bf16_2d(&v.tm_lo, v.lo, Mf, D, D, 128));
+    TRY(make_tmap_store_2d(&v.st_hi, v.hi, true, Mf, D, D));
+    TRY(make_tmap_store_2d(&v.st_lo, v.lo, true, Mf, D, D));
+    TRY(make_tmap_store_2d(&v.st32_hi, v.hi, true, Mf, D, D, 32));
+    TRY(make_tmap_store_2d(&v.st32_lo, v.lo, true, Mf, D, D, 32));
+    TRY(make_tmap_store_2d(&h->st_h_fr, h->h + off, false, Mf, D, D));
+    TRY(make_tmap_store_2d(&h->st32_h_fr, h->h + off, false, Mf, D, D, 32));
+  }
+  for (int l = 0; l < L && !h->offline; ++l)
     TRY(make_tmap_store_2d(&h->tm_cyc[l], h->cyc + (size_t)l * (Beff + 32) * D, false, Beff + 32, D, D, 32));
   TRY(make_tmap_store_2d(&h->st_h, h->h, false, h->M, D, D));
   TRY(make_tmap_store_2d(&h->st_tmp, h->tmp, false, h->M, D, D));
-  if ((I & 3) == 0) TRY(make_tmap_store_2d(&h->st_x0e, h->x0e, false, h->M, I, I));
-  TRY(make_tmap_bf16_3d(&h->tm_qkv_hi, h->qkv_s.hi, 3 * D, Beff, T, T <= 64 ? 64 : 128));
-  TRY(make_tmap_bf16_3d(&h->tm_qkv_lo, h->qkv_s.lo, 3 * D, Beff, T, T <= 64 ? 64 : 128));
-  TRY(make_tmap_bf16_3d(&h->tm_att_hi, h->att.hi, D, Beff, T, 32));
-  TRY(make_tmap_bf16_3d(&h->tm_att_lo, h->att.lo, D, Beff, T, 32));
+  if ((I & 3) == 0) TRY(make_tmap_store_2d(&h->st_x0e, h->x0e, false, Mf, I, I));
+  TRY(make_tmap_bf16_3d(&h->tm_qkv_hi, h->qkv_s.hi, 3 * D, Beff, S, S <= 64 ? 64 : 128));
+  TRY(make_tmap_bf16_3d(&h->tm_qkv_lo, h->qkv_s.lo, 3 * D, Beff, S, S <= 64 ? 64 : 128));
+  TRY(make_tmap_bf16_3d(&h->tm_att_hi, h->att.hi, D, Beff, S, 32));
+  TRY(make_tmap_bf16_3d(&h->tm_att_lo, h->att.lo, D, Beff, S, 32));
   if (h->has_cond) {
     // cond_emb[b'] for b' in [0, Beff): conditional rows [0,B), unconditional rows [B,2B) under guidance
     if (text_model) {
@@ -442,9 +471,10 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
       layers::gather_rows_kernel<<<B, 128, 0, s>>>(h->action_emb, action, h->cond_emb, h->num_actions, 1);
       count_launch();
     }
-    // ccond[b'] = P . cond_emb[b']   (folded 1-token cross-attention of every layer)
-    layers::launch_sgemm(h->cond_emb, D, 1, h->P, 1, D, nullptr, nullptr, h->ccond, (int64_t)L * D, Beff, L * D, D, 0,
-                         s);
+    // ccond[b'] = P . cond_emb[b']   (folded 1-token cross-attention of every layer; offline: cond_emb joins token 0)
+    if (!h->offline)
+      layers::launch_sgemm(h->cond_emb, D, 1, h->P, 1, D, nullptr, nullptr, h->ccond, (int64_t)L * D, Beff, L * D, D, 0,
+                           s);
   }
   REGEN_LAUNCH_CHECK();
   h->cond_ready = true;
@@ -462,25 +492,34 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
                   h->T);
   REGEN_CHECK_ARG(!h->guidance || cfg_scale, "regen_denoise: guidance was requested but cfg_scale is null");
   cudaStream_t s = (cudaStream_t)stream;
-  const int M = h->M, I = h->I, L = h->L, Beff = h->Beff;
+  const int M = h->M, I = h->I, L = h->L, Beff = h->Beff, S = h->S;
+  const bool offline = h->offline;
+  const int Mf = T * Beff;                              // frame rows
+  const size_t fr_off = offline ? (size_t)Beff * D : 0;  // offline: the frames follow the Beff condition-token rows
 
   // A operand of the input projection: split x into bf16 (hi, lo), K padded to a multiple of 64,
   // batch duplicated under guidance
   {
     ProfScope prof(h, CLS_OTHER, s);
-    layers::launch_split_rows(x_tbi, I, h->a_in.hi, h->a_in.lo, h->Kin, I, M, B, h->guidance ? 2 : 1, s);
+    layers::launch_split_rows(x_tbi, I, h->a_in.hi, h->a_in.lo, h->Kin, I, Mf, B, h->guidance ? 2 : 1, s);
+    if (offline) {  // token 0 = timestep embedding + condition embedding + pe[0]   (model/cmdm.py:234-235)
+      launch_pdl(layers::build_emb_rows_kernel, dim3(Beff), dim3(128), 0, s, (const float*)h->e2tab,
+                 h->has_cond ? (const float*)h->cond_emb : (const float*)nullptr, (const float*)h->pe, t, h->h, h->h_s.hi,
+                 h->h_s.lo, B, h->desc.num_table_steps);
+      count_launch();
+    }
   }
 
   // h = x . W_in'^T + condbias      (input_process + fuse_process + positional encoding, hoisted parts in condbias)
   {
-    gemm::Params p = gp(M, D, h->Kin);
+    gemm::Params p = gp(Mf, D, h->Kin);
     p.residual = h->condbias; p.ld_res = D;
-    p.out_f32 = h->h; p.ld_out = D;
-    p.out_hi = h->h_s.hi; p.out_lo = h->h_s.lo; p.ld_split = D;
-    const CUtensorMap hmaps[2] = {h->st_h, h->st32_h};
-    TRY(run_gemm(h, h->a_in, h->w_in, p, hmaps, &h->h_s, s));
+    p.out_f32 = h->h + fr_off; p.ld_out = D;
+    p.out_hi = h->h_s.hi + fr_off; p.out_lo = h->h_s.lo + fr_off; p.ld_split = D;
+    const CUtensorMap hmaps[2] = {offline ? h->st_h_fr : h->st_h, offline ? h->st32_h_fr : h->st32_h};
+    TRY(run_gemm(h, h->a_in, h->w_in, p, hmaps, offline ? &h->h_fr : &h->h_s, s));
   }
-  if (h->fused_ln) {
+  if (h->fused_ln && !offline) {
     ProfScope prof(h, CLS_OTHER, s);
     launch_pdl(layers::build_cyc_kernel, dim3(Beff + 32, L), dim3(128), 0, s, h->ctab,
                h->has_cond ? (const float*)h->ccond : (const float*)nullptr, t, h->cyc, L, B, Beff,
@@ -503,8 +542,9 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
             h->qkv, h->att.hi, h->att.lo, T, Beff);
       } else {
         attn::Params ap;
-        ap.out_hi = h->att.hi; ap.out_lo = h->att.lo; ap.T = T; ap.Beff = Beff; ap.dbg = 0; ap.timeline = nullptr;
-        cudaError_t e = T <= 64 ? attn::launch<64>(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s)
+        ap.out_hi = h->att.hi; ap.out_lo = h->att.lo; ap.T = S; ap.Beff = Beff; ap.causal = offline ? 0 : 1; ap.dbg = 0;
+        ap.timeline = nullptr;
+        cudaError_t e = S <= 64 ? attn::launch<64>(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s)
                                 : attn::launch<128>(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s);
         if (e != cudaSuccess) {
           set_error("attention launch (T=%d Beff=%d) failed: %s", T, Beff, cudaGetErrorString(e));
@@ -513,7 +553,24 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       }
       count_launch();
     }
-    if (h->fused_ln) {  // h = LN2( LN1(h + attn . W_o^T + b_o) + c_l[b] )   -- one kernel
+    if (offline) {  // encoder layer: h = LN1(h + attn . W_o^T + b_o)   (nn.TransformerEncoderLayer, post-norm)
+      ProfScope prof(h, CLS_GEMM, s);
+      gemmln::Params q;
+      q.M = M; q.K = D; q.Beff = Beff; q.bias = ld.bo; q.g1 = ld.n1w; q.b1 = ld.n1b; q.g2 = nullptr; q.b2 = nullptr;
+      q.ln_eps = layers::LN_EPS;
+      q.prefetch_res = h->prefetch_res ? 1 : 0;
+      q.timeline = g_test_timeline;
+      cudaError_t e = h->desc.precision == 0
+          ? gemmln::launch<true, false>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->st32_h,
+                                        h->h_s.st64_hi, h->h_s.st64_lo, q, s)
+          : gemmln::launch<false, false>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->st32_h,
+                                         h->h_s.st64_hi, h->h_s.st64_lo, q, s);
+      if (e != cudaSuccess) {
+        set_error("fused out_proj+LayerNorm launch failed: %s", cudaGetErrorString(e));
+        return REGEN_ECUDA;
+      }
+      count_launch();
+    } else if (h->fused_ln) {  // h = LN2( LN1(h + attn . W_o^T + b_o) + c_l[b] )   -- one kernel
       ProfScope prof(h, CLS_GEMM, s);
       gemmln::Params q;
       q.M = M; q.K = D; q.Beff = Beff; q.bias = ld.bo; q.g1 = ld.n1w; q.b1 = ld.n1b; q.g2 = ld.n2w; q.b2 = ld.n2b;
@@ -557,10 +614,11 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       p.out_hi = h->ffn.hi; p.out_lo = h->ffn.lo; p.ld_split = FF;
       TRY(run_gemm(h, h->h_s, ld.w1, p, nullptr, &h->ffn, s));
     }
-    if (h->fused_ln) {  // h = LN3(h + ffn . W_2^T + b_2)   -- one kernel
+    if (h->fused_ln || offline) {  // h = LN3(h + ffn . W_2^T + b_2)   -- one kernel (encoder layer: norm2)
       ProfScope prof(h, CLS_GEMM, s);
       gemmln::Params q;
-      q.M = M; q.K = FF; q.Beff = Beff; q.bias = ld.b2; q.g1 = ld.n3w; q.b1 = ld.n3b; q.g2 = nullptr; q.b2 = nullptr;
+      q.M = M; q.K = FF; q.Beff = Beff; q.bias = ld.b2; q.g1 = offline ? ld.n2w : ld.n3w; q.b1 = offline ? ld.n2b : ld.n3b;
+      q.g2 = nullptr; q.b2 = nullptr;
       q.ln_eps = layers::LN_EPS;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
       q.timeline = g_test_timeline;
@@ -596,7 +654,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
     }
   }
   {  // x0 = h . W_out^T + b_out   (output_process; rows already in [T,B,I] order)
-    gemm::Params p = gp(M, I, D);
+    gemm::Params p = gp(Mf, I, D);
     p.bias = h->b_out;
     p.out_f32 = h->guidance ? h->x0e : x0_tbi; p.ld_out = I;
     CUtensorMap st_x0[2];
@@ -604,11 +662,11 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
     if ((I & 3) == 0 && h->tma_store) {
       // store maps (box 16 and box 32) of the output buffer; a caller-owned output is encoded per call (~1 us each)
       float* dst = h->guidance ? h->x0e : x0_tbi;
-      TRY(make_tmap_store_2d(&st_x0[0], dst, false, M, I, I, 16));
-      TRY(make_tmap_store_2d(&st_x0[1], dst, false, M, I, I, 32));
+      TRY(make_tmap_store_2d(&st_x0[0], dst, false, Mf, I, I, 16));
+      TRY(make_tmap_store_2d(&st_x0[1], dst, false, Mf, I, I, 32));
       om = st_x0;
     }
-    TRY(run_gemm(h, h->h_s, h->w_out, p, om, nullptr, s));
+    TRY(run_gemm(h, offline ? h->h_fr : h->h_s, h->w_out, p, om, nullptr, s));
   }
   if (h->guidance) {
     int64_t total = (int64_t)T * B * I;
@@ -725,7 +783,8 @@ int regen_test_attention(const float* qkv, float* out, int32_t B, int32_t T, int
   if (!rc) rc = make_tmap_bf16_3d(&tol, ol, D, B, T, 32);
   if (!rc) {
     attn::Params ap;
-    ap.out_hi = oh; ap.out_lo = ol; ap.T = T; ap.Beff = B; ap.dbg = dbg; ap.timeline = g_test_timeline;
+    ap.out_hi = oh; ap.out_lo = ol; ap.T = T; ap.Beff = B; ap.causal = (dbg & 2) ? 0 : 1; ap.dbg = dbg & 1;
+    ap.timeline = g_test_timeline;
     cudaError_t e = T <= 64 ? attn::launch<64>(th, tl, toh, tol, ap, s) : attn::launch<128>(th, tl, toh, tol, ap, s);
     if (e == cudaSuccess) {
       layers::merge_split_kernel<<<grid_cap(ceil_div((int64_t)M * D, 256)), 256, 0, s>>>(oh, ol, out, (int64_t)M * D);

@@ -24,8 +24,9 @@ def positional_table(max_len, d):
 
 
 def state_dict_spec(njoints=56, nfeats=6, latent_dim=512, ff_size=1024, num_layers=8,
-                    cond_mode="no_cond", num_actions=1, clip_dim=512, cm_mode="concat"):
-    """Ordered list of (key, shape, kind); kind in {'w','b','ln_w','ln_b','emb'}."""
+                    cond_mode="no_cond", num_actions=1, clip_dim=512, cm_mode="concat", arch="online"):
+    """Ordered list of (key, shape, kind); kind in {'w','b','ln_w','ln_b','emb'}.  arch 'online' gives the
+    nn.TransformerDecoder keys (model/cmdm.py:75-81), 'offline' the nn.TransformerEncoder keys (:63-71)."""
     D, I, Fd = latent_dim, njoints * nfeats, ff_size
     spec = [
         ("input_process.poseEmbedding.weight", (D, I), "w"),
@@ -35,7 +36,21 @@ def state_dict_spec(njoints=56, nfeats=6, latent_dim=512, ff_size=1024, num_laye
     ]
     if cm_mode == "concat":
         spec += [("fuse_process.weight", (D, 2 * D), "w"), ("fuse_process.bias", (D,), "b")]
-    for l in range(num_layers):
+    for l in range(num_layers if arch == "offline" else 0):
+        p = "seqTransEncoder.layers.%d." % l
+        spec += [
+            (p + "self_attn.in_proj_weight", (3 * D, D), "w"),
+            (p + "self_attn.in_proj_bias", (3 * D,), "b"),
+            (p + "self_attn.out_proj.weight", (D, D), "w"),
+            (p + "self_attn.out_proj.bias", (D,), "b"),
+            (p + "linear1.weight", (Fd, D), "w"),
+            (p + "linear1.bias", (Fd,), "b"),
+            (p + "linear2.weight", (D, Fd), "w"),
+            (p + "linear2.bias", (D,), "b"),
+            (p + "norm1.weight", (D,), "ln_w"), (p + "norm1.bias", (D,), "ln_b"),
+            (p + "norm2.weight", (D,), "ln_w"), (p + "norm2.bias", (D,), "ln_b"),
+        ]
+    for l in range(num_layers if arch != "offline" else 0):
         p = "seqTransDecoder.layers.%d." % l
         spec += [
             (p + "self_attn.in_proj_weight", (3 * D, D), "w"),

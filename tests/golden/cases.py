@@ -56,3 +56,30 @@ LOOP_CASES = {
 }
 
 RESPACINGS = ["", "ddim5", "ddim20", "ddim100", "25", "10,15,20", "1000"]
+
+
+# arch='offline' (model/cmdm.py:63-71, 228-238): nn.TransformerEncoder, condition token first, no causal mask.
+# Separate golden file (forward_offline.npz, make_golden_offline.py) so the online goldens stay untouched.
+OFFLINE_MODELS = {
+    "ntu_off": dict(MODELS["ntu"], arch="offline"),
+    "chi3d_off_add": dict(MODELS["chi3d"], arch="offline", cm_mode="add"),
+    "hml_off": dict(MODELS["hml"], arch="offline"),
+}
+
+
+def synth_kw_offline(name):
+    m = OFFLINE_MODELS[name]
+    return dict(njoints=m["njoints"], nfeats=m["nfeats"], latent_dim=m["latent_dim"], ff_size=m["ff_size"],
+                num_layers=m["num_layers"], cond_mode=m["cond_mode"], num_actions=m["num_actions"],
+                clip_dim=512, cm_mode=m["cm_mode"], arch="offline")
+
+
+OFFLINE_FORWARD_CASES = {
+    "off_ntu": dict(model="ntu_off", B=2, T=60, t=[999, 3], wseed=4, xseed=20),
+    "off_ntu_ragged_T37": dict(model="ntu_off", B=3, T=37, t=[5, 500, 77], wseed=4, xseed=21),
+    "off_chi3d_add_cfg": dict(model="chi3d_off_add", B=2, T=150, t=[640, 12], wseed=5, xseed=22, cfg_scale=2.5),
+    "off_hml_text": dict(model="hml_off", B=2, T=196, t=[321, 900], wseed=6, xseed=23),
+}
+OFFLINE_LOOP_CASES = {
+    "off_loop_ntu_p10": dict(model="ntu_off", B=2, T=60, respacing="ddim10", ddim=False, wseed=4, xseed=20, seed=11),
+}

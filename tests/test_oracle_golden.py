@@ -79,3 +79,37 @@ def test_rot6d_matches_reference():
     g = np.load(os.path.join(HERE, "rot6d.npz"))
     R = sampler_ref.rotation_6d_to_matrix(torch.from_numpy(g["d6"])).numpy()
     assert np.allclose(R, g["R"], atol=1e-6, equal_nan=True)
+
+
+def _kw_off(mk):
+    return dict(_kw(mk), arch="offline")
+
+
+@pytest.mark.parametrize("name", sorted(cases.OFFLINE_FORWARD_CASES))
+def test_offline_forward_matches_reference(name):
+    """arch='offline' (model/cmdm.py:63-71, 228-238) against the reference's outputs (make_golden_offline.py)."""
+    c = cases.OFFLINE_FORWARD_CASES[name]
+    mk = cases.OFFLINE_MODELS[c["model"]]
+    gold = np.load(os.path.join(HERE, "forward_offline.npz"))[name]
+    x, y = synthetic.make_inputs(c["B"], mk["njoints"], mk["nfeats"], c["T"], seed=c["xseed"],
+                                 cond_mode=mk["cond_mode"], num_actions=mk["num_actions"], scale=c.get("cfg_scale"))
+    sd = synthetic.make_state_dict(seed=c["wseed"], **cases.synth_kw_offline(c["model"]))
+    fwd = cmdm_ref.cfg_forward if "cfg_scale" in c else cmdm_ref.cmdm_forward
+    with torch.no_grad():
+        out = fwd(sd, x, torch.tensor(c["t"], dtype=torch.long), y, **_kw_off(mk))
+    assert out.shape == gold.shape
+    assert np.abs(out.numpy() - gold).max() < TOL
+
+
+def test_offline_sampling_loop_matches_reference():
+    name = "off_loop_ntu_p10"
+    c = cases.OFFLINE_LOOP_CASES[name]
+    mk = cases.OFFLINE_MODELS[c["model"]]
+    gold = np.load(os.path.join(HERE, "loops_offline.npz"))[name]
+    _, y = synthetic.make_inputs(c["B"], mk["njoints"], mk["nfeats"], c["T"], seed=c["xseed"])
+    sd = synthetic.make_state_dict(seed=c["wseed"], **cases.synth_kw_offline(c["model"]))
+    smp = sampler_ref.Sampler(timestep_respacing=c["respacing"])
+    torch.manual_seed(c["seed"])
+    out, _ = smp.loop(lambda xx, tt: cmdm_ref.cmdm_forward(sd, xx, tt, y, **_kw_off(mk)),
+                      (c["B"], mk["njoints"], mk["nfeats"], c["T"]))
+    assert np.abs(out.numpy() - gold).max() < TOL

@@ -44,9 +44,26 @@ def run(name, model_name, B, T, cfg, ddim, respacing, K=30, W=5):
     nn = (_lib.c_int * 4)()
     _lib.check(lib.regen_profile_end(inner._handle.ptr, ms, nn), "pe")
     dt = time.perf_counter() - t0
-    print("%-34s B=%3d T=%3d cfg=%d: %.3f ms/step (%.1f steps/s) | gemm %.3f attn %.3f ln %.3f other %.3f ms" % (
-        name, B, T, cfg, dt / K * 1e3, K / dt, ms[0] / K, ms[1] / K, ms[2] / K, ms[3] / K))
     gen.close()
+    # throughput through the CUDA-graph driver (what p_sample_loop / ddim_sample_loop use)
+    img = torch.randn(*shape, device=dev)
+    gen = sess.run(diff, "ddim" if ddim else "p", img, list(range(n))[::-1], False, 0.0, graph=True, unroll=10)
+    done = 0
+    while done < 11:
+        done += next(gen)["steps"]
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    KG = 0
+    while KG < (60 if n >= 100 else 20):
+        KG += next(gen)["steps"]
+    e1.record()
+    torch.cuda.synchronize()
+    gms = e0.elapsed_time(e1) / KG
+    gen.close()
+    print("%-34s B=%3d T=%3d cfg=%d: graph driver %.3f ms/step (%.1f steps/s) | host-enqueued %.3f ms/step | "
+          "gemm %.3f attn %.3f ln %.3f other %.3f ms" % (name, B, T, cfg, gms, 1e3 / gms, dt / K * 1e3, ms[0] / K,
+                                                         ms[1] / K, ms[2] / K, ms[3] / K))
 
 
 run("config1 NTU B=1 (latency)", "ntu", 1, 60, False, False, [1000], K=100)

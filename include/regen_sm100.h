@@ -204,6 +204,13 @@ int regen_test_gemm(const float* A, const float* W, const float* bias, const flo
 /* Bring-up instrumentation for regen_test_gemm: when set to a device buffer of 128 uint64, CTA 0 of the next test
  * GEMMs records SM clock values at pipeline events (see gemm_sm100.cuh Params::timeline).  NULL disables. */
 int regen_test_gemm_timeline(unsigned long long* device_buf128);
+/* Bring-up instrumentation: from now on the tcgen05 kernels regen_denoise launches (GEMM, fused GEMM+LN, attention) log
+ * into device_buf[2*slot] = earliest "inputs available" time and [2*slot+1] = latest CTA exit time (nanoseconds of the
+ * GPU global timer, atomicMin / atomicMax -- initialise to ~0 / 0), slot = launch order since this call.  The slots are
+ * baked into captured graphs; capacity_slots = 0 turns logging off.  The GEMM kernels also store every CTA's exit time
+ * at device_buf[2*capacity_slots + slot*160 + blockIdx.x] (the buffer must hold 2*cap + 160*cap words).
+ * Used by tools/step_timeline.py only. */
+int regen_test_step_log(regen_handle* h, unsigned long long* device_buf, int32_t capacity_slots);
 
 /* Kernel-level test hook (tests/ only): causal 4-head self-attention (head_dim 128) of a seq-first q|k|v
  * tensor through the tcgen05 attention kernel -- the arithmetic of nn.MultiheadAttention with the causal

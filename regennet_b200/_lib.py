@@ -66,6 +66,7 @@ _SIGNATURES = {
     "regen_denoise": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "regen_test_gemm": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
     "regen_test_gemm_timeline": (c_int, [c_void_p]),
+    "regen_test_step_log": (c_int, [c_void_p, c_void_p, c_int]),
     "regen_test_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
 }
 

@@ -59,6 +59,8 @@ struct Params {
   int causal;  // 1: additive causal mask of model/cmdm.py:168-171 (arch 'online'); 0: no mask (arch 'offline')
   int dbg;  // test-hook only: bit 0 swaps the LBO / SBO fields of the V descriptor (bring-up A/B switch)
   unsigned long long* timeline;  // bring-up instrumentation (null in production): CTA 0 stamps clock64() at events
+  unsigned long long* steplog;   // whole-step timeline (ptx::steplog_begin / steplog_end), null in production
+  int steplog_slot, steplog_cta;  // steplog_cta: word offset of the per-CTA exit-time table (0 = off)
 };
 
 #define REGEN_ATL(k)                                                                      \
@@ -127,6 +129,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   const uint32_t tmem_base = *tmem_base_smem;
   ptx::griddep_wait();    // PDL: q | k | v come from the preceding QKV GEMM
   ptx::griddep_launch();  // the successor launches once every CTA of this grid has started
+  ptx::steplog_begin(p.steplog, p.steplog_slot);
   if (threadIdx.x == 0) REGEN_ATL(1);
 
   if (warp == 0) {
@@ -332,6 +335,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   ptx::tcgen05_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) REGEN_ATL(9);
+  ptx::steplog_end(p.steplog, p.steplog_slot, p.steplog_cta);
   if (warp == 0) {
     ptx::tcgen05_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);

@@ -61,6 +61,8 @@ struct Params {
   float ln_eps;
   int prefetch_res;              // 1: L2-prefetch the residual tile during the main loop (REGEN_DEBUG_NO_RES_PREFETCH=1 -> 0)
   unsigned long long* timeline;  // bring-up instrumentation (null in production), see tools/ln_timeline.py
+  unsigned long long* steplog;   // whole-step timeline (ptx::steplog_begin / steplog_end), null in production
+  int steplog_slot, steplog_cta;  // steplog_cta: word offset of the per-CTA exit-time table (0 = off)
 };
 
 #define REGEN_LTL(k)                                                                                   \
@@ -135,6 +137,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   const uint32_t tmem_base = *tmem_base_smem;
   ptx::griddep_wait();    // PDL: the setup above overlapped the previous kernel's tail
   ptx::griddep_launch();
+  ptx::steplog_begin(p.steplog, p.steplog_slot);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -462,6 +465,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 
   ptx::tcgen05_fence_before();
   ptx::cluster_sync();
+  ptx::steplog_end(p.steplog, p.steplog_slot, p.steplog_cta);
   if (threadIdx.x == 0) REGEN_LTL(10);
   if (warp == 1) {
     ptx::tcgen05_fence_after();

@@ -58,6 +58,8 @@ struct Params {
   //   [9+2i] MMA of tile i: last instruction issued  [40+2i] epilogue of tile i: accumulator ready  [41+2i] done
   //   [80..] fine-grained stamps inside the first epilogue sub-chunks of tile 0 (warp 2)
   unsigned long long* timeline;
+  unsigned long long* steplog;  // whole-step timeline (ptx::steplog_begin / steplog_end), null in production
+  int steplog_slot, steplog_cta;  // steplog_cta: word offset of the per-CTA exit-time table (0 = off)
 };
 
 #define REGEN_TL(slot)                                                        \
@@ -428,6 +430,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   // PDL: everything above overlapped the previous kernel's tail; its results are needed from here on
   ptx::griddep_wait();
   ptx::griddep_launch();
+  ptx::steplog_begin(p.steplog, p.steplog_slot);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -519,6 +522,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   if (p.tma_store && warp >= 2 && lane == 0) ptx::bulk_wait<0>();  // all bulk stores of this thread complete
   ptx::tcgen05_fence_before();
   __syncthreads();
+  ptx::steplog_end(p.steplog, p.steplog_slot, p.steplog_cta);
   if (warp == 1) {
     ptx::tcgen05_fence_after();
     ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -629,6 +633,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   const uint32_t tmem_base = *tmem_base_smem;
   ptx::griddep_wait();    // PDL: the setup above overlapped the previous kernel's tail
   ptx::griddep_launch();  // the next kernel's CTAs may take over each SM as soon as this CTA exits
+  ptx::steplog_begin(p.steplog, p.steplog_slot);
   if (threadIdx.x == 0) REGEN_TL(1);
 
   if (warp == 0) {
@@ -729,6 +734,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   if (p.tma_store && warp >= 2 && lane == 0) ptx::bulk_wait<0>();  // all bulk stores of this thread complete
   ptx::tcgen05_fence_before();
   ptx::cluster_sync();  // no CTA may exit (or free TMEM) while its peer can still touch its smem / barriers
+  ptx::steplog_end(p.steplog, p.steplog_slot, p.steplog_cta);
   if (threadIdx.x == 0) REGEN_TL(2);
   if (warp == 1) {
     ptx::tcgen05_fence_after();

@@ -65,6 +65,8 @@ struct regen_handle {
   CUtensorMap st32_h;                // h with box 32 x 32: residual load + store of the fused GEMM+LayerNorm kernel
   bool tma_store = true;             // REGEN_DEBUG_NO_TMA_STORE=1: st.global epilogue (A/B measurements)
   bool fused_ln = true;              // REGEN_DEBUG_NO_FUSED_LN=1: GEMM -> tmp -> LayerNorm kernels
+  unsigned long long* steplog = nullptr;  // regen_test_step_log: whole-step timeline buffer (2 words per launch slot)
+  int steplog_slot = 0, steplog_cap = 0;
   bool prefetch_res = true;          // REGEN_DEBUG_NO_RES_PREFETCH=1: no L2 prefetch of the residual tile (A/B)
   float* cyc = nullptr;              // [L][max_batch + 32][512] row-cyclic cross-attention constants (per denoise)
   CUtensorMap tm_cyc[REGEN_MAX_LAYERS];
@@ -164,6 +166,11 @@ int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, gemm::Params
       om.hi = wide ? osplit->st32_hi : osplit->st_hi;
       om.lo = wide ? osplit->st32_lo : osplit->st_lo;
     }
+  }
+  if (h->steplog && h->steplog_slot < h->steplog_cap) {
+    p.steplog = h->steplog;
+    p.steplog_slot = h->steplog_slot++;
+    p.steplog_cta = 2 * h->steplog_cap;
   }
   cudaError_t e;
   if (use_pair_kernel(p.M))
@@ -544,6 +551,8 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
         attn::Params ap;
         ap.out_hi = h->att.hi; ap.out_lo = h->att.lo; ap.T = S; ap.Beff = Beff; ap.causal = offline ? 0 : 1; ap.dbg = 0;
         ap.timeline = nullptr;
+        ap.steplog = nullptr; ap.steplog_slot = 0; ap.steplog_cta = 0;
+        if (h->steplog && h->steplog_slot < h->steplog_cap) { ap.steplog = h->steplog; ap.steplog_slot = h->steplog_slot++; }
         cudaError_t e = S <= 64 ? attn::launch<64>(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s)
                                 : attn::launch<128>(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s);
         if (e != cudaSuccess) {
@@ -560,6 +569,10 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       q.ln_eps = layers::LN_EPS;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
       q.timeline = g_test_timeline;
+      q.steplog = nullptr; q.steplog_slot = 0; q.steplog_cta = 0;
+      if (h->steplog && h->steplog_slot < h->steplog_cap) {
+        q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;
+      }
       cudaError_t e = h->desc.precision == 0
           ? gemmln::launch<true, false>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->st32_h,
                                         h->h_s.st64_hi, h->h_s.st64_lo, q, s)
@@ -577,6 +590,10 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       q.ln_eps = layers::LN_EPS;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
       q.timeline = g_test_timeline;
+      q.steplog = nullptr; q.steplog_slot = 0; q.steplog_cta = 0;
+      if (h->steplog && h->steplog_slot < h->steplog_cap) {
+        q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;
+      }
       cudaError_t e = h->desc.precision == 0
           ? gemmln::launch<true, true>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->tm_cyc[l],
                                        h->h_s.st64_hi, h->h_s.st64_lo, q, s)
@@ -622,6 +639,10 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       q.ln_eps = layers::LN_EPS;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
       q.timeline = g_test_timeline;
+      q.steplog = nullptr; q.steplog_slot = 0; q.steplog_cta = 0;
+      if (h->steplog && h->steplog_slot < h->steplog_cap) {
+        q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;
+      }
       cudaError_t e = h->desc.precision == 0
           ? gemmln::launch<true, false>(h->ffn.tm_hi, h->ffn.tm_lo, ld.w2.tm_hi2, ld.w2.tm_lo2, h->st32_h, h->st32_h,
                                         h->h_s.st64_hi, h->h_s.st64_lo, q, s)
@@ -714,6 +735,14 @@ int regen_profile_end(regen_handle* h, float* ms, int32_t* launches) {
 
 // Kernel-level test hook: C = A . W^T (+bias)(+residual)(gelu) through the tcgen05 GEMM, fp32 in / out.
 
+int regen_test_step_log(regen_handle* h, unsigned long long* device_buf, int32_t capacity_slots) {
+  REGEN_CHECK_ARG(h && capacity_slots >= 0, "regen_test_step_log: bad argument");
+  h->steplog = capacity_slots > 0 ? device_buf : nullptr;
+  h->steplog_cap = capacity_slots;
+  h->steplog_slot = 0;
+  return REGEN_OK;
+}
+
 int regen_test_gemm_timeline(unsigned long long* device_buf128) {
   g_test_timeline = device_buf128;
   return REGEN_OK;
@@ -742,7 +771,7 @@ int regen_test_gemm(const float* A, const float* W, const float* bias, const flo
     gemm::Params p = gp(M, N, Kp);
     p.bias = bias; p.residual = residual; p.ld_res = N; p.out_f32 = out; p.ld_out = N; p.gelu = gelu;
     p.timeline = g_test_timeline;
-    gemm::OutMaps om;
+    gemm::OutMaps om;  // (gp() zeroed steplog)
     const char* nt = getenv("REGEN_DEBUG_NO_TMA_STORE");
     if ((N & 3) == 0 && !(nt && nt[0] == '1') &&
         make_tmap_store_2d(&om.f32, out, false, M, N, N, 16) == REGEN_OK)
@@ -785,6 +814,7 @@ int regen_test_attention(const float* qkv, float* out, int32_t B, int32_t T, int
     attn::Params ap;
     ap.out_hi = oh; ap.out_lo = ol; ap.T = T; ap.Beff = B; ap.causal = (dbg & 2) ? 0 : 1; ap.dbg = dbg & 1;
     ap.timeline = g_test_timeline;
+    ap.steplog = nullptr; ap.steplog_slot = 0; ap.steplog_cta = 0;
     cudaError_t e = T <= 64 ? attn::launch<64>(th, tl, toh, tol, ap, s) : attn::launch<128>(th, tl, toh, tol, ap, s);
     if (e == cudaSuccess) {
       layers::merge_split_kernel<<<grid_cap(ceil_div((int64_t)M * D, 256)), 256, 0, s>>>(oh, ol, out, (int64_t)M * D);

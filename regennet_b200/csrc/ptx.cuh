@@ -64,6 +64,27 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+// Whole-step GPU timeline (bring-up instrumentation, tools/step_timeline.py): when a kernel gets a non-null log pointer,
+// thread 0 of every CTA folds the nanosecond global timer into record `slot` -- [0] = earliest "inputs available"
+// (right after griddepcontrol.wait), [1] = latest CTA exit -- so kernel spans and the gaps between kernels of a replayed
+// CUDA graph can be read back without a system profiler (nsys is not available on the GPU boxes).
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void steplog_begin(unsigned long long* log, int slot) {
+  if (log && threadIdx.x == 0) atomicMin(log + 2 * slot, globaltimer_ns());
+}
+// per_cta_base > 0: additionally store every CTA's own exit time at log[per_cta_base + slot * 160 + blockIdx.x]
+__device__ __forceinline__ void steplog_end(unsigned long long* log, int slot, int per_cta_base = 0) {
+  if (log && threadIdx.x == 0) {
+    const unsigned long long t = globaltimer_ns();
+    atomicMax(log + 2 * slot + 1, t);
+    if (per_cta_base > 0) log[per_cta_base + slot * 160 + blockIdx.x] = t;
+  }
+}
+
 // Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
 // start while its predecessor in the stream is still running: griddep_wait() blocks until the predecessor grid has
 // completed and its memory operations are visible (a no-op for ordinary launches); griddep_launch() lets the successor

@@ -255,3 +255,30 @@ def test_inpainting_fast_route_matches_generic_route_and_oracle(built_lib, monke
     err = (out.cpu() - want).abs().max().item()
     print("16-step in-betweening loop max abs err vs oracle %.3e" % err)
     assert err < TOL
+
+
+def test_graph_driver_with_editing_arguments(built_lib, monkeypatch):
+    """skip_timesteps / init_image (q_sample start, sample/edit.py), a caller-supplied noise tensor and progress=True go
+    through the same graph driver; all must equal the step-by-step driver bit for bit."""
+    model, sd = get_model("ntu", 0)
+    shape = (2, 56, 6, 60)
+    _, y = synthetic.make_inputs(2, 56, 6, 60, seed=71)
+    yc = to_cuda(y)
+    d = _diffusion("ddim30")
+    g = torch.Generator().manual_seed(72)
+    init_image = torch.randn(*shape, generator=g).cuda()
+    noise = torch.randn(*shape, generator=g).cuda()
+    outs = []
+    for mode in ("0", "6"):
+        monkeypatch.setenv("REGEN_CUDA_GRAPH", mode)
+        torch.manual_seed(4)
+        outs.append(d.p_sample_loop(model, shape, noise=noise.clone(), clip_denoised=False, model_kwargs={"y": yc},
+                                    skip_timesteps=7, init_image=init_image, progress=True))
+    assert torch.equal(outs[0], outs[1])
+    # dump_steps keeps every requested intermediate sample: step-by-step driver, values equal to the plain loop's prefix
+    monkeypatch.setenv("REGEN_CUDA_GRAPH", "")
+    torch.manual_seed(4)
+    dumps = d.p_sample_loop(model, shape, clip_denoised=False, model_kwargs={"y": yc}, dump_steps=[0, 10, 29])
+    torch.manual_seed(4)
+    final = d.p_sample_loop(model, shape, clip_denoised=False, model_kwargs={"y": yc})
+    assert len(dumps) == 3 and torch.equal(dumps[-1], final)

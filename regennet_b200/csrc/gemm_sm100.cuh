@@ -53,6 +53,7 @@ struct Params {
   int ld_split;
   int gelu;                 // exact-erf GELU after bias/residual
   int tma_store;            // 1: outputs are written with TMA stores through the tm_o* tensor maps (needs N % 4 == 0)
+  int tail_split;           // pair kernel: the tiles of the last, partial wave are cut into 1 / 2 / 4 column slices (set by launch2)
   // bring-up instrumentation (test hook only, null in production): CTA 0 records clock64() at pipeline events
   //   [0] kernel entry  [1] setup done  [2] kernel exit  [8+2i] MMA of tile i: operands of first k-block landed
   //   [9+2i] MMA of tile i: last instruction issued  [40+2i] epilogue of tile i: accumulator ready  [41+2i] done
@@ -604,6 +605,20 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   const int tiles_n = (p.N + BN - 1) / BN;
   const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
   const int num_tiles = tiles_n * tiles_m;
+  // Work units.  The tiles of all complete waves are 256 x BN; the tiles of the last, partial wave (R = num_tiles mod
+  // num_clusters of them, which would keep R clusters busy for a whole tile time while the others idle) are cut into
+  // `split` column slices of BN / split columns, R * split <= num_clusters, so the tail costs 1 / split of a tile.
+  const int split = p.tail_split > 1 ? p.tail_split : 1;
+  const int full_tiles = split > 1 ? (num_tiles / num_clusters) * num_clusters : num_tiles;
+  const int num_units = full_tiles + (num_tiles - full_tiles) * split;
+  auto decode = [&](int u, int& tile, int& ncol0, int& width) {
+    if (u < full_tiles) {
+      tile = u; ncol0 = 0; width = BN;
+    } else {
+      const int k = u - full_tiles;
+      tile = full_tiles + k / split; width = BN / split; ncol0 = (k % split) * width;
+    }
+  };
   if (threadIdx.x == 0) REGEN_TL(0);
 
   if (warp == 0 && lane == 0) {
@@ -641,9 +656,12 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int u = cluster_id; u < num_units; u += num_clusters) {
+        int tile, ncol0, width;
+        decode(u, tile, ncol0, width);
         const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM;
-        const int nw = (tile % tiles_n) * BN + (int)rank * (BN / 2);
+        // this CTA's half of the W slice; the box always has BN / 2 rows, a narrower slice just uses its first rows
+        const int nw = (tile % tiles_n) * BN + ncol0 + (int)rank * (width / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
@@ -664,11 +682,13 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (rank == 0 && lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(2 * BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      for (int u = cluster_id; u < num_units; u += num_clusters, ++it) {
+        int tile, ncol0, width;
+        decode(u, tile, ncol0, width);
+        const uint32_t idesc = ptx::umma_idesc_bf16_f32(2 * BM, width);
         const int buf = it & 1;
         ptx::mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);  // both CTAs drained this accumulator
         ptx::tcgen05_fence_after();
@@ -711,18 +731,24 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const int part = (warp - 2) >> 2;
     uint8_t* stg = staging + (warp - 2) * (C::STG_BYTES / EW);
     int it = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
-      const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM, n0 = (tile % tiles_n) * BN;
+    for (int u = cluster_id; u < num_units; u += num_clusters, ++it) {
+      int tile, ncol0, width;
+      decode(u, tile, ncol0, width);
+      const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM, n0 = (tile % tiles_n) * BN + ncol0;
       const int buf = it & 1;
       ptx::mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
       if (warp == 2 && lane == 0 && it < 16) REGEN_TL(40 + 2 * it);
       ptx::tcgen05_fence_after();
       const uint32_t acc = tmem_base + (uint32_t)(buf * BN + part * PCOLS) + ((uint32_t)(q * 32) << 16);
-      if constexpr (EW == 16)
-        epilogue_slice32<PCOLS>(p, &tm_o32, &tm_ohi, &tm_olo, stg, acc, m0 + q * 32, n0 + part * PCOLS, lane);
-      else
-        epilogue_slice<RES, true>(p, &tm_o32, &tm_ohi, &tm_olo, stg, acc, m0 + q * 32, n0 + part * PCOLS, PCOLS, lane,
-                                  warp == 2 && it == 0);
+      // a column slice narrower than the tile only has accumulator columns [0, width): the other parts just release
+      if (part * PCOLS < width) {
+        if constexpr (EW == 16)
+          epilogue_slice32<PCOLS>(p, &tm_o32, &tm_ohi, &tm_olo, stg, acc, m0 + q * 32, n0 + part * PCOLS, lane);
+        else
+          epilogue_slice<RES, true>(p, &tm_o32, &tm_ohi, &tm_olo, stg, acc, m0 + q * 32, n0 + part * PCOLS,
+                                    width - part * PCOLS < PCOLS ? width - part * PCOLS : PCOLS, lane,
+                                    warp == 2 && it == 0);
+      }
       if (warp == 2 && lane == 0 && it < 16) REGEN_TL(41 + 2 * it);
       ptx::tcgen05_fence_before();
       __syncwarp();
@@ -756,16 +782,28 @@ inline cudaError_t launch2_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo
   }
   const int64_t tiles = ceil_div(p.N, BN) * ceil_div(p.M, 2 * BM);
   int clusters = (int)(tiles < kNumSMs / 2 ? tiles : kNumSMs / 2);
-  {
-    static int cap = -1;  // REGEN_DEBUG_GEMM_MAXCLUSTERS: bring-up only (L2-bandwidth experiments)
-    if (cap < 0) {
-      const char* e = getenv("REGEN_DEBUG_GEMM_MAXCLUSTERS");
-      cap = e ? atoi(e) : 0;
-    }
-    if (cap > 0 && clusters > cap) clusters = cap;
+  static int cap = -1, no_split = -1;  // REGEN_DEBUG_GEMM_MAXCLUSTERS / REGEN_DEBUG_NO_TAIL_SPLIT: bring-up A/B switches
+  if (cap < 0) {
+    const char* e = getenv("REGEN_DEBUG_GEMM_MAXCLUSTERS");
+    cap = e ? atoi(e) : 0;
+    const char* e2 = getenv("REGEN_DEBUG_NO_TAIL_SPLIT");
+    no_split = (e2 && e2[0] == '1') ? 1 : 0;
+  }
+  if (cap > 0 && clusters > cap) clusters = cap;
+  // tail of the persistent schedule: R tiles left for the last wave -> cut them into 2 or 4 column slices if that still
+  // fits one wave (FFN1 at config 2: 240 tiles on 74 clusters, R = 18 -> 72 slices of 64 columns; a lone small GEMM
+  // with fewer tiles than clusters is spread over up to 4x as many SMs the same way)
+  Params q = p;
+  q.tail_split = 1;
+  if (!no_split && cap <= 0) {
+    const int maxc = kNumSMs / 2;
+    const int rem = tiles >= maxc ? (int)(tiles % maxc) : (int)tiles;
+    if (rem > 0 && 4 * rem <= maxc) q.tail_split = 4;
+    else if (rem > 0 && 2 * rem <= maxc) q.tail_split = 2;
+    if (tiles < maxc) clusters = (int)tiles * q.tail_split;  // every slice gets its own cluster
   }
   return launch_pdl(gemm2_tn_kernel<BN, SPLIT, EW, RES>, dim3(2 * clusters), dim3(64 + 32 * EW), C::SMEM_BYTES, stream, a_hi,
-                    a_lo, w_hi, w_lo, o.f32, o.hi, o.lo, p);
+                    a_lo, w_hi, w_lo, o.f32, o.hi, o.lo, q);
 }
 
 template <int BN, bool SPLIT>

@@ -1,4 +1,5 @@
-// Causal self-attention on tcgen05 tensor cores (sm_100a), bf16x3 operands, fp32 softmax.
+// Self-attention on tcgen05 tensor cores (sm_100a), bf16x3 operands, fp32 softmax; causal (arch 'online') or unmasked
+// (arch 'offline', Params::causal = 0).
 //
 // One CTA per (sample b, head h, 128-query block).  q | k | v arrive as bf16 (hi, lo) pairs
 // [T*Beff, 3*512] (rows seq-first, written by the QKV GEMM epilogue) and are fetched with 3-D TMA boxes
@@ -11,7 +12,8 @@
 //   O[128 x 128] += P[128 x TB] . V_chunk[TB x 128]        (B operand MN-major: V tiles are used as loaded)
 //   out          = O / rowsum  -> bf16 (hi, lo) [T*Beff, 512], the A operand of the output projection.
 //
-// TB = 64 (T <= 64: ~100 KB of shared memory, two CTAs per SM) or 128 (longer sequences, key chunks of 128 with the
+// TB = 64 (T <= 64: K and V share a buffer, O reuses S's TMEM columns: ~69 KB of shared memory, 128 TMEM columns, three
+// CTAs per SM) or 128 (longer sequences, one CTA per SM, key chunks of 128 with the
 // scores of all chunks resident in TMEM so the row max is exact before any exponential is taken).
 // Reference semantics: nn.MultiheadAttention with the additive causal mask of model/cmdm.py:168-171, 220-227.
 #pragma once

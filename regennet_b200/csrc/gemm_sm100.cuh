@@ -6,14 +6,16 @@
 //   * SPLIT mode ("bf16x3"): every fp32 operand is carried as a (hi, lo) bf16 pair and each k-step
 //     issues three MMAs  A_hi.W_hi + A_hi.W_lo + A_lo.W_hi  into the same TMEM accumulator, which
 //     restores ~16 significand bits (max abs error ~2e-5 on the CMDM forward instead of 1e-2);
-//   * epilogue: 4 warps read the accumulator with tcgen05.ld (32x32b: one thread = one output
-//     row), add bias / residual, optionally apply exact-erf GELU, and store fp32 and/or a bf16
-//     (hi, lo) pair for the next GEMM's A operand.
+//   * epilogue: 8 warps (16 in the pair kernel's no-residual variant) read the accumulator with tcgen05.ld (32x32b:
+//     one thread = one output row), add bias / residual, optionally apply exact-erf GELU, and write fp32 and/or a bf16
+//     (hi, lo) pair for the next GEMM's A operand -- staged in shared memory as swizzled TMA boxes and stored with
+//     cp.async.bulk.tensor.
 //
-// Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
-// Persistent: one CTA per SM loops over 128 x BN output tiles; the fp32 accumulator is double buffered in
-// TMEM so the epilogue of one tile overlaps the main loop of the next; epilogue traffic is staged
-// through shared memory so every global access is a full, coalesced 128-byte (fp32) / 64-byte (bf16) row segment.
+// Two kernels: gemm_tn_kernel (one CTA per 128 x BN tile; tiny batches, M <= 128) and gemm2_tn_kernel (CTA pair,
+// cta_group::2, 256 x BN tiles; everything else).  Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2.. = epilogue.  Both are persistent (one CTA per SM looping over tiles); the fp32 accumulator is double buffered
+// in TMEM so the epilogue of one tile overlaps the main loop of the next; every kernel is launched with programmatic
+// stream serialization and waits (griddepcontrol.wait) after its prologue.
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"

@@ -78,10 +78,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// LN = false (input projection): h <- A.W^T + b + residual, no LayerNorm, ONE sweep; tm_res is then only the residual
+// LOAD map (the loop-invariant conditioning bias) and tm_c the fp32 STORE map of h.
 // tm_res: fp32 [M, 512] residual stream h (box 32 x 32, SWIZZLE_128B) -- used for the residual LOAD and the h STORE
 // tm_c  : fp32 [Beff + 32, 512] cyclic per-sample constant (row r = c[r % Beff]); only read with CHAIN
 // tm_ohi / tm_olo: bf16 [M, 512] split of h (store, box 32 rows x 64 columns, SWIZZLE_128B)
-template <bool SPLIT, bool CHAIN, int EW>
+template <bool SPLIT, bool CHAIN, int EW, bool LN = true>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Epi<EW, CHAIN>::THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -252,6 +254,77 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       const bool tr = warp == 2 && lane == 0 && it == 0;
       if (tr) REGEN_LTL(3);
       ptx::tcgen05_fence_after();
+      if constexpr (!LN) {
+        // ---- no LayerNorm: single sweep  h = acc + bias + residual -> fp32 + bf16 (hi, lo).
+        // staging slots: fp32 F[2] = 0, 1 | hi tile = 2 | lo tile = 3 | residual ring (2 deep) = 4, 5
+        static_assert(!CHAIN, "the no-LayerNorm sweep has no c table");
+        uint8_t* rring = my + 4 * SLOT;
+        if (lane == 0) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            ptx::mbar_expect_tx(&rbar[s], SLOT);
+            ptx::tma_load_2d(rring + s * SLOT, &tm_res, &rbar[s], n_base + SC * s, row0);
+          }
+        }
+        uint32_t ra[32], rb[32];
+        auto sweep = [&](uint32_t (&r)[32], int sc) {
+          const int slot = sc & 1, u = sc >> 1, half = sc & 1;
+          uint8_t* fb = my + (sc & 1) * SLOT;
+          uint8_t* hb = my + 2 * SLOT;
+          uint8_t* lb = my + 3 * SLOT;
+          // F[sc & 1] was stored by group sc - 2, the single hi / lo tile pair by group sc - 1 (sc even)
+          if (sc >= 2 && lane == 0) {
+            if (half == 0) ptx::bulk_wait_read<0>(); else ptx::bulk_wait_read<1>();
+          }
+          ptx::mbar_wait(&rbar[slot], (uint32_t)(it * (E::NSC / 2) + sc / 2) & 1);
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              const int j = 2 * c + jj;
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + sc * SC + 4 * j);
+              const float4 rj = *reinterpret_cast<const float4*>(rring + slot * SLOT + off_f32(lane, j));
+              const float z0 = __uint_as_float(r[4 * j]) + b4.x + rj.x, z1 = __uint_as_float(r[4 * j + 1]) + b4.y + rj.y;
+              const float z2 = __uint_as_float(r[4 * j + 2]) + b4.z + rj.z, z3 = __uint_as_float(r[4 * j + 3]) + b4.w + rj.w;
+              *reinterpret_cast<float4*>(fb + off_f32(lane, j)) = make_float4(z0, z1, z2, z3);
+              const uint32_t h0 = gemm::pack_bf16x2(z0, z1), h1 = gemm::pack_bf16x2(z2, z3);
+              hw[2 * jj] = h0;
+              hw[2 * jj + 1] = h1;
+              lw[2 * jj] = gemm::pack_bf16x2(z0 - __uint_as_float(h0 << 16), z1 - __uint_as_float(h0 & 0xffff0000u));
+              lw[2 * jj + 1] = gemm::pack_bf16x2(z2 - __uint_as_float(h1 << 16), z3 - __uint_as_float(h1 & 0xffff0000u));
+            }
+            *reinterpret_cast<uint4*>(hb + off_f32(lane, half * 4 + c)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(lb + off_f32(lane, half * 4 + c)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();  // staging complete, every lane has read the residual slot
+          if (lane == 0) {
+            if (sc + 2 < E::NSC) {
+              ptx::mbar_expect_tx(&rbar[slot], SLOT);
+              ptx::tma_load_2d(rring + slot * SLOT, &tm_res, &rbar[slot], n_base + SC * (sc + 2), row0);
+            }
+            ptx::tma_store_2d(&tm_c, fb, n_base + SC * sc, row0);
+            if (half) {
+              ptx::tma_store_2d(&tm_ohi, hb, n_base + 2 * SC * u, row0);
+              ptx::tma_store_2d(&tm_olo, lb, n_base + 2 * SC * u, row0);
+            }
+            ptx::bulk_commit();
+          }
+        };
+        __syncwarp();
+        ptx::tmem_ld_32x32b_x32(lane_addr, ra);
+#pragma unroll 1
+        for (int sc = 0; sc < E::NSC; sc += 2) {
+          ptx::tmem_ld_wait(ra);
+          ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)((sc + 1) * SC), rb);
+          sweep(ra, sc);
+          ptx::tmem_ld_wait(rb);
+          if (sc + 2 < E::NSC) ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)((sc + 2) * SC), ra);
+          sweep(rb, sc + 1);
+        }
+      } else {
       // prime the residual (and c) rings
       if (lane == 0) {
 #pragma unroll
@@ -449,6 +522,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         pass3(rb, sc + 1);
       }
       // accumulator and operand ring are free again
+      }
       if (tr) REGEN_LTL(8);
       if (lane == 0) ptx::bulk_wait_read<0>();
       if (tr) REGEN_LTL(9);
@@ -473,20 +547,20 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
 }
 
-template <bool SPLIT, bool CHAIN, int EW>
+template <bool SPLIT, bool CHAIN, int EW, bool LN = true>
 inline cudaError_t launch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                const CUtensorMap& w_lo, const CUtensorMap& res, const CUtensorMap& c,
                                const CUtensorMap& ohi, const CUtensorMap& olo, const Params& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_ln_kernel<SPLIT, CHAIN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_ln_kernel<SPLIT, CHAIN, EW, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int64_t tiles = ceil_div(p.M, 2 * BM);
   const int clusters = (int)(tiles < kNumSMs / 2 ? tiles : kNumSMs / 2);
-  return launch_pdl(gemm_ln_kernel<SPLIT, CHAIN, EW>, dim3(2 * clusters), dim3(Epi<EW, CHAIN>::THREADS), SMEM_BYTES, stream, a_hi,
+  return launch_pdl(gemm_ln_kernel<SPLIT, CHAIN, EW, LN>, dim3(2 * clusters), dim3(Epi<EW, CHAIN>::THREADS), SMEM_BYTES, stream, a_hi,
                     a_lo, w_hi, w_lo, res, c, ohi, olo, p);
 }
 
@@ -505,6 +579,14 @@ inline cudaError_t launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, cons
   }
   return ew == 16 ? launch_impl<SPLIT, CHAIN, 16>(a_hi, a_lo, w_hi, w_lo, res, c, ohi, olo, p, stream)
                   : launch_impl<SPLIT, CHAIN, 8>(a_hi, a_lo, w_hi, w_lo, res, c, ohi, olo, p, stream);
+}
+
+// h <- A.W^T + bias + residual without LayerNorm (input projection): `res` = residual LOAD map, `out32` = fp32 STORE map
+template <bool SPLIT>
+inline cudaError_t launch_noln(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                               const CUtensorMap& w_lo, const CUtensorMap& res, const CUtensorMap& out32,
+                               const CUtensorMap& ohi, const CUtensorMap& olo, const Params& p, cudaStream_t stream) {
+  return launch_impl<SPLIT, false, 8, false>(a_hi, a_lo, w_hi, w_lo, res, out32, ohi, olo, p, stream);
 }
 
 }  // namespace gemmln

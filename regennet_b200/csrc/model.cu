@@ -58,6 +58,7 @@ struct regen_handle {
   SplitBuf h_fr;                     // offline: view of h_s without the condition-token rows (A operand of the output
                                      // projection, bf16 outputs of the input projection); maps rebuilt per prepare_cond
   CUtensorMap st_h_fr, st32_h_fr;    // offline: fp32 h without the condition-token rows (stores of the input projection)
+  CUtensorMap ld32_condbias;         // conditioning bias [T*Beff, 512] as 32 x 32 boxes (residual load of the input projection)
   float* e2tab = nullptr;            // offline: timestep-embedding table [num_table_steps, 512] (model/cmdm.py:291-298)
   CUtensorMap tm_qkv_hi, tm_qkv_lo;  // 3-D [T, Beff, 1536] views of qkv_s for the attention kernel (per prepare_cond)
   CUtensorMap tm_att_hi, tm_att_lo;  // 3-D [T, Beff, 512] store views of the attention output (box 32 frames x 64 d)
@@ -440,6 +441,7 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
     TRY(make_tmap_store_2d(&sb->st64_lo, sb->lo, true, h->M, sb->cols, sb->cols, 64));
   }
   TRY(make_tmap_store_2d(&h->st32_h, h->h, false, h->M, D, D, 32));
+  TRY(make_tmap_store_2d(&h->ld32_condbias, h->condbias, false, Mf, D, D, 32));
   if (h->offline) {
     // views without the Beff condition-token rows: outputs of the input projection, A operand of the output projection
     const size_t off = (size_t)Beff * D;
@@ -451,6 +453,8 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
     TRY(make_tmap_store_2d(&v.st_lo, v.lo, true, Mf, D, D));
     TRY(make_tmap_store_2d(&v.st32_hi, v.hi, true, Mf, D, D, 32));
     TRY(make_tmap_store_2d(&v.st32_lo, v.lo, true, Mf, D, D, 32));
+    TRY(make_tmap_store_2d(&v.st64_hi, v.hi, true, Mf, D, D, 64));
+    TRY(make_tmap_store_2d(&v.st64_lo, v.lo, true, Mf, D, D, 64));
     TRY(make_tmap_store_2d(&h->st_h_fr, h->h + off, false, Mf, D, D));
     TRY(make_tmap_store_2d(&h->st32_h_fr, h->h + off, false, Mf, D, D, 32));
   }
@@ -524,7 +528,32 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
     p.out_f32 = h->h + fr_off; p.ld_out = D;
     p.out_hi = h->h_s.hi + fr_off; p.out_lo = h->h_s.lo + fr_off; p.ld_split = D;
     const CUtensorMap hmaps[2] = {offline ? h->st_h_fr : h->st_h, offline ? h->st32_h_fr : h->st32_h};
-    TRY(run_gemm(h, h->a_in, h->w_in, p, hmaps, offline ? &h->h_fr : &h->h_s, s));
+    if (h->fused_ln && Mf > 128) {
+      // full-row (256 x 512) tiles through the fused kernel's machinery without LayerNorm: the residual arrives by
+      // TMA and the outputs leave in one sweep (34.6 -> ~24 us at config 2; the generic residual epilogue is
+      // bound by LSU round trips)
+      ProfScope prof(h, CLS_GEMM, s);
+      gemmln::Params q;
+      memset(&q, 0, sizeof(q));
+      q.M = Mf; q.K = h->Kin; q.Beff = Beff; q.ln_eps = layers::LN_EPS;
+      q.prefetch_res = h->prefetch_res ? 1 : 0;
+      if (h->steplog && h->steplog_slot < h->steplog_cap) {
+        q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;
+      }
+      const SplitBuf& ob = offline ? h->h_fr : h->h_s;
+      cudaError_t e = h->desc.precision == 0
+          ? gemmln::launch_noln<true>(h->a_in.tm_hi, h->a_in.tm_lo, h->w_in.tm_hi2, h->w_in.tm_lo2, h->ld32_condbias,
+                                      hmaps[1], ob.st64_hi, ob.st64_lo, q, s)
+          : gemmln::launch_noln<false>(h->a_in.tm_hi, h->a_in.tm_lo, h->w_in.tm_hi2, h->w_in.tm_lo2, h->ld32_condbias,
+                                       hmaps[1], ob.st64_hi, ob.st64_lo, q, s);
+      if (e != cudaSuccess) {
+        set_error("input projection launch failed: %s", cudaGetErrorString(e));
+        return REGEN_ECUDA;
+      }
+      count_launch();
+    } else {
+      TRY(run_gemm(h, h->a_in, h->w_in, p, hmaps, offline ? &h->h_fr : &h->h_s, s));
+    }
   }
   if (h->fused_ln && !offline) {
     ProfScope prof(h, CLS_OTHER, s);

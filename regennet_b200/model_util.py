@@ -1,105 +1,82 @@
-"""Model / diffusion factory -- mirror of the reference's ``utils/model_util.py``."""
+"""Model / diffusion factory with the call surface of the reference's ``utils/model_util.py``:
+``create_model_and_diffusion(args, data)``, ``get_model_args``, ``create_gaussian_diffusion``, ``load_model_wo_clip``.
+
+``args`` is the reference's argparse namespace (utils/parser_util.py), ``data`` its DataLoader (only
+``data.dataset.num_actions`` / ``num_person`` are read).
+"""
 from . import gaussian_diffusion as gd
 from .cmdm import CMDM
 from .respace import SpacedDiffusion, space_timesteps
 
+# skeleton size per body model and feature width per pose representation (utils/model_util.py:38-47)
+_JOINTS = {"smpl": 25, "smplx": 56}
+_FEATS = {"rot6d": 6, "xyz": 3}
+# text datasets use the HumanML vector representation instead (:49-56): (data_rep, njoints, nfeats)
+_HML = {"humanml": ("hml_vec", 263, 1), "kit": ("hml_vec", 251, 1)}
+_FRAMES = {"ntu": 60, "chi3d": 150}
+_DIFFUSION_STEPS = 1000
+
 
 def load_model_wo_clip(model, state_dict):
-    """utils/model_util.py:5-8."""
-    missing_keys, unexpected_keys = model.load_state_dict(state_dict, strict=False)
-    assert len(unexpected_keys) == 0
-    assert all([k.startswith('clip_model.') for k in missing_keys])
+    """Load a checkpoint that was saved without the frozen CLIP weights: nothing unexpected, only clip_model.* missing."""
+    result = model.load_state_dict(state_dict, strict=False)
+    assert len(result.unexpected_keys) == 0
+    assert all([name.startswith('clip_model.') for name in result.missing_keys])
 
 
 def create_model_and_diffusion(args, data):
-    """utils/model_util.py:11-17."""
-    setting = args.setting
-    if setting == 'cmdm':
+    if args.setting == 'cmdm':
         model = CMDM(**get_model_args(args, data))
-        args.num_person = 1  # Attention here
-    diffusion = create_gaussian_diffusion(args)
-    return model, diffusion
+        args.num_person = 1   # the reactor alone is diffused; the actor is the condition (utils/model_util.py:15)
+    return model, create_gaussian_diffusion(args)
+
+
+def _cond_mode(args):
+    if args.unconstrained:
+        return 'no_cond'
+    return 'text' if args.dataset in _HML else 'action'
 
 
 def get_model_args(args, data):
-    """utils/model_util.py:20-72."""
-    clip_version = 'ViT-B/32'
-    action_emb = 'tensor'
-    if args.unconstrained:
-        cond_mode = 'no_cond'
-    elif args.dataset in ['kit', 'humanml']:
-        cond_mode = 'text'
-    else:
-        cond_mode = 'action'
-    num_actions = data.dataset.num_actions if hasattr(data.dataset, 'num_actions') else 1
-    num_person = data.dataset.num_person if hasattr(data.dataset, 'num_person') else 1
-
-    data_rep = args.pose_rep
+    """Constructor kwargs of CMDM for the reference's command-line arguments (utils/model_util.py:20-72)."""
+    ds = data.dataset
     body_model = args.body_model
-    if body_model == 'smpl':
-        njoints = 25
-    elif body_model == 'smplx':
-        njoints = 56
-    if data_rep == 'rot6d':
-        nfeats = 6
-    elif data_rep == 'xyz':
-        nfeats = 3
-
-    if args.dataset == 'humanml':
-        data_rep = 'hml_vec'
-        njoints = 263
-        nfeats = 1
-    elif args.dataset == 'kit':
-        data_rep = 'hml_vec'
-        njoints = 251
-        nfeats = 1
-
-    if args.dataset == 'ntu':
-        num_frames = 60
-    elif args.dataset == 'chi3d':
-        num_frames = 150
-
-    return {'modeltype': '', 'njoints': njoints, 'nfeats': nfeats, 'num_actions': num_actions,
-            'num_person': num_person, 'num_frames': num_frames,
-            'translation': True, 'pose_rep': 'rot6d', 'glob': True, 'glob_rot': True,
-            'latent_dim': args.latent_dim, 'ff_size': 1024, 'num_layers': args.layers, 'num_heads': 4,
-            'dropout': 0.1, 'activation': "gelu", 'data_rep': data_rep, 'cond_mode': cond_mode,
-            'cond_mask_prob': args.cond_mask_prob, 'action_emb': action_emb, 'arch': args.arch,
-            'cm_mode': args.cm_mode, 'body_model': body_model, 'wo_pos_emb': args.wo_pos_emb,
-            'emb_trans_dec': args.emb_trans_dec, 'clip_version': clip_version, 'dataset': args.dataset}
+    data_rep = args.pose_rep
+    shape = {}
+    if body_model in _JOINTS:
+        shape['njoints'] = _JOINTS[body_model]
+    if data_rep in _FEATS:
+        shape['nfeats'] = _FEATS[data_rep]
+    if args.dataset in _HML:
+        data_rep, shape['njoints'], shape['nfeats'] = _HML[args.dataset]
+    kw = dict(modeltype='', translation=True, pose_rep='rot6d', glob=True, glob_rot=True, ff_size=1024, num_heads=4,
+              dropout=0.1, activation="gelu", action_emb='tensor', clip_version='ViT-B/32')
+    kw.update(njoints=shape['njoints'], nfeats=shape['nfeats'],
+              num_actions=getattr(ds, 'num_actions', 1), num_person=getattr(ds, 'num_person', 1),
+              num_frames=_FRAMES[args.dataset], latent_dim=args.latent_dim, num_layers=args.layers,
+              data_rep=data_rep, cond_mode=_cond_mode(args), cond_mask_prob=args.cond_mask_prob, arch=args.arch,
+              cm_mode=args.cm_mode, body_model=body_model, wo_pos_emb=args.wo_pos_emb,
+              emb_trans_dec=args.emb_trans_dec, dataset=args.dataset)
+    return kw
 
 
 def create_gaussian_diffusion(args):
-    """utils/model_util.py:75-117."""
-    predict_xstart = True  # we always predict x_start (a.k.a. x0), that's our deal!
-    steps = 1000
-    scale_beta = 1.  # no scaling
-    timestep_respacing = args.timestep_respacing
-    learn_sigma = False
-    rescale_timesteps = False
-
-    betas = gd.get_named_beta_schedule(args.noise_schedule, steps, scale_beta)
-    loss_type = gd.LossType.MSE
-
-    if not timestep_respacing:
-        timestep_respacing = [steps]
-
+    """The sampler the reference builds (utils/model_util.py:75-117): 1000 base steps of the named schedule, x0
+    prediction, fixed variance (small or large), optional respacing."""
+    respacing = args.timestep_respacing or [_DIFFUSION_STEPS]
+    var_type = gd.ModelVarType.FIXED_SMALL if args.sigma_small else gd.ModelVarType.FIXED_LARGE
+    loss_weights = {name: getattr(args, name) for name in
+                    ('lambda_vel', 'lambda_rcxyz', 'lambda_fc', 'lambda_orient', 'lambda_body', 'lambda_transl')}
     return SpacedDiffusion(
-        use_timesteps=space_timesteps(steps, timestep_respacing),
-        betas=betas,
-        model_mean_type=(gd.ModelMeanType.EPSILON if not predict_xstart else gd.ModelMeanType.START_X),
-        model_var_type=((gd.ModelVarType.FIXED_LARGE if not args.sigma_small else gd.ModelVarType.FIXED_SMALL)
-                        if not learn_sigma else gd.ModelVarType.LEARNED_RANGE),
-        loss_type=loss_type,
-        rescale_timesteps=rescale_timesteps,
-        lambda_vel=args.lambda_vel,
-        lambda_rcxyz=args.lambda_rcxyz,
-        lambda_fc=args.lambda_fc,
-        lambda_orient=args.lambda_orient,
-        lambda_body=args.lambda_body,
-        lambda_transl=args.lambda_transl,
+        use_timesteps=space_timesteps(_DIFFUSION_STEPS, respacing),
+        betas=gd.get_named_beta_schedule(args.noise_schedule, _DIFFUSION_STEPS, 1.),
+        model_mean_type=gd.ModelMeanType.START_X,
+        model_var_type=var_type,
+        loss_type=gd.LossType.MSE,
+        rescale_timesteps=False,
         data_rep=args.pose_rep,
         num_person=args.num_person,
         body_model=args.body_model,
         vel_threshold=args.vel_threshold,
+        **loss_weights,
     )

@@ -197,3 +197,43 @@ def test_oracle_inpainting_blend_matches_reference_expression():
     out, x0 = smp.loop(model, shape)
     assert torch.equal(out[mask], motion[mask]) and torch.equal(x0[mask], motion[mask])
     assert not torch.equal(out[~mask], motion[~mask])
+
+
+@pytest.mark.reference
+def test_model_util_and_respace_equal_the_imported_reference():
+    """Where /root/reference exists (build container): get_model_args returns the reference's kwargs for a matrix of
+    command lines, space_timesteps the same sets, and create_gaussian_diffusion the same fp64 tables."""
+    from argparse import Namespace
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    ref_shim.install()
+    import importlib
+    ref_mu = importlib.import_module("utils.model_util")
+    ref_rs = importlib.import_module("diffusion.respace")
+    from regennet_b200 import model_util, respace
+
+    def ds(**kw):
+        return type("D", (), {"dataset": type("S", (), kw)})
+
+    base = dict(pose_rep="rot6d", latent_dim=512, layers=8, cond_mask_prob=0.1, cm_mode="concat", wo_pos_emb=False,
+                emb_trans_dec=False, setting="cmdm")
+    for dataset, body, unc, arch, data in [("ntu", "smplx", True, "online", ds(num_actions=26, num_person=2)),
+                                           ("chi3d", "smplx", False, "online", ds(num_actions=8)),
+                                           ("ntu", "smpl", False, "offline", ds()),
+                                           ("chi3d", "smplx", True, "offline", ds(num_person=2))]:
+        args = Namespace(dataset=dataset, body_model=body, unconstrained=unc, arch=arch, **base)
+        assert model_util.get_model_args(args, data) == ref_mu.get_model_args(args, data), (dataset, body, unc, arch)
+    for n, spec in [(1000, "ddim100"), (1000, "ddim7"), (1000, "10,15,20"), (1000, [250]), (1000, "1000"), (50, "13")]:
+        assert respace.space_timesteps(n, spec) == ref_rs.space_timesteps(n, spec), spec
+    with pytest.raises(ValueError):
+        respace.space_timesteps(1000, "ddim999")
+    with pytest.raises(ValueError):
+        respace.space_timesteps(10, "6,6")
+    dargs = Namespace(noise_schedule="cosine", sigma_small=False, timestep_respacing="ddim20", lambda_vel=0.0,
+                      lambda_rcxyz=0.0, lambda_fc=0.0, lambda_orient=0.0, lambda_body=0.0, lambda_transl=0.0,
+                      pose_rep="rot6d", num_person=1, body_model="smplx", vel_threshold=0.01)
+    ours, ref = model_util.create_gaussian_diffusion(dargs), ref_mu.create_gaussian_diffusion(dargs)
+    assert ours.timestep_map == ref.timestep_map and ours.model_var_type.name == ref.model_var_type.name
+    for f in ["betas", "alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2", "posterior_log_variance_clipped"]:
+        assert np.array_equal(getattr(ours, f), getattr(ref, f)), f

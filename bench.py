@@ -83,12 +83,13 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
+                pw.append(float(r[2]))
                 for n, v in zip(names, r[3:7]):
                     if v.strip().lower().startswith("active"):
                         reasons.add(n)
@@ -96,7 +97,7 @@ class ClockSampler:
                 pass
         if sm:
             out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+                   "samples": len(sm), "power_w_max": float(max(pw)) if pw else None}
         return out
 
 

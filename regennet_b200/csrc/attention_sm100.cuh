@@ -221,6 +221,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float sc = 0.08838834764831845f * 1.4426950408889634f;  // 1/sqrt(128) * log2(e)
 
+    // Warps whose 32 rows all lie beyond the sequence (T = 60: rows 64..127 of the 128-row MMA tile, i.e. half of the
+    // softmax warps) only keep the P barrier's arrival count: their P rows stay undefined, which only feeds the unused
+    // rows 64..127 of O, and they neither stage nor store anything.
+    const bool warp_live = q0 + q * 32 < p.T && q * 32 < (TB == 64 ? 64 : 128);
+    if (!warp_live) {
+      for (int kc = 0; kc < nkc; ++kc) {
+        if (kc > 0) ptx::mbar_wait(barO, (kc - 1) & 1);
+        ptx::mbar_arrive(barP);
+      }
+    } else {
     for (int kc = 0; kc < nkc; ++kc) ptx::mbar_wait(&barS[kc], 0);  // all score chunks complete
     ptx::tcgen05_fence_after();
     // pass 1: exact row maximum over the causal window (this warp's key half of every chunk, then exchange)
@@ -331,6 +341,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       ptx::bulk_commit();
       ptx::bulk_wait<0>();
     }
+    }  // warp_live
   }
 
   if (warp == 1 && lane == 0) REGEN_ATL(8);

@@ -233,8 +233,57 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     } else {
     for (int kc = 0; kc < nkc; ++kc) ptx::mbar_wait(&barS[kc], 0);  // all score chunks complete
     ptx::tcgen05_fence_after();
+    float mx = -INFINITY, sum = 0.f;
+    auto row_max = [&](const uint32_t (&v)[32], int j0) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j0 + j <= jmax && j0 + j < p.T) mx = fmaxf(mx, __uint_as_float(v[j]));
+    };
+    // P for 32 keys starting at key c0 of chunk kc: exp2, bf16 (hi, lo) split, K-major SW128 A-operand layout
+    auto emit_p = [&](const uint32_t (&v)[32], int kc, int c0) {
+#pragma unroll
+      for (int j8 = 0; j8 < 32; j8 += 8) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = kc * TB + c0 + j8 + 2 * e;
+          float p0 = 0.f, p1 = 0.f;
+          if (row_ok && j <= jmax) p0 = exp2f((__uint_as_float(v[j8 + 2 * e]) - mx) * sc);
+          if (row_ok && j + 1 <= jmax) p1 = exp2f((__uint_as_float(v[j8 + 2 * e + 1]) - mx) * sc);
+          sum += p0 + p1;
+          __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+          hw[e] = *reinterpret_cast<uint32_t*>(&hh);
+          __nv_bfloat162 ll = __floats2bfloat162_rn(p0 - __uint_as_float(hw[e] << 16), p1 - __uint_as_float(hw[e] & 0xffff0000u));
+          lw[e] = *reinterpret_cast<uint32_t*>(&ll);
+        }
+        // 16-byte chunk index XOR (row & 7)
+        const int jj = c0 + j8;  // key offset inside the chunk
+        const uint32_t off = (uint32_t)(jj >> 6) * C::P_TILE + (uint32_t)r * 128 +
+                             ((((uint32_t)(jj & 63) >> 3) ^ ((uint32_t)r & 7)) << 4);
+        *reinterpret_cast<uint4*>(sQ + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(sQ + (TB / 64) * C::P_TILE + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+    };
+    if constexpr (C::COMPACT) {
+      // one key chunk of 64, one warp per lane quarter: the 64 scores of the row are read from TMEM ONCE and stay in
+      // registers for the maximum and the exponentials
+      uint32_t s0[32], s1[32];
+      __syncwarp();
+      ptx::tmem_ld_32x32b_x32(lane_addr + S_COL, s0);
+      ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + 32u, s1);
+      ptx::tmem_ld_wait(s0);
+      ptx::tmem_ld_wait(s1);
+      row_max(s0, 0);
+      row_max(s1, 32);
+      if (!row_ok) mx = 0.f;
+      if (warp == 1 && lane == 0) REGEN_ATL(4);
+      emit_p(s0, 0, 0);
+      emit_p(s1, 0, 32);
+      ptx::fence_proxy_async_smem();  // make the generic-proxy stores visible to the tensor core (async proxy)
+      ptx::mbar_arrive(barP);
+      if (warp == 1 && lane == 0) REGEN_ATL(5);
+    } else {
     // pass 1: exact row maximum over the causal window (this warp's key half of every chunk, then exchange)
-    float mx = -INFINITY;
     for (int kc = 0; kc < nkc; ++kc) {
 #pragma unroll 1
       for (int c0 = half * KH; c0 < half * KH + KH; c0 += 32) {
@@ -242,10 +291,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         __syncwarp();
         ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + (uint32_t)(kc * TB + c0), v);
         ptx::tmem_ld_wait();
-        const int j0 = kc * TB + c0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j0 + j <= jmax && j0 + j < p.T) mx = fmaxf(mx, __uint_as_float(v[j]));
+        row_max(v, kc * TB + c0);
       }
     }
     if (NH == 2) {
@@ -255,7 +301,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     }
     if (!row_ok) mx = 0.f;
     if (warp == 1 && lane == 0) REGEN_ATL(4);
-    float sum = 0.f;
     for (int kc = 0; kc < nkc; ++kc) {
       if (kc > 0) ptx::mbar_wait(barO, (kc - 1) & 1);  // previous P chunk consumed by the tensor core
 #pragma unroll 1
@@ -264,32 +309,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         __syncwarp();
         ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + (uint32_t)(kc * TB + c0), v);
         ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j8 = 0; j8 < 32; j8 += 8) {
-          uint32_t hw[4], lw[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = kc * TB + c0 + j8 + 2 * e;
-            float p0 = 0.f, p1 = 0.f;
-            if (row_ok && j <= jmax) p0 = exp2f((__uint_as_float(v[j8 + 2 * e]) - mx) * sc);
-            if (row_ok && j + 1 <= jmax) p1 = exp2f((__uint_as_float(v[j8 + 2 * e + 1]) - mx) * sc);
-            sum += p0 + p1;
-            __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
-            hw[e] = *reinterpret_cast<uint32_t*>(&hh);
-            __nv_bfloat162 ll = __floats2bfloat162_rn(p0 - __uint_as_float(hw[e] << 16), p1 - __uint_as_float(hw[e] & 0xffff0000u));
-            lw[e] = *reinterpret_cast<uint32_t*>(&ll);
-          }
-          // K-major SW128 A-operand layout: 16-byte chunk index XOR (row & 7)
-          const int jj = c0 + j8;  // key offset inside the chunk
-          const uint32_t off = (uint32_t)(jj >> 6) * C::P_TILE + (uint32_t)r * 128 +
-                               ((((uint32_t)(jj & 63) >> 3) ^ ((uint32_t)r & 7)) << 4);
-          *reinterpret_cast<uint4*>(sQ + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          *reinterpret_cast<uint4*>(sQ + (TB / 64) * C::P_TILE + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        }
+        emit_p(v, kc, c0);
       }
       ptx::fence_proxy_async_smem();  // make the generic-proxy stores visible to the tensor core (async proxy)
       ptx::mbar_arrive(barP);
       if (warp == 1 && lane == 0 && kc == 0) REGEN_ATL(5);
+    }
     }
     if (NH == 2) {
       s_sum[r * 2 + half] = sum;
@@ -305,12 +330,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     // staging: (DW / 64) hi tiles + as many lo tiles of 4 KB per warp, 64 KB per CTA: the dead K/V buffers, or in
     // compact mode the dead P (= Q) and K/V buffers, which are contiguous
     uint8_t* st = (C::COMPACT ? sQ : sK) + (warp - 1) * (DW / 64) * 8192;
-#pragma unroll 1
-    for (int c0 = 0; c0 < DW; c0 += 32) {
-      uint32_t v[32];
-      __syncwarp();
-      ptx::tmem_ld_32x32b_x32(lane_addr + O_COL + (uint32_t)(half * DW + c0), v);
-      ptx::tmem_ld_wait();
+    auto stage_o = [&](const uint32_t (&v)[32], int c0) {
       uint8_t* st_hi = st + (c0 >> 6) * 8192;
       uint8_t* st_lo = st_hi + 4096;
 #pragma unroll
@@ -328,6 +348,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         const uint32_t off = (uint32_t)lane * 128 + (((uint32_t)chunk ^ ((uint32_t)lane & 7)) << 4);
         *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         *reinterpret_cast<uint4*>(st_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+    };
+    {  // the next 32 columns of O are in flight while the current ones are scaled, split and staged
+      static_assert((DW / 32) % 2 == 0, "O columns are processed in (va, vb) pairs");
+      uint32_t va[32], vb[32];
+      const uint32_t o_addr = lane_addr + O_COL + (uint32_t)(half * DW);
+      __syncwarp();
+      ptx::tmem_ld_32x32b_x32(o_addr, va);
+#pragma unroll 1
+      for (int c0 = 0; c0 < DW; c0 += 64) {
+        ptx::tmem_ld_wait(va);
+        ptx::tmem_ld_32x32b_x32(o_addr + (uint32_t)(c0 + 32), vb);
+        stage_o(va, c0);
+        ptx::tmem_ld_wait(vb);
+        if (c0 + 64 < DW) ptx::tmem_ld_32x32b_x32(o_addr + (uint32_t)(c0 + 64), va);
+        stage_o(vb, c0 + 32);
       }
     }
     ptx::fence_proxy_async_smem();

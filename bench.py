@@ -213,7 +213,10 @@ def run_ours(args):
     gemm_ms, attn_ms, ln_ms, other_ms = [cls_ms[i] / KP for i in range(4)]
 
     # ------------------------------------------------------------------ e2e: public API, host buffers in and out
-    e2e_diff = mkdiff([K])
+    # the call a user makes is ONE p_sample_loop over the workload's whole 1000-step schedule (quick runs with a small
+    # --steps keep a K-step respaced loop so that they stay quick)
+    KE = 1000 if K >= 50 else K
+    e2e_diff = mkdiff([KE])
     out_host = torch.empty(shape, dtype=torch.float32).pin_memory()
 
     def e2e_once():
@@ -230,8 +233,8 @@ def run_ours(args):
         e2e_once()
         e2e_runs.append(time.perf_counter() - t0)
     e2e_s = sorted(e2e_runs)[1]
-    h2d = cm_host.numel() * 4 / K
-    d2h = out_host.numel() * 4 / K
+    h2d = cm_host.numel() * 4 / KE
+    d2h = out_host.numel() * 4 / KE
 
     # ------------------------------------------------------------------ reduce over ranks (max time)
     times = torch.tensor([ms, e2e_s * 1000.0], device=dev, dtype=torch.float64)
@@ -266,11 +269,13 @@ def run_ours(args):
                        "driver": ("CUDA graph replay, %d steps per graph" % U) if U else "host-enqueued steps",
                        "l2": "working set per step (weights 107 MB + activations ~300 MB) exceeds the 126 MB L2"},
             "poses_per_sec": steps_per_s * B * T,
-            "frames_per_sec_e2e_1000_steps": world * B * T / (1000.0 * (ms_max / K) / 1000.0),
-            "e2e": {"value": world * K / (e2e_ms_max / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "frames_per_sec_e2e_1000_steps": (world * B * T / (e2e_ms_max / 1000.0)) if KE == 1000
+                                             else world * B * T / (1000.0 * (ms_max / K) / 1000.0),
+            "e2e": {"value": world * KE / (e2e_ms_max / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
                     "what": "SpacedDiffusion(%d steps).p_sample_loop(CMDM, ...) with pinned-host cmotion in and "
-                            "pinned-host samples out, wall clock incl. Python; median of 3 loops" % K,
+                            "pinned-host samples out, wall clock incl. Python; median of 3 loops" % KE,
+                    "steps": KE,
                     "runs_ms": [round(1e3 * v, 2) for v in e2e_runs]},
             "gpu_launches": launches,
             "clocks": clk,

@@ -39,7 +39,7 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
   static_assert(STAGES >= 2, "need at least a double buffer");
-  static_assert(BN == 128 || BN == 256, "BN must be 128 or 256 (TMEM_COLS a power of two <= 512)");
+  static_assert(BN == 64 || BN == 128 || BN == 256, "BN must be 64, 128 or 256 (TMEM_COLS a power of two <= 512)");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
@@ -536,7 +536,8 @@ struct OutMaps {  // store-side tensor maps (only read when Params::tma_store !=
   CUtensorMap f32, hi, lo;
 };
 
-// Host launcher.  Tensor maps: A maps have box {64, 128}; W maps have box {64, BN}.
+// Host launcher.  Tensor maps: A maps have box {64, 128}; W maps have box {64, BN}.  BN = 64 is the small-batch shape:
+// a GEMM with at most 128 rows is bound by streaming W, so it is cut into N / 64 column tiles to use N / 64 SMs.
 template <int BN, bool SPLIT>
 inline cudaError_t launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                           const CUtensorMap& w_lo, const OutMaps& o, const Params& p, cudaStream_t stream) {

@@ -20,6 +20,7 @@ struct SplitBuf {  // bf16 (hi, lo) operand pair + its TMA maps
   bf16 *hi = nullptr, *lo = nullptr;
   CUtensorMap tm_hi, tm_lo;      // box rows: 128 for activations (A operand), 256 for weights (single-CTA kernel)
   CUtensorMap tm_hi2, tm_lo2;    // weights only: box rows 128 = one CTA's half of the W tile in the CTA-pair kernel
+  CUtensorMap tm_hi3, tm_lo3;    // weights only: box rows 64 = the W tile of the small-batch single-CTA kernel (BN = 64)
   CUtensorMap st_hi, st_lo;      // activations only: store-side maps (box 32 x 16), rebuilt per prepare_cond with rows = M
   CUtensorMap st32_hi, st32_lo;  // same with box 32 x 32 (16-warp GEMM epilogue)
   CUtensorMap st64_hi, st64_lo;  // same with box 32 x 64, 128-byte rows (fused GEMM+LayerNorm epilogue)
@@ -130,6 +131,8 @@ int alloc_split(regen_handle* h, SplitBuf* s, size_t rows, size_t cols, uint32_t
   TRY(make_tmap_bf16_2d(&s->tm_lo, s->lo, rows, cols, cols, box_rows));
   TRY(make_tmap_bf16_2d(&s->tm_hi2, s->hi, rows, cols, cols, 128));
   TRY(make_tmap_bf16_2d(&s->tm_lo2, s->lo, rows, cols, cols, 128));
+  TRY(make_tmap_bf16_2d(&s->tm_hi3, s->hi, rows, cols, cols, 64));
+  TRY(make_tmap_bf16_2d(&s->tm_lo3, s->lo, rows, cols, cols, 64));
   s->cols = cols;
   return REGEN_OK;
 }
@@ -178,8 +181,8 @@ int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, gemm::Params
     e = h->desc.precision == 0 ? gemm::launch2<256, true>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, om, p, s)
                                : gemm::launch2<256, false>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, om, p, s);
   else
-    e = h->desc.precision == 0 ? gemm::launch<256, true>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, om, p, s)
-                               : gemm::launch<256, false>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, om, p, s);
+    e = h->desc.precision == 0 ? gemm::launch<64, true>(a.tm_hi, a.tm_lo, w.tm_hi3, w.tm_lo3, om, p, s)
+                               : gemm::launch<64, false>(a.tm_hi, a.tm_lo, w.tm_hi3, w.tm_lo3, om, p, s);
   if (e != cudaSuccess) {
     set_error("gemm launch (M=%d N=%d K=%d) failed: %s", p.M, p.N, p.K, cudaGetErrorString(e));
     return REGEN_ECUDA;
@@ -505,6 +508,10 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
   cudaStream_t s = (cudaStream_t)stream;
   const int M = h->M, I = h->I, L = h->L, Beff = h->Beff, S = h->S;
   const bool offline = h->offline;
+  // At most one 128-row tile (single samples, short sequences): every GEMM is bound by streaming its weights, and the
+  // full-row fused GEMM+LayerNorm kernel would do that through ONE CTA pair; the N / 64-way tiled GEMM + a separate
+  // LayerNorm kernel spreads it over up to 24 SMs instead.
+  const bool fused = h->fused_ln && M > 128;
   const int Mf = T * Beff;                              // frame rows
   const size_t fr_off = offline ? (size_t)Beff * D : 0;  // offline: the frames follow the Beff condition-token rows
 
@@ -528,7 +535,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
     p.out_f32 = h->h + fr_off; p.ld_out = D;
     p.out_hi = h->h_s.hi + fr_off; p.out_lo = h->h_s.lo + fr_off; p.ld_split = D;
     const CUtensorMap hmaps[2] = {offline ? h->st_h_fr : h->st_h, offline ? h->st32_h_fr : h->st32_h};
-    if (h->fused_ln && Mf > 128) {
+    if (fused && Mf > 128) {
       // full-row (256 x 512) tiles through the fused kernel's machinery without LayerNorm: the residual arrives by
       // TMA and the outputs leave in one sweep (34.6 -> ~24 us at config 2; the generic residual epilogue is
       // bound by LSU round trips)
@@ -555,7 +562,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       TRY(run_gemm(h, h->a_in, h->w_in, p, hmaps, offline ? &h->h_fr : &h->h_s, s));
     }
   }
-  if (h->fused_ln && !offline) {
+  if (fused && !offline) {
     ProfScope prof(h, CLS_OTHER, s);
     launch_pdl(layers::build_cyc_kernel, dim3(Beff + 32, L), dim3(128), 0, s, h->ctab,
                h->has_cond ? (const float*)h->ccond : (const float*)nullptr, t, h->cyc, L, B, Beff,
@@ -591,7 +598,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       }
       count_launch();
     }
-    if (offline) {  // encoder layer: h = LN1(h + attn . W_o^T + b_o)   (nn.TransformerEncoderLayer, post-norm)
+    if (offline && fused) {  // encoder layer: h = LN1(h + attn . W_o^T + b_o)   (nn.TransformerEncoderLayer, post-norm)
       ProfScope prof(h, CLS_GEMM, s);
       gemmln::Params q;
       q.M = M; q.K = D; q.Beff = Beff; q.bias = ld.bo; q.g1 = ld.n1w; q.b1 = ld.n1b; q.g2 = nullptr; q.b2 = nullptr;
@@ -612,7 +619,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
         return REGEN_ECUDA;
       }
       count_launch();
-    } else if (h->fused_ln) {  // h = LN2( LN1(h + attn . W_o^T + b_o) + c_l[b] )   -- one kernel
+    } else if (fused) {  // h = LN2( LN1(h + attn . W_o^T + b_o) + c_l[b] )   -- one kernel
       ProfScope prof(h, CLS_GEMM, s);
       gemmln::Params q;
       q.M = M; q.K = D; q.Beff = Beff; q.bias = ld.bo; q.g1 = ld.n1w; q.b1 = ld.n1b; q.g2 = ld.n2w; q.b2 = ld.n2b;
@@ -642,7 +649,16 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       const CUtensorMap tmaps[2] = {h->st_tmp, h->st_tmp};
       TRY(run_gemm(h, h->att, ld.wo, p, tmaps, nullptr, s));
     }
-    {  // h = LN2( LN1(tmp) + c_l[b] )
+    if (offline) {  // h = LN1(tmp)   (encoder layer)
+      layers::LnParams q;
+      memset(&q, 0, sizeof(q));
+      q.in = h->tmp; q.g1 = ld.n1w; q.b1 = ld.n1b;
+      q.out_f32 = h->h; q.out_hi = h->h_s.hi; q.out_lo = h->h_s.lo; q.M = M;
+      q.B = B; q.Beff = Beff;
+      ProfScope prof(h, CLS_LN, s);
+      layers::layernorm_kernel<false><<<(unsigned)ceil_div(M, 8), 256, 0, s>>>(q);
+      count_launch();
+    } else {  // h = LN2( LN1(tmp) + c_l[b] )
       layers::LnParams q;
       q.in = h->tmp; q.g1 = ld.n1w; q.b1 = ld.n1b; q.g2 = ld.n2w; q.b2 = ld.n2b;
       q.ctab = h->ctab + (size_t)l * D;
@@ -660,7 +676,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       p.out_hi = h->ffn.hi; p.out_lo = h->ffn.lo; p.ld_split = FF;
       TRY(run_gemm(h, h->h_s, ld.w1, p, nullptr, &h->ffn, s));
     }
-    if (h->fused_ln || offline) {  // h = LN3(h + ffn . W_2^T + b_2)   -- one kernel (encoder layer: norm2)
+    if (fused) {  // h = LN3(h + ffn . W_2^T + b_2)   -- one kernel (encoder layer: norm2)
       ProfScope prof(h, CLS_GEMM, s);
       gemmln::Params q;
       q.M = M; q.K = FF; q.Beff = Beff; q.bias = ld.b2; q.g1 = offline ? ld.n2w : ld.n3w; q.b1 = offline ? ld.n2b : ld.n3b;
@@ -694,7 +710,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
     {  // h = LN3(tmp)
       layers::LnParams q;
       memset(&q, 0, sizeof(q));
-      q.in = h->tmp; q.g1 = ld.n3w; q.b1 = ld.n3b;
+      q.in = h->tmp; q.g1 = offline ? ld.n2w : ld.n3w; q.b1 = offline ? ld.n2b : ld.n3b;
       q.out_f32 = h->h; q.out_hi = h->h_s.hi; q.out_lo = h->h_s.lo; q.M = M;
       q.B = B; q.Beff = Beff;
       ProfScope prof(h, CLS_LN, s);

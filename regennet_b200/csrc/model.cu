@@ -508,10 +508,10 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
   cudaStream_t s = (cudaStream_t)stream;
   const int M = h->M, I = h->I, L = h->L, Beff = h->Beff, S = h->S;
   const bool offline = h->offline;
-  // At most one 128-row tile (single samples, short sequences): every GEMM is bound by streaming its weights, and the
-  // full-row fused GEMM+LayerNorm kernel would do that through ONE CTA pair; the N / 64-way tiled GEMM + a separate
-  // LayerNorm kernel spreads it over up to 24 SMs instead.
-  const bool fused = h->fused_ln && M > 128;
+  // The fused GEMM+LayerNorm kernel gives one 256-row tile to a CTA pair, so it uses 2 * ceil(M / 256) SMs.  Below half
+  // of the machine the N-tiled GEMM + a separate warp-per-row LayerNorm kernel is faster (measured crossover at M ~ 9 500:
+  // B = 32, T = 60 runs 0.705 instead of 1.022 ms per step; single samples use the 64-column single-CTA GEMM tiles).
+  const bool fused = h->fused_ln && ceil_div(M, 256) >= kNumSMs / 4;
   const int Mf = T * Beff;                              // frame rows
   const size_t fr_off = offline ? (size_t)Beff * D : 0;  // offline: the frames follow the Beff condition-token rows
 

@@ -249,6 +249,8 @@ struct LnParams {
 
 template <bool CHAIN>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
+  ptx::griddep_wait();  // PDL: p.in is the preceding GEMM's output
+  ptx::griddep_launch();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= p.M) return;

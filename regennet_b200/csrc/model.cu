@@ -656,7 +656,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       q.out_f32 = h->h; q.out_hi = h->h_s.hi; q.out_lo = h->h_s.lo; q.M = M;
       q.B = B; q.Beff = Beff;
       ProfScope prof(h, CLS_LN, s);
-      layers::layernorm_kernel<false><<<(unsigned)ceil_div(M, 8), 256, 0, s>>>(q);
+      launch_pdl(layers::layernorm_kernel<false>, dim3((unsigned)ceil_div(M, 8)), dim3(256), 0, s, q);
       count_launch();
     } else {  // h = LN2( LN1(tmp) + c_l[b] )
       layers::LnParams q;
@@ -666,7 +666,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       q.t = t; q.ld_c = L * D; q.B = B; q.Beff = Beff; q.n_table = h->desc.num_table_steps;
       q.out_f32 = h->h; q.out_hi = h->h_s.hi; q.out_lo = h->h_s.lo; q.M = M;
       ProfScope prof(h, CLS_LN, s);
-      layers::layernorm_kernel<true><<<(unsigned)ceil_div(M, 8), 256, 0, s>>>(q);
+      launch_pdl(layers::layernorm_kernel<true>, dim3((unsigned)ceil_div(M, 8)), dim3(256), 0, s, q);
       count_launch();
     }
     }
@@ -714,7 +714,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       q.out_f32 = h->h; q.out_hi = h->h_s.hi; q.out_lo = h->h_s.lo; q.M = M;
       q.B = B; q.Beff = Beff;
       ProfScope prof(h, CLS_LN, s);
-      layers::layernorm_kernel<false><<<(unsigned)ceil_div(M, 8), 256, 0, s>>>(q);
+      launch_pdl(layers::layernorm_kernel<false>, dim3((unsigned)ceil_div(M, 8)), dim3(256), 0, s, q);
       count_launch();
     }
     }

@@ -92,6 +92,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   uint64_t* barP = bars + 5;   // P chunk written by the 128 softmax threads
   uint64_t* barO = bars + 6;   // P.V chunk complete (tcgen05.commit)
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* barK1 = bars + 8;  // TB = 128: second key chunk, loaded at kernel start into the (still free) V buffer
+  uint64_t* barV1 = bars + 9;  // TB = 128: second value chunk (its load may be issued before the first has landed, so it
+                               // cannot share barV: an arrive on a phase with no pending arrival is undefined)
   float* s_max = reinterpret_cast<float*>(smem + NBUF * C::OPERAND + 1024);   // [128 rows][2 key halves]
   float* s_sum = s_max + 256;
 
@@ -114,6 +117,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       ptx::prefetch_tmap(&tm_lo);
       ptx::mbar_init(barQ, 1);
       ptx::mbar_init(barK, 1);
+      ptx::mbar_init(barK1, 1);
+      ptx::mbar_init(barV1, 1);
       ptx::mbar_init(barV, 1);
       ptx::mbar_init(&barS[0], 1);
       ptx::mbar_init(&barS[1], 1);
@@ -144,9 +149,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         ptx::tma_load_3d(dst + 2 * C::TILE, &tm_lo, bar, col0, b, t0);
         ptx::tma_load_3d(dst + 3 * C::TILE, &tm_lo, bar, col0 + 64, b, t0);
       };
+      // Buffer rotation (TB = 128, two key chunks): K_0 -> sK and K_1 -> sV are both fetched at the start; V_0 takes sK as
+      // soon as S_0 is complete and V_1 takes sV as soon as S_1 is, i.e. both V loads run behind the softmax passes and
+      // no operand load sits between two MMA phases.  One key chunk: K_0 -> sK, V_0 -> sV at the start.
+      const bool rotate = !C::COMPACT && nkc > 1;
       load_operand(sQ, barQ, h * HD, q0);
       load_operand(sK, barK, DM + h * HD, 0);
-      if (!C::COMPACT) load_operand(sV, barV, 2 * DM + h * HD, 0);
+      if (rotate) load_operand(sV, barK1, DM + h * HD, TB);
+      else if (!C::COMPACT) load_operand(sV, barV, 2 * DM + h * HD, 0);
 
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16_f32(128, TB);
       // P.V: B operand (V) is MN-major -> b_major bit 16
@@ -156,35 +166,37 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       // ---- scores: S_kc = Q . K_kc^T for every key chunk (all chunks stay resident in TMEM)
       ptx::mbar_wait(barQ, 0);
       for (int kc = 0; kc < nkc; ++kc) {
-        ptx::mbar_wait(barK, kc & 1);
+        if (kc == 0) ptx::mbar_wait(barK, 0); else ptx::mbar_wait(barK1, 0);
         if (kc == 0) REGEN_ATL(2);
         ptx::tcgen05_fence_after();
         const uint32_t accS = tmem_base + S_COL + (uint32_t)(kc * TB);
+        const uint32_t aKc = kc == 0 ? aK : aV;                      // K_1 sits in the V buffer
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t tile = (uint32_t)(k >> 2) * C::TILE;        // d 0-63 | d 64-127
           const uint32_t adv = (uint32_t)(k & 3) * 32;               // 16 bf16 inside the swizzle row
           const uint64_t q_hi = ptx::umma_desc_k_sw128(aQ + tile + adv);
           const uint64_t q_lo = ptx::umma_desc_k_sw128(aQ + 2 * C::TILE + tile + adv);
-          const uint64_t k_hi = ptx::umma_desc_k_sw128(aK + tile + adv);
-          const uint64_t k_lo = ptx::umma_desc_k_sw128(aK + 2 * C::TILE + tile + adv);
+          const uint64_t k_hi = ptx::umma_desc_k_sw128(aKc + tile + adv);
+          const uint64_t k_lo = ptx::umma_desc_k_sw128(aKc + 2 * C::TILE + tile + adv);
           ptx::mma_f16_ss(accS, q_lo, k_hi, idesc_s, k != 0);
           ptx::mma_f16_ss(accS, q_hi, k_lo, idesc_s, 1);
           ptx::mma_f16_ss(accS, q_hi, k_hi, idesc_s, 1);
         }
         ptx::tcgen05_commit(&barS[kc]);
-        ptx::mbar_wait(&barS[kc], 0);  // K buffer (and finally Q) free again
+        ptx::mbar_wait(&barS[kc], 0);  // this chunk's K buffer (and finally Q) free again
         if (kc == 0) REGEN_ATL(3);
-        if (kc + 1 < nkc) load_operand(sK, barK, DM + h * HD, (kc + 1) * TB);
+        if (rotate) load_operand(kc == 0 ? sK : sV, kc == 0 ? barV : barV1, 2 * DM + h * HD, kc * TB);  // V_kc -> K_kc's buffer
       }
       if (C::COMPACT) load_operand(sV, barV, 2 * DM + h * HD, 0);  // K is dead: V takes its buffer during the softmax
       // ---- O += P_kc . V_kc
       for (int kc = 0; kc < nkc; ++kc) {
         ptx::mbar_wait(barP, kc & 1);  // P chunk is in shared memory (written through the generic proxy + fence)
-        ptx::mbar_wait(barV, kc & 1);
+        if (kc == 0) ptx::mbar_wait(barV, 0); else ptx::mbar_wait(barV1, 0);
         if (kc == 0) REGEN_ATL(6);
         ptx::tcgen05_fence_after();
         const uint32_t accO = tmem_base + O_COL;
+        const uint32_t aVc = (rotate && kc == 0) ? aK : aV;          // rotation: V_0 in sK, V_1 in sV
 #pragma unroll
         for (int k = 0; k < TB / 16; ++k) {
           // A = P: [128 rows x 64 keys] tiles, K-major; k-step = 16 keys
@@ -193,17 +205,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
           const uint64_t p_lo = ptx::umma_desc_k_sw128(aQ + (TB / 64) * C::P_TILE + ptile);
           // B = V: [TB keys x 64 d] tiles; 16 keys = 16 rows of 128 bytes; second d half at +TILE
           const uint32_t lbo = (p.dbg & 1) ? 1024u : (uint32_t)C::TILE, sbo = (p.dbg & 1) ? (uint32_t)C::TILE : 1024u;
-          const uint64_t v_hi = umma_desc_mn_sw128(aV + (uint32_t)k * 2048, lbo, sbo);
-          const uint64_t v_lo = umma_desc_mn_sw128(aV + 2 * C::TILE + (uint32_t)k * 2048, lbo, sbo);
+          const uint64_t v_hi = umma_desc_mn_sw128(aVc + (uint32_t)k * 2048, lbo, sbo);
+          const uint64_t v_lo = umma_desc_mn_sw128(aVc + 2 * C::TILE + (uint32_t)k * 2048, lbo, sbo);
           ptx::mma_f16_ss(accO, p_lo, v_hi, idesc_o, (kc | k) != 0);
           ptx::mma_f16_ss(accO, p_hi, v_lo, idesc_o, 1);
           ptx::mma_f16_ss(accO, p_hi, v_hi, idesc_o, 1);
         }
         ptx::tcgen05_commit(barO);
-        if (kc + 1 < nkc) {
-          ptx::mbar_wait(barO, kc & 1);  // V and P buffers free
-          load_operand(sV, barV, 2 * DM + h * HD, (kc + 1) * TB);
-        }
       }
     }
   } else {

@@ -95,6 +95,21 @@ int regen_cfg_combine(const float* cond, const float* uncond, const float* scale
  * mask01 holds 0.0f / 1.0f; all three arrays share one memory layout (the sampler uses [T,B,I]). */
 int regen_inpaint_blend(float* x0, const float* motion, const float* mask01, int64_t n_elem, void* stream);
 
+/* PLMS sampler (diffusion/gaussian_diffusion.py:1007-1098; no caller in the reference, off the hot path).  Element e
+ * belongs to sample b = (e / inner) % B; tables are fp32 device arrays of n_table entries indexed by t[b] + t_shift
+ * (negative indices wrap).  regen_plms_eps: eps = (sqrt_recip_ac*x - clip(x0)) / sqrt_recipm1_ac, pred = clip(x0) (nullable).
+ * regen_plms_combine: eps' from the history, e0 newest: order 1..4 Adams-Bashforth (:1075-1086), 5 = (e0 + e1) / 2 (:1066).
+ * regen_plms_finish: mode 0  pred' = sra*x - srm1*eps', mean = pred'*sqrt(ac_prev) + sqrt(1 - ac_prev)*eps',
+ *                            out = mean*(t != 0) + pred*(1 - (t != 0));   mode 1  out = pred*sqrt(ac_prev) + sqrt(1 - ac_prev)*eps'. */
+int regen_plms_eps(const float* x, const float* x0, float* eps, float* pred, const int64_t* t,
+                   const float* sqrt_recip_ac, const float* sqrt_recipm1_ac, int64_t n_elem, int64_t inner,
+                   int32_t B, int32_t n_table, int32_t t_shift, int32_t clip_denoised, void* stream);
+int regen_plms_combine(const float* e0, const float* e1, const float* e2, const float* e3, float* out,
+                       int64_t n_elem, int32_t order, void* stream);
+int regen_plms_finish(const float* x, const float* eps_prime, const float* pred, float* out, const int64_t* t,
+                      const float* sqrt_recip_ac, const float* sqrt_recipm1_ac, const float* ac_prev, int64_t n_elem,
+                      int64_t inner, int32_t B, int32_t n_table, int32_t mode, void* stream);
+
 int regen_rot6d_to_matrix(const float* d6, float* R, int64_t n, void* stream);
 
 /* Post-sampling tail.  Temporal Gaussian smoothing = scipy.ndimage.gaussian_filter1d(x, sigma,

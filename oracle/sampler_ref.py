@@ -6,6 +6,7 @@ Follows
   * diffusion/gaussian_diffusion.py:508-560  p_sample
   * diffusion/gaussian_diffusion.py:675-742  p_sample_loop_progressive
   * diffusion/gaussian_diffusion.py:744-794  ddim_sample
+  * diffusion/gaussian_diffusion.py:1007-1098, 1132-1202  plms_sample / plms_sample_loop
   * diffusion/gaussian_diffusion.py:1604-1617 _extract_into_tensor (fp64 gather, THEN cast to fp32)
   * diffusion/respace.py:117-129             _WrappedModel timestep remap (integer gather)
   * utils/rotation_conversions.py:513-534    rotation_6d_to_matrix
@@ -73,6 +74,55 @@ class Sampler:
         mean = x0 * torch.sqrt(abp) + torch.sqrt(1 - abp - sigma ** 2) * eps
         nonzero = (t != 0).float().view(-1, *([1] * (nd - 1)))
         return mean + nonzero * sigma * noise, x0
+
+    def plms_sample(self, model, x, t, order=2, old_out=None, clip_denoised=False):
+        """diffusion/gaussian_diffusion.py:1007-1098 (no cond_fn): pseudo improved Euler for the first step when
+        order > 1, Adams-Bashforth of order min(order, len(history)) afterwards."""
+        tab = self.tab
+        nd = x.dim()
+
+        def model_eps(xx, tt):
+            _, _, x0 = self.p_mean_variance(model, xx, tt, clip_denoised)
+            eps = (_extract(tab.sqrt_recip_alphas_cumprod, tt, nd) * xx - x0) / _extract(tab.sqrt_recipm1_alphas_cumprod, tt, nd)
+            return eps, x0
+
+        def x0_from_eps(eps):
+            return _extract(tab.sqrt_recip_alphas_cumprod, t, nd) * x - _extract(tab.sqrt_recipm1_alphas_cumprod, t, nd) * eps
+
+        abp = _extract(tab.alphas_cumprod_prev, t, nd)
+        eps, x0 = model_eps(x, t)
+        if order > 1 and old_out is None:
+            old_eps = [eps]
+            mean_pred = x0 * torch.sqrt(abp) + torch.sqrt(1 - abp) * eps
+            eps_2, _ = model_eps(mean_pred, t - 1)
+            eps_prime = (eps + eps_2) / 2
+        else:
+            old_eps = old_out["old_eps"]
+            old_eps.append(eps)
+            k = min(order, len(old_eps))
+            if k == 1:
+                eps_prime = old_eps[-1]
+            elif k == 2:
+                eps_prime = (3 * old_eps[-1] - old_eps[-2]) / 2
+            elif k == 3:
+                eps_prime = (23 * old_eps[-1] - 16 * old_eps[-2] + 5 * old_eps[-3]) / 12
+            else:
+                eps_prime = (55 * old_eps[-1] - 59 * old_eps[-2] + 37 * old_eps[-3] - 9 * old_eps[-4]) / 24
+        mean_pred = x0_from_eps(eps_prime) * torch.sqrt(abp) + torch.sqrt(1 - abp) * eps_prime
+        if len(old_eps) >= order:
+            old_eps.pop(0)
+        nonzero = (t != 0).float().view(-1, *([1] * (nd - 1)))
+        return {"sample": mean_pred * nonzero + x0 * (1 - nonzero), "pred_xstart": x0, "old_eps": old_eps}
+
+    def plms_loop(self, model, shape, order=2, clip_denoised=False, init_noise=None):
+        """:1132-1202."""
+        img = init_noise if init_noise is not None else torch.randn(*shape)
+        old = None
+        with torch.no_grad():
+            for i in list(range(self.num_timesteps))[::-1]:
+                old = self.plms_sample(model, img, torch.tensor([i] * shape[0]), order, old, clip_denoised)
+                img = old["sample"]
+        return img
 
     def loop(self, model, shape, noise_fn=None, ddim=False, eta=0.0, clip_denoised=False, init_noise=None):
         """model(x, t_original) -> x0.  Noise is drawn as the reference does: th.randn(*shape) for x_N

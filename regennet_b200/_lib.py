@@ -52,6 +52,9 @@ _SIGNATURES = {
     "regen_ddim_update": (c_int, [c_void_p] * 10 + [c_float, c_i64, c_i64, c_int, c_int, c_void_p]),
     "regen_cfg_combine": (c_int, [c_void_p] * 4 + [c_i64, c_i64, c_int, c_void_p]),
     "regen_inpaint_blend": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    "regen_plms_eps": (c_int, [c_void_p] * 7 + [c_i64, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
+    "regen_plms_combine": (c_int, [c_void_p] * 5 + [c_i64, c_int, c_void_p]),
+    "regen_plms_finish": (c_int, [c_void_p] * 8 + [c_i64, c_i64, c_int, c_int, c_int, c_void_p]),
     "regen_rot6d_to_matrix": (c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
     "regen_gaussian_filter1d_time": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, ctypes.c_double,
                                              ctypes.c_double, c_void_p]),

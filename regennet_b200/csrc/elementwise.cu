@@ -187,6 +187,74 @@ __global__ void __launch_bounds__(kThreads) inpaint_blend_kernel(float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// PLMS (pseudo linear multistep) sampler pieces, diffusion/gaussian_diffusion.py:1007-1098.  Off the hot path (no caller
+// in the reference uses it); three small HBM-bound kernels keep its arithmetic in the library, in torch's operation order.
+// Tables are indexed with t[b] + t_shift, negative indices wrapping like Python's (the corrector evaluates at t - 1).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int plms_index(const int64_t* t, int b, int shift, int n_table) {
+  int64_t i = t[b] + shift;
+  if (i < 0) i += n_table;
+  return (int)(i < 0 ? 0 : (i >= n_table ? n_table - 1 : i));
+}
+
+// eps = (sqrt_recip_ac[t] * x - clip(x0)) / sqrt_recipm1_ac[t]      (_predict_eps_from_xstart, :418-423); pred = clip(x0)
+__global__ void __launch_bounds__(kThreads) plms_eps_kernel(const float* __restrict__ x, const float* __restrict__ x0,
+                                                            float* __restrict__ eps, float* __restrict__ pred,
+                                                            const int64_t* __restrict__ t, const float* __restrict__ sra,
+                                                            const float* __restrict__ srm1, uint32_t n, uint32_t inner,
+                                                            uint32_t B, int n_table, int t_shift, int clip) {
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const int k = plms_index(t, (int)((i / inner) % B), t_shift, n_table);
+    const float v0 = clampf(x0[i], clip);
+    eps[i] = __fdiv_rn(__fsub_rn(__fmul_rn(__ldg(sra + k), x[i]), v0), __ldg(srm1 + k));
+    if (pred) pred[i] = v0;
+  }
+}
+
+// eps' from the history (e0 newest): order 1..4 = Adams-Bashforth (:1075-1086), 5 = improved Euler (e0 + e1) / 2 (:1066)
+__global__ void __launch_bounds__(kThreads) plms_combine_kernel(const float* __restrict__ e0, const float* __restrict__ e1,
+                                                                const float* __restrict__ e2, const float* __restrict__ e3,
+                                                                float* __restrict__ out, uint32_t n, int order) {
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    float r;
+    if (order == 1) r = e0[i];
+    else if (order == 2) r = __fdiv_rn(__fsub_rn(__fmul_rn(3.f, e0[i]), e1[i]), 2.f);
+    else if (order == 3)
+      r = __fdiv_rn(__fadd_rn(__fsub_rn(__fmul_rn(23.f, e0[i]), __fmul_rn(16.f, e1[i])), __fmul_rn(5.f, e2[i])), 12.f);
+    else if (order == 4)
+      r = __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(__fmul_rn(55.f, e0[i]), __fmul_rn(59.f, e1[i])), __fmul_rn(37.f, e2[i])),
+                              __fmul_rn(9.f, e3[i])), 24.f);
+    else r = __fdiv_rn(__fadd_rn(e0[i], e1[i]), 2.f);
+    out[i] = r;
+  }
+}
+
+// mode 0: pred' = sra[t] x - srm1[t] eps';  mean = pred' sqrt(abar_prev[t]) + sqrt(1 - abar_prev[t]) eps';
+//         out = mean * (t != 0) + pred * (1 - (t != 0))                                             (:1068-1095)
+// mode 1: out = pred sqrt(abar_prev[t]) + sqrt(1 - abar_prev[t]) eps'     (improved-Euler predictor, :1064)
+__global__ void __launch_bounds__(kThreads) plms_finish_kernel(const float* __restrict__ x, const float* __restrict__ epsp,
+                                                               const float* __restrict__ pred, float* __restrict__ out,
+                                                               const int64_t* __restrict__ t, const float* __restrict__ sra,
+                                                               const float* __restrict__ srm1, const float* __restrict__ acp,
+                                                               uint32_t n, uint32_t inner, uint32_t B, int n_table, int mode) {
+  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) {
+    const int b = (int)((i / inner) % B);
+    const int k = plms_index(t, b, 0, n_table);
+    const float ap = __ldg(acp + k);
+    const float s1 = __fsqrt_rn(ap), s2 = __fsqrt_rn(__fsub_rn(1.f, ap));
+    const float e = epsp[i];
+    if (mode == 1) {
+      out[i] = __fadd_rn(__fmul_rn(pred[i], s1), __fmul_rn(s2, e));
+    } else {
+      const float pp = __fsub_rn(__fmul_rn(__ldg(sra + k), x[i]), __fmul_rn(__ldg(srm1 + k), e));
+      const float mean = __fadd_rn(__fmul_rn(pp, s1), __fmul_rn(s2, e));
+      const float nz = t[b] != 0 ? 1.f : 0.f;
+      out[i] = __fadd_rn(__fmul_rn(mean, nz), __fmul_rn(pred[i], __fsub_rn(1.f, nz)));
+    }
+  }
+}
+
 // utils/rotation_conversions.py:529-534.  One rotation per thread; the block's 6-float inputs and
 // 9-float outputs are staged through shared memory so global traffic is float4-coalesced.
 constexpr int kRotPerBlock = 256;
@@ -481,6 +549,50 @@ int regen_inpaint_blend(float* x0, const float* motion, const float* mask01, int
     REGEN_CUDA(launch_pdl(inpaint_blend_kernel<false>, dim3(grid_for(n_elem)), dim3(kThreads), 0, s, x0, motion, mask01,
                           (uint32_t)n_elem));
   }
+  count_launch();
+  return REGEN_OK;
+}
+
+int regen_plms_eps(const float* x, const float* x0, float* eps, float* pred, const int64_t* t, const float* sqrt_recip_ac,
+                   const float* sqrt_recipm1_ac, int64_t n_elem, int64_t inner, int32_t B, int32_t n_table, int32_t t_shift,
+                   int32_t clip_denoised, void* stream) {
+  REGEN_CHECK_ARG(x && x0 && eps && t && sqrt_recip_ac && sqrt_recipm1_ac, "plms_eps: null pointer");
+  REGEN_CHECK_ARG(n_elem >= 0 && n_elem < (int64_t)1 << 32 && inner > 0 && B > 0 && n_table > 0, "plms_eps: bad sizes");
+  if (n_elem == 0) return REGEN_OK;
+  plms_eps_kernel<<<grid_for(n_elem), kThreads, 0, (cudaStream_t)stream>>>(x, x0, eps, pred, t, sqrt_recip_ac,
+                                                                          sqrt_recipm1_ac, (uint32_t)n_elem,
+                                                                          (uint32_t)inner, (uint32_t)B, n_table, t_shift,
+                                                                          clip_denoised);
+  REGEN_LAUNCH_CHECK();
+  count_launch();
+  return REGEN_OK;
+}
+
+int regen_plms_combine(const float* e0, const float* e1, const float* e2, const float* e3, float* out, int64_t n_elem,
+                       int32_t order, void* stream) {
+  REGEN_CHECK_ARG(e0 && out && order >= 1 && order <= 5, "plms_combine: bad argument");
+  REGEN_CHECK_ARG((order == 1) || e1, "plms_combine: history too short for the order");
+  REGEN_CHECK_ARG((order != 3 && order != 4) || e2, "plms_combine: history too short for the order");
+  REGEN_CHECK_ARG(order != 4 || e3, "plms_combine: history too short for the order");
+  REGEN_CHECK_ARG(n_elem >= 0 && n_elem < (int64_t)1 << 32, "plms_combine: bad n_elem");
+  if (n_elem == 0) return REGEN_OK;
+  plms_combine_kernel<<<grid_for(n_elem), kThreads, 0, (cudaStream_t)stream>>>(e0, e1, e2, e3, out, (uint32_t)n_elem, order);
+  REGEN_LAUNCH_CHECK();
+  count_launch();
+  return REGEN_OK;
+}
+
+int regen_plms_finish(const float* x, const float* eps_prime, const float* pred, float* out, const int64_t* t,
+                      const float* sqrt_recip_ac, const float* sqrt_recipm1_ac, const float* ac_prev, int64_t n_elem,
+                      int64_t inner, int32_t B, int32_t n_table, int32_t mode, void* stream) {
+  REGEN_CHECK_ARG(eps_prime && pred && out && t && ac_prev && (mode == 0 || mode == 1), "plms_finish: bad argument");
+  REGEN_CHECK_ARG(mode == 1 || (x && sqrt_recip_ac && sqrt_recipm1_ac), "plms_finish: null pointer");
+  REGEN_CHECK_ARG(n_elem >= 0 && n_elem < (int64_t)1 << 32 && inner > 0 && B > 0 && n_table > 0, "plms_finish: bad sizes");
+  if (n_elem == 0) return REGEN_OK;
+  plms_finish_kernel<<<grid_for(n_elem), kThreads, 0, (cudaStream_t)stream>>>(x, eps_prime, pred, out, t, sqrt_recip_ac,
+                                                                             sqrt_recipm1_ac, ac_prev, (uint32_t)n_elem,
+                                                                             (uint32_t)inner, (uint32_t)B, n_table, mode);
+  REGEN_LAUNCH_CHECK();
   count_launch();
   return REGEN_OK;
 }

@@ -5,8 +5,8 @@ Same names, argument meaning and error behaviour as the reference for everything
 sampling callers use (sample/cgenerate.py:121-135, eval/a2m/stgcn_eval.py:38-69):
 ``get_named_beta_schedule``, ``GaussianDiffusion(...)`` with its fp64 tables,
 ``p_mean_variance``, ``p_sample``, ``p_sample_loop(_progressive)``, ``ddim_sample``,
-``ddim_sample_loop(_progressive)``.  Training losses, PLMS and the learned-variance /
-epsilon-prediction variants are out of scope (utils/model_util.py:75-117 hard-wires START_X with
+``ddim_sample_loop(_progressive)``, ``plms_sample`` / ``plms_sample_loop(_progressive)``.  Training losses and the
+learned-variance / epsilon-prediction variants are out of scope (utils/model_util.py:75-117 hard-wires START_X with
 a fixed variance) and raise NotImplementedError.
 
 Two routes:
@@ -404,6 +404,120 @@ class GaussianDiffusion:
             raise NotImplementedError("ddim_sample_with_grad is off the sampling hot path")
         yield from self._loop("ddim", model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device,
                               progress, skip_timesteps, init_image, randomize_class, False, eta)
+
+    # ------------------------------------------------------------------------------------- PLMS
+    def _plms_align(self, x, x0):
+        """Operands of the PLMS kernels in the model output's memory layout (same rule as _update)."""
+        _lib.require_cuda_f32(x, "x")
+        _lib.require_cuda_f32(x0, "model output")
+        if x.dim() == 4:
+            lay = _layout_of(x0)
+            if lay is None:
+                x0, lay = x0.contiguous(), "bjft"
+            new = lambda: _empty_in_layout(x.shape, lay, x.device)
+            inner = x[0].numel() if lay == "bjft" else x.shape[1] * x.shape[2]
+            return _to_layout(x, lay), x0, new, inner
+        x0 = x0.contiguous()
+        return x.contiguous(), x0, (lambda: th.empty_like(x0)), (x[0].numel() if x.dim() > 1 else 1)
+
+    def plms_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
+                    cond_fn_with_grad=False, order=2, old_out=None):
+        """Pseudo linear multistep step (:1007-1098) -> {"sample", "pred_xstart", "old_eps"}.  The model runs through
+        _call_model (fused denoiser kernels for this package's CMDM); the eps / Adams-Bashforth / x_{t-1} arithmetic
+        runs in regen_plms_eps / regen_plms_combine / regen_plms_finish."""
+        if not int(order) or not 1 <= order <= 4:
+            raise ValueError('order is invalid (should be int from 1-4).')
+        if cond_fn is not None or cond_fn_with_grad:
+            raise NotImplementedError("cond_fn score conditioning is off the sampling hot path")
+        self._check_supported()
+        L, tab, B = _lib.lib(), self._tables(x.device), x.shape[0]
+        n_table = self.num_timesteps
+        t = t.to(device=x.device, dtype=th.int64).contiguous()
+        sp = _lib.stream_ptr(x.device)
+
+        def model_eps(xin, tt, shift):
+            """eps and (clipped) pred_xstart of the model at (xin, tt); tables at tt (= t + shift)."""
+            x0 = self._call_model(model, xin, tt, denoised_fn, model_kwargs)
+            xl, x0, new, inner = self._plms_align(xin, x0)
+            eps, pred = new(), new()
+            _lib.check(L.regen_plms_eps(_lib.ptr(xl), _lib.ptr(x0), _lib.ptr(eps), _lib.ptr(pred), _lib.ptr(t),
+                                        _lib.ptr(tab["sqrt_recip_ac"]), _lib.ptr(tab["sqrt_recipm1_ac"]), xl.numel(), inner,
+                                        B, n_table, shift, int(bool(clip_denoised)), sp), "regen_plms_eps")
+            return xl, eps, pred, new, inner
+
+        def finish(xl, epsp, pred, new, inner, mode):
+            out = new()
+            _lib.check(L.regen_plms_finish(_lib.ptr(xl), _lib.ptr(epsp), _lib.ptr(pred), _lib.ptr(out), _lib.ptr(t),
+                                           _lib.ptr(tab["sqrt_recip_ac"]), _lib.ptr(tab["sqrt_recipm1_ac"]),
+                                           _lib.ptr(tab["ac_prev"]), xl.numel(), inner, B, n_table, mode, sp),
+                       "regen_plms_finish")
+            return out
+
+        def combine(hist, code, new):
+            out = new()
+            e = [hist[-1 - i] if i < len(hist) else None for i in range(4)]
+            _lib.check(L.regen_plms_combine(_lib.ptr(e[0]), _lib.ptr(e[1]), _lib.ptr(e[2]), _lib.ptr(e[3]), _lib.ptr(out),
+                                            out.numel(), code, sp), "regen_plms_combine")
+            return out
+
+        xl, eps, pred, new, inner = model_eps(x, t, 0)
+        if order > 1 and old_out is None:
+            # pseudo improved Euler: predictor with eps, second model evaluation at t - 1, average of the two eps
+            old_eps = [eps]
+            mean_pred = finish(xl, eps, pred, new, inner, 1)
+            _, eps_2, _, _, _ = model_eps(mean_pred, t - 1, -1)
+            eps_prime = combine([eps, eps_2], 5, new)
+        else:
+            old_eps = old_out["old_eps"]
+            old_eps.append(eps)
+            eps_prime = combine(old_eps, min(order, len(old_eps)), new)
+        sample = finish(xl, eps_prime, pred, new, inner, 0)
+        if len(old_eps) >= order:
+            old_eps.pop(0)
+        return {"sample": sample, "pred_xstart": pred, "old_eps": old_eps}
+
+    def plms_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                         model_kwargs=None, device=None, progress=False, skip_timesteps=0, init_image=None,
+                         randomize_class=False, cond_fn_with_grad=False, order=2):
+        """:1100-1130."""
+        final = None
+        for sample in self.plms_sample_loop_progressive(
+                model, shape, noise=noise, clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn,
+                model_kwargs=model_kwargs, device=device, progress=progress, skip_timesteps=skip_timesteps,
+                init_image=init_image, randomize_class=randomize_class, cond_fn_with_grad=cond_fn_with_grad, order=order):
+            final = sample
+        return final["sample"]
+
+    def plms_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                                     model_kwargs=None, device=None, progress=False, skip_timesteps=0, init_image=None,
+                                     randomize_class=False, cond_fn_with_grad=False, order=2):
+        """:1132-1202 (deterministic: the only random draw is x_T)."""
+        if device is None:
+            device = next(model.parameters()).device
+        assert isinstance(shape, (tuple, list))
+        img = noise if noise is not None else th.randn(*shape, device=device)
+        if skip_timesteps and init_image is None:
+            init_image = th.zeros_like(img)
+        indices = list(range(self.num_timesteps - skip_timesteps))[::-1]
+        if init_image is not None:
+            my_t = th.ones([shape[0]], device=device, dtype=th.long) * indices[0]
+            img = self.q_sample(init_image, my_t, img)
+        if progress:
+            from tqdm.auto import tqdm
+            indices = tqdm(indices)
+        old_out = None
+        for i in indices:
+            t = th.tensor([i] * shape[0], device=device)
+            if randomize_class and 'y' in model_kwargs:
+                model_kwargs['y'] = th.randint(low=0, high=model.num_classes, size=model_kwargs['y'].shape,
+                                               device=model_kwargs['y'].device)
+            with th.no_grad():
+                out = self.plms_sample(model, img, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                       cond_fn=cond_fn, model_kwargs=model_kwargs, cond_fn_with_grad=cond_fn_with_grad,
+                                       order=order, old_out=old_out)
+                yield out
+                old_out = out
+                img = out["sample"]
 
     def _loop(self, kind, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device, progress,
               skip_timesteps, init_image, randomize_class, const_noise, eta, graph_ok=False):

@@ -83,3 +83,15 @@ OFFLINE_FORWARD_CASES = {
 OFFLINE_LOOP_CASES = {
     "off_loop_ntu_p10": dict(model="ntu_off", B=2, T=60, respacing="ddim10", ddim=False, wseed=4, xseed=20, seed=11),
 }
+
+# PLMS sampler (diffusion/gaussian_diffusion.py:1007-1202); goldens in loops_plms.npz (make_golden_plms.py).
+# order 2 exercises the pseudo-improved-Euler first step (second model call at t - 1) and Adams-Bashforth 2;
+# order 4 walks through Adams-Bashforth 2..4 as the history fills.  order=1 from a fresh loop raises TypeError in the
+# reference (old_out is None at :1067), so it has no golden; the tests check that this package raises the same.
+PLMS_LOOP_CASES = {
+    "plms_ntu_o2": dict(model="ntu", B=2, T=60, respacing="ddim10", order=2, wseed=0, xseed=10, seed=21),
+    "plms_ntu_o4": dict(model="ntu", B=1, T=37, respacing="ddim12", order=4, wseed=1, xseed=11, seed=22),
+    "plms_chi3d_cfg_o3": dict(model="chi3d", B=2, T=150, respacing="ddim8", order=3, wseed=2, xseed=13, seed=23,
+                              cfg_scale=2.5),
+    "plms_ntu_o2_clip": dict(model="ntu", B=2, T=60, respacing="ddim6", order=2, wseed=0, xseed=10, seed=24, clip=True),
+}

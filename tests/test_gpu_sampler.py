@@ -304,3 +304,67 @@ def test_full_size_loop_graph_equals_step_by_step_and_is_deterministic(built_lib
     last = list(d.p_sample_loop_progressive(model, shape, noise=outs[0], clip_denoised=False, model_kwargs={"y": yc},
                                             skip_timesteps=13))[-1]
     assert torch.equal(last["sample"], last["pred_xstart"])
+
+
+# ------------------------------------------------------------------------------------------ PLMS
+@pytest.mark.parametrize("name", sorted(cases.PLMS_LOOP_CASES))
+def test_plms_loop_reproduces_reference_golden(built_lib, name):
+    """plms_sample_loop (diffusion/gaussian_diffusion.py:1100-1202) through the public API vs the samples the imported
+    reference produced on CPU (tests/golden/make_golden_plms.py).  PLMS draws x_T only, so no RNG patching is needed."""
+    c = cases.PLMS_LOOP_CASES[name]
+    mk = cases.MODELS[c["model"]]
+    gold = torch.from_numpy(np.load(os.path.join(HERE, "loops_plms.npz"))[name])
+    model, sd = get_model(c["model"], c["wseed"])
+    _, y = synthetic.make_inputs(c["B"], mk["njoints"], mk["nfeats"], c["T"], seed=c["xseed"],
+                                 cond_mode=mk["cond_mode"], num_actions=mk["num_actions"], scale=c.get("cfg_scale"))
+    d = _diffusion(c["respacing"])
+    run = ClassifierFreeSampleModel(model) if "cfg_scale" in c else model
+    shape = (c["B"], mk["njoints"], mk["nfeats"], c["T"])
+    torch.manual_seed(c["seed"])
+    init = torch.randn(*shape)
+    launches0 = built_lib.regen_launch_count()
+    out = d.plms_sample_loop(run, shape, noise=init.cuda(), clip_denoised=bool(c.get("clip")),
+                             model_kwargs={"y": to_cuda(y)}, order=c["order"])
+    assert built_lib.regen_launch_count() > launches0
+    assert out.shape == gold.shape
+    err = (out.cpu() - gold).abs().max().item()
+    print("%s: %d steps order %d, max abs err vs reference golden %.3e" % (name, d.num_timesteps, c["order"], err))
+    assert err < TOL
+
+
+def test_plms_step_arithmetic_matches_oracle_on_injected_model_outputs(built_lib):
+    """The three PLMS kernels alone: a fake model (fixed linear map of x, per-sample timestep-dependent) makes the whole
+    difference arithmetic, so the fp32 operation order must reproduce the oracle to rounding."""
+    B, shape = 3, (3, 5, 6, 17)
+    smp = sampler_ref.Sampler(timestep_respacing="ddim7")
+    d = _diffusion("ddim7")
+
+    class Fake(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+
+        def forward(self, x, t, y=None):
+            return 0.7 * x + 0.001 * t.float().view(-1, 1, 1, 1)
+
+    torch.manual_seed(3)
+    init = torch.randn(*shape)
+    for order in (2, 3, 4):
+        ora = smp.plms_loop(lambda xx, tt: 0.7 * xx + 0.001 * tt.float().view(-1, 1, 1, 1), shape, order=order,
+                            init_noise=init.clone())
+        out = d.plms_sample_loop(Fake().cuda(), shape, noise=init.cuda(), clip_denoised=False, order=order)
+        err = (out.cpu() - ora).abs().max().item()
+        print("order %d: max abs err %.3e (absmax %.3f)" % (order, err, ora.abs().max()))
+        assert err < 1e-5 * max(1.0, ora.abs().max().item())
+
+
+def test_plms_error_behaviour(built_lib):
+    model, _ = get_model("ntu", 0)
+    d = _diffusion("ddim5")
+    x = torch.randn(1, 56, 6, 60, device="cuda")
+    t = torch.tensor([4], device="cuda")
+    _, y = synthetic.make_inputs(1, 56, 6, 60, seed=1)
+    with pytest.raises(ValueError, match="order is invalid"):
+        d.plms_sample(model, x, t, model_kwargs={"y": to_cuda(y)}, order=5)
+    with pytest.raises(TypeError):  # the reference dereferences old_out=None at :1067 when order == 1
+        d.plms_sample(model, x, t, model_kwargs={"y": to_cuda(y)}, order=1)

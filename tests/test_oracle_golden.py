@@ -113,3 +113,28 @@ def test_offline_sampling_loop_matches_reference():
     out, _ = smp.loop(lambda xx, tt: cmdm_ref.cmdm_forward(sd, xx, tt, y, **_kw_off(mk)),
                       (c["B"], mk["njoints"], mk["nfeats"], c["T"]))
     assert np.abs(out.numpy() - gold).max() < TOL
+
+
+@pytest.mark.parametrize("name", sorted(cases.PLMS_LOOP_CASES))
+def test_plms_loop_matches_reference(name):
+    """PLMS (diffusion/gaussian_diffusion.py:1007-1202) against the reference's plms_sample_loop (make_golden_plms.py)."""
+    c = cases.PLMS_LOOP_CASES[name]
+    mk = cases.MODELS[c["model"]]
+    gold = np.load(os.path.join(HERE, "loops_plms.npz"))[name]
+    _, y = synthetic.make_inputs(c["B"], mk["njoints"], mk["nfeats"], c["T"], seed=c["xseed"],
+                                 cond_mode=mk["cond_mode"], num_actions=mk["num_actions"], scale=c.get("cfg_scale"))
+    sd = _sd(c["model"], c["wseed"])
+    fwd = cmdm_ref.cfg_forward if "cfg_scale" in c else cmdm_ref.cmdm_forward
+    smp = sampler_ref.Sampler(timestep_respacing=c["respacing"])
+    torch.manual_seed(c["seed"])
+    out = smp.plms_loop(lambda xx, tt: fwd(sd, xx, tt, y, **_kw(mk)), (c["B"], mk["njoints"], mk["nfeats"], c["T"]),
+                        order=c["order"], clip_denoised=bool(c.get("clip")))
+    assert out.shape == gold.shape
+    assert np.abs(out.numpy() - gold).max() < TOL
+
+
+def test_plms_order1_from_fresh_loop_raises_like_reference():
+    # the reference dereferences old_out (None) at :1067 when order == 1 on the first step
+    smp = sampler_ref.Sampler(timestep_respacing="ddim5")
+    with pytest.raises(TypeError):
+        smp.plms_loop(lambda xx, tt: xx, (1, 2, 3, 4), order=1)

@@ -34,9 +34,12 @@ struct Cfg {
   static constexpr int P_BYTES = 2 * (TB / 64) * P_TILE;
   static_assert(P_BYTES == OPERAND, "P aliases the Q operand region");
   // TB = 64 ("compact"): K and V share one buffer (V is fetched while the softmax runs) and O reuses the TMEM columns
-  // of S, so a CTA needs ~69 KB of shared memory, 128 TMEM columns and 160 threads: three CTAs per SM.
+  // of S, so a CTA needs ~69 KB of shared memory, 128 TMEM columns and 288 threads: three CTAs per SM.
   static constexpr bool COMPACT = TB == 64;
-  static constexpr int SW = COMPACT ? 4 : 8;                 // softmax / epilogue warps
+  // softmax / epilogue warps: two per TMEM lane quarter, each owns half of a chunk's key columns (softmax) and half of
+  // the head dimension (epilogue).  The compact kernel ran 4 warps (one per quarter, 64 scores per thread) in the first
+  // version; two warps per quarter halve the per-thread softmax and read-out work on the CTA's latency chain.
+  static constexpr int SW = 8;
   static constexpr int THREADS = 32 + 32 * SW;               // + warp 0: TMA + MMA control
   static constexpr int SMEM_BYTES = (COMPACT ? 2 : 3) * OPERAND + 4096 + 1024;  // + barriers / row statistics
 };
@@ -273,20 +276,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       }
     };
     if constexpr (C::COMPACT) {
-      // one key chunk of 64, one warp per lane quarter: the 64 scores of the row are read from TMEM ONCE and stay in
-      // registers for the maximum and the exponentials
-      uint32_t s0[32], s1[32];
+      // one key chunk of 64, two warps per lane quarter: this warp's 32 scores of the row are read from TMEM ONCE and
+      // stay in registers for the maximum and the exponentials; the row maximum is exchanged with the sibling warp
+      static_assert(KH == 32, "compact softmax: one 32-column TMEM load per warp");
+      uint32_t s0[32];
       __syncwarp();
-      ptx::tmem_ld_32x32b_x32(lane_addr + S_COL, s0);
-      ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + 32u, s1);
+      ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + (uint32_t)(half * KH), s0);
       ptx::tmem_ld_wait(s0);
-      ptx::tmem_ld_wait(s1);
-      row_max(s0, 0);
-      row_max(s1, 32);
+      row_max(s0, half * KH);
+      s_max[r * 2 + half] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      mx = fmaxf(mx, s_max[r * 2 + (half ^ 1)]);
       if (!row_ok) mx = 0.f;
       if (warp == 1 && lane == 0) REGEN_ATL(4);
-      emit_p(s0, 0, 0);
-      emit_p(s1, 0, 32);
+      emit_p(s0, 0, half * KH);
       ptx::fence_proxy_async_smem();  // make the generic-proxy stores visible to the tensor core (async proxy)
       ptx::mbar_arrive(barP);
       if (warp == 1 && lane == 0) REGEN_ATL(5);

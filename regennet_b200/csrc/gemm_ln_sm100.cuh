@@ -14,6 +14,12 @@
 // 2 (N halves) x 3 (bf16x3) MMAs of 256x256x16 per k-step.  Epilogue (8 warps per CTA, after the main loop, the
 // operand ring is reused as staging): the residual and c tiles arrive by TMA (4-deep ring per warp), v / y are kept in
 // TMEM between the passes (tcgen05.st), outputs (fp32 h + bf16 hi/lo) leave by TMA stores.
+//
+// R16 = true (default): the residual stream lives in HBM only as its bf16 (hi, lo) pair.  The residual tile is loaded
+// as two 32 x 64 bf16 boxes (128-byte rows) and rebuilt as hi + lo, and the final pass stores hi / lo only: the final
+// pass is bound by the TMA row rate (one box row per ~2.6 cycles), so dropping the fp32 copy halves its 128 row requests
+// per 64 columns and the bytes written.  The residual then carries 16 significand bits (forward error ~3e-5 instead of
+// ~1.5e-5, tolerance 1e-3).  R16 = false (REGEN_DEBUG_F32_RESIDUAL=1) keeps the fp32 copy of h.
 #pragma once
 #include "common.cuh"
 #include "gemm_sm100.cuh"
@@ -59,6 +65,7 @@ struct Params {
   int M, K, Beff;
   const float *bias, *g1, *b1, *g2, *b2;  // [512] each (g2/b2 unused without CHAIN)
   float ln_eps;
+  int store_f32;                 // LN = false only: 1 = also store the fp32 copy of h through tm_c (0 with R16 consumers)
   int prefetch_res;              // 1: L2-prefetch the residual tile during the main loop (REGEN_DEBUG_NO_RES_PREFETCH=1 -> 0)
   unsigned long long* timeline;  // bring-up instrumentation (null in production), see tools/ln_timeline.py
   unsigned long long* steplog;   // whole-step timeline (ptx::steplog_begin / steplog_end), null in production
@@ -83,7 +90,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // tm_res: fp32 [M, 512] residual stream h (box 32 x 32, SWIZZLE_128B) -- used for the residual LOAD and the h STORE
 // tm_c  : fp32 [Beff + 32, 512] cyclic per-sample constant (row r = c[r % Beff]); only read with CHAIN
 // tm_ohi / tm_olo: bf16 [M, 512] split of h (store, box 32 rows x 64 columns, SWIZZLE_128B)
-template <bool SPLIT, bool CHAIN, int EW, bool LN = true>
+template <bool SPLIT, bool CHAIN, int EW, bool LN = true, bool R16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Epi<EW, CHAIN>::THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -102,6 +109,12 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   uint64_t* tmem_empty_bar = bars + 5;   // leader's copy: 16 arrivals (epilogue warps of both CTAs)
   uint64_t* epi_done_bar = bars + 6;     // local: 8 arrivals, operand ring free again for the producer
   using E = Epi<EW, CHAIN>;
+  // R16: residual ring of RING_P pair slots (hi box | lo box, 8 KB, two sub-chunks each), c ring of RC fp32 slots
+  static_assert(!R16 || (EW == 8 && LN), "the bf16 (hi, lo) residual variant is built for 8 epilogue warps");
+  constexpr int RING_P = CHAIN ? 2 : 3;
+  constexpr int RC = R16 ? 2 : E::RING_C;
+  constexpr int NP = E::NSC / 2;         // sub-chunk pairs per warp
+  static_assert(!R16 || (RING_P * 2 + (CHAIN ? RC : 0)) * SLOT <= E::WARP_BYTES, "R16 staging budget");
   uint64_t* ring_bar = bars + 8;         // [EW warps][8]: res slots 0..3, c slots 4..7
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 8 + 8 * EW);
 
@@ -166,8 +179,14 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           // into L2 during the main loop, which leaves DRAM bandwidth unused: 64 boxes of 32 x 32 spread over the k-blocks.
           if (p.prefetch_res) {
             const int per_kb = (64 + num_kb - 1) / num_kb;
-            for (int i = kb * per_kb; i < (kb + 1) * per_kb && i < 64; ++i)
-              ptx::tma_prefetch_l2_2d(&tm_res, (i & 15) * SC, m0 + (i >> 4) * 32);
+            for (int i = kb * per_kb; i < (kb + 1) * per_kb && i < 64; ++i) {
+              if constexpr (R16) {  // 32 hi + 32 lo boxes of 32 rows x 64 columns
+                const int k = i >> 1;
+                ptx::tma_prefetch_l2_2d((i & 1) ? &tm_olo : &tm_ohi, (k & 7) * 2 * SC, m0 + (k >> 3) * 32);
+              } else {
+                ptx::tma_prefetch_l2_2d(&tm_res, (i & 15) * SC, m0 + (i >> 4) * 32);
+              }
+            }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -235,7 +254,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     named_bar_sync(5, 32 * EW);
     uint8_t* my = smem + ew * E::WARP_BYTES;
     uint8_t* res_ring = my;
-    uint8_t* c_ring = my + E::RING_R * SLOT;
+    uint8_t* c_ring = my + (R16 ? RING_P * 2 : E::RING_R) * SLOT;
     uint8_t* out_buf = my;                             // 3 x NOB x 4 KB, used after both rings are drained
     uint64_t* rbar = ring_bar + ew * 8;                // [0..2] residual slots, [4..6] c slots
     const float* s_bias = s_par + hf * E::WCOLS;
@@ -288,7 +307,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               const float4 rj = *reinterpret_cast<const float4*>(rring + slot * SLOT + off_f32(lane, j));
               const float z0 = __uint_as_float(r[4 * j]) + b4.x + rj.x, z1 = __uint_as_float(r[4 * j + 1]) + b4.y + rj.y;
               const float z2 = __uint_as_float(r[4 * j + 2]) + b4.z + rj.z, z3 = __uint_as_float(r[4 * j + 3]) + b4.w + rj.w;
-              *reinterpret_cast<float4*>(fb + off_f32(lane, j)) = make_float4(z0, z1, z2, z3);
+              if (p.store_f32) *reinterpret_cast<float4*>(fb + off_f32(lane, j)) = make_float4(z0, z1, z2, z3);
               const uint32_t h0 = gemm::pack_bf16x2(z0, z1), h1 = gemm::pack_bf16x2(z2, z3);
               hw[2 * jj] = h0;
               hw[2 * jj + 1] = h1;
@@ -305,7 +324,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               ptx::mbar_expect_tx(&rbar[slot], SLOT);
               ptx::tma_load_2d(rring + slot * SLOT, &tm_res, &rbar[slot], n_base + SC * (sc + 2), row0);
             }
-            ptx::tma_store_2d(&tm_c, fb, n_base + SC * sc, row0);
+            if (p.store_f32) ptx::tma_store_2d(&tm_c, fb, n_base + SC * sc, row0);
             if (half) {
               ptx::tma_store_2d(&tm_ohi, hb, n_base + 2 * SC * u, row0);
               ptx::tma_store_2d(&tm_olo, lb, n_base + 2 * SC * u, row0);
@@ -327,14 +346,23 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       } else {
       // prime the residual (and c) rings
       if (lane == 0) {
+        if constexpr (R16) {
 #pragma unroll
-        for (int s = 0; s < E::RING_R; ++s) {
-          ptx::mbar_expect_tx(&rbar[s], SLOT);
-          ptx::tma_load_2d(res_ring + s * SLOT, &tm_res, &rbar[s], n_base + SC * s, row0);
+          for (int s = 0; s < RING_P; ++s) {
+            ptx::mbar_expect_tx(&rbar[s], 2 * SLOT);
+            ptx::tma_load_2d(res_ring + s * 2 * SLOT, &tm_ohi, &rbar[s], n_base + 2 * SC * s, row0);
+            ptx::tma_load_2d(res_ring + s * 2 * SLOT + SLOT, &tm_olo, &rbar[s], n_base + 2 * SC * s, row0);
+          }
+        } else {
+#pragma unroll
+          for (int s = 0; s < E::RING_R; ++s) {
+            ptx::mbar_expect_tx(&rbar[s], SLOT);
+            ptx::tma_load_2d(res_ring + s * SLOT, &tm_res, &rbar[s], n_base + SC * s, row0);
+          }
         }
         if (CHAIN) {
 #pragma unroll
-          for (int s = 0; s < E::RING_C; ++s) {
+          for (int s = 0; s < RC; ++s) {
             ptx::mbar_expect_tx(&rbar[4 + s], SLOT);
             ptx::tma_load_2d(c_ring + s * SLOT, &tm_c, &rbar[4 + s], n_base + SC * s, crow0);
           }
@@ -347,6 +375,42 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       // ---- pass 1: v = acc + bias + residual, row statistics, v -> TMEM
       float sum = 0.f, sq = 0.f;
       auto pass1 = [&](uint32_t (&r)[32], int sc) {
+        if constexpr (R16) {
+          // residual = hi + lo from the pair slot of sub-chunks (2u, 2u + 1): 32 rows x 64 bf16, 128-byte rows
+          const int u = sc >> 1, half = sc & 1, slot = u % RING_P;
+          if (half == 0)
+            ptx::mbar_wait(&rbar[slot], (uint32_t)(it * ((NP - slot + RING_P - 1) / RING_P) + u / RING_P) & 1);
+          const uint8_t* hs = res_ring + slot * 2 * SLOT;
+          const uint8_t* ls = hs + SLOT;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {  // 8 columns per 16-byte chunk of hi / lo
+            const uint4 h4 = *reinterpret_cast<const uint4*>(hs + off_f32(lane, half * 4 + c));
+            const uint4 l4 = *reinterpret_cast<const uint4*>(ls + off_f32(lane, half * 4 + c));
+            const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              const int j = 2 * c + jj;
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + sc * SC + 4 * j);
+              const float r0 = __uint_as_float(hw[2 * jj] << 16) + __uint_as_float(lw[2 * jj] << 16);
+              const float r1 = __uint_as_float(hw[2 * jj] & 0xffff0000u) + __uint_as_float(lw[2 * jj] & 0xffff0000u);
+              const float r2 = __uint_as_float(hw[2 * jj + 1] << 16) + __uint_as_float(lw[2 * jj + 1] << 16);
+              const float r3 = __uint_as_float(hw[2 * jj + 1] & 0xffff0000u) + __uint_as_float(lw[2 * jj + 1] & 0xffff0000u);
+              float v0 = __uint_as_float(r[4 * j]) + b4.x + r0, v1 = __uint_as_float(r[4 * j + 1]) + b4.y + r1;
+              float v2 = __uint_as_float(r[4 * j + 2]) + b4.z + r2, v3 = __uint_as_float(r[4 * j + 3]) + b4.w + r3;
+              sum += (v0 + v1) + (v2 + v3);
+              sq = fmaf(v0, v0, sq); sq = fmaf(v1, v1, sq); sq = fmaf(v2, v2, sq); sq = fmaf(v3, v3, sq);
+              r[4 * j] = __float_as_uint(v0); r[4 * j + 1] = __float_as_uint(v1);
+              r[4 * j + 2] = __float_as_uint(v2); r[4 * j + 3] = __float_as_uint(v3);
+            }
+          }
+          ptx::tmem_st_32x32b_x32(lane_addr + (uint32_t)(sc * SC), r);
+          __syncwarp();  // every lane has read its half of the pair slot
+          if (half == 1 && lane == 0 && u + RING_P < NP) {
+            ptx::mbar_expect_tx(&rbar[slot], 2 * SLOT);
+            ptx::tma_load_2d(res_ring + slot * 2 * SLOT, &tm_ohi, &rbar[slot], n_base + 2 * SC * (u + RING_P), row0);
+            ptx::tma_load_2d(res_ring + slot * 2 * SLOT + SLOT, &tm_olo, &rbar[slot], n_base + 2 * SC * (u + RING_P), row0);
+          }
+        } else {
         constexpr int RING = E::RING_R;
         const int slot = sc % RING;
         // slot `slot` is filled ceil((NSC - slot) / RING) times per tile; this is fill number sc / RING of this tile
@@ -367,6 +431,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         if (lane == 0 && sc + RING < E::NSC) {
           ptx::mbar_expect_tx(&rbar[slot], SLOT);
           ptx::tma_load_2d(res_ring + slot * SLOT, &tm_res, &rbar[slot], n_base + SC * (sc + RING), row0);
+        }
         }
       };
       __syncwarp();
@@ -401,7 +466,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         // ---- pass 2: y = LN1(v) + c, statistics of y, y -> TMEM
         float sum2 = 0.f, sq2 = 0.f;
         auto pass2 = [&](uint32_t (&r)[32], int sc) {
-          constexpr int RING = E::RING_C;
+          constexpr int RING = RC;
           const int slot = sc % RING;
           ptx::mbar_wait(&rbar[4 + slot], (uint32_t)(it * ((E::NSC - slot + RING - 1) / RING) + sc / RING) & 1);
 #pragma unroll
@@ -464,12 +529,17 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       auto pass3 = [&](uint32_t (&r)[32], int sc) {
         const int u = sc >> 1, half = sc & 1;
         uint8_t* fb = out_buf + (sc % E::NOB) * SLOT;
-        uint8_t* hb = out_buf + (E::NOB + (u % E::NOB)) * SLOT;
-        uint8_t* lb = out_buf + (2 * E::NOB + (u % E::NOB)) * SLOT;
+        uint8_t* hb = out_buf + ((R16 ? 0 : E::NOB) + (u % E::NOB)) * SLOT;
+        uint8_t* lb = out_buf + ((R16 ? 1 : 2) * E::NOB + (u % E::NOB)) * SLOT;
         if (tr && sc == 2) REGEN_LTL(11);
+        if constexpr (R16) {
+          // one bulk group per sub-chunk PAIR: H/L[u % NOB] were last stored by the group of pair u - NOB
+          if (half == 0 && u >= E::NOB && lane == 0) ptx::bulk_wait_read<E::NOB - 1>();
+        } else {
         // F[sc % NOB] was last stored by group sc - NOB; H/L[u % NOB] by group 2 (u - NOB) + 1 = sc - 2 NOB + 1 (sc even):
         // both are complete once at most NOB - 1 groups are pending
         if (sc >= E::NOB && lane == 0) ptx::bulk_wait_read<E::NOB - 1>();
+        }
         __syncwarp();
         if (tr && sc == 2) REGEN_LTL(12);
 #pragma unroll
@@ -484,7 +554,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const float z1 = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * g4.y + b4.y;
             const float z2 = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * g4.z + b4.z;
             const float z3 = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * g4.w + b4.w;
-            *reinterpret_cast<float4*>(fb + off_f32(lane, j)) = make_float4(z0, z1, z2, z3);
+            if constexpr (!R16) *reinterpret_cast<float4*>(fb + off_f32(lane, j)) = make_float4(z0, z1, z2, z3);
             const uint32_t h0 = gemm::pack_bf16x2(z0, z1), h1 = gemm::pack_bf16x2(z2, z3);
             hw[2 * jj] = h0;
             hw[2 * jj + 1] = h1;
@@ -496,6 +566,17 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           *reinterpret_cast<uint4*>(lb + off_f32(lane, half * 4 + c)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
         if (tr && sc == 2) REGEN_LTL(13);
+        if constexpr (R16) {
+          if (half) {  // the pair's hi / lo tiles are complete: one fence, two stores, one group
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_2d(&tm_ohi, hb, n_base + 2 * SC * u, row0);
+              ptx::tma_store_2d(&tm_olo, lb, n_base + 2 * SC * u, row0);
+              ptx::bulk_commit();
+            }
+          }
+        } else {
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (tr && sc == 2) REGEN_LTL(14);
@@ -506,6 +587,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             ptx::tma_store_2d(&tm_olo, lb, n_base + 2 * SC * u, row0);
           }
           ptx::bulk_commit();
+        }
         }
       };
       __syncwarp();  // both rings fully consumed by every lane: their memory becomes the output buffers
@@ -547,41 +629,44 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
 }
 
-template <bool SPLIT, bool CHAIN, int EW, bool LN = true>
+template <bool SPLIT, bool CHAIN, int EW, bool LN = true, bool R16 = false>
 inline cudaError_t launch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                const CUtensorMap& w_lo, const CUtensorMap& res, const CUtensorMap& c,
                                const CUtensorMap& ohi, const CUtensorMap& olo, const Params& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_ln_kernel<SPLIT, CHAIN, EW, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_ln_kernel<SPLIT, CHAIN, EW, LN, R16>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int64_t tiles = ceil_div(p.M, 2 * BM);
   const int clusters = (int)(tiles < kNumSMs / 2 ? tiles : kNumSMs / 2);
-  return launch_pdl(gemm_ln_kernel<SPLIT, CHAIN, EW, LN>, dim3(2 * clusters), dim3(Epi<EW, CHAIN>::THREADS), SMEM_BYTES, stream, a_hi,
-                    a_lo, w_hi, w_lo, res, c, ohi, olo, p);
+  return launch_pdl(gemm_ln_kernel<SPLIT, CHAIN, EW, LN, R16>, dim3(2 * clusters), dim3(Epi<EW, CHAIN>::THREADS), SMEM_BYTES,
+                    stream, a_hi, a_lo, w_hi, w_lo, res, c, ohi, olo, p);
 }
 
 // 8 epilogue warps per CTA by default.  Measured on B200 (round 1): 16 warps change the three epilogue passes by < 10 %
 // (10.2k/8.9k/16.8k vs 11.2k/9.8k/18.6k cycles) -- the passes are bound by TMEM and shared-memory traffic (256 KB read +
 // 256 KB written per pass per CTA), not by per-warp latency -- and cost register spills at the 96-register cap of 576
-// threads, so 16 stays an A/B switch (REGEN_DEBUG_LN_EW=16).
+// threads, so 16 stays an A/B switch (REGEN_DEBUG_LN_EW=16, fp32-residual variant only).
+// r16: residual stream as bf16 (hi, lo) only (see the header comment); `res` is then unused, ohi / olo are loaded AND stored.
 template <bool SPLIT, bool CHAIN>
 inline cudaError_t launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                           const CUtensorMap& w_lo, const CUtensorMap& res, const CUtensorMap& c, const CUtensorMap& ohi,
-                          const CUtensorMap& olo, const Params& p, cudaStream_t stream) {
+                          const CUtensorMap& olo, const Params& p, cudaStream_t stream, bool r16) {
   static int ew = 0;
   if (!ew) {
     const char* e = getenv("REGEN_DEBUG_LN_EW");
     ew = (e && atoi(e) == 16) ? 16 : 8;
   }
+  if (r16) return launch_impl<SPLIT, CHAIN, 8, true, true>(a_hi, a_lo, w_hi, w_lo, res, c, ohi, olo, p, stream);
   return ew == 16 ? launch_impl<SPLIT, CHAIN, 16>(a_hi, a_lo, w_hi, w_lo, res, c, ohi, olo, p, stream)
                   : launch_impl<SPLIT, CHAIN, 8>(a_hi, a_lo, w_hi, w_lo, res, c, ohi, olo, p, stream);
 }
 
 // h <- A.W^T + bias + residual without LayerNorm (input projection): `res` = residual LOAD map, `out32` = fp32 STORE map
+// (written only with Params::store_f32)
 template <bool SPLIT>
 inline cudaError_t launch_noln(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                const CUtensorMap& w_lo, const CUtensorMap& res, const CUtensorMap& out32,

@@ -69,6 +69,7 @@ struct regen_handle {
   bool fused_ln = true;              // REGEN_DEBUG_NO_FUSED_LN=1: GEMM -> tmp -> LayerNorm kernels
   unsigned long long* steplog = nullptr;  // regen_test_step_log: whole-step timeline buffer (2 words per launch slot)
   int steplog_slot = 0, steplog_cap = 0;
+  bool res16 = true;                 // REGEN_DEBUG_F32_RESIDUAL=1: fused GEMM+LN kernels keep the fp32 copy of h (A/B)
   bool prefetch_res = true;          // REGEN_DEBUG_NO_RES_PREFETCH=1: no L2 prefetch of the residual tile (A/B)
   float* cyc = nullptr;              // [L][max_batch + 32][512] row-cyclic cross-attention constants (per denoise)
   CUtensorMap tm_cyc[REGEN_MAX_LAYERS];
@@ -235,6 +236,8 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
     h->fused_ln = h->tma_store && !(e3 && e3[0] == '1');
     const char* e4 = getenv("REGEN_DEBUG_NO_RES_PREFETCH");
     h->prefetch_res = !(e4 && e4[0] == '1');
+    const char* e4b = getenv("REGEN_DEBUG_F32_RESIDUAL");
+    h->res16 = !(e4b && e4b[0] == '1');
   }
   const size_t Mx = (size_t)h->Mmax;
   int rc = REGEN_OK;
@@ -544,6 +547,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       memset(&q, 0, sizeof(q));
       q.M = Mf; q.K = h->Kin; q.Beff = Beff; q.ln_eps = layers::LN_EPS;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
+      q.store_f32 = h->res16 ? 0 : 1;  // the fused consumers rebuild the residual from (hi, lo)
       if (h->steplog && h->steplog_slot < h->steplog_cap) {
         q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;
       }
@@ -602,7 +606,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       ProfScope prof(h, CLS_GEMM, s);
       gemmln::Params q;
       q.M = M; q.K = D; q.Beff = Beff; q.bias = ld.bo; q.g1 = ld.n1w; q.b1 = ld.n1b; q.g2 = nullptr; q.b2 = nullptr;
-      q.ln_eps = layers::LN_EPS;
+      q.ln_eps = layers::LN_EPS; q.store_f32 = 0;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
       q.timeline = g_test_timeline;
       q.steplog = nullptr; q.steplog_slot = 0; q.steplog_cta = 0;
@@ -611,9 +615,9 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       }
       cudaError_t e = h->desc.precision == 0
           ? gemmln::launch<true, false>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->st32_h,
-                                        h->h_s.st64_hi, h->h_s.st64_lo, q, s)
+                                        h->h_s.st64_hi, h->h_s.st64_lo, q, s, h->res16)
           : gemmln::launch<false, false>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->st32_h,
-                                         h->h_s.st64_hi, h->h_s.st64_lo, q, s);
+                                         h->h_s.st64_hi, h->h_s.st64_lo, q, s, h->res16);
       if (e != cudaSuccess) {
         set_error("fused out_proj+LayerNorm launch failed: %s", cudaGetErrorString(e));
         return REGEN_ECUDA;
@@ -623,7 +627,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       ProfScope prof(h, CLS_GEMM, s);
       gemmln::Params q;
       q.M = M; q.K = D; q.Beff = Beff; q.bias = ld.bo; q.g1 = ld.n1w; q.b1 = ld.n1b; q.g2 = ld.n2w; q.b2 = ld.n2b;
-      q.ln_eps = layers::LN_EPS;
+      q.ln_eps = layers::LN_EPS; q.store_f32 = 0;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
       q.timeline = g_test_timeline;
       q.steplog = nullptr; q.steplog_slot = 0; q.steplog_cta = 0;
@@ -632,9 +636,9 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       }
       cudaError_t e = h->desc.precision == 0
           ? gemmln::launch<true, true>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->tm_cyc[l],
-                                       h->h_s.st64_hi, h->h_s.st64_lo, q, s)
+                                       h->h_s.st64_hi, h->h_s.st64_lo, q, s, h->res16)
           : gemmln::launch<false, true>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->tm_cyc[l],
-                                        h->h_s.st64_hi, h->h_s.st64_lo, q, s);
+                                        h->h_s.st64_hi, h->h_s.st64_lo, q, s, h->res16);
       if (e != cudaSuccess) {
         set_error("fused out_proj+LayerNorm launch failed: %s", cudaGetErrorString(e));
         return REGEN_ECUDA;
@@ -681,7 +685,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       gemmln::Params q;
       q.M = M; q.K = FF; q.Beff = Beff; q.bias = ld.b2; q.g1 = offline ? ld.n2w : ld.n3w; q.b1 = offline ? ld.n2b : ld.n3b;
       q.g2 = nullptr; q.b2 = nullptr;
-      q.ln_eps = layers::LN_EPS;
+      q.ln_eps = layers::LN_EPS; q.store_f32 = 0;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
       q.timeline = g_test_timeline;
       q.steplog = nullptr; q.steplog_slot = 0; q.steplog_cta = 0;
@@ -690,9 +694,9 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       }
       cudaError_t e = h->desc.precision == 0
           ? gemmln::launch<true, false>(h->ffn.tm_hi, h->ffn.tm_lo, ld.w2.tm_hi2, ld.w2.tm_lo2, h->st32_h, h->st32_h,
-                                        h->h_s.st64_hi, h->h_s.st64_lo, q, s)
+                                        h->h_s.st64_hi, h->h_s.st64_lo, q, s, h->res16)
           : gemmln::launch<false, false>(h->ffn.tm_hi, h->ffn.tm_lo, ld.w2.tm_hi2, ld.w2.tm_lo2, h->st32_h, h->st32_h,
-                                         h->h_s.st64_hi, h->h_s.st64_lo, q, s);
+                                         h->h_s.st64_hi, h->h_s.st64_lo, q, s, h->res16);
       if (e != cudaSuccess) {
         set_error("fused linear2+LayerNorm launch failed: %s", cudaGetErrorString(e));
         return REGEN_ECUDA;

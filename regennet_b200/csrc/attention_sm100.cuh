@@ -62,7 +62,8 @@ struct Params {
   __nv_bfloat16* out_lo;
   int T, Beff;
   int causal;  // 1: additive causal mask of model/cmdm.py:168-171 (arch 'online'); 0: no mask (arch 'offline')
-  int dbg;  // test-hook only: bit 0 swaps the LBO / SBO fields of the V descriptor (bring-up A/B switch)
+  int dbg;  // bit 0 (test hook only) swaps the LBO / SBO fields of the V descriptor (bring-up A/B switch);
+            // bit 2: wait for the bulk stores' global writes before exit (default; REGEN_DEBUG_EXIT_WAIT_READ=1 clears it, A/B: no measurable difference)
   unsigned long long* timeline;  // bring-up instrumentation (null in production): CTA 0 stamps clock64() at events
   unsigned long long* steplog;   // whole-step timeline (ptx::steplog_begin / steplog_end), null in production
   int steplog_slot, steplog_cta;  // steplog_cta: word offset of the per-CTA exit-time table (0 = off)
@@ -386,7 +387,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         ptx::tma_store_3d(&tm_olo, st + tile * 8192 + 4096, h * HD + half * DW + tile * 64, b, q0 + q * 32);
       }
       ptx::bulk_commit();
-      ptx::bulk_wait<0>();
+      // the staging tiles must have been read before the CTA exits; the kernel boundary orders the global writes
+      if (p.dbg & 4) ptx::bulk_wait<0>(); else ptx::bulk_wait_read<0>();
     }
     }  // warp_live
   }

@@ -65,6 +65,8 @@ struct Params {
   int M, K, Beff;
   const float *bias, *g1, *b1, *g2, *b2;  // [512] each (g2/b2 unused without CHAIN)
   float ln_eps;
+  int exit_wait_full;            // 1: wait for the bulk stores' global writes before exit (default; REGEN_DEBUG_EXIT_WAIT_READ=1 clears it, A/B: no measurable difference)
+  int nob16;                     // R16 only: output staging depth of the final pass (2 or 3 hi / lo tile pairs per warp)
   int store_f32;                 // LN = false only: 1 = also store the fp32 copy of h through tm_c (0 with R16 consumers)
   int prefetch_res;              // 1: L2-prefetch the residual tile during the main loop (REGEN_DEBUG_NO_RES_PREFETCH=1 -> 0)
   unsigned long long* timeline;  // bring-up instrumentation (null in production), see tools/ln_timeline.py
@@ -461,6 +463,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       }
       float mean = sum * inv_n;
       float rstd = 1.0f / sqrtf(fmaxf(sq * inv_n - mean * mean, 0.f) + p.ln_eps);
+      // (x - mean) * rstd * g + b as two FMAs: x * rstd + (-mean * rstd), then * g + b (the passes are issue-bound)
+      float nmr = -mean * rstd;
 
       if (CHAIN) {
         // ---- pass 2: y = LN1(v) + c, statistics of y, y -> TMEM
@@ -474,10 +478,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const float4 g4 = *reinterpret_cast<const float4*>(s_g1 + sc * SC + 4 * j);
             const float4 b4 = *reinterpret_cast<const float4*>(s_b1 + sc * SC + 4 * j);
             const float4 cj = *reinterpret_cast<const float4*>(c_ring + slot * SLOT + off_f32(lane, j));
-            float y0 = (__uint_as_float(r[4 * j]) - mean) * rstd * g4.x + b4.x + cj.x;
-            float y1 = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * g4.y + b4.y + cj.y;
-            float y2 = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * g4.z + b4.z + cj.z;
-            float y3 = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * g4.w + b4.w + cj.w;
+            float y0 = fmaf(fmaf(__uint_as_float(r[4 * j]), rstd, nmr), g4.x, b4.x) + cj.x;
+            float y1 = fmaf(fmaf(__uint_as_float(r[4 * j + 1]), rstd, nmr), g4.y, b4.y) + cj.y;
+            float y2 = fmaf(fmaf(__uint_as_float(r[4 * j + 2]), rstd, nmr), g4.z, b4.z) + cj.z;
+            float y3 = fmaf(fmaf(__uint_as_float(r[4 * j + 3]), rstd, nmr), g4.w, b4.w) + cj.w;
             sum2 += (y0 + y1) + (y2 + y3);
             sq2 = fmaf(y0, y0, sq2); sq2 = fmaf(y1, y1, sq2); sq2 = fmaf(y2, y2, sq2); sq2 = fmaf(y3, y3, sq2);
             r[4 * j] = __float_as_uint(y0); r[4 * j + 1] = __float_as_uint(y1);
@@ -516,6 +520,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         }
         mean = sum2 * inv_n;
         rstd = 1.0f / sqrtf(fmaxf(sq2 * inv_n - mean * mean, 0.f) + p.ln_eps);
+        nmr = -mean * rstd;
       }
 
       // ---- final pass: z = LN(.), fp32 + bf16 (hi, lo) out through TMA stores.  Measured on B200: the TMA unit retires
@@ -528,13 +533,16 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       const float* bb = CHAIN ? s_b2 : s_b1;
       auto pass3 = [&](uint32_t (&r)[32], int sc) {
         const int u = sc >> 1, half = sc & 1;
+        const int nob = R16 ? p.nob16 : E::NOB;
         uint8_t* fb = out_buf + (sc % E::NOB) * SLOT;
-        uint8_t* hb = out_buf + ((R16 ? 0 : E::NOB) + (u % E::NOB)) * SLOT;
-        uint8_t* lb = out_buf + ((R16 ? 1 : 2) * E::NOB + (u % E::NOB)) * SLOT;
+        uint8_t* hb = out_buf + (R16 ? 2 * (u % nob) : E::NOB + (u % E::NOB)) * SLOT;
+        uint8_t* lb = out_buf + (R16 ? 2 * (u % nob) + 1 : 2 * E::NOB + (u % E::NOB)) * SLOT;
         if (tr && sc == 2) REGEN_LTL(11);
         if constexpr (R16) {
-          // one bulk group per sub-chunk PAIR: H/L[u % NOB] were last stored by the group of pair u - NOB
-          if (half == 0 && u >= E::NOB && lane == 0) ptx::bulk_wait_read<E::NOB - 1>();
+          // one bulk group per sub-chunk PAIR: H/L[u % nob] were last stored by the group of pair u - nob
+          if (half == 0 && u >= nob && lane == 0) {
+            if (nob == 3) ptx::bulk_wait_read<2>(); else ptx::bulk_wait_read<1>();
+          }
         } else {
         // F[sc % NOB] was last stored by group sc - NOB; H/L[u % NOB] by group 2 (u - NOB) + 1 = sc - 2 NOB + 1 (sc even):
         // both are complete once at most NOB - 1 groups are pending
@@ -550,10 +558,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const int j = 2 * c + jj;
             const float4 g4 = *reinterpret_cast<const float4*>(gg + sc * SC + 4 * j);
             const float4 b4 = *reinterpret_cast<const float4*>(bb + sc * SC + 4 * j);
-            const float z0 = (__uint_as_float(r[4 * j]) - mean) * rstd * g4.x + b4.x;
-            const float z1 = (__uint_as_float(r[4 * j + 1]) - mean) * rstd * g4.y + b4.y;
-            const float z2 = (__uint_as_float(r[4 * j + 2]) - mean) * rstd * g4.z + b4.z;
-            const float z3 = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * g4.w + b4.w;
+            const float z0 = fmaf(fmaf(__uint_as_float(r[4 * j]), rstd, nmr), g4.x, b4.x);
+            const float z1 = fmaf(fmaf(__uint_as_float(r[4 * j + 1]), rstd, nmr), g4.y, b4.y);
+            const float z2 = fmaf(fmaf(__uint_as_float(r[4 * j + 2]), rstd, nmr), g4.z, b4.z);
+            const float z3 = fmaf(fmaf(__uint_as_float(r[4 * j + 3]), rstd, nmr), g4.w, b4.w);
             if constexpr (!R16) *reinterpret_cast<float4*>(fb + off_f32(lane, j)) = make_float4(z0, z1, z2, z3);
             const uint32_t h0 = gemm::pack_bf16x2(z0, z1), h1 = gemm::pack_bf16x2(z2, z3);
             hw[2 * jj] = h0;
@@ -616,7 +624,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       }
       named_bar_sync(1 + q, 32 * E::PARTS);  // the statistics slots are rewritten by the next tile
     }
-    if (lane == 0) ptx::bulk_wait<0>();
+    // every tile already waited until its stores had READ the staging tiles; the kernel boundary (griddepcontrol.wait in
+    // the dependent grid) orders the global writes, so waiting for their completion here only lengthens the exit
+    if (lane == 0 && p.exit_wait_full) ptx::bulk_wait<0>();
   }
 
   ptx::tcgen05_fence_before();

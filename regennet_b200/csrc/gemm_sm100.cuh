@@ -55,6 +55,9 @@ struct Params {
   int ld_split;
   int gelu;                 // exact-erf GELU after bias/residual
   int tma_store;            // 1: outputs are written with TMA stores through the tm_o* tensor maps (needs N % 4 == 0)
+  int exit_wait_full;       // 1: wait for the bulk stores' global writes before exit (default; REGEN_DEBUG_EXIT_WAIT_READ=1 clears it, A/B: no measurable difference)
+  int pair64;               // 16-warp pair kernel, bf16 (hi, lo) outputs only: 64-column store boxes through warp pairs (tm_ohi /
+                            // tm_olo must then be the 32 x 64 box maps)
   int tail_split;           // pair kernel: the tiles of the last, partial wave are cut into 1 / 2 / 4 column slices (set by launch2)
   // bring-up instrumentation (test hook only, null in production): CTA 0 records clock64() at pipeline events
   //   [0] kernel entry  [1] setup done  [2] kernel exit  [8+2i] MMA of tile i: operands of first k-block landed
@@ -103,6 +106,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 // byte offset of 16-byte chunk `c` of row `r` inside a staged tile
 __device__ __forceinline__ int stg_off_f32(int r, int c) { return r * 64 + ((c ^ ((r >> 1) & 3)) << 4); }   // SWIZZLE_64B
+__device__ __forceinline__ int stg_off_128(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }          // SWIZZLE_128B
 __device__ __forceinline__ int stg_off_bf16(int r, int c) { return r * 32 + ((c ^ ((r >> 2) & 1)) << 4); }  // SWIZZLE_32B
 
 #define REGEN_TLF(k)                                                                              \
@@ -377,6 +381,77 @@ __device__ __forceinline__ void epilogue_slice32(const Params& p, const CUtensor
   }
 }
 
+// 16-warp kernels, bf16 (hi, lo) outputs only (QKV, FFN1): the TMA unit retires about one box row per ~2.6 cycles whatever
+// its length (measured in the fused GEMM+LN kernel), so 64-byte rows cost twice the row requests of 128-byte rows.  Two
+// warps of the same TMEM lane quarter (column parts 2k and 2k + 1) therefore own 128 columns TOGETHER and emit them as
+// two 64-column groups: in group g warp `sub` converts columns 64 g + 32 sub .. + 32 and writes the left / right 64
+// bytes of every 128-byte row of ONE shared 4 KB staging tile (32 rows x 64 bf16, SWIZZLE_128B = the two warps' 2 KB
+// budgets), and warp sub = 0 issues the store.  Per tile and CTA: 1024 instead of 2048 store row requests.
+__device__ __forceinline__ void epilogue_pair64(const Params& p, const CUtensorMap* tm_ohi, const CUtensorMap* tm_olo,
+                                                uint8_t* stg, uint32_t acc, int row0, int n0, int width, int sub,
+                                                int bar_id, int lane) {
+  auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); };
+  // bias of this warp's 2 x 32 columns: lane holds columns n0 + 64 (lane / 16) + 32 sub + 2 (lane % 16) .. + 1
+  float2 b2 = make_float2(0.f, 0.f);
+  {
+    const int col = n0 + 64 * (lane >> 4) + 32 * sub + 2 * (lane & 15);
+    if (p.bias && col + 1 < p.N) b2 = __ldg(reinterpret_cast<const float2*>(p.bias + col));
+  }
+  const bool issuer = sub == 0 && lane == 0;
+#pragma unroll 1
+  for (int g = 0; g < 2; ++g) {
+    if (64 * g >= width || n0 + 64 * g >= p.N) break;  // uniform across the pair
+    uint32_t r[32];
+    __syncwarp();
+    ptx::tmem_ld_32x32b_x32(acc + (uint32_t)(64 * g + 32 * sub), r);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const int src = 16 * g + (j >> 1);
+      float v0 = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, b2.x, src);
+      float v1 = __uint_as_float(r[j + 1]) + __shfl_sync(0xffffffffu, b2.y, src);
+      if (p.gelu) {
+        v0 = gelu_erf(v0);
+        v1 = gelu_erf(v1);
+      }
+      r[j] = __float_as_uint(v0);
+      r[j + 1] = __float_as_uint(v1);
+    }
+    uint32_t lw[16];
+    if (issuer) ptx::bulk_wait_read<0>();  // the previous store from the shared tile has been read
+    pair_sync();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t hw[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float a = __uint_as_float(r[8 * c + 2 * k]), b = __uint_as_float(r[8 * c + 2 * k + 1]);
+        hw[k] = pack_bf16x2(a, b);
+        lw[4 * c + k] = pack_bf16x2(a - __uint_as_float(hw[k] << 16), b - __uint_as_float(hw[k] & 0xffff0000u));
+      }
+      *reinterpret_cast<uint4*>(stg + stg_off_128(lane, 4 * sub + c)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    }
+    ptx::fence_proxy_async_smem();
+    pair_sync();  // both halves of the hi tile are staged
+    if (issuer) {
+      ptx::tma_store_2d(tm_ohi, stg, n0 + 64 * g, row0);
+      ptx::bulk_commit();
+      ptx::bulk_wait_read<0>();
+    }
+    pair_sync();  // hi tile read: the staging tile takes the lo halves
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<uint4*>(stg + stg_off_128(lane, 4 * sub + c)) =
+          make_uint4(lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]);
+    ptx::fence_proxy_async_smem();
+    pair_sync();
+    if (issuer) {
+      ptx::tma_store_2d(tm_olo, stg, n0 + 64 * g, row0);
+      ptx::bulk_commit();
+    }
+  }
+}
+
 // Persistent kernel: grid = min(#tiles, #SMs); CTA c processes tiles c, c + grid, ... (n fastest, so
 // CTAs running concurrently share A tiles through L2).  The accumulator is double buffered in TMEM
 // (2 x BN columns): the epilogue of tile i overlaps the TMA/MMA main loop of tile i + 1.
@@ -522,7 +597,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
 
   // ------------------------------------------------------------------ teardown
-  if (p.tma_store && warp >= 2 && lane == 0) ptx::bulk_wait<0>();  // all bulk stores of this thread complete
+  // the staging tiles must have been READ before the CTA exits; completion of the global writes is ordered by the
+  // kernel boundary (exit_wait_full = 1 waits for it here, A/B switch)
+  if (p.tma_store && warp >= 2 && lane == 0) {
+    if (p.exit_wait_full) ptx::bulk_wait<0>(); else ptx::bulk_wait_read<0>();
+  }
   ptx::tcgen05_fence_before();
   __syncthreads();
   ptx::steplog_end(p.steplog, p.steplog_slot, p.steplog_cta);
@@ -744,7 +823,14 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       ptx::tcgen05_fence_after();
       const uint32_t acc = tmem_base + (uint32_t)(buf * BN + part * PCOLS) + ((uint32_t)(q * 32) << 16);
       // a column slice narrower than the tile only has accumulator columns [0, width): the other parts just release
-      if (part * PCOLS < width) {
+      if (EW == 16 && p.pair64) {
+        // warp pair (parts 2k, 2k + 1) of lane quarter q: 128 columns through one shared 4 KB staging tile
+        const int k = part >> 1, pidx = k * 4 + ((warp - 2) & 3);
+        if (k * 128 < width)
+          epilogue_pair64(p, &tm_ohi, &tm_olo, staging + pidx * 4096,
+                          tmem_base + (uint32_t)(buf * BN + k * 128) + ((uint32_t)(q * 32) << 16), m0 + q * 32,
+                          n0 + k * 128, width - k * 128, part & 1, 1 + pidx, lane);
+      } else if (part * PCOLS < width) {
         if constexpr (EW == 16)
           epilogue_slice32<PCOLS>(p, &tm_o32, &tm_ohi, &tm_olo, stg, acc, m0 + q * 32, n0 + part * PCOLS, lane);
         else
@@ -760,7 +846,11 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   }
 
   // ------------------------------------------------------------------ teardown
-  if (p.tma_store && warp >= 2 && lane == 0) ptx::bulk_wait<0>();  // all bulk stores of this thread complete
+  // the staging tiles must have been READ before the CTA exits; completion of the global writes is ordered by the
+  // kernel boundary (exit_wait_full = 1 waits for it here, A/B switch)
+  if (p.tma_store && warp >= 2 && lane == 0) {
+    if (p.exit_wait_full) ptx::bulk_wait<0>(); else ptx::bulk_wait_read<0>();
+  }
   ptx::tcgen05_fence_before();
   ptx::cluster_sync();  // no CTA may exit (or free TMEM) while its peer can still touch its smem / barriers
   ptx::steplog_end(p.steplog, p.steplog_slot, p.steplog_cta);

@@ -69,6 +69,10 @@ struct regen_handle {
   bool fused_ln = true;              // REGEN_DEBUG_NO_FUSED_LN=1: GEMM -> tmp -> LayerNorm kernels
   unsigned long long* steplog = nullptr;  // regen_test_step_log: whole-step timeline buffer (2 words per launch slot)
   int steplog_slot = 0, steplog_cap = 0;
+  bool exit_wait_full = true;        // REGEN_DEBUG_EXIT_WAIT_READ=1: kernels only wait until their bulk stores have READ the staging
+                                     // tiles before exit (measured: no difference, so the conservative full wait stays the default)
+  int nob16 = 2;                     // REGEN_DEBUG_LN_NOB=3: three output staging tile pairs in the R16 final pass (A/B)
+  bool store64 = true;               // REGEN_DEBUG_NO_STORE64=1: 32-column store boxes in the 16-warp GEMM epilogue (A/B)
   bool res16 = true;                 // REGEN_DEBUG_F32_RESIDUAL=1: fused GEMM+LN kernels keep the fp32 copy of h (A/B)
   bool prefetch_res = true;          // REGEN_DEBUG_NO_RES_PREFETCH=1: no L2 prefetch of the residual tile (A/B)
   float* cyc = nullptr;              // [L][max_batch + 32][512] row-cyclic cross-attention constants (per denoise)
@@ -162,6 +166,7 @@ int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, gemm::Params
   ProfScope prof(h, CLS_GEMM, s);
   gemm::OutMaps om;
   p.tma_store = 0;
+  p.exit_wait_full = h->exit_wait_full ? 1 : 0;
   if (h->tma_store && (p.N & 3) == 0 && (!p.out_f32 || o32) && (!p.out_hi || osplit)) {
     p.tma_store = 1;
     // the 16-epilogue-warp pair kernel (no residual, one kind of output) stores 32-column boxes, everything else 16
@@ -170,6 +175,12 @@ int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, gemm::Params
     if (osplit) {
       om.hi = wide ? osplit->st32_hi : osplit->st_hi;
       om.lo = wide ? osplit->st32_lo : osplit->st_lo;
+      // bf16-pair outputs only (QKV, FFN1): 64-column boxes (128-byte rows) through warp pairs, half the store row requests
+      if (wide && h->store64 && !p.out_f32 && (p.N & 63) == 0) {
+        p.pair64 = 1;
+        om.hi = osplit->st64_hi;
+        om.lo = osplit->st64_lo;
+      }
     }
   }
   if (h->steplog && h->steplog_slot < h->steplog_cap) {
@@ -238,6 +249,12 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
     h->prefetch_res = !(e4 && e4[0] == '1');
     const char* e4b = getenv("REGEN_DEBUG_F32_RESIDUAL");
     h->res16 = !(e4b && e4b[0] == '1');
+    const char* e4e = getenv("REGEN_DEBUG_EXIT_WAIT_READ");
+    h->exit_wait_full = !(e4e && e4e[0] == '1');
+    const char* e4d = getenv("REGEN_DEBUG_LN_NOB");
+    h->nob16 = (e4d && e4d[0] == '3') ? 3 : 2;
+    const char* e4c = getenv("REGEN_DEBUG_NO_STORE64");
+    h->store64 = !(e4c && e4c[0] == '1');
   }
   const size_t Mx = (size_t)h->Mmax;
   int rc = REGEN_OK;
@@ -548,6 +565,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       q.M = Mf; q.K = h->Kin; q.Beff = Beff; q.ln_eps = layers::LN_EPS;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
       q.store_f32 = h->res16 ? 0 : 1;  // the fused consumers rebuild the residual from (hi, lo)
+      q.exit_wait_full = h->exit_wait_full ? 1 : 0;
       if (h->steplog && h->steplog_slot < h->steplog_cap) {
         q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;
       }
@@ -589,7 +607,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
             h->qkv, h->att.hi, h->att.lo, T, Beff);
       } else {
         attn::Params ap;
-        ap.out_hi = h->att.hi; ap.out_lo = h->att.lo; ap.T = S; ap.Beff = Beff; ap.causal = offline ? 0 : 1; ap.dbg = 0;
+        ap.out_hi = h->att.hi; ap.out_lo = h->att.lo; ap.T = S; ap.Beff = Beff; ap.causal = offline ? 0 : 1; ap.dbg = h->exit_wait_full ? 4 : 0;
         ap.timeline = nullptr;
         ap.steplog = nullptr; ap.steplog_slot = 0; ap.steplog_cta = 0;
         if (h->steplog && h->steplog_slot < h->steplog_cap) { ap.steplog = h->steplog; ap.steplog_slot = h->steplog_slot++; }
@@ -606,7 +624,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       ProfScope prof(h, CLS_GEMM, s);
       gemmln::Params q;
       q.M = M; q.K = D; q.Beff = Beff; q.bias = ld.bo; q.g1 = ld.n1w; q.b1 = ld.n1b; q.g2 = nullptr; q.b2 = nullptr;
-      q.ln_eps = layers::LN_EPS; q.store_f32 = 0;
+      q.ln_eps = layers::LN_EPS; q.store_f32 = 0; q.nob16 = h->nob16; q.exit_wait_full = h->exit_wait_full ? 1 : 0;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
       q.timeline = g_test_timeline;
       q.steplog = nullptr; q.steplog_slot = 0; q.steplog_cta = 0;
@@ -627,7 +645,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       ProfScope prof(h, CLS_GEMM, s);
       gemmln::Params q;
       q.M = M; q.K = D; q.Beff = Beff; q.bias = ld.bo; q.g1 = ld.n1w; q.b1 = ld.n1b; q.g2 = ld.n2w; q.b2 = ld.n2b;
-      q.ln_eps = layers::LN_EPS; q.store_f32 = 0;
+      q.ln_eps = layers::LN_EPS; q.store_f32 = 0; q.nob16 = h->nob16; q.exit_wait_full = h->exit_wait_full ? 1 : 0;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
       q.timeline = g_test_timeline;
       q.steplog = nullptr; q.steplog_slot = 0; q.steplog_cta = 0;
@@ -685,7 +703,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       gemmln::Params q;
       q.M = M; q.K = FF; q.Beff = Beff; q.bias = ld.b2; q.g1 = offline ? ld.n2w : ld.n3w; q.b1 = offline ? ld.n2b : ld.n3b;
       q.g2 = nullptr; q.b2 = nullptr;
-      q.ln_eps = layers::LN_EPS; q.store_f32 = 0;
+      q.ln_eps = layers::LN_EPS; q.store_f32 = 0; q.nob16 = h->nob16; q.exit_wait_full = h->exit_wait_full ? 1 : 0;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
       q.timeline = g_test_timeline;
       q.steplog = nullptr; q.steplog_slot = 0; q.steplog_cta = 0;

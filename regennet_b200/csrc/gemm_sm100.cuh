@@ -58,6 +58,7 @@ struct Params {
   int exit_wait_full;       // 1: wait for the bulk stores' global writes before exit (default; REGEN_DEBUG_EXIT_WAIT_READ=1 clears it, A/B: no measurable difference)
   int pair64;               // 16-warp pair kernel, bf16 (hi, lo) outputs only: 64-column store boxes through warp pairs (tm_ohi /
                             // tm_olo must then be the 32 x 64 box maps)
+  int slice_w_rows;         // pair kernel: rows of the W box the slice maps (tm_ws_*) load per CTA (set by launch2)
   int tail_split;           // pair kernel: the tiles of the last, partial wave are cut into 1 / 2 / 4 column slices (set by launch2)
   // bring-up instrumentation (test hook only, null in production): CTA 0 records clock64() at pipeline events
   //   [0] kernel entry  [1] setup done  [2] kernel exit  [8+2i] MMA of tile i: operands of first k-block landed
@@ -665,7 +666,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                 const __grid_constant__ CUtensorMap tm_o32, const __grid_constant__ CUtensorMap tm_ohi,
-                const __grid_constant__ CUtensorMap tm_olo, const Params p) {
+                const __grid_constant__ CUtensorMap tm_olo, const __grid_constant__ CUtensorMap tm_ws_hi,
+                const __grid_constant__ CUtensorMap tm_ws_lo, const Params p) {
   using C = Cfg2<BN, SPLIT, EW>;
   extern __shared__ uint8_t smem_raw[];
   // 1 KB alignment by pointer arithmetic on the __shared__ array (NOT an integer round trip): the compiler keeps the
@@ -742,17 +744,23 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         int tile, ncol0, width;
         decode(u, tile, ncol0, width);
         const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM;
-        // this CTA's half of the W slice; the box always has BN / 2 rows, a narrower slice just uses its first rows
+        // this CTA's half of the W slice.  Whole tiles load the BN / 2-row box; column slices of the tail load the narrow
+        // slice box (slice_w_rows rows: a slice is bound by its operand loads, not by its MMAs), of which the first
+        // width / 2 rows are used
         const int nw = (tile % tiles_n) * BN + ncol0 + (int)rank * (width / 2);
+        const bool slice = width < BN;
+        const CUtensorMap* wmap_hi = slice ? &tm_ws_hi : &tm_w_hi;
+        const CUtensorMap* wmap_lo = slice ? &tm_ws_lo : &tm_w_lo;
+        const uint32_t stage_tx = (SPLIT ? 2u : 1u) * (uint32_t)(C::A_BYTES + (slice ? p.slice_w_rows * BK * 2 : C::W_BYTES));
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
-          if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * stage_tx);
           ptx::tma_load_2d_2sm(st, &tm_a_hi, &full_bar[stage], kb * BK, m0);
-          ptx::tma_load_2d_2sm(st + C::A_BYTES, &tm_w_hi, &full_bar[stage], kb * BK, nw);
+          ptx::tma_load_2d_2sm(st + C::A_BYTES, wmap_hi, &full_bar[stage], kb * BK, nw);
           if (SPLIT) {
             ptx::tma_load_2d_2sm(st + C::A_BYTES + C::W_BYTES, &tm_a_lo, &full_bar[stage], kb * BK, m0);
-            ptx::tma_load_2d_2sm(st + 2 * C::A_BYTES + C::W_BYTES, &tm_w_lo, &full_bar[stage], kb * BK, nw);
+            ptx::tma_load_2d_2sm(st + 2 * C::A_BYTES + C::W_BYTES, wmap_lo, &full_bar[stage], kb * BK, nw);
           }
           if (++stage == C::STAGES) {
             stage = 0;
@@ -862,9 +870,16 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
 }
 
 // W tensor maps for the pair kernel need box {64, BN/2}.
+// narrow W boxes for the column slices of the tail (null -> the slices load the full BN / 2-row box)
+struct SliceMaps {
+  const CUtensorMap *hi32 = nullptr, *lo32 = nullptr;  // box {64, 32}: quarter slices (tail_split = 4)
+  const CUtensorMap *hi64 = nullptr, *lo64 = nullptr;  // box {64, 64}: half slices (tail_split = 2)
+};
+
 template <int BN, bool SPLIT, int EW, bool RES>
 inline cudaError_t launch2_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
-                                const CUtensorMap& w_lo, const OutMaps& o, const Params& p, cudaStream_t stream) {
+                                const CUtensorMap& w_lo, const OutMaps& o, const Params& p, cudaStream_t stream,
+                                const SliceMaps& sm) {
   using C = Cfg2<BN, SPLIT, EW>;
   static bool configured = false;
   if (!configured) {
@@ -895,17 +910,25 @@ inline cudaError_t launch2_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo
     else if (rem > 0 && 2 * rem <= maxc) q.tail_split = 2;
     if (tiles < maxc) clusters = (int)tiles * q.tail_split;  // every slice gets its own cluster
   }
+  const CUtensorMap *ws_hi = &w_hi, *ws_lo = &w_lo;
+  q.slice_w_rows = BN / 2;
+  if (q.tail_split == 4 && sm.hi32 && sm.lo32) {
+    ws_hi = sm.hi32; ws_lo = sm.lo32; q.slice_w_rows = 32;
+  } else if (q.tail_split == 2 && sm.hi64 && sm.lo64) {
+    ws_hi = sm.hi64; ws_lo = sm.lo64; q.slice_w_rows = 64;
+  }
   return launch_pdl(gemm2_tn_kernel<BN, SPLIT, EW, RES>, dim3(2 * clusters), dim3(64 + 32 * EW), C::SMEM_BYTES, stream, a_hi,
-                    a_lo, w_hi, w_lo, o.f32, o.hi, o.lo, q);
+                    a_lo, w_hi, w_lo, o.f32, o.hi, o.lo, *ws_hi, *ws_lo, q);
 }
 
 template <int BN, bool SPLIT>
 inline cudaError_t launch2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
-                           const CUtensorMap& w_lo, const OutMaps& o, const Params& p, cudaStream_t stream) {
+                           const CUtensorMap& w_lo, const OutMaps& o, const Params& p, cudaStream_t stream,
+                           const SliceMaps& sm = SliceMaps()) {
   // 16 epilogue warps whenever no residual is added and the outputs leave through TMA stores
   if (!p.residual && p.tma_store && !(p.out_f32 && p.out_hi))
-    return launch2_impl<BN, SPLIT, 16, false>(a_hi, a_lo, w_hi, w_lo, o, p, stream);
-  return launch2_impl<BN, SPLIT, 8, true>(a_hi, a_lo, w_hi, w_lo, o, p, stream);
+    return launch2_impl<BN, SPLIT, 16, false>(a_hi, a_lo, w_hi, w_lo, o, p, stream, sm);
+  return launch2_impl<BN, SPLIT, 8, true>(a_hi, a_lo, w_hi, w_lo, o, p, stream, sm);
 }
 
 }  // namespace gemm

@@ -21,6 +21,8 @@ struct SplitBuf {  // bf16 (hi, lo) operand pair + its TMA maps
   CUtensorMap tm_hi, tm_lo;      // box rows: 128 for activations (A operand), 256 for weights (single-CTA kernel)
   CUtensorMap tm_hi2, tm_lo2;    // weights only: box rows 128 = one CTA's half of the W tile in the CTA-pair kernel
   CUtensorMap tm_hi3, tm_lo3;    // weights only: box rows 64 = the W tile of the small-batch single-CTA kernel (BN = 64)
+                                 //               and of a half-width tail slice of the CTA-pair kernel
+  CUtensorMap tm_hi4, tm_lo4;    // weights only: box rows 32 = one CTA's half of a quarter-width tail slice (pair kernel)
   CUtensorMap st_hi, st_lo;      // activations only: store-side maps (box 32 x 16), rebuilt per prepare_cond with rows = M
   CUtensorMap st32_hi, st32_lo;  // same with box 32 x 32 (16-warp GEMM epilogue)
   CUtensorMap st64_hi, st64_lo;  // same with box 32 x 64, 128-byte rows (fused GEMM+LayerNorm epilogue)
@@ -69,6 +71,7 @@ struct regen_handle {
   bool fused_ln = true;              // REGEN_DEBUG_NO_FUSED_LN=1: GEMM -> tmp -> LayerNorm kernels
   unsigned long long* steplog = nullptr;  // regen_test_step_log: whole-step timeline buffer (2 words per launch slot)
   int steplog_slot = 0, steplog_cap = 0;
+  bool narrow_slices = true;         // REGEN_DEBUG_WIDE_SLICES=1: tail slices of the pair GEMM load the full-height W box (A/B)
   bool exit_wait_full = true;        // REGEN_DEBUG_EXIT_WAIT_READ=1: kernels only wait until their bulk stores have READ the staging
                                      // tiles before exit (measured: no difference, so the conservative full wait stays the default)
   int nob16 = 2;                     // REGEN_DEBUG_LN_NOB=3: three output staging tile pairs in the R16 final pass (A/B)
@@ -138,6 +141,8 @@ int alloc_split(regen_handle* h, SplitBuf* s, size_t rows, size_t cols, uint32_t
   TRY(make_tmap_bf16_2d(&s->tm_lo2, s->lo, rows, cols, cols, 128));
   TRY(make_tmap_bf16_2d(&s->tm_hi3, s->hi, rows, cols, cols, 64));
   TRY(make_tmap_bf16_2d(&s->tm_lo3, s->lo, rows, cols, cols, 64));
+  TRY(make_tmap_bf16_2d(&s->tm_hi4, s->hi, rows, cols, cols, 32));
+  TRY(make_tmap_bf16_2d(&s->tm_lo4, s->lo, rows, cols, cols, 32));
   s->cols = cols;
   return REGEN_OK;
 }
@@ -189,9 +194,12 @@ int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, gemm::Params
     p.steplog_cta = 2 * h->steplog_cap;
   }
   cudaError_t e;
-  if (use_pair_kernel(p.M))
-    e = h->desc.precision == 0 ? gemm::launch2<256, true>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, om, p, s)
-                               : gemm::launch2<256, false>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, om, p, s);
+  if (use_pair_kernel(p.M)) {
+    gemm::SliceMaps sm;
+    if (h->narrow_slices) { sm.hi32 = &w.tm_hi4; sm.lo32 = &w.tm_lo4; sm.hi64 = &w.tm_hi3; sm.lo64 = &w.tm_lo3; }
+    e = h->desc.precision == 0 ? gemm::launch2<256, true>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, om, p, s, sm)
+                               : gemm::launch2<256, false>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, om, p, s, sm);
+  }
   else
     e = h->desc.precision == 0 ? gemm::launch<64, true>(a.tm_hi, a.tm_lo, w.tm_hi3, w.tm_lo3, om, p, s)
                                : gemm::launch<64, false>(a.tm_hi, a.tm_lo, w.tm_hi3, w.tm_lo3, om, p, s);
@@ -249,6 +257,8 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
     h->prefetch_res = !(e4 && e4[0] == '1');
     const char* e4b = getenv("REGEN_DEBUG_F32_RESIDUAL");
     h->res16 = !(e4b && e4b[0] == '1');
+    const char* e4f = getenv("REGEN_DEBUG_WIDE_SLICES");
+    h->narrow_slices = !(e4f && e4f[0] == '1');
     const char* e4e = getenv("REGEN_DEBUG_EXIT_WAIT_READ");
     h->exit_wait_full = !(e4e && e4e[0] == '1');
     const char* e4d = getenv("REGEN_DEBUG_LN_NOB");

@@ -95,3 +95,27 @@ PLMS_LOOP_CASES = {
                               cfg_scale=2.5),
     "plms_ntu_o2_clip": dict(model="ntu", B=2, T=60, respacing="ddim6", order=2, wseed=0, xseed=10, seed=24, clip=True),
 }
+
+# arch='online' with cm_mode='add' (model/cmdm.py:207-211: x + cmotion embedding instead of fuse_process(concat)).
+# Goldens in forward_add.npz / loops_add.npz (make_golden_add.py).
+ADD_MODELS = {
+    "ntu_add": dict(MODELS["ntu"], cm_mode="add"),
+    "chi3d_add": dict(MODELS["chi3d"], cm_mode="add"),
+}
+
+
+def synth_kw_add(name):
+    m = ADD_MODELS[name]
+    return dict(njoints=m["njoints"], nfeats=m["nfeats"], latent_dim=m["latent_dim"], ff_size=m["ff_size"],
+                num_layers=m["num_layers"], cond_mode=m["cond_mode"], num_actions=m["num_actions"],
+                clip_dim=512, cm_mode="add")
+
+
+ADD_FORWARD_CASES = {
+    "add_ntu": dict(model="ntu_add", B=2, T=60, t=[999, 3], wseed=7, xseed=30),
+    "add_ntu_ragged_T37": dict(model="ntu_add", B=3, T=37, t=[5, 500, 77], wseed=7, xseed=31),
+    "add_chi3d_cfg": dict(model="chi3d_add", B=2, T=150, t=[640, 12], wseed=8, xseed=32, cfg_scale=2.5),
+}
+ADD_LOOP_CASES = {
+    "add_loop_ntu_p10": dict(model="ntu_add", B=2, T=60, respacing="ddim10", ddim=False, wseed=7, xseed=30, seed=12),
+}

@@ -162,3 +162,54 @@ def test_conditioning_cache_is_not_fooled_by_allocator_address_reuse(built_lib):
         del cm
     # (the allocator normally reuses one or two addresses here, which is what makes the scenario real)
     assert len(ptrs) <= 6
+
+
+# ------------------------------------------------------------------------------ cm_mode='add' (arch='online')
+_add_models = {}
+
+
+def get_add_model(name, wseed):
+    key = (name, wseed)
+    if key not in _add_models:
+        m = CMDM(**cases.ADD_MODELS[name])
+        sd = synthetic.make_state_dict(seed=wseed, **cases.synth_kw_add(name))
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        assert not unexpected and all(k.startswith("clip_model.") for k in missing)
+        assert not hasattr(m, "fuse_process")   # model/cmdm.py:60-61: fuse_process exists only for cm_mode='concat'
+        _add_models[key] = (m.cuda().eval(), sd)
+    return _add_models[key]
+
+
+@pytest.mark.parametrize("name", sorted(cases.ADD_FORWARD_CASES))
+def test_add_mode_forward_matches_reference_golden(built_lib, name):
+    """x + cmotion embedding instead of fuse_process(concat) (model/cmdm.py:207-211), goldens from make_golden_add.py."""
+    c = cases.ADD_FORWARD_CASES[name]
+    mk = cases.ADD_MODELS[c["model"]]
+    gold = torch.from_numpy(np.load(os.path.join(HERE, "forward_add.npz"))[name])
+    model, sd = get_add_model(c["model"], c["wseed"])
+    x, y = synthetic.make_inputs(c["B"], mk["njoints"], mk["nfeats"], c["T"], seed=c["xseed"],
+                                 cond_mode=mk["cond_mode"], num_actions=mk["num_actions"], scale=c.get("cfg_scale"))
+    run = ClassifierFreeSampleModel(model) if "cfg_scale" in c else model
+    with torch.no_grad():
+        out = run(x.cuda(), torch.tensor(c["t"], dtype=torch.long).cuda(), to_cuda(y))
+    assert out.shape == gold.shape
+    err = (out.cpu() - gold).abs().max().item()
+    print("%s: max abs err vs reference golden %.3e" % (name, err))
+    assert err < TOL_TIGHT
+
+
+def test_add_mode_full_batch_matches_oracle(built_lib):
+    """B = 256 (fused GEMM+LayerNorm route) with cm_mode='add' against the oracle on a strided subset of samples."""
+    mk = cases.ADD_MODELS["ntu_add"]
+    model, sd = get_add_model("ntu_add", 7)
+    B, T = 256, 60
+    x, y = synthetic.make_inputs(B, 56, 6, T, seed=300)
+    t = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        out = model(x.cuda(), t.cuda(), to_cuda(y)).cpu()
+    sel = torch.tensor([0, 17, 128, 255])
+    with torch.no_grad():
+        want = cmdm_ref.cmdm_forward(sd, x[sel], t[sel], {"cmotion": y["cmotion"][sel]}, **_kw(mk))
+    err = (out[sel] - want).abs().max().item()
+    print("add mode B=256: max abs err vs oracle %.3e" % err)
+    assert err < TOL_TIGHT

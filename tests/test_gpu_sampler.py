@@ -368,3 +368,23 @@ def test_plms_error_behaviour(built_lib):
         d.plms_sample(model, x, t, model_kwargs={"y": to_cuda(y)}, order=5)
     with pytest.raises(TypeError):  # the reference dereferences old_out=None at :1067 when order == 1
         d.plms_sample(model, x, t, model_kwargs={"y": to_cuda(y)}, order=1)
+
+
+def test_add_mode_loop_reproduces_reference_golden(built_lib):
+    """arch='online' with cm_mode='add': 10-step ancestral loop vs the reference's samples (make_golden_add.py)."""
+    from test_gpu_denoiser import get_add_model
+    name = "add_loop_ntu_p10"
+    c = cases.ADD_LOOP_CASES[name]
+    mk = cases.ADD_MODELS[c["model"]]
+    gold = torch.from_numpy(np.load(os.path.join(HERE, "loops_add.npz"))[name])
+    model, sd = get_add_model(c["model"], c["wseed"])
+    _, y = synthetic.make_inputs(c["B"], mk["njoints"], mk["nfeats"], c["T"], seed=c["xseed"])
+    d = _diffusion(c["respacing"])
+    shape = (c["B"], mk["njoints"], mk["nfeats"], c["T"])
+    torch.manual_seed(c["seed"])
+    init = torch.randn(*shape)
+    with cpu_rng_stream():
+        out = d.p_sample_loop(model, shape, noise=init.cuda(), clip_denoised=False, model_kwargs={"y": to_cuda(y)})
+    err = (out.cpu() - gold).abs().max().item()
+    print("%s: max abs err vs reference golden %.3e" % (name, err))
+    assert err < TOL

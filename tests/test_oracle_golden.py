@@ -138,3 +138,34 @@ def test_plms_order1_from_fresh_loop_raises_like_reference():
     smp = sampler_ref.Sampler(timestep_respacing="ddim5")
     with pytest.raises(TypeError):
         smp.plms_loop(lambda xx, tt: xx, (1, 2, 3, 4), order=1)
+
+
+@pytest.mark.parametrize("name", sorted(cases.ADD_FORWARD_CASES))
+def test_add_mode_forward_matches_reference(name):
+    """arch='online', cm_mode='add' (model/cmdm.py:207-211) against the reference's outputs (make_golden_add.py)."""
+    c = cases.ADD_FORWARD_CASES[name]
+    mk = cases.ADD_MODELS[c["model"]]
+    gold = np.load(os.path.join(HERE, "forward_add.npz"))[name]
+    x, y = synthetic.make_inputs(c["B"], mk["njoints"], mk["nfeats"], c["T"], seed=c["xseed"],
+                                 cond_mode=mk["cond_mode"], num_actions=mk["num_actions"], scale=c.get("cfg_scale"))
+    sd = synthetic.make_state_dict(seed=c["wseed"], **cases.synth_kw_add(c["model"]))
+    assert "fuse_process.weight" not in sd
+    fwd = cmdm_ref.cfg_forward if "cfg_scale" in c else cmdm_ref.cmdm_forward
+    with torch.no_grad():
+        out = fwd(sd, x, torch.tensor(c["t"], dtype=torch.long), y, **_kw(mk))
+    assert out.shape == gold.shape
+    assert np.abs(out.numpy() - gold).max() < TOL
+
+
+def test_add_mode_sampling_loop_matches_reference():
+    name = "add_loop_ntu_p10"
+    c = cases.ADD_LOOP_CASES[name]
+    mk = cases.ADD_MODELS[c["model"]]
+    gold = np.load(os.path.join(HERE, "loops_add.npz"))[name]
+    _, y = synthetic.make_inputs(c["B"], mk["njoints"], mk["nfeats"], c["T"], seed=c["xseed"])
+    sd = synthetic.make_state_dict(seed=c["wseed"], **cases.synth_kw_add(c["model"]))
+    smp = sampler_ref.Sampler(timestep_respacing=c["respacing"])
+    torch.manual_seed(c["seed"])
+    out, _ = smp.loop(lambda xx, tt: cmdm_ref.cmdm_forward(sd, xx, tt, y, **_kw(mk)),
+                      (c["B"], mk["njoints"], mk["nfeats"], c["T"]))
+    assert np.abs(out.numpy() - gold).max() < TOL

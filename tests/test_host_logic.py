@@ -4,6 +4,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 import cases
 from regennet_b200 import gaussian_diffusion as gd
@@ -237,3 +238,38 @@ def test_model_util_and_respace_equal_the_imported_reference():
     assert ours.timestep_map == ref.timestep_map and ours.model_var_type.name == ref.model_var_type.name
     for f in ["betas", "alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2", "posterior_log_variance_clipped"]:
         assert np.array_equal(getattr(ours, f), getattr(ref, f)), f
+
+
+def test_results_writer_matches_cgenerate_format(tmp_path):
+    """sample/cgenerate.py:167-192: concatenation over repetitions, cut to num_samples * num_repetitions, pickled dict with
+    the reference's keys, caption / length side files, existing directory replaced."""
+    from regennet_b200.results import ResultsWriter, load_results
+    bs, J, F, T = 3, 56, 6, 8
+    w = ResultsWriter(num_samples=2, num_repetitions=2)     # batches of 3 are cut to 2 * 2 = 4 entries in total
+    g = torch.Generator().manual_seed(0)
+    reps = []
+    for rep in range(2):
+        motion = torch.randn(bs, J, 3, T, generator=g)
+        output = torch.randn(bs, J, F, T, generator=g)
+        cmotion = torch.randn(bs, J, F, T, generator=g)
+        lengths = torch.tensor([T, T - 1, T - 2])
+        text = ["a%d_%d" % (rep, i) for i in range(bs)]
+        w.add(motion, output, cmotion, lengths, text)
+        reps.append((motion, output, cmotion, lengths, text))
+    out_dir = tmp_path / "samples"
+    out_dir.mkdir()
+    (out_dir / "stale.txt").write_text("old")               # the reference rmtree()s an existing output directory
+    path = w.save(str(out_dir))
+    assert not (out_dir / "stale.txt").exists()
+    r = load_results(path)
+    assert sorted(r) == sorted(['motion', 'output', 'cmotion', 'text', 'lengths', 'num_samples', 'num_repetitions'])
+    assert r['motion'].shape == (4, J, 3, T) and r['output'].shape == (4, J, F, T) and r['cmotion'].shape == (4, J, F, T)
+    want = np.concatenate([reps[0][1].numpy(), reps[1][1].numpy()], axis=0)[:4]
+    assert np.array_equal(r['output'], want)
+    assert r['text'] == ["a0_0", "a0_1", "a0_2", "a1_0"]
+    assert r['lengths'].tolist() == [T, T - 1, T - 2, T]
+    assert r['num_samples'] == 2 and r['num_repetitions'] == 2
+    assert (out_dir / "results.txt").read_text().split("\n") == r['text']
+    assert (out_dir / "results_len.txt").read_text().split("\n") == [str(T), str(T - 1), str(T - 2), str(T)]
+    with pytest.raises(ValueError):
+        ResultsWriter(1, 1).save(str(tmp_path / "empty"))

@@ -404,6 +404,288 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   }
 }
 
+// =====================================================================================================
+// Multi-chunk compact kernel for 64 < T <= 256 ("MC"): the compact kernel's footprint generalised to several key chunks.
+//
+// One CTA per (sample b, head h, 64-query block).  Keys / values stream in chunks of 64 through TWO 32 KB operand buffers;
+// the operand sequence K_0 .. K_{n-1}, V_0 .. V_{n-1} alternates between them (operand j -> buffer j & 1) and operand j is
+// fetched as soon as the MMAs that read operand j - 2 have completed, so every load runs behind an MMA / softmax phase.
+// The scores of all (<= 4) chunks stay resident in TMEM columns [0, 64 n) so the row maximum is exact before any
+// exponential; P chunks are double buffered inside the dead Q buffer (valid rows 0..63 only: hi | lo | hi | lo, 8 KB each)
+// and O (128 columns) overwrites the score columns of chunks 0 and 1 once BOTH have been turned into P.
+// Footprint: 3 x 32 KB + barriers of shared memory, 256 TMEM columns, 288 threads -> two CTAs per SM (the 128-key-chunk
+// kernel above runs one), and a 64-row query block wastes fewer MMA rows on the ragged last block (T = 150: 22 of 64
+// rows instead of 22 of 128).  Every barrier is used exactly once per CTA (parity 0): no phase bookkeeping.
+// =====================================================================================================
+struct CfgMC {
+  static constexpr int TILE = 64 * 128;          // 64 rows x 64 bf16
+  static constexpr int OPERAND = 4 * TILE;       // hi d0-63 | hi d64-127 | lo d0-63 | lo d64-127  (32 KB)
+  static constexpr int MAXC = 4;                 // key chunks of 64: T <= 256
+  static constexpr int SW = 8;
+  static constexpr int THREADS = 32 + 32 * SW;
+  static constexpr int SMEM_BYTES = 3 * OPERAND + 4096 + 1024;
+  static constexpr uint32_t TMEM_COLS = 256;
+};
+
+__global__ void __launch_bounds__(CfgMC::THREADS, 2)
+attention_mc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                    const __grid_constant__ CUtensorMap tm_ohi, const __grid_constant__ CUtensorMap tm_olo, const Params p) {
+  using C = CfgMC;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                       // Q, later the two P buffers
+  uint8_t* sB0 = smem + C::OPERAND;         // operand buffers (K / V chunks)
+  uint8_t* sB1 = smem + 2 * C::OPERAND;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * C::OPERAND);
+  uint64_t* barQ = bars + 0;
+  uint64_t* barOp = bars + 1;               // [8]  operand j landed (K_0..K_{n-1}, V_0..V_{n-1})
+  uint64_t* barS = bars + 9;                // [4]  S chunk complete (tcgen05.commit)
+  uint64_t* barP = bars + 13;               // [4]  P chunk written by all softmax threads
+  uint64_t* barPV = bars + 17;              // [4]  P.V chunk complete (tcgen05.commit)
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 21);
+  float* s_max = reinterpret_cast<float*>(smem + 3 * C::OPERAND + 1024);   // [64 rows][2 key halves]
+  float* s_sum = s_max + 256;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qblocks = (p.T + 63) / 64;
+  const int qb = blockIdx.x % qblocks;
+  const int bh = blockIdx.x / qblocks;
+  const int h = bh & 3, b = bh >> 2;
+  const int q0 = qb * 64;
+  const int kv_len = p.causal ? min(p.T, q0 + 64) : p.T;
+  const int n = (kv_len + 63) / 64;         // key chunks, 1..4
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tm_hi);
+      ptx::prefetch_tmap(&tm_lo);
+      ptx::mbar_init(barQ, 1);
+      for (int i = 0; i < 2 * C::MAXC; ++i) ptx::mbar_init(&barOp[i], 1);
+      for (int i = 0; i < C::MAXC; ++i) {
+        ptx::mbar_init(&barS[i], 1);
+        ptx::mbar_init(&barP[i], 32 * C::SW);
+        ptx::mbar_init(&barPV[i], 1);
+      }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_base_smem, C::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+  ptx::griddep_wait();
+  ptx::griddep_launch();
+  ptx::steplog_begin(p.steplog, p.steplog_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ control thread: TMA + MMA issue
+      auto load_operand = [&](uint8_t* dst, uint64_t* bar, int col0, int t0) {
+        ptx::mbar_expect_tx(bar, C::OPERAND);
+        ptx::tma_load_3d(dst, &tm_hi, bar, col0, b, t0);
+        ptx::tma_load_3d(dst + C::TILE, &tm_hi, bar, col0 + 64, b, t0);
+        ptx::tma_load_3d(dst + 2 * C::TILE, &tm_lo, bar, col0, b, t0);
+        ptx::tma_load_3d(dst + 3 * C::TILE, &tm_lo, bar, col0 + 64, b, t0);
+      };
+      // operand j of the sequence K_0..K_{n-1}, V_0..V_{n-1} -> buffer j & 1
+      auto load_op = [&](int j) {
+        uint8_t* dst = (j & 1) ? sB1 : sB0;
+        if (j < n) load_operand(dst, &barOp[j], DM + h * HD, j * 64);
+        else load_operand(dst, &barOp[j], 2 * DM + h * HD, (j - n) * 64);
+      };
+      load_operand(sQ, barQ, h * HD, q0);
+      load_op(0);
+      load_op(1);  // K_1, or V_0 when there is a single key chunk (2 n >= 2 always)
+
+      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16_f32(128, 64);
+      constexpr uint32_t idesc_o = ptx::umma_idesc_bf16_f32(128, HD) | (1u << 16);  // B (V) is MN-major
+      const uint32_t aQ = ptx::smem_u32(sQ), aB0 = ptx::smem_u32(sB0), aB1 = ptx::smem_u32(sB1);
+
+      // ---- scores: S_kc = Q . K_kc^T into TMEM columns [64 kc, 64 kc + 64)
+      ptx::mbar_wait(barQ, 0);
+      for (int kc = 0; kc < n; ++kc) {
+        ptx::mbar_wait(&barOp[kc], 0);
+        ptx::tcgen05_fence_after();
+        const uint32_t accS = tmem_base + (uint32_t)(kc * 64);
+        const uint32_t aK = (kc & 1) ? aB1 : aB0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t tile = (uint32_t)(k >> 2) * C::TILE;
+          const uint32_t adv = (uint32_t)(k & 3) * 32;
+          const uint64_t q_hi = ptx::umma_desc_k_sw128(aQ + tile + adv);
+          const uint64_t q_lo = ptx::umma_desc_k_sw128(aQ + 2 * C::TILE + tile + adv);
+          const uint64_t k_hi = ptx::umma_desc_k_sw128(aK + tile + adv);
+          const uint64_t k_lo = ptx::umma_desc_k_sw128(aK + 2 * C::TILE + tile + adv);
+          ptx::mma_f16_ss(accS, q_lo, k_hi, idesc_s, k != 0);
+          ptx::mma_f16_ss(accS, q_hi, k_lo, idesc_s, 1);
+          ptx::mma_f16_ss(accS, q_hi, k_hi, idesc_s, 1);
+        }
+        ptx::tcgen05_commit(&barS[kc]);
+        ptx::mbar_wait(&barS[kc], 0);              // K_kc consumed: its buffer takes operand kc + 2
+        if (kc + 2 < 2 * n) load_op(kc + 2);
+      }
+      // ---- O += P_kc . V_kc  (O in TMEM columns [0, 128) = the dead scores of chunks 0 and 1)
+      for (int kc = 0; kc < n; ++kc) {
+        ptx::mbar_wait(&barP[kc], 0);
+        if (kc == 0 && n > 1) ptx::mbar_wait(&barP[1], 0);   // S_1 has been read too before O overwrites it
+        ptx::mbar_wait(&barOp[n + kc], 0);
+        ptx::tcgen05_fence_after();
+        const uint32_t accO = tmem_base;
+        const uint32_t aV = ((n + kc) & 1) ? aB1 : aB0;
+        const uint32_t aP = aQ + (uint32_t)(kc & 1) * 16384u;   // P buffer kc & 1: hi at +0, lo at +8 KB
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t p_hi = ptx::umma_desc_k_sw128(aP + (uint32_t)k * 32);
+          const uint64_t p_lo = ptx::umma_desc_k_sw128(aP + 8192u + (uint32_t)k * 32);
+          const uint64_t v_hi = umma_desc_mn_sw128(aV + (uint32_t)k * 2048, (uint32_t)C::TILE, 1024u);
+          const uint64_t v_lo = umma_desc_mn_sw128(aV + 2 * C::TILE + (uint32_t)k * 2048, (uint32_t)C::TILE, 1024u);
+          ptx::mma_f16_ss(accO, p_lo, v_hi, idesc_o, (kc | k) != 0);
+          ptx::mma_f16_ss(accO, p_hi, v_lo, idesc_o, 1);
+          ptx::mma_f16_ss(accO, p_hi, v_hi, idesc_o, 1);
+        }
+        ptx::tcgen05_commit(&barPV[kc]);
+        if (n + kc + 2 < 2 * n) {                   // V_kc consumed: its buffer takes V_{kc + 2}
+          ptx::mbar_wait(&barPV[kc], 0);
+          load_op(n + kc + 2);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue (warps 1..8)
+    const int q = warp & 3, half = (warp - 1) >> 2;   // TMEM lane quarter; key half (softmax) / head-dim half (epilogue)
+    const int r = q * 32 + lane;                      // row of the 128-row MMA tile == TMEM lane; rows >= 64 are padding
+    const int i = q0 + r;                             // query frame
+    const bool row_ok = r < 64 && i < p.T;
+    const int jmax = p.causal ? i : p.T - 1;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float sc = 0.08838834764831845f * 1.4426950408889634f;  // 1/sqrt(128) * log2(e)
+    const bool warp_live = q * 32 < 64 && q0 + q * 32 < p.T;
+    if (!warp_live) {
+      for (int kc = 0; kc < n; ++kc) ptx::mbar_arrive(&barP[kc]);   // keep the arrival counts only
+    } else {
+      for (int kc = 0; kc < n; ++kc) ptx::mbar_wait(&barS[kc], 0);
+      ptx::tcgen05_fence_after();
+      float mx = -INFINITY, sum = 0.f;
+      // pass 1: exact row maximum over this warp's 32 keys of every chunk, then exchange with the sibling warp
+      for (int kc = 0; kc < n; ++kc) {
+        uint32_t v[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(kc * 64 + half * 32), v);
+        ptx::tmem_ld_wait(v);
+        const int j0 = kc * 64 + half * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j0 + j <= jmax && j0 + j < p.T) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
+      s_max[r * 2 + half] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      mx = fmaxf(mx, s_max[r * 2 + (half ^ 1)]);
+      if (!row_ok) mx = 0.f;
+      // pass 2: P chunks (exp2, bf16 hi / lo split, K-major SW128 A-operand layout) into the P buffer kc & 1
+      for (int kc = 0; kc < n; ++kc) {
+        if (kc >= 2) ptx::mbar_wait(&barPV[kc - 2], 0);   // the tensor core is done with this P buffer
+        uint32_t v[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(kc * 64 + half * 32), v);
+        ptx::tmem_ld_wait(v);
+        uint8_t* pb = sQ + (kc & 1) * 16384;
+#pragma unroll
+        for (int j8 = 0; j8 < 32; j8 += 8) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = kc * 64 + half * 32 + j8 + 2 * e;
+            float p0 = 0.f, p1 = 0.f;
+            if (row_ok && j <= jmax) p0 = exp2f((__uint_as_float(v[j8 + 2 * e]) - mx) * sc);
+            if (row_ok && j + 1 <= jmax) p1 = exp2f((__uint_as_float(v[j8 + 2 * e + 1]) - mx) * sc);
+            sum += p0 + p1;
+            __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+            hw[e] = *reinterpret_cast<uint32_t*>(&hh);
+            __nv_bfloat162 ll = __floats2bfloat162_rn(p0 - __uint_as_float(hw[e] << 16), p1 - __uint_as_float(hw[e] & 0xffff0000u));
+            lw[e] = *reinterpret_cast<uint32_t*>(&ll);
+          }
+          const int jj = half * 32 + j8;  // key offset inside the chunk
+          const uint32_t off = (uint32_t)r * 128 + ((((uint32_t)jj >> 3) ^ ((uint32_t)r & 7)) << 4);
+          *reinterpret_cast<uint4*>(pb + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(pb + 8192 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+        ptx::tcgen05_fence_before();    // this warp's tcgen05.ld of S_kc is ordered before the MMAs that overwrite it
+        ptx::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        ptx::mbar_arrive(&barP[kc]);
+      }
+      s_sum[r * 2 + half] = sum;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      sum += s_sum[r * 2 + (half ^ 1)];
+      // epilogue: O / rowsum -> bf16 (hi, lo); this warp owns head-dim columns [64 half, 64 half + 64); staged as one
+      // 32 x 64 hi tile + one lo tile (4 KB each) in the dead Q / operand buffers, written with TMA stores
+      ptx::mbar_wait(&barPV[n - 1], 0);
+      ptx::tcgen05_fence_after();
+      const float inv = 1.f / sum;
+      uint8_t* st_hi = sQ + (warp - 1) * 8192;
+      uint8_t* st_lo = st_hi + 4096;
+      const uint32_t o_addr = lane_addr + (uint32_t)(half * 64);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32b_x32(o_addr + (uint32_t)c0, v);
+        ptx::tmem_ld_wait(v);
+#pragma unroll
+        for (int j8 = 0; j8 < 32; j8 += 8) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = __uint_as_float(v[j8 + 2 * e]) * inv, b2 = __uint_as_float(v[j8 + 2 * e + 1]) * inv;
+            __nv_bfloat162 hh = __floats2bfloat162_rn(a, b2);
+            hw[e] = *reinterpret_cast<uint32_t*>(&hh);
+            __nv_bfloat162 ll = __floats2bfloat162_rn(a - __uint_as_float(hw[e] << 16), b2 - __uint_as_float(hw[e] & 0xffff0000u));
+            lw[e] = *reinterpret_cast<uint32_t*>(&ll);
+          }
+          const int chunk = (c0 + j8) >> 3;
+          const uint32_t off = (uint32_t)lane * 128 + (((uint32_t)chunk ^ ((uint32_t)lane & 7)) << 4);
+          *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(st_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_store_3d(&tm_ohi, st_hi, h * HD + half * 64, b, q0 + q * 32);
+        ptx::tma_store_3d(&tm_olo, st_lo, h * HD + half * 64, b, q0 + q * 32);
+        ptx::bulk_commit();
+        ptx::bulk_wait<0>();
+      }
+    }
+  }
+
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::steplog_end(p.steplog, p.steplog_slot, p.steplog_cta);
+  if (warp == 0) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// tm_hi / tm_lo must be the 3-D q|k|v maps with 64-FRAME boxes (like the compact kernel's)
+inline cudaError_t launch_mc(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const CUtensorMap& tm_ohi,
+                             const CUtensorMap& tm_olo, const Params& p, cudaStream_t s) {
+  using C = CfgMC;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (p.T > 64 * C::MAXC) return cudaErrorInvalidValue;
+  const int qblocks = (p.T + 63) / 64;
+  return launch_pdl(attention_mc_kernel, dim3(p.Beff * 4 * qblocks), dim3(C::THREADS), C::SMEM_BYTES, s, tm_hi, tm_lo,
+                    tm_ohi, tm_olo, p);
+}
+
 template <int TB>
 inline cudaError_t launch(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, const CUtensorMap& tm_ohi,
                           const CUtensorMap& tm_olo, const Params& p, cudaStream_t s) {

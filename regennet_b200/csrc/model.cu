@@ -71,6 +71,9 @@ struct regen_handle {
   bool fused_ln = true;              // REGEN_DEBUG_NO_FUSED_LN=1: GEMM -> tmp -> LayerNorm kernels
   unsigned long long* steplog = nullptr;  // regen_test_step_log: whole-step timeline buffer (2 words per launch slot)
   int steplog_slot = 0, steplog_cap = 0;
+  int attn_mc_mode = 2;              // multi-chunk compact attention kernel (2 CTAs / SM) for 64 < S <= 256: 2 = auto (when the
+                                     // last 128-query block would be at most half full), REGEN_ATTN_MC=0 never, =1 always
+  bool attn_mc = false;              // decision for the current S (set by regen_prepare_cond)
   bool narrow_slices = true;         // REGEN_DEBUG_WIDE_SLICES=1: tail slices of the pair GEMM load the full-height W box (A/B)
   bool exit_wait_full = true;        // REGEN_DEBUG_EXIT_WAIT_READ=1: kernels only wait until their bulk stores have READ the staging
                                      // tiles before exit (measured: no difference, so the conservative full wait stays the default)
@@ -257,6 +260,8 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
     h->prefetch_res = !(e4 && e4[0] == '1');
     const char* e4b = getenv("REGEN_DEBUG_F32_RESIDUAL");
     h->res16 = !(e4b && e4b[0] == '1');
+    const char* e4g = getenv("REGEN_ATTN_MC");
+    if (e4g && (e4g[0] == '0' || e4g[0] == '1')) h->attn_mc_mode = e4g[0] - '0';
     const char* e4f = getenv("REGEN_DEBUG_WIDE_SLICES");
     h->narrow_slices = !(e4f && e4f[0] == '1');
     const char* e4e = getenv("REGEN_DEBUG_EXIT_WAIT_READ");
@@ -496,8 +501,14 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
   TRY(make_tmap_store_2d(&h->st_h, h->h, false, h->M, D, D));
   TRY(make_tmap_store_2d(&h->st_tmp, h->tmp, false, h->M, D, D));
   if ((I & 3) == 0) TRY(make_tmap_store_2d(&h->st_x0e, h->x0e, false, Mf, I, I));
-  TRY(make_tmap_bf16_3d(&h->tm_qkv_hi, h->qkv_s.hi, 3 * D, Beff, S, S <= 64 ? 64 : 128));
-  TRY(make_tmap_bf16_3d(&h->tm_qkv_lo, h->qkv_s.lo, 3 * D, Beff, S, S <= 64 ? 64 : 128));
+  // 64-frame boxes for the compact (S <= 64) and the multi-chunk compact (64 < S <= 256) attention kernels
+  // Measured (config 3, S = 150: attention 1.54 -> 1.11 ms per step; config 5, S = 196: 0.84 -> 0.86): the multi-chunk
+  // kernel wins when the 128-query-block kernel would run a mostly empty last block, and ties otherwise.
+  h->attn_mc = S > 64 && S <= 256 &&
+               (h->attn_mc_mode == 1 || (h->attn_mc_mode == 2 && ceil_div(S, 64) < 2 * ceil_div(S, 128)));
+  const uint32_t qkv_box = (S <= 64 || h->attn_mc) ? 64 : 128;
+  TRY(make_tmap_bf16_3d(&h->tm_qkv_hi, h->qkv_s.hi, 3 * D, Beff, S, qkv_box));
+  TRY(make_tmap_bf16_3d(&h->tm_qkv_lo, h->qkv_s.lo, 3 * D, Beff, S, qkv_box));
   TRY(make_tmap_bf16_3d(&h->tm_att_hi, h->att.hi, D, Beff, S, 32));
   TRY(make_tmap_bf16_3d(&h->tm_att_lo, h->att.lo, D, Beff, S, 32));
   if (h->has_cond) {
@@ -622,6 +633,8 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
         ap.steplog = nullptr; ap.steplog_slot = 0; ap.steplog_cta = 0;
         if (h->steplog && h->steplog_slot < h->steplog_cap) { ap.steplog = h->steplog; ap.steplog_slot = h->steplog_slot++; }
         cudaError_t e = S <= 64 ? attn::launch<64>(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s)
+                        : h->attn_mc
+                                ? attn::launch_mc(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s)
                                 : attn::launch<128>(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s);
         if (e != cudaSuccess) {
           set_error("attention launch (T=%d Beff=%d) failed: %s", T, Beff, cudaGetErrorString(e));
@@ -883,8 +896,9 @@ int regen_test_attention(const float* qkv, float* out, int32_t B, int32_t T, int
   REGEN_CUDA(cudaMalloc(&ol, M * D * 2));
   layers::launch_split_rows(qkv, 3 * D, qh, ql, 3 * D, 3 * D, (int)M, 1, 1, s);
   CUtensorMap th, tl, toh, tol;
-  int rc = make_tmap_bf16_3d(&th, qh, 3 * D, B, T, T <= 64 ? 64 : 128);
-  if (!rc) rc = make_tmap_bf16_3d(&tl, ql, 3 * D, B, T, T <= 64 ? 64 : 128);
+  const bool mc = (dbg & 8) && T > 64 && T <= 256;   // bit 3: multi-chunk compact kernel
+  int rc = make_tmap_bf16_3d(&th, qh, 3 * D, B, T, (T <= 64 || mc) ? 64 : 128);
+  if (!rc) rc = make_tmap_bf16_3d(&tl, ql, 3 * D, B, T, (T <= 64 || mc) ? 64 : 128);
   if (!rc) rc = make_tmap_bf16_3d(&toh, oh, D, B, T, 32);
   if (!rc) rc = make_tmap_bf16_3d(&tol, ol, D, B, T, 32);
   if (!rc) {
@@ -892,7 +906,9 @@ int regen_test_attention(const float* qkv, float* out, int32_t B, int32_t T, int
     ap.out_hi = oh; ap.out_lo = ol; ap.T = T; ap.Beff = B; ap.causal = (dbg & 2) ? 0 : 1; ap.dbg = dbg & 1;
     ap.timeline = g_test_timeline;
     ap.steplog = nullptr; ap.steplog_slot = 0; ap.steplog_cta = 0;
-    cudaError_t e = T <= 64 ? attn::launch<64>(th, tl, toh, tol, ap, s) : attn::launch<128>(th, tl, toh, tol, ap, s);
+    cudaError_t e = T <= 64 ? attn::launch<64>(th, tl, toh, tol, ap, s)
+                    : mc    ? attn::launch_mc(th, tl, toh, tol, ap, s)
+                            : attn::launch<128>(th, tl, toh, tol, ap, s);
     if (e == cudaSuccess) {
       layers::merge_split_kernel<<<grid_cap(ceil_div((int64_t)M * D, 256)), 256, 0, s>>>(oh, ol, out, (int64_t)M * D);
       e = cudaStreamSynchronize(s);

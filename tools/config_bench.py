@@ -66,7 +66,12 @@ def run(name, model_name, B, T, cfg, ddim, respacing, K=30, W=5):
                                                          ms[1] / K, ms[2] / K, ms[3] / K))
 
 
-run("config1 NTU B=1 (latency)", "ntu", 1, 60, False, False, [1000], K=100)
-run("config2 NTU B=256", "ntu", 256, 60, False, False, [1000])
-run("config3 Chi3D CFG B=128 T=150", "chi3d", 128, 150, True, False, [1000])
-run("config5 HML text CFG DDIM100 B=64", "hml", 64, 196, True, True, "ddim100")
+only = set(sys.argv[1:])   # e.g. `config_bench.py 3 5` runs configs 3 and 5 only
+if not only or "1" in only:
+    run("config1 NTU B=1 (latency)", "ntu", 1, 60, False, False, [1000], K=100)
+if not only or "2" in only:
+    run("config2 NTU B=256", "ntu", 256, 60, False, False, [1000])
+if not only or "3" in only:
+    run("config3 Chi3D CFG B=128 T=150", "chi3d", 128, 150, True, False, [1000])
+if not only or "5" in only:
+    run("config5 HML text CFG DDIM100 B=64", "hml", 64, 196, True, True, "ddim100")

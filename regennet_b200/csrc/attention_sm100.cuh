@@ -15,6 +15,8 @@
 // TB = 64 (T <= 64: K and V share a buffer, O reuses S's TMEM columns: ~69 KB of shared memory, 128 TMEM columns, three
 // CTAs per SM) or 128 (longer sequences, one CTA per SM, key chunks of 128 with the
 // scores of all chunks resident in TMEM so the row max is exact before any exponential is taken).
+// A third kernel (attention_mc_kernel, below) covers 64 < T <= 256 with the compact footprint (64-query blocks, 64-key
+// chunks, two CTAs per SM); model.cu picks it when the last 128-query block would be at most half full.
 // Reference semantics: nn.MultiheadAttention with the additive causal mask of model/cmdm.py:168-171, 220-227.
 #pragma once
 #include "common.cuh"

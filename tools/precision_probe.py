@@ -61,6 +61,12 @@ def make_mm(scheme):
             return ah @ bh + al @ bh
         if terms == "x3":
             return al @ bh + ah @ bl + ah @ bh
+        if terms == "hi16_corr8g":  # corrections as PLAIN e4m3 products with global power-of-two scales whose sum is 15,
+            # accumulated first and folded in by the first main-term MMA's scale-input-d (D = A.B + D * 2^-15):
+            #   (A_lo * 2^11) . (W_hi * 2^4)  +  (A_hi * 2^0) . (W_lo * 2^15)
+            e4 = lambda v: v.to(torch.float8_e4m3fn).float()
+            corr = e4(al * 2.0 ** 11) @ e4(bh * 2.0 ** 4) + e4(ah) @ e4(bl * 2.0 ** 15)
+            return ah @ bh + corr * 2.0 ** -15
         if terms == "hi16_corr8":   # main term in fp16, both correction terms as block-scaled e4m3 products (2x MMA rate)
             return ah @ bh + q8_blocks(al, -1) @ q8_blocks(bh, -2) + q8_blocks(ah, -1) @ q8_blocks(bl, -2)
         raise ValueError(terms)
@@ -117,6 +123,8 @@ SCHEMES = [
     ("fp16 x3", "fp16:x3", "fp16:x3", False, 3),
     ("fp16 hi.hi + two block-scaled e4m3 correction products", "fp16:hi16_corr8", "fp16:hi16_corr8", False, 2),
     ("bf16 hi.hi + two block-scaled e4m3 correction products", "bf16:hi16_corr8", "bf16:hi16_corr8", False, 2),
+    ("fp16 hi.hi + plain e4m3 corrections, global scales 2^11/2^4, 2^0/2^15", "fp16:hi16_corr8g", "fp16:hi16_corr8g", False, 2),
+    ("same for the Linear layers only; attention fp16 x3", "fp16:hi16_corr8g", "fp16:x3", False, 2),
 ]
 
 

@@ -150,5 +150,33 @@ def main():
     return rows
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--loop" not in sys.argv:
     main()
+
+
+def loop_errors(respacing="ddim50"):
+    """Final-sample error of a whole respaced p_sample_loop (same noise stream) under a scheme vs the fp32 oracle."""
+    from oracle import sampler_ref
+    mk = cases.MODELS["ntu"]
+    kw = dict(num_layers=mk["num_layers"], nhead=mk["num_heads"], cond_mode=mk["cond_mode"], cm_mode=mk["cm_mode"])
+    sd = synthetic.make_state_dict(seed=0, **cases.synth_kw("ntu"))
+    _, y = synthetic.make_inputs(2, 56, 6, 60, seed=50)
+    shape = (2, 56, 6, 60)
+
+    def run():
+        smp = sampler_ref.Sampler(timestep_respacing=respacing)
+        torch.manual_seed(10)
+        out, _ = smp.loop(lambda xx, tt: cmdm_ref.cmdm_forward(sd, xx, tt, y, **kw), shape)
+        return out
+
+    ref = run()
+    for label, lin, att, r16, mmas in SCHEMES:
+        if lin in ("fp32", "bf16:x1", "fp16:x1", "fp16:a1_w2", "fp16:a2_w1"):
+            continue
+        with patched(make_mm(lin), make_mm(att), r16):
+            out = run()
+        print("%-58s %s loop: final-sample max abs err %.3e" % (label, respacing, (out - ref).abs().max().item()), flush=True)
+
+
+if __name__ == "__main__" and "--loop" in sys.argv:
+    loop_errors()

@@ -119,3 +119,12 @@ ADD_FORWARD_CASES = {
 ADD_LOOP_CASES = {
     "add_loop_ntu_p10": dict(model="ntu_add", B=2, T=60, respacing="ddim10", ddim=False, wseed=7, xseed=30, seed=12),
 }
+
+# Evaluation feature extractor (ST-GCN, eval/a2m/recognition/models/stgcn.py); goldens in stgcn.npz (make_golden_stgcn.py).
+# Oracle only so far (oracle/stgcn_ref.py): SURVEY.md 8f row 3 has no CUDA path yet.
+STGCN_CASES = {
+    # two persons (actor + reactor stacked along the feature axis, 6 rot6d features each), as eval/a2m/stgcn/evaluate.py:15-20
+    "stgcn_p2": dict(layout="ntu-rgb+d", in_channels=12, num_class=26, num_person=2, N=3, T=60, wseed=0, xseed=40),
+    # single person, odd length (the stride-2 blocks round 37 -> 19 -> 10)
+    "stgcn_p1_T37": dict(layout="ntu-rgb+d", in_channels=6, num_class=8, num_person=1, N=2, T=37, wseed=1, xseed=41),
+}

@@ -169,3 +169,20 @@ def test_add_mode_sampling_loop_matches_reference():
     out, _ = smp.loop(lambda xx, tt: cmdm_ref.cmdm_forward(sd, xx, tt, y, **_kw(mk)),
                       (c["B"], mk["njoints"], mk["nfeats"], c["T"]))
     assert np.abs(out.numpy() - gold).max() < TOL
+
+
+@pytest.mark.parametrize("name", sorted(cases.STGCN_CASES))
+def test_stgcn_oracle_matches_reference(name):
+    """Evaluation feature extractor (oracle only so far): oracle/stgcn_ref.py against the reference's
+    STGCN.forward outputs (eval/a2m/recognition/models/stgcn.py:76-126; tests/golden/make_golden_stgcn.py)."""
+    from oracle import stgcn_ref
+    c = cases.STGCN_CASES[name]
+    g = np.load(os.path.join(HERE, "stgcn.npz"))
+    A = torch.from_numpy(g[name + ".A"])
+    sd = stgcn_ref.make_state_dict(A, c["in_channels"], c["num_class"], c["num_person"], seed=c["wseed"])
+    x = torch.randn(c["N"], A.shape[1], c["in_channels"], c["T"], generator=torch.Generator().manual_seed(c["xseed"]))
+    with torch.no_grad():
+        feat, yhat = stgcn_ref.stgcn_forward(sd, x, c["num_person"])
+    assert feat.shape == (c["N"], 256) and yhat.shape == (c["N"], c["num_class"])
+    assert np.abs(feat.numpy() - g[name + ".features"]).max() < TOL
+    assert np.abs(yhat.numpy() - g[name + ".yhat"]).max() < TOL

@@ -128,3 +128,6 @@ STGCN_CASES = {
     # single person, odd length (the stride-2 blocks round 37 -> 19 -> 10)
     "stgcn_p1_T37": dict(layout="ntu-rgb+d", in_channels=6, num_class=8, num_person=1, N=2, T=37, wseed=1, xseed=41),
 }
+STGCN_GRAPH_LAYOUTS = ["ntu-rgb+d", "ntu_edge", "openpose"]
+# the SMPL kinematic tree (parent of joint j), used to exercise the kintree-driven layouts without body-model files
+STGCN_SMPL_PARENTS = [-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21]

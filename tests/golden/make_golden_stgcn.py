@@ -45,6 +45,20 @@ def main():
         out[name + ".A"] = A.numpy()
         out[name + ".features"] = ref["features"].numpy()
         out[name + ".yhat"] = ref["yhat"].numpy()
+    # adjacency partitions of the reference's Graph for every file-free layout / strategy (float64, compared bit for bit)
+    from eval.a2m.recognition.models.stgcnutils.graph import Graph
+    for layout in cases.STGCN_GRAPH_LAYOUTS:
+        for strategy in ("uniform", "distance", "spatial"):
+            for hop in (1, 2):
+                out["graph.%s.%s.%d" % (layout, strategy, hop)] = Graph(layout=layout, strategy=strategy, max_hop=hop).A
+    # kinematic-tree layout ('smpl') through a synthetic tree written to a temporary kintree_table.pkl
+    import pickle
+    import tempfile
+    kt = np.stack([np.array(cases.STGCN_SMPL_PARENTS), np.arange(24)])
+    with tempfile.NamedTemporaryFile(suffix=".pkl", delete=False) as f:
+        pickle.dump(kt, f)
+    out["graph.smpl.spatial.1"] = Graph(layout="smpl", strategy="spatial", kintree_path=f.name).A
+    os.unlink(f.name)
     np.savez(os.path.join(HERE, "stgcn.npz"), **out)
 
 

@@ -273,3 +273,26 @@ def test_results_writer_matches_cgenerate_format(tmp_path):
     assert (out_dir / "results_len.txt").read_text().split("\n") == [str(T), str(T - 1), str(T - 2), str(T)]
     with pytest.raises(ValueError):
         ResultsWriter(1, 1).save(str(tmp_path / "empty"))
+
+
+def test_stgcn_graph_adjacency_bit_exact():
+    """regennet_b200/stgcn_graph.py against the reference's Graph(...).A (stgcnutils/graph.py) stored by
+    tests/golden/make_golden_stgcn.py: every file-free layout x strategy x max_hop, and 'smpl' through a kinematic tree."""
+    from regennet_b200 import stgcn_graph
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stgcn.npz"))
+    n = 0
+    for layout in cases.STGCN_GRAPH_LAYOUTS:
+        for strategy in ("uniform", "distance", "spatial"):
+            for hop in (1, 2):
+                want = g["graph.%s.%s.%d" % (layout, strategy, hop)]
+                got = stgcn_graph.adjacency(layout, strategy, max_hop=hop)
+                assert got.shape == want.shape and np.array_equal(got, want), (layout, strategy, hop)
+                n += 1
+    assert n == 18
+    kt = np.stack([np.array(cases.STGCN_SMPL_PARENTS), np.arange(24)])
+    assert np.array_equal(stgcn_graph.adjacency("smpl", "spatial", kintree=kt), g["graph.smpl.spatial.1"])
+    assert np.array_equal(g["stgcn_p2.A"], stgcn_graph.adjacency("ntu-rgb+d", "spatial").astype(np.float32))
+    with pytest.raises(ValueError):
+        stgcn_graph.adjacency("smplx", "spatial")          # needs the body model's kinematic tree
+    with pytest.raises(NotImplementedError):
+        stgcn_graph.adjacency("nope")

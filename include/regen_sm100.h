@@ -208,6 +208,39 @@ int regen_profile_begin(regen_handle* h);
 int regen_profile_end(regen_handle* h, float* ms, int32_t* launches);
 
 /* ------------------------------------------------------------------------------------------
+ * Evaluation feature extractor: ST-GCN inference.  Replaces STGCN.forward of
+ * eval/a2m/recognition/models/stgcn.py:76-126 (st_gcn blocks :145-213, graph convolution
+ * eval/a2m/recognition/models/stgcnutils/tgcn.py:55-64) in model.eval() mode.
+ * STATUS: built against the pinned oracle without GPU time left in its round; see regennet_b200/csrc/stgcn.cu.
+ *
+ * Packed weights: ONE fp32 device buffer, tensors in this order, each contiguous in its state-dict shape:
+ *   A [K,V,V];  data_bn {weight, bias, running_mean, running_var} [in_channels*V];
+ *   for block i = 0..9 (channels 64,64,64,64,128,128,128,256,256,256; temporal stride 2 at i = 4 and 7):
+ *     gcn.conv.weight [K*Cout,Cin], gcn.conv.bias [K*Cout], tcn.0 {weight,bias,running_mean,running_var} [Cout],
+ *     tcn.2.weight [Cout,Cout,9], tcn.2.bias [Cout], tcn.3 {weight,bias,running_mean,running_var} [Cout],
+ *     (i = 4, 7 only) residual.0.weight [Cout,Cin], residual.0.bias [Cout], residual.1 {4 x [Cout]},
+ *     edge_importance.i [K,V,V];
+ *   fcn.weight [num_class,256], fcn.bias [num_class].
+ * regen_stgcn_packed_size returns the number of floats (negative for a bad descriptor).
+ * regen_stgcn_forward: output fp32 [N, V, in_channels, T] (the sampler's batch["output"]; in_channels =
+ * C * num_person with the persons stacked along that axis) -> features fp32 [N,256], yhat fp32 [N,num_class].
+ * ---------------------------------------------------------------------------------------- */
+typedef struct regen_stgcn regen_stgcn;
+typedef struct {
+  int32_t in_channels; /* C * num_person */
+  int32_t num_person;  /* 1 or 2 */
+  int32_t num_class;
+  int32_t num_node;    /* V */
+  int32_t num_part;    /* K adjacency partitions */
+} regen_stgcn_desc;
+int64_t regen_stgcn_packed_size(const regen_stgcn_desc* d);
+int regen_stgcn_create(regen_stgcn** h, int32_t device, const regen_stgcn_desc* d);
+int regen_stgcn_load_weights(regen_stgcn* h, const float* packed, int64_t n_floats, void* stream);
+int regen_stgcn_forward(regen_stgcn* h, const float* output, int32_t N, int32_t T, float* features, float* yhat,
+                        void* stream);
+void regen_stgcn_destroy(regen_stgcn* h);
+
+/* ------------------------------------------------------------------------------------------
  * Kernel-level test hook (used by tests/ only): out[M,N] = act(A[M,K] . W[N,K]^T + bias + residual)
  * through the same tcgen05/TMA GEMM kernel the denoiser uses (the arithmetic of every nn.Linear on
  * the path, torch F.linear).  fp32 device buffers in and out; synchronises the stream.

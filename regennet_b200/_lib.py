@@ -39,6 +39,10 @@ class WeightPtrs(ctypes.Structure):
         [("layers", LayerWeights * REGEN_MAX_LAYERS)]
 
 
+class StgcnDesc(ctypes.Structure):
+    _fields_ = [(n, c_int) for n in ("in_channels", "num_person", "num_class", "num_node", "num_part")]
+
+
 _SIGNATURES = {
     # name: (restype, argtypes)
     "regen_version": (ctypes.c_char_p, []),
@@ -67,6 +71,11 @@ _SIGNATURES = {
     "regen_load_weights": (c_int, [c_void_p, ctypes.POINTER(WeightPtrs), c_void_p]),
     "regen_prepare_cond": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "regen_denoise": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "regen_stgcn_packed_size": (c_i64, [ctypes.POINTER(StgcnDesc)]),
+    "regen_stgcn_create": (c_int, [ctypes.POINTER(c_void_p), c_int, ctypes.POINTER(StgcnDesc)]),
+    "regen_stgcn_load_weights": (c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
+    "regen_stgcn_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "regen_stgcn_destroy": (None, [c_void_p]),
     "regen_test_gemm": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
     "regen_test_gemm_timeline": (c_int, [c_void_p]),
     "regen_test_step_log": (c_int, [c_void_p, c_void_p, c_int]),

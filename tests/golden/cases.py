@@ -131,3 +131,15 @@ STGCN_CASES = {
 STGCN_GRAPH_LAYOUTS = ["ntu-rgb+d", "ntu_edge", "openpose"]
 # the SMPL kinematic tree (parent of joint j), used to exercise the kintree-driven layouts without body-model files
 STGCN_SMPL_PARENTS = [-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21]
+
+METRIC_LABELS = 6
+
+
+def metric_inputs():
+    """Seeded feature matrices / labels for the evaluation-metric goldens (FID, diversity, multimodality, accuracy)."""
+    import torch
+    g = torch.Generator().manual_seed(123)
+    f1 = torch.randn(120, 256, generator=g)
+    f2 = 0.9 * torch.randn(150, 256, generator=g) + 0.1
+    labels = torch.randint(0, METRIC_LABELS - 1, (120,), generator=g)   # the last label never occurs (zero quota)
+    return f1, f2, labels

@@ -59,6 +59,27 @@ def main():
         pickle.dump(kt, f)
     out["graph.smpl.spatial.1"] = Graph(layout="smpl", strategy="spatial", kintree_path=f.name).A
     os.unlink(f.name)
+    # evaluation metrics (eval/a2m/stgcn/{fid,diversity,accuracy}.py) on seeded feature matrices
+    from eval.a2m.stgcn.accuracy import calculate_accuracy
+    from eval.a2m.stgcn.diversity import calculate_diversity_multimodality
+    from eval.a2m.stgcn.fid import calculate_fid
+    import scipy.linalg as sla
+    try:
+        sla.sqrtm(np.eye(2), disp=False)
+    except TypeError:   # this container's scipy (>= 1.18) dropped `disp`; give the unmodified reference the old signature
+        _sqrtm = sla.sqrtm
+        sla.sqrtm = lambda a, disp=True, **kw: _sqrtm(a, **kw) if disp else (_sqrtm(a, **kw), 0.0)
+    f1, f2, labels = cases.metric_inputs()
+    s1 = (np.mean(f1.numpy(), axis=0), np.cov(f1.numpy(), rowvar=False))
+    s2 = (np.mean(f2.numpy(), axis=0), np.cov(f2.numpy(), rowvar=False))
+    out["metrics.fid"] = np.float64(calculate_fid(s1, s2))
+    out["metrics.fid_self"] = np.float64(calculate_fid(s1, s1))
+    out["metrics.div_mm"] = np.array(calculate_diversity_multimodality(f1, labels, cases.METRIC_LABELS, seed=7))
+    loader = [{"yhat": f1[i:i + 40, :cases.METRIC_LABELS], "y": labels[i:i + 40]} for i in range(0, f1.shape[0], 40)]
+    acc, conf = calculate_accuracy(None, loader, cases.METRIC_LABELS, lambda b: b, "cpu")
+    out["metrics.accuracy"] = np.float64(acc)
+    out["metrics.confusion"] = conf.numpy()
+    print("metrics: fid %.6f div/mm %s acc %.4f" % (out["metrics.fid"], out["metrics.div_mm"], acc))
     np.savez(os.path.join(HERE, "stgcn.npz"), **out)
 
 

@@ -296,3 +296,20 @@ def test_stgcn_graph_adjacency_bit_exact():
         stgcn_graph.adjacency("smplx", "spatial")          # needs the body model's kinematic tree
     with pytest.raises(NotImplementedError):
         stgcn_graph.adjacency("nope")
+
+
+def test_eval_metrics_match_reference_goldens():
+    """regennet_b200/eval_metrics.py against eval/a2m/stgcn/{fid,diversity,accuracy}.py run on the same seeded features
+    (tests/golden/make_golden_stgcn.py); the pair sampling consumes numpy's global generator in the reference's order."""
+    from regennet_b200 import eval_metrics as em
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stgcn.npz"))
+    f1, f2, labels = cases.metric_inputs()
+    s1, s2 = em.calculate_activation_statistics(f1), em.calculate_activation_statistics(f2)
+    assert abs(em.calculate_fid(s1, s2) - float(g["metrics.fid"])) < 1e-9 * max(1.0, abs(float(g["metrics.fid"])))
+    assert abs(em.calculate_fid(s1, s1) - float(g["metrics.fid_self"])) < 1e-6
+    div, mm = em.calculate_diversity_multimodality(f1, labels, cases.METRIC_LABELS, seed=7)
+    assert np.allclose([div, mm], g["metrics.div_mm"], rtol=0, atol=1e-6)
+    loader = [{"yhat": f1[i:i + 40, :cases.METRIC_LABELS], "y": labels[i:i + 40]} for i in range(0, f1.shape[0], 40)]
+    acc, conf = em.calculate_accuracy(None, loader, cases.METRIC_LABELS, lambda b: b, "cpu")
+    assert abs(acc - float(g["metrics.accuracy"])) < 1e-7
+    assert np.array_equal(conf.numpy(), g["metrics.confusion"])       # integer counts: bit-exact

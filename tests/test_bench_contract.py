@@ -32,3 +32,46 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
 
 def test_reference_arm_other_ranks_exit_without_work():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == ""
+
+
+def test_gpu_arm_line_has_every_contract_key():
+    """Static check (no GPU): the dict literal bench.py prints on rank 0 of the GPU arm carries every key of the bench
+    contract, and every name its value expressions use is bound in that function (a typo would only surface on the box)."""
+    import ast
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    found = None
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fn):
+            if isinstance(node, ast.Assign) and isinstance(node.value, ast.Dict) and \
+                    any(isinstance(k, ast.Constant) and k.value == "roofline_hbm" for k in node.value.keys):
+                found = (fn, node.value)
+    assert found, "the GPU arm's JSON dict was not found in bench.py"
+    fn, d = found
+    keys = {k.value for k in d.keys if isinstance(k, ast.Constant)}
+    need = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+            "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "roofline_hbm", "roofline_attention"}
+    assert need <= keys, sorted(need - keys)
+    sub = {k.value: v for k, v in zip(d.keys, d.values) if isinstance(k, ast.Constant)}
+    for name in ("roofline", "roofline_attention"):
+        rk = {k.value for k in sub[name].keys if isinstance(k, ast.Constant)}
+        assert {"bound", "achieved", "peak", "unit", "frac"} <= rk, (name, rk)
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= {k.value for k in sub["e2e"].keys}
+    # names read inside the dict must be assigned (or be parameters / imports / builtins) in the enclosing function or module
+    bound = {a.arg for a in fn.args.args} | set(dir(__builtins__) if not isinstance(__builtins__, dict) else __builtins__)
+    for n in ast.walk(fn):
+        if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Store):
+            bound.add(n.id)
+        elif isinstance(n, (ast.Import, ast.ImportFrom)):
+            bound |= {(a.asname or a.name).split(".")[0] for a in n.names}
+        elif isinstance(n, (ast.FunctionDef, ast.Lambda)) and n is not fn:
+            bound |= {a.arg for a in n.args.args}
+    for n in ast.iter_child_nodes(tree):
+        if isinstance(n, (ast.FunctionDef, ast.ClassDef)):
+            bound.add(n.name)
+        elif isinstance(n, (ast.Import, ast.ImportFrom)):
+            bound |= {(a.asname or a.name).split(".")[0] for a in n.names}
+        elif isinstance(n, ast.Assign):
+            bound |= {t.id for t in n.targets if isinstance(t, ast.Name)}
+    used = {n.id for n in ast.walk(d) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)}
+    assert used <= bound, sorted(used - bound)

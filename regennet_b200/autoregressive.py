@@ -36,7 +36,27 @@ def _rep_batch(v, B, G):
     return v
 
 
-def auto_regressive_sample(sample_fn, model, shape, model_kwargs, setting='cmdm', truncate=True, frames_per_call=1,
+def _model_arch(model):
+    """arch of the denoiser behind `model`, unwrapping ClassifierFreeSampleModel (``.model``); None when unknown."""
+    seen = 0
+    while model is not None and seen < 4:
+        arch = getattr(model, 'arch', None)
+        if arch is not None:
+            return arch
+        model = getattr(model, 'model', None)
+        seen += 1
+    return None
+
+
+def _cut_time(v, shape, Tc):
+    """Per-frame conditioning entries (same [B, V, C, T] shape as the motion: inpainting mask / motion) follow the
+    truncated time axis."""
+    if torch.is_tensor(v) and tuple(v.shape) == tuple(shape) and Tc < shape[-1]:
+        return v[..., :Tc]
+    return v
+
+
+def auto_regressive_sample(sample_fn, model, shape, model_kwargs, setting='cmdm', truncate=None, frames_per_call=1,
                            clip_denoised=False, **sample_kwargs):
     """-> output [B, V, 2C, T] (``setting='cmdm'``: actor motion | generated reaction, eval/a2m/stgcn_eval.py:61-62)
     or [B, V, C, T].
@@ -44,7 +64,20 @@ def auto_regressive_sample(sample_fn, model, shape, model_kwargs, setting='cmdm'
     sample_fn: ``diffusion.p_sample_loop`` / ``ddim_sample_loop`` (called as in the reference, :58).
     model_kwargs['y']['cmotion'] is the full actor motion [B, V, C, T]; as in the reference it is left in
     model_kwargs on return.  Extra keyword arguments go to sample_fn.
+
+    truncate: run loop f on the first f + 1 frames only.  That is the same function of the inputs ONLY for a causal
+    denoiser (``arch='online'``); for ``arch='offline'`` (bidirectional encoder, model/cmdm.py:228-238) or an unknown
+    model, frame f of the reference also depends on the noise of later frames, so ``truncate=True`` raises there and
+    the default (``None``) resolves to True for 'online' and to False -- the literal reference loop -- otherwise.
     """
+    arch = _model_arch(model)
+    causal = arch == 'online'
+    if truncate is None:
+        truncate = causal
+    if truncate and not causal:
+        raise ValueError("auto_regressive_sample(truncate=True) needs a causal denoiser (arch='online'); this model has "
+                         "arch=%r, whose frame f depends on later frames (eval/a2m/stgcn_eval.py:50-67 semantics): "
+                         "pass truncate=False" % (arch,))
     y = model_kwargs['y']
     cmotion_bak = y['cmotion']
     B, V, C, T = cmotion_bak.shape
@@ -61,7 +94,7 @@ def auto_regressive_sample(sample_fn, model, shape, model_kwargs, setting='cmdm'
         cm = torch.zeros((g, B, V, C, Tc), device=dev, dtype=cmotion_bak.dtype)
         for j, f in enumerate(frames):
             cm[j, ..., :f + 1] = cmotion_bak[..., :f + 1]
-        yk = {k: _rep_batch(v, B, g) for k, v in y.items() if k != 'cmotion'}
+        yk = {k: _rep_batch(_cut_time(v, (B, V, C, T), Tc), B, g) for k, v in y.items() if k != 'cmotion'}
         yk['cmotion'] = cm.view(g * B, V, C, Tc)
         kw = dict(model_kwargs)
         kw['y'] = yk

@@ -70,6 +70,20 @@ class EmbedAction(nn.Module):
         self.action_embedding = nn.Parameter(torch.randn(num_actions, latent_dim))
 
 
+def _cfg_scale(scale, B, device):
+    """y['scale'] as a contiguous CUDA fp32 [B] vector.  The reference broadcasts ``y['scale'].view(-1, 1, 1, 1)``
+    (model/cfg_sampler.py:31), so one element (shared by the batch) or B elements are legal; anything else would make the
+    kernel read past the buffer and is rejected here."""
+    if not torch.is_tensor(scale):
+        scale = torch.as_tensor(scale, dtype=torch.float32)
+    scale = _lib.require_cuda_f32(scale.to(device), "y['scale']").reshape(-1)
+    if scale.numel() == 1 and B != 1:
+        scale = scale.expand(B)
+    if scale.numel() != B:
+        raise ValueError("y['scale'] must hold 1 or B=%d guidance scales, got %d" % (B, scale.numel()))
+    return scale.contiguous()
+
+
 class _Handle:
     """Owns one regen_handle (device buffers sized for max_batch x max_frames)."""
 
@@ -217,7 +231,17 @@ class CMDM(nn.Module):
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
+        body = getattr(getattr(self, 'rot2xyz', None), 'smpl_model', None)
+        if body is not None:        # model/cmdm.py:255-257: the body model follows .to() / .cuda()
+            body._apply(fn)
         self._invalidate()
+        return out
+
+    def train(self, *args, **kwargs):
+        out = super().train(*args, **kwargs)
+        body = getattr(getattr(self, 'rot2xyz', None), 'smpl_model', None)
+        if body is not None:        # model/cmdm.py:260-262
+            body.train(*args, **kwargs)
         return out
 
     def _invalidate(self):
@@ -238,7 +262,7 @@ class CMDM(nn.Module):
             raise RuntimeError("regennet_b200.CMDM runs on CUDA (sm_100a) only; move the model and inputs to a GPU "
                                "-- there is no CPU fallback for the sampling hot path")
         L = _lib.lib()
-        table_steps = 1000 if self.sequence_pos_encoder.pe.shape[0] >= 1000 else self.sequence_pos_encoder.pe.shape[0]
+        table_steps = self._table_steps()
         desc = _lib.ModelDesc(latent_dim=self.latent_dim, num_heads=self.num_heads, ff_size=self.ff_size,
                               num_layers=self.num_layers, input_feats=self.input_feats,
                               cm_mode=1 if self.cm_mode == 'concat' else 0,
@@ -306,6 +330,15 @@ class CMDM(nn.Module):
         action = text = None
         if 'action' in self.cond_mode:
             action = y['action'][:, 0].to(device=device, dtype=torch.long).contiguous()
+            # the reference's embedding lookup raises on a bad class id (model/cmdm.py:363-365); checked once per
+            # conditioning tensor (cached below), not per step
+            akey = (id(y['action']), y['action']._version)
+            if getattr(self, '_action_checked', None) != akey:
+                lo, hi = int(action.min()), int(action.max())
+                if lo < 0 or hi >= self.num_actions:
+                    raise IndexError("y['action'] holds class ids in [%d, %d]; the model has %d actions"
+                                     % (lo, hi, self.num_actions))
+                self._action_checked = akey
         if 'text' in self.cond_mode:
             if 'text_embed' in y:
                 text = y['text_embed']
@@ -328,6 +361,18 @@ class CMDM(nn.Module):
             self._cond_keepalive = (srcs, cm, action, text)
         return handle
 
+    def _table_steps(self):
+        pe_len = self.sequence_pos_encoder.pe.shape[0]
+        return 1000 if pe_len >= 1000 else pe_len
+
+    def _check_timesteps(self, lo, hi):
+        """The timestep embedding is a table of ``_table_steps()`` rows of pe (model/cmdm.py:291-298 indexes pe[t]):
+        out-of-range steps raise here instead of being clamped in the kernel."""
+        n = self._table_steps()
+        if lo < 0 or hi >= n:
+            raise IndexError("timestep %d outside the denoiser's timestep table [0, %d) (negative steps wrap in the "
+                             "reference's pe[t] lookup and are not supported)" % (lo if lo < 0 else hi, n))
+
     def _denoise_tbi(self, handle, x_tbi, t, scale, B, T):
         """x_tbi [T,B,I] contiguous -> x0 [T,B,I] (new tensor)."""
         out = torch.empty_like(x_tbi)
@@ -345,9 +390,13 @@ class CMDM(nn.Module):
         guidance = scale is not None
         handle = self._prepare(y, bs, nframes, x.device, guidance)
         x_tbi = _to_layout(x, "tbi").permute(3, 0, 1, 2)          # [T,B,J,F] contiguous
+        if timesteps.numel() != bs:
+            raise ValueError("timesteps must hold one step per sample (%d), got %d" % (bs, timesteps.numel()))
         t = timesteps.to(device=x.device, dtype=torch.long).contiguous()
+        if not torch.cuda.is_current_stream_capturing():
+            self._check_timesteps(int(t.min()), int(t.max()))   # generic (host-driven) route: one sync per call
         if guidance:
-            scale = _lib.require_cuda_f32(scale.to(x.device), "y['scale']").reshape(-1).contiguous()
+            scale = _cfg_scale(scale, bs, x.device)
         out = self._denoise_tbi(handle, x_tbi, t, scale, bs, nframes)
         # [T,B,J,F] -> [B,J,F,T] as a permuted view, like the reference (model/cmdm.py:353-354)
         return out.view(nframes, bs, njoints, nfeats).permute(1, 2, 3, 0)
@@ -423,9 +472,12 @@ class SamplingSession:
         handle = m._prepare(self.y, B, T, dev, guidance)
         scale = None
         if guidance:
-            scale = _lib.require_cuda_f32(self.scale.to(dev), "y['scale']").reshape(-1).contiguous()
+            scale = _cfg_scale(self.scale, B, dev)
         idx = [int(i) for i in indices]
         n = len(idx)
+        if n:
+            tm = [int(self.timestep_map[i]) for i in idx]
+            m._check_timesteps(min(tm), max(tm))                    # host integers: free
         bar = None
         if progress:
             from tqdm.auto import tqdm

@@ -44,6 +44,21 @@ void set_error(const char* fmt, ...);
 
 constexpr int kNumSMs = 148;  // B200
 
+// RAII: make `device` current for the scope and restore the caller's device afterwards, so a handle that lives on
+// cuda:1 can be created / used / destroyed (possibly from a garbage collector) without flipping the thread's device.
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) changed = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 // number of kernels this library has launched in this process (regen_launch_count)
 extern long long g_launches;
 inline void count_launch(int n = 1) { g_launches += n; }

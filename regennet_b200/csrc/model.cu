@@ -240,7 +240,12 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
   REGEN_CHECK_ARG(d->max_frames + d->arch <= 256, "regen_create: max_frames=%d exceeds the attention kernel's limit of "
                   "256 tokens (two key chunks of 128 resident in tensor memory)", d->max_frames);
   REGEN_CHECK_ARG((int64_t)d->max_batch * d->max_frames < (1 << 24), "regen_create: max_batch*max_frames too large");
-  REGEN_CUDA(cudaSetDevice(device));
+  {
+    int ndev = 0;
+    REGEN_CUDA(cudaGetDeviceCount(&ndev));
+    REGEN_CHECK_ARG(device >= 0 && device < ndev, "regen_create: device %d out of range (%d devices)", device, ndev);
+  }
+  DeviceGuard guard(device);
   regen_handle* h = new regen_handle();
   h->desc = *d;
   h->device = device;
@@ -326,7 +331,7 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
 
 void regen_destroy(regen_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
 }
@@ -334,6 +339,7 @@ void regen_destroy(regen_handle* h) {
 int regen_load_weights(regen_handle* h, const regen_weight_ptrs* w, void* stream) {
   REGEN_CHECK_ARG(h && w, "regen_load_weights: null argument");
   REGEN_CHECK_ARG(!h->loaded, "regen_load_weights: weights already loaded (create a new handle to reload)");
+  DeviceGuard guard(h->device);
   REGEN_CHECK_ARG(w->in_w && w->in_b && w->cmo_w && w->cmo_b && w->t0_w && w->t0_b && w->t2_w && w->t2_b && w->pe &&
                       w->out_w && w->out_b, "regen_load_weights: null weight pointer");
   REGEN_CHECK_ARG(h->desc.cm_mode == 0 || (w->fuse_w && w->fuse_b), "regen_load_weights: cm_mode=concat needs fuse_process");
@@ -437,6 +443,7 @@ int regen_load_weights(regen_handle* h, const regen_weight_ptrs* w, void* stream
 int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t* action, const float* text_feat,
                        int32_t B, int32_t T, int32_t guidance, int32_t uncond, void* stream) {
   REGEN_CHECK_ARG(h && cmotion_bjft, "regen_prepare_cond: null argument");
+  DeviceGuard guard(h->device);
   if (!h->loaded) {
     set_error("regen_prepare_cond: weights not loaded");
     return REGEN_ESTATE;
@@ -539,6 +546,7 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
 int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const float* cfg_scale, float* x0_tbi,
                   int32_t B, int32_t T, void* stream) {
   REGEN_CHECK_ARG(h && x_tbi && t && x0_tbi, "regen_denoise: null argument");
+  DeviceGuard guard(h->device);
   if (!h->cond_ready) {
     set_error("regen_denoise: regen_prepare_cond has not been called");
     return REGEN_ESTATE;

@@ -103,7 +103,6 @@ int64_t regen_stgcn_packed_size(const regen_stgcn_desc* d) {
 int regen_stgcn_create(regen_stgcn** out, int32_t device, const regen_stgcn_desc* d) {
   REGEN_CHECK_ARG(out, "regen_stgcn_create: null handle pointer");
   REGEN_CHECK_ARG(desc_ok(d), "regen_stgcn_create: bad descriptor");
-  REGEN_CUDA(cudaSetDevice(device));
   regen_stgcn* h = new regen_stgcn();
   h->d = *d;
   h->device = device;
@@ -114,7 +113,7 @@ int regen_stgcn_create(regen_stgcn** out, int32_t device, const regen_stgcn_desc
 
 void regen_stgcn_destroy(regen_stgcn* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   free_ws(h);
   cudaFree(h->packed);
   cudaFree(h->aeff);
@@ -123,6 +122,7 @@ void regen_stgcn_destroy(regen_stgcn* h) {
 
 int regen_stgcn_load_weights(regen_stgcn* h, const float* packed, int64_t n_floats, void* stream) {
   REGEN_CHECK_ARG(h && packed, "regen_stgcn_load_weights: null argument");
+  DeviceGuard guard(h->device);
   const int64_t need = walk(h->d, nullptr, nullptr);
   REGEN_CHECK_ARG(n_floats == need, "regen_stgcn_load_weights: packed buffer has %lld floats, the descriptor needs %lld",
                   (long long)n_floats, (long long)need);
@@ -154,7 +154,7 @@ int regen_stgcn_forward(regen_stgcn* h, const float* output, int32_t N, int32_t 
   }
   if (N == 0) return REGEN_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  REGEN_CUDA(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   const int P = h->d.num_person, V = h->d.num_node, K = h->d.num_part, C = h->d.in_channels / P;
   if (h->T_ws < T) {
     REGEN_CUDA(cudaStreamSynchronize(s));

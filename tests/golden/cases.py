@@ -143,3 +143,66 @@ def metric_inputs():
     f2 = 0.9 * torch.randn(150, 256, generator=g) + 0.1
     labels = torch.randint(0, METRIC_LABELS - 1, (120,), generator=g)   # the last label never occurs (zero quota)
     return f1, f2, labels
+
+
+# model.rot2xyz(...) call sites (sample/cgenerate.py:156, eval/a2m/stgcn_eval.py:81): goldens in rot2xyz.npz
+# (make_golden_rot2xyz.py) from the reference's Rotation2xyz / Rotation2xyz_x run with StubBodyModel in place of the
+# smplx layers (their files are licensed and absent); everything around the skinning call is the reference's own code.
+ROT2XYZ_CASES = {
+    # name: body_model, B, J (incl. translation row), persons, T, masked tail frames per sample, glob, jointstype
+    "x_p1_full": dict(body_model="smplx", B=3, J=56, P=1, T=9, cut=[0, 0, 0], glob=True, jointstype="smplx", seed=60),
+    "x_p1_mask": dict(body_model="smplx", B=3, J=56, P=1, T=9, cut=[0, 4, 7], glob=True, jointstype="smplx", seed=61),
+    "x_p2_mask": dict(body_model="smplx", B=2, J=56, P=2, T=7, cut=[2, 0], glob=True, jointstype="smplx", seed=62),
+    "x_p2_vertices": dict(body_model="smplx", B=2, J=56, P=2, T=5, cut=[0, 1], glob=True, jointstype="vertices", seed=63),
+    "x_p1_globrot": dict(body_model="smplx", B=2, J=56, P=1, T=6, cut=[1, 0], glob=False, jointstype="smplx", seed=64),
+    "s_p1_mask": dict(body_model="smpl", B=3, J=25, P=1, T=8, cut=[0, 3, 5], glob=True, jointstype="smpl", seed=65),
+    "s_p2_mask": dict(body_model="smpl", B=2, J=25, P=2, T=6, cut=[1, 0], glob=True, jointstype="vibe", seed=66),
+    "s_p1_globrot": dict(body_model="smpl", B=2, J=25, P=1, T=5, cut=[0, 2], glob=False, jointstype="a2m", seed=67),
+}
+ROT2XYZ_GLOB_ROT = [3.141592653589793, 0.0, 0.0]   # the value the reference's callers use for glob=False
+
+
+def rot2xyz_inputs(c):
+    """Seeded pose tensor x [B, J, 6 P, T] and frame mask [B, T] (True = valid) of a ROT2XYZ case."""
+    import torch
+    g = torch.Generator().manual_seed(c["seed"])
+    x = torch.randn(c["B"], c["J"], 6 * c["P"], c["T"], generator=g)
+    mask = torch.ones(c["B"], c["T"], dtype=torch.bool)
+    for b, k in enumerate(c["cut"]):
+        if k:
+            mask[b, c["T"] - k:] = False
+    return x, mask
+
+
+def stub_body_model(kind):
+    """Deterministic stand-in for model/smpl.py's SMPL / SMPLX layers with their call contract: ``num_betas``, keyword
+    call, dict of [n, joints, 3] per jointstype.  Joints depend on every argument it is given (global orientation, each
+    pose rotation, betas), so a wrong slice / order / mask in the caller changes the result."""
+    import torch
+
+    class StubBodyModel(torch.nn.Module):
+        num_betas = 10
+
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(7 if kind == "smplx" else 8)
+            self.n_out = {"smplx": 55, "smpl": 24, "vibe": 49, "a2m": 18, "a2mpl": 30, "vertices": 40}
+            self.register_buffer("rest", torch.randn(64, 3, generator=g))
+            self.register_buffer("mix", 0.1 * torch.randn(64, 80, generator=g))
+            self.register_buffer("dirs", torch.randn(80, 3, generator=g))
+            self.register_buffer("shape_dirs", 0.05 * torch.randn(10, 64, 3, generator=g))
+
+        def forward(self, body_pose=None, global_orient=None, betas=None, left_hand_pose=None, right_hand_pose=None,
+                    return_verts=True, **kw):
+            assert not kw, kw
+            parts = [p for p in (body_pose, left_hand_pose, right_hand_pose) if p is not None]
+            pose = torch.cat(parts, 1)                                        # [n, K, 3, 3]
+            n, K = pose.shape[:2]
+            local = torch.einsum("nkij,kj->nki", pose, self.dirs[:K])         # each rotation acts on its own direction
+            pts = self.rest[None] + torch.einsum("jk,nki->nji", self.mix[:, :K], local)
+            pts = pts + torch.einsum("nb,bji->nji", betas, self.shape_dirs)
+            go = global_orient.reshape(n, 3, 3)
+            pts = torch.einsum("nij,nkj->nki", go, pts)                       # [n, 64, 3]
+            return {name: pts[:, :m] for name, m in self.n_out.items()}
+
+    return StubBodyModel().eval()

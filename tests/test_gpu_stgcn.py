@@ -2,10 +2,8 @@
 ``regennet_b200.stgcn.STGCN`` -> regen_stgcn_* (regennet_b200/csrc/stgcn.cu) vs the golden outputs of the imported
 reference (tests/golden/make_golden_stgcn.py) and the oracle.
 
-The CUDA path was written after its round's GPU budget had been spent.  Its arithmetic (the per-element functions the
-kernels execute, the packed-weight walk, the block schedule, chunking and workspace sizing) is verified on the CPU by
-tests/test_stgcn_hostcheck.py; the launch code has not run on a GPU yet, so these tests are xfail(strict=False): they
-report XPASS once the path is seen green on a B200 and cannot turn the suite red before that."""
+The per-element arithmetic, the packed-weight walk, the block schedule, chunking and workspace sizing are additionally
+verified on the CPU by tests/test_stgcn_hostcheck.py."""
 import os
 
 import numpy as np
@@ -16,8 +14,7 @@ import cases
 from oracle import stgcn_ref
 from regennet_b200.stgcn import STGCN
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="ST-GCN launch code not yet run on a GPU (arithmetic verified on the CPU)")]
+pytestmark = pytest.mark.gpu
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = 1e-4   # fp32 CUDA-core arithmetic, summation order differs from torch's convolutions
 

@@ -168,19 +168,42 @@ def test_auto_regressive_driver_indexing():
     def oracle_loop(f, cmotion):
         return torch.cumsum(cmotion, dim=-1) * (1.0 + action.view(-1, 1, 1, 1).float())
 
+    from types import SimpleNamespace
+    online = SimpleNamespace(model=SimpleNamespace(arch="online"))     # as seen through ClassifierFreeSampleModel
+    offline = SimpleNamespace(arch="offline")
     for setting in ("cmdm", "sample"):
         want = sampler_ref.auto_regressive(oracle_loop, cm, setting=setting)
-        for G, trunc in [(1, False), (1, True), (4, True), (4, False), (9, True), (20, True)]:
+        for G, trunc in [(1, False), (1, True), (4, True), (4, False), (9, True), (20, True), (3, None)]:
             calls.clear()
             y = {"cmotion": cm.clone(), "action": action, "action_text": ["a"] * B, "tag": "kept"}
-            got = auto_regressive_sample(fake_loop, None, (B, V, C, T), {"y": y}, setting=setting, truncate=trunc,
+            got = auto_regressive_sample(fake_loop, online, (B, V, C, T), {"y": y}, setting=setting, truncate=trunc,
                                          frames_per_call=G)
             assert torch.equal(got, want), (setting, G, trunc)
             assert torch.equal(y["cmotion"], cm)
             Ge = min(G, T)
             assert len(calls) == (T + Ge - 1) // Ge
-            if trunc:
+            if trunc or trunc is None:     # None resolves to True for the causal arch
                 assert [c[-1] for c in calls] == [min(k * Ge + Ge, T) for k in range(len(calls))]
+    # truncation is only valid for the causal denoiser: a bidirectional / unknown model must run the literal loop
+    y = {"cmotion": cm.clone(), "action": action, "action_text": ["a"] * B, "tag": "kept"}
+    for mdl in (offline, None):
+        with pytest.raises(ValueError, match="causal"):
+            auto_regressive_sample(fake_loop, mdl, (B, V, C, T), {"y": y}, truncate=True)
+        calls.clear()
+        auto_regressive_sample(fake_loop, mdl, (B, V, C, T), {"y": y}, frames_per_call=2)
+        assert all(c[-1] == T for c in calls)
+    # per-frame conditioning (motion editing) follows the truncated time axis and the stacked batch
+    seen = []
+
+    def edit_loop(model, shape, clip_denoised, model_kwargs):
+        yy = model_kwargs["y"]
+        assert tuple(yy["inpainting_mask"].shape) == tuple(shape) == tuple(yy["inpainted_motion"].shape)
+        seen.append(tuple(shape))
+        return yy["cmotion"]
+    y = {"cmotion": cm.clone(), "inpainting_mask": torch.zeros(B, V, C, T, dtype=torch.bool),
+         "inpainted_motion": torch.zeros(B, V, C, T)}
+    auto_regressive_sample(edit_loop, online, (B, V, C, T), {"y": y}, frames_per_call=2)
+    assert seen[0] == (2 * B, V, C, 2) and seen[-1] == (B, V, C, T)
 
 
 def test_oracle_inpainting_blend_matches_reference_expression():

@@ -9,10 +9,17 @@ and actor motion (no checkpoints / datasets are distributable).  One "step" = on
 the loop over the whole per-GPU batch: noise draw + CMDM forward + posterior update.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline      dominant kernel class (tcgen05 GEMMs): algorithmic FLOPs / measured device time
-  roofline_hbm  the fused posterior-update kernel against the measured HBM copy bandwidth
-  cpu_baseline  the CPU oracle (port of the reference algorithm) on this box's host cores
-  breakdown_ms  per-step device time per kernel class (CUDA events inside the library)
+  sustained        the same device-resident measurement over >= 1 s of graph replays (power-capped steady state)
+  e2e              regennet_b200.dist.sharded_sample(diffusion.p_sample_loop, ...) over the full 1000-step schedule with the
+                   conditioning on the (pinned) host, the all-gather of the generated batch and the device->host copy of the
+                   result inside the timed region; `collective_ms` is the all-gather alone (CUDA events)
+  roofline         tcgen05 GEMM class from the IN-GRAPH GPU timeline of a replayed step (global-timer stamps written by the
+                   kernels themselves: spans sum to <= ms_per_step); `kernels` lists every kernel type of the step
+  roofline_hbm / roofline_rot6d   the posterior-update and rot6d->rotmat kernels against the measured HBM bandwidth,
+                   timed alone over rotating buffer sets larger than L2
+  other_configs    device-resident step time of BASELINE configs 1, 3, 5 (per-GPU shapes), N = 1 only
+  library_baseline the reference's own torch-eager path on this GPU (fp32 and TF32), N = 1 only
+  cpu_baseline     the reference's own p_sample_loop on this box's host cores at the true B = 256, N = 1 only
 """
 import argparse
 import json
@@ -32,19 +39,28 @@ import torch  # noqa: E402
 B_DEFAULT, T_DEFAULT = 256, 60
 METRIC = "denoising_steps_per_sec"
 UNIT = "steps/s (1 step = one p_sample over B=256 x T=60 poses per GPU, summed over GPUs)"
+DATA = "synthetic (seeded random-init weights, random actor motion)"
 
 
-def model_cfg():
+def model_cfg(name="ntu"):
     import cases
-    return cases.MODELS["ntu"], cases.synth_kw("ntu")
+    return cases.MODELS[name], cases.synth_kw(name)
 
 
 def flops_per_step(B, T, I=336, L=8):
-    """algorithmic FLOPs (2/MAC); GEMM part and attention part separately."""
+    """algorithmic FLOPs (2/MAC); GEMM part, attention part, per-sample part."""
     gemm_tok = L * (2 * 512 * 1536 + 2 * 512 * 512 + 4 * 512 * 1024) + 2 * I * 512 + 2 * 512 * 512 + 2 * 512 * I
     attn_tok = L * 4 * T * 512
     per_sample = 2 * 2 * 512 * 512 + L * 2 * 2 * 512 * 512
     return B * T * gemm_tok, B * T * attn_tok, B * per_sample
+
+
+def kernel_flops(M, T, I=336):
+    """Algorithmic FLOPs per launch of each kernel type of the fused route (M token rows, input projection K padded to
+    a multiple of 64 is NOT counted: algorithmic = the reference's Linear shapes)."""
+    return {"in_proj": 2 * M * I * 512 + 2 * M * 512 * 512,   # input_process + the x half of fuse_process (folded)
+            "qkv": 2 * M * 512 * 1536, "attn": 4 * M * T * 512, "out+LN": 2 * M * 512 * 512,
+            "ffn1": 2 * M * 512 * 1024, "lin2+LN": 2 * M * 1024 * 512, "out_proj": 2 * M * 512 * I}
 
 
 def measured_peaks():
@@ -101,283 +117,566 @@ class ClockSampler:
         return out
 
 
-def build_ours(device, B, T):
+def make_diffusion(respacing):
     from regennet_b200 import gaussian_diffusion as gd
-    from regennet_b200 import respace, synthetic
+    from regennet_b200 import respace
+    betas = gd.get_named_beta_schedule("cosine", 1000, 1.0)
+    return respace.SpacedDiffusion(use_timesteps=respace.space_timesteps(1000, respacing), betas=betas,
+                                   model_mean_type=gd.ModelMeanType.START_X,
+                                   model_var_type=gd.ModelVarType.FIXED_SMALL, loss_type=gd.LossType.MSE)
+
+
+def build_ours(device, B=None, T=None, name="ntu"):
+    from regennet_b200 import synthetic
     from regennet_b200.cmdm import CMDM
-    mk, sk = model_cfg()
+    mk, sk = model_cfg(name)
     model = CMDM(**mk)
     model.load_state_dict(synthetic.make_state_dict(seed=0, **sk), strict=False)
     model = model.to(device).eval()
-    betas = gd.get_named_beta_schedule("cosine", 1000, 1.0)
-
-    def diffusion(respacing):
-        return respace.SpacedDiffusion(use_timesteps=respace.space_timesteps(1000, respacing), betas=betas,
-                                       model_mean_type=gd.ModelMeanType.START_X,
-                                       model_var_type=gd.ModelVarType.FIXED_SMALL, loss_type=gd.LossType.MSE)
-    return model, diffusion
+    return model, make_diffusion
 
 
+# ------------------------------------------------------------------------------------------------ GPU arm pieces
+def device_steps(sess, diffusion, kind, img, K, W, unroll, barrier=None):
+    """K device-resident steps of the loop through the CUDA-graph driver, CUDA-event timed after >= W warm-up steps.
+    -> (ms, steps_timed, steps_warm, launches)"""
+    from regennet_b200 import _lib
+    lib = _lib.lib()
+    n = diffusion.num_timesteps
+    indices = list(range(n))[::-1]
+    gen = sess.run(diffusion, kind, img, indices, False, 0.0, graph=unroll > 0, unroll=unroll or None)
+    done = 0
+    while done < max(W, 1 + unroll):      # the first step is host-enqueued; the first replay warms the graph
+        done += next(gen)["steps"]
+    W_done = done
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    n0 = lib.regen_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    K_done = 0
+    while K_done < K and W_done + K_done + max(unroll, 1) <= n:
+        K_done += next(gen)["steps"]
+    e1.record()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(lib.regen_launch_count() - n0)
+    gen.close()
+    return ms, K_done, W_done, launches
+
+
+def in_graph_timeline(model, sess, diffusion, img, steps_logged=2):
+    """GPU-side timeline of `steps_logged` consecutive steps inside ONE replayed CUDA graph: every tcgen05 kernel stamps
+    the GPU's nanosecond global timer after griddepcontrol.wait and at its last CTA's exit (regen_test_step_log), so the
+    spans are what the kernels cost in the pipeline the `value` is measured in.  -> {name: (avg span us, launches/step)},
+    total span ms/step, gaps ms/step"""
+    from regennet_b200 import _lib
+    lib = _lib.lib()
+    dev = img.device
+    CAP = 256
+    U = steps_logged
+    log = torch.zeros(2 * CAP + 160 * CAP, dtype=torch.int64, device=dev)
+    model.__dict__.pop("_graph_cache", None)       # graphs captured so far carry no log slots
+    gen = sess.run(diffusion, "p", img, list(range(diffusion.num_timesteps))[::-1], False, 0.0, graph=True, unroll=U)
+    next(gen)
+    _lib.check(lib.regen_test_step_log(model._handle.ptr, _lib.ptr(log), CAP), "step_log")
+    for _ in range(4):                             # capture (slots are baked into the graph) + warm replays
+        next(gen)
+    torch.cuda.synchronize()
+    init = torch.zeros(2 * CAP + 160 * CAP, dtype=torch.int64)
+    init[0:2 * CAP:2] = torch.iinfo(torch.int64).max
+    log.copy_(init)
+    next(gen)
+    torch.cuda.synchronize()
+    _lib.check(lib.regen_test_step_log(model._handle.ptr, None, 0), "step_log off")
+    gen.close()
+    model.__dict__.pop("_graph_cache", None)       # the logged graph holds pointers into `log`: never replay it again
+    v = log.cpu()[:2 * CAP].view(CAP, 2)
+    n = int((v[:, 1] > 0).sum())
+    L = model.num_layers
+    names = ["in_proj"] + [k for _ in range(L) for k in ("qkv", "attn", "out+LN", "ffn1", "lin2+LN")] + ["out_proj"]
+    per = len(names)
+    assert n == U * per, "timeline: %d kernel records, expected %d" % (n, U * per)
+    agg, span_tot, gap_tot = {}, 0, 0
+    for i in range(n):
+        s, e = int(v[i, 0]), int(v[i, 1])
+        a = agg.setdefault(names[i % per], [0, 0])
+        a[0] += 1
+        a[1] += e - s
+        span_tot += e - s
+        if i:
+            gap_tot += s - int(v[i - 1, 1])
+    out = {k: (c[1] / c[0] / 1e3, c[0] / U) for k, c in agg.items()}
+    return out, span_tot / U / 1e6, gap_tot / U / 1e6
+
+
+def hbm_kernels(dev, B, T, J=56, F=6):
+    """The two elementwise kernels of the path timed ALONE over rotating buffer sets whose total exceeds the 126 MB L2
+    (every launch streams from / to HBM).  -> (update ms, rot6d ms, n_elem, n_rot)"""
+    from regennet_b200 import _lib, rotation_conversions
+    d = make_diffusion([1000])
+    n_elem = B * J * F * T
+    SETS = 8                                                      # 8 x 4 x 20.6 MB = 660 MB
+    xs = [torch.randn(T, B, J, F, device=dev).permute(1, 2, 3, 0) for _ in range(3 * SETS)]
+    outs = [torch.empty(T, B, J, F, device=dev).permute(1, 2, 3, 0) for _ in range(SETS)]
+    t = torch.full((B,), 500, dtype=torch.long, device=dev)
+    reps = 5
+
+    def upd(i):
+        k = i % SETS
+        d._update("p", xs[3 * k], xs[3 * k + 1], xs[3 * k + 2], t, False, out=outs[k])
+
+    for i in range(SETS):
+        upd(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps * SETS):
+        upd(i)
+    e1.record()
+    torch.cuda.synchronize()
+    upd_ms = e0.elapsed_time(e1) / (reps * SETS)
+    # rot6d -> rotmat at the size the sample of this config produces: B*T frames x 55 joints
+    n_rot = B * T * (J - 1)
+    lib = _lib.lib()
+    srcs = [torch.randn(n_rot, 6, device=dev) for _ in range(SETS)]      # 8 x (20 + 30) MB
+    dsts = [torch.empty(n_rot, 3, 3, device=dev) for _ in range(SETS)]
+    sp = _lib.stream_ptr(dev)
+
+    def rot(i):
+        k = i % SETS
+        _lib.check(lib.regen_rot6d_to_matrix(_lib.ptr(srcs[k]), _lib.ptr(dsts[k]), n_rot, sp), "rot6d")
+
+    for i in range(SETS):
+        rot(i)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(reps * SETS):
+        rot(i)
+    e1.record()
+    torch.cuda.synchronize()
+    rot_ms = e0.elapsed_time(e1) / (reps * SETS)
+    del rotation_conversions
+    return upd_ms, rot_ms, n_elem, n_rot
+
+
+def other_configs(dev, peaks):
+    """BASELINE configs 1, 3, 5 at their per-GPU shapes: device-resident ms/step through the graph driver + algorithmic
+    TFLOP/s.  (Config 4 is config 2 per GPU; it is what `--gpus 8` runs.)"""
+    import cases
+    from regennet_b200 import synthetic
+    from regennet_b200.cfg_sampler import ClassifierFreeSampleModel
+    out = {}
+    specs = [("config1", "ntu", 1, 60, False, False, [1000], 200, "NTU B=1 T=60, 1000-step DDPM (latency-bound, no roofline)"),
+             ("config3", "chi3d", 128, 150, True, False, [1000], 40, "Chi3D B=128 T=150, action-conditioned CFG (effective batch 256)"),
+             ("config5", "hml", 64, 196, True, True, "ddim100", 40,
+              "hml_vec 263x1 B=64 per GPU T=196, text-conditioned CFG, DDIM-100")]
+    for key, name, B, T, cfg, ddim, respacing, K, what in specs:
+        mk = cases.MODELS[name]
+        model, _ = build_ours(dev, name=name)
+        diff = make_diffusion(respacing)
+        _, y = synthetic.make_inputs(B, mk["njoints"], mk["nfeats"], T, seed=10, cond_mode=mk["cond_mode"],
+                                     num_actions=mk["num_actions"], scale=2.5 if cfg else None)
+        yc = {k: v.to(dev) for k, v in y.items()}
+        run_model = ClassifierFreeSampleModel(model) if cfg else model
+        shape = (B, mk["njoints"], mk["nfeats"], T)
+        img = torch.randn(*shape, device=dev)
+        sess = diff._fast_session(run_model, shape, {"y": yc}, None, None, False, False, img)
+        ms, Kd, Wd, _ = device_steps(sess, diff, "ddim" if ddim else "p", img, K, 5, 10)
+        Beff = 2 * B if cfg else B
+        fg, fa, fs = flops_per_step(Beff, T, mk["njoints"] * mk["nfeats"])
+        tf = (fg + fa + fs) / (ms / Kd / 1e3) / 1e12
+        # end to end through the public API (full schedule, host conditioning in, host sample out)
+        host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in y.items()}
+        res = torch.empty(shape).pin_memory()
+        fn = diff.ddim_sample_loop if ddim else diff.p_sample_loop
+
+        def once():
+            yd = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
+            s = fn(run_model, shape, clip_denoised=False, model_kwargs={"y": yd})
+            res.copy_(s, non_blocking=True)
+            torch.cuda.synchronize()
+        once()
+        t0 = time.perf_counter()
+        once()
+        e2e_s = time.perf_counter() - t0
+        out[key] = {"workload": what, "ms_per_step": ms / Kd, "steps_per_s": 1e3 * Kd / ms, "steps_timed": Kd,
+                    "algorithmic_gflop_per_step": (fg + fa + fs) / 1e9, "tflops": tf,
+                    "frac_of_bf16_sustained": None if key == "config1" else tf / peaks["tf_sust"],
+                    "e2e_loop_s": e2e_s, "e2e_steps": diff.num_timesteps,
+                    "e2e_steps_per_s": diff.num_timesteps / e2e_s, "e2e_frames_per_s": B * T / e2e_s}
+        del model, sess, run_model
+        torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ reference legs
+def reference_stepper(device, B, T, name="ntu"):
+    """One p_sample step at a time of the REFERENCE's own sampling path (unmodified files staged under oracle/_ref by
+    oracle/make_ref.sh, or /root/reference in the build container): SpacedDiffusion.p_sample_loop_progressive over
+    model/cmdm.py's CMDM in torch eager.  Falls back to the oracle port (kind "port") when no reference tree is there.
+    -> (kind, step_fn, model, make_forward_inputs)"""
+    from regennet_b200 import synthetic
+    from oracle import ref_shim
+    mk, sk = model_cfg(name)
+    sd = synthetic.make_state_dict(seed=0, **sk)
+    _, y = synthetic.make_inputs(B, mk["njoints"], mk["nfeats"], T, seed=10)
+    shape = (B, mk["njoints"], mk["nfeats"], T)
+    if ref_shim.available():
+        import warnings
+        warnings.filterwarnings("ignore")
+        model, diffusion = ref_shim.build_reference(mk, {})
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not unexpected
+        model.to(device)      # the reference's CMDM._apply returns None (model/cmdm.py:255-257): no chaining
+        model.eval()
+        yd = {"cmotion": y["cmotion"].to(device)}
+        state = {"gen": None}
+
+        def step():
+            if state["gen"] is None:
+                state["gen"] = diffusion.p_sample_loop_progressive(model, shape, clip_denoised=False,
+                                                                   model_kwargs={"y": yd})
+            try:
+                next(state["gen"])
+            except StopIteration:
+                state["gen"] = None
+                step()
+
+        def forward(x, t):
+            with torch.no_grad():
+                return model(x, t, y=yd)
+        return "reference", step, forward, shape
+    from oracle import cmdm_ref, sampler_ref
+    sdd = {k: v.to(device) for k, v in sd.items()}
+    yd = {"cmotion": y["cmotion"].to(device)}
+    smp = sampler_ref.Sampler()
+    kw = dict(num_layers=8, nhead=4, cond_mode="no_cond", cm_mode="concat")
+    state = {"x": torch.randn(*shape, device=device), "i": 999}
+
+    def forward(x, t):
+        with torch.no_grad():
+            return cmdm_ref.cmdm_forward(sdd, x, t, yd, **kw)
+
+    def step():
+        with torch.no_grad():
+            t = torch.tensor([state["i"]] * B, device=device)
+            state["x"], _ = smp.p_sample(forward, state["x"], t, torch.randn_like)
+            state["i"] = state["i"] - 1 if state["i"] > 0 else 999
+    return "port", step, forward, shape
+
+
+def cpu_reference(K, W, T, B=B_DEFAULT, budget_s=150.0):
+    """K p_sample steps of the reference's CPU path at the TRUE batch B (no extrapolation) on all host threads; K is cut
+    so that the run stays inside budget_s.  -> dict(value, steps, kind, cores, seconds, ms_per_step)"""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kind, step, _, _ = reference_stepper(torch.device("cpu"), B, T)
+    t0 = time.perf_counter()
+    step()
+    first = time.perf_counter() - t0
+    for _ in range(max(0, min(W, 3) - 1)):
+        step()
+    K_run = max(2, min(K, int(budget_s / max(first, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(K_run):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": K_run / dt, "steps": K_run, "kind": kind, "cores": cores, "seconds": dt,
+            "ms_per_step": 1e3 * dt / K_run}
+
+
+def cpu_baseline(budget_s, T):
+    r = cpu_reference(K=10 ** 6, W=2, T=T, budget_s=budget_s)
+    return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+            "sample": "%d consecutive p_sample steps (steps 997.. of the 1000-step loop) of %s at the true B=%d, T=%d, "
+                      "torch fp32 on %d host threads, %.1f s" % (
+                          r["steps"], "the reference's own SpacedDiffusion.p_sample_loop + CMDM (oracle/_ref)"
+                          if r["kind"] == "reference" else "the CPU oracle port", B_DEFAULT, T, r["cores"], r["seconds"])}
+
+
+def library_baseline(dev, B, T, ours_forward=None):
+    """The reference's torch-eager path on THIS GPU (nn.TransformerDecoder, cuBLAS / SDPA kernels): strict fp32 and TF32."""
+    kind, step, forward, shape = reference_stepper(dev, B, T)
+    out = {"kind": kind + " code, torch eager on the GPU", "unit": UNIT}
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn(*shape, generator=g).to(dev)
+    t = torch.full((B,), 500, dtype=torch.long, device=dev)
+    res = {}
+    for mode, tf32 in (("fp32", False), ("tf32", True)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        for _ in range(5):
+            step()
+        torch.cuda.synchronize()
+        K = 30
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        res[mode] = forward(x, t).float()
+        out[mode] = {"steps_per_s": 1e3 / ms, "ms_per_step": ms}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    out["tf32"]["max_abs_err_vs_fp32_forward"] = (res["tf32"] - res["fp32"]).abs().max().item()
+    if ours_forward is not None:
+        out["ours_max_abs_err_vs_fp32_forward"] = (ours_forward(x, t) - res["fp32"]).abs().max().item()
+    out["note"] = ("same B=%d, T=%d p_sample step (noise draw + forward + posterior update), steps 994.. of the 1000-step loop, "
+                   "CUDA-event timed, 30 steps after 5 warm-up; tolerance of the path is 1e-3" % (B, T))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     from regennet_b200 import _lib, synthetic
+    from regennet_b200 import dist as rdist
+    import torch.distributed as dist
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        rdist.setup_dist("nccl")
     B, T, K, W = args.batch, args.frames, args.steps, args.warmup
     J, F = 56, 6
     I = J * F
     shape = (B, J, F, T)
-    model, mkdiff = build_ours(dev, B, T)
-    lib = _lib.lib()
-
-    # per-rank shard: independent samples, rank-offset seeds
-    _, y = synthetic.make_inputs(B, J, F, T, seed=10 + rank)
-    cm_host = y["cmotion"].pin_memory()
-    torch.manual_seed(10 + rank)
+    model, mkdiff = build_ours(dev)
 
     def barrier():
         if world > 1:
-            import torch.distributed as dist
             dist.barrier()
+
+    # per-rank shard: independent samples, rank-offset seeds (SURVEY.md 8e)
+    _, y = synthetic.make_inputs(B, J, F, T, seed=10 + rank)
+    torch.manual_seed(10 + rank)
 
     # ------------------------------------------------------------------ value: device-resident K steps
     full = mkdiff([1000])
-    yc = {"cmotion": cm_host.to(dev)}
+    yc = {"cmotion": y["cmotion"].to(dev)}
     img = torch.randn(*shape, device=dev)
     sess = full._fast_session(model, shape, {"y": yc}, None, None, False, False, img)
     assert sess is not None, "fast route not taken"
-    indices = list(range(full.num_timesteps))[::-1]
-    assert K + W <= len(indices)
+    assert K + W + 13 <= 1000, "steps + warmup must fit the 1000-step loop"
     # steps per captured CUDA graph: the largest divisor of K in [4, 12] (1 if there is none)
     U = max([u for u in range(4, 13) if K % u == 0] or [1])
     if os.environ.get("REGEN_CUDA_GRAPH", "") == "0":
         U = 0
-    gen = sess.run(full, "p", img, indices, False, 0.0, graph=U > 0, unroll=U or None)
-    W_done = 0
-    while W_done < max(W, 1 + U):      # first step is enqueued by the host; the first replay warms the graph
-        W_done += next(gen)["steps"]
-    assert K + W_done <= len(indices)
-    W = W_done
-    torch.cuda.synchronize()
-    barrier()
     clocks = ClockSampler(local_rank)
-    n0 = lib.regen_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    K_done = 0
-    while K_done < K:
-        K_done += next(gen)["steps"]
-    e1.record()
-    torch.cuda.synchronize()
-    barrier()
-    assert K_done == K, (K_done, K)
-    ms = e0.elapsed_time(e1)
-    launches = int(lib.regen_launch_count() - n0)
+    ms, K_done, W, launches = device_steps(sess, full, "p", img, K, W, U, barrier)
     clk = clocks.stop()
-    gen.close()
+    assert K_done == K, (K_done, K)
 
-    # ------------------------------------------------------------------ per-class device time (profiling pass)
-    handle = model._handle
-    gen = sess.run(full, "p", img, indices, False, 0.0)
-    for _ in range(2):
-        next(gen)
-    torch.cuda.synchronize()
-    upd_events = []
-    orig_update = full._update
+    # ------------------------------------------------------------------ sustained: >= 1 s of the same replays
+    sus_ms, sus_K, _, _ = device_steps(sess, full, "p", img, 900, 13, 10 if U else 0, barrier)
 
-    def timed_update(*a, **k):
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        r = orig_update(*a, **k)
-        a1.record()
-        upd_events.append((a0, a1))
-        return r
+    # ------------------------------------------------------------------ in-graph timeline -> rooflines
+    spans, span_ms, gap_ms = in_graph_timeline(model, sess, full, img)
+    upd_ms, rot_ms, n_elem, n_rot = hbm_kernels(dev, B, T)
 
-    full._update = timed_update
-    KP = min(K, 20)
-    _lib.check(lib.regen_profile_begin(handle.ptr), "profile_begin")
-    for _ in range(KP):
-        next(gen)
-    cls_ms = (_lib.c_float * 4)()
-    cls_n = (_lib.c_int * 4)()
-    _lib.check(lib.regen_profile_end(handle.ptr, cls_ms, cls_n), "profile_end")
-    full._update = orig_update
-    gen.close()
-    upd_ms = sum(a.elapsed_time(b) for a, b in upd_events[1:]) / max(1, len(upd_events) - 1)
-    gemm_ms, attn_ms, ln_ms, other_ms = [cls_ms[i] / KP for i in range(4)]
-
-    # ------------------------------------------------------------------ e2e: public API, host buffers in and out
-    # the call a user makes is ONE p_sample_loop over the workload's whole 1000-step schedule (quick runs with a small
-    # --steps keep a K-step respaced loop so that they stay quick)
-    KE = 1000 if K >= 50 else K
+    # ------------------------------------------------------------------ e2e: public multi-GPU API, host buffers in and out
+    # ONE regennet_b200.dist.sharded_sample(diffusion.p_sample_loop, ...) over the workload's whole 1000-step schedule: the
+    # global conditioning batch lives in pinned host memory, each rank copies its shard, samples it (seed + rank) and the
+    # generated batch is reassembled by the path's one collective, all inside the timed region; rank 0 then copies the
+    # gathered batch to the host (the other ranks their own shard).
+    KE = 1000
     e2e_diff = mkdiff([KE])
-    out_host = torch.empty(shape, dtype=torch.float32).pin_memory()
+    gshape = (world * B, J, F, T)
+    _, yg = synthetic.make_inputs(world * B, J, F, T, seed=10)
+    cm_host = yg["cmotion"].pin_memory()
+    out_host = torch.empty(gshape if rank == 0 else shape, dtype=torch.float32).pin_memory()
+    timing = {}
 
     def e2e_once():
-        ycm = {"cmotion": cm_host.to(dev, non_blocking=True)}
-        s = e2e_diff.p_sample_loop(model, shape, clip_denoised=False, model_kwargs={"y": ycm})
-        out_host.copy_(s, non_blocking=True)
+        timing.clear()
+        g = rdist.sharded_sample(e2e_diff.p_sample_loop, model, gshape, {"y": {"cmotion": cm_host}}, seed=10, device=dev,
+                                 timing=timing, clip_denoised=False)
+        out_host.copy_(g if rank == 0 else timing["local"], non_blocking=True)
         torch.cuda.synchronize()
+        return g
 
-    e2e_once()  # warm-up (allocator, handle, graph capture)
-    e2e_runs = []
-    for _ in range(3):  # three timed loops, the median is reported (a single 0.2 s wall-clock sample is noisy)
+    e2e_once()  # warm-up (allocator, graph capture, NCCL channels)
+    e2e_runs, coll = [], []
+    for _ in range(3):  # three timed loops, the median is reported
         barrier()
         t0 = time.perf_counter()
-        e2e_once()
+        gathered = e2e_once()
         e2e_runs.append(time.perf_counter() - t0)
+        if "collective_events" in timing:
+            coll.append(timing["collective_events"][0].elapsed_time(timing["collective_events"][1]))
     e2e_s = sorted(e2e_runs)[1]
-    h2d = cm_host.numel() * 4 / KE
-    d2h = out_host.numel() * 4 / KE
+    coll_ms = sorted(coll)[len(coll) // 2] if coll else 0.0
+    h2d = B * I * T * 4 / KE                       # this rank's shard of the conditioning, per step
+    d2h = out_host.numel() * 4 / KE                # rank 0: the gathered batch
+    # the gathered batch is in rank order and identical on every rank
+    lo, hi = rdist.shard_bounds(world * B, rank, world)
+    gather_ok = bool(torch.equal(gathered[lo:hi], timing["local"]))
+    chk = torch.tensor([gathered.double().sum().item()], device=dev, dtype=torch.float64)
+    chk_lo, chk_hi = chk.clone(), chk.clone()
 
     # ------------------------------------------------------------------ reduce over ranks (max time)
-    times = torch.tensor([ms, e2e_s * 1000.0], device=dev, dtype=torch.float64)
+    times = torch.tensor([ms, e2e_s * 1000.0, sus_ms / sus_K, coll_ms], device=dev, dtype=torch.float64)
+    ok_t = torch.tensor([1.0 if gather_ok else 0.0], device=dev, dtype=torch.float64)
     if world > 1:
-        import torch.distributed as dist
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        # the one collective of the path: reassemble the generated batch
-        gathered = torch.empty((world * B, J, F, T), device=dev)
-        dist.all_gather_into_tensor(gathered, out_host.to(dev).contiguous())
-    ms_max, e2e_ms_max = times.tolist()
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        dist.all_reduce(chk_lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(chk_hi, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max, sus_ms_step, coll_ms_max = times.tolist()
+    gather_ok = bool(ok_t.item() == 1.0) and chk_lo.item() == chk_hi.item()
 
     if rank == 0:
         peaks = measured_peaks()
         f_gemm, f_attn, f_small = flops_per_step(B, T, I)
         steps_per_s = world * K / (ms_max / 1000.0)
-        gemm_tf = f_gemm / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
-        n_elem = B * I * T
-        upd_gbs = 16.0 * n_elem / (upd_ms / 1000.0) / 1e9 if upd_ms > 0 else 0.0
+        M = B * T
+        kf = kernel_flops(M, T, I)
+        gemm_names = ("in_proj", "qkv", "out+LN", "ffn1", "lin2+LN", "out_proj")
+        gemm_ms = sum(spans[k][0] * spans[k][1] for k in gemm_names) / 1e3
+        attn_ms = spans["attn"][0] * spans["attn"][1] / 1e3
+        gemm_launches = sum(spans[k][1] for k in gemm_names)
+        gemm_tf = f_gemm / (gemm_ms / 1000.0) / 1e12
+        attn_tf = f_attn / (attn_ms / 1000.0) / 1e12
+        kernels = {k: {"span_us": spans[k][0], "launches_per_step": spans[k][1], "algorithmic_gflop": kf[k] / 1e9,
+                       "tflops": kf[k] / (spans[k][0] * 1e-6) / 1e12,
+                       "frac": kf[k] / (spans[k][0] * 1e-6) / 1e12 / peaks["tf_sust"]} for k in spans}
+        upd_gbs = 16.0 * n_elem / (upd_ms / 1000.0) / 1e9
+        rot_gbs = 60.0 * n_rot / (rot_ms / 1000.0) / 1e9
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("_gemm_class_avg_dram_bytes_per_launch")
+        for tname in ("r02_traffic.json", "r01_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get("_gemm_class_avg_dram_bytes_per_launch")
+                break
         line = {
             "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 (3 bf16 tcgen05 MMAs per product, fp32 accumulate; fp32 LN/softmax/update, residual stream as a bf16 (hi, lo) pair)",
-            "data": "synthetic (seeded random-init weights, random actor motion)",
+            "data": DATA,
             "config": {"workload": "BASELINE configs[1]: NTU120-AS online unconstrained 8-layer CMDM, SMPL-X rot6d "
                                    "56x6, T=%d, B=%d per GPU, 1000-step cosine DDPM p_sample_loop (steps %d..%d timed)"
                                    % (T, B, 999 - W, 999 - W - K + 1),
                        "batch_per_gpu": B, "frames": T, "layers": 8, "parallelism": "dp%d (independent shards)" % world,
                        "driver": ("CUDA graph replay, %d steps per graph" % U) if U else "host-enqueued steps",
                        "l2": "working set per step (weights 107 MB + activations ~300 MB) exceeds the 126 MB L2"},
+            "sustained": {"value": world * 1000.0 / sus_ms_step, "unit": UNIT, "steps": sus_K, "ms_per_step": sus_ms_step,
+                          "seconds": sus_ms / 1e3,
+                          "what": "the same device-resident measurement over 900 consecutive steps of the loop (> 1 s of back-"
+                                  "to-back graph replays: the board settles at its power-capped clock); `value` above is the "
+                                  "--steps K burst"},
             "poses_per_sec": steps_per_s * B * T,
-            "frames_per_sec_e2e_1000_steps": (world * B * T / (e2e_ms_max / 1000.0)) if KE == 1000
-                                             else world * B * T / (1000.0 * (ms_max / K) / 1000.0),
+            "frames_per_sec_e2e_1000_steps": world * B * T / (e2e_ms_max / 1000.0),
             "e2e": {"value": world * KE / (e2e_ms_max / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
-                    "what": "SpacedDiffusion(%d steps).p_sample_loop(CMDM, ...) with pinned-host cmotion in and "
-                            "pinned-host samples out, wall clock incl. Python; median of 3 loops" % KE,
-                    "steps": KE,
+                    "what": "regennet_b200.dist.sharded_sample(SpacedDiffusion(1000 steps).p_sample_loop, CMDM, global batch "
+                            "%d) with the conditioning in pinned host memory (each rank copies its shard), the all-gather of "
+                            "the generated batch and the copy of the result to pinned host memory inside the timed region; "
+                            "wall clock incl. Python, max over ranks of the median of 3 loops" % (world * B),
+                    "steps": KE, "collective_ms": coll_ms_max,
+                    "collective": "all_gather_into_tensor of [%d,%d,%d,%d] fp32 (%.1f MB total), CUDA events"
+                                  % (world * B, J, F, T, world * B * I * T * 4 / 1e6) if world > 1 else "none (one rank)",
+                    "gather_check": "rank order and cross-rank checksum ok" if gather_ok else "FAILED",
                     "runs_ms": [round(1e3 * v, 2) for v in e2e_runs]},
             "gpu_launches": launches,
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "tcgen05 GEMM class: gemm2_tn_kernel<256,bf16x3> (QKV, FFN1, in/out projections) + "
-                                   "gemm_ln_kernel (out_proj+LN1+LN2, linear2+LN3 fused), %d launches per step" % (2 + 4 * 8),
+            "roofline": {"bound": "tensor", "kernel": "tcgen05 GEMM class: gemm2_tn_kernel<256,bf16x3> (QKV, FFN1, output projection) + "
+                                   "gemm_ln_kernel (input projection, out_proj+LN1+LN2, linear2+LN3 fused), %d launches per step"
+                                   % gemm_launches,
                          "achieved": gemm_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
                          "frac": gemm_tf / peaks["tf_sust"], "traffic": traffic,
-                         "traffic_note": "DRAM bytes per GEMM-class launch (ncu dram__bytes_read+write, profiles/r01_traffic.json); "
+                         "ms_per_step": gemm_ms,
+                         "how": "in-graph GPU timeline: global-timer stamps written by the kernels of a replayed 2-step "
+                                "CUDA graph (after griddepcontrol.wait / at the last CTA's exit); spans sum to %.3f ms and "
+                                "gaps (elementwise kernels, Philox) to %.3f ms per step" % (span_ms, gap_ms),
+                         "traffic_note": "DRAM bytes per GEMM-class launch (ncu dram__bytes_read+write, profiles/); "
                                          "algorithmic operand+result bytes per launch: QKV 129 MB, FFN1 100 MB, fused N=512 GEMMs 96-128 MB",
                          "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % peaks["src"],
                          "note": "achieved counts ALGORITHMIC flops (1 MAC per product); the bf16x3 parity mode "
                                  "executes 3 MMAs per product, so frac is capped at 1/3"},
+            "kernels": kernels,
             "roofline_hbm": {"bound": "hbm", "kernel": "p_sample_update_kernel", "achieved": upd_gbs,
                              "peak": peaks["hbm"], "unit": "GB/s", "frac": upd_gbs / peaks["hbm"],
-                             "bytes_per_element": 16},
+                             "bytes_per_element": 16, "ms": upd_ms,
+                             "how": "timed alone, 40 launches rotating over 8 buffer sets (660 MB > L2), CUDA events"},
+            "roofline_rot6d": {"bound": "hbm", "kernel": "rot6d_kernel (rotation_6d_to_matrix)", "achieved": rot_gbs,
+                               "peak": peaks["hbm"], "unit": "GB/s", "frac": rot_gbs / peaks["hbm"],
+                               "bytes_per_rotation": 60, "rotations": n_rot, "ms": rot_ms,
+                               "how": "B*T*55 rotations of one generated batch, 40 launches rotating over 8 buffer sets "
+                                      "(405 MB > L2), CUDA events"},
             "roofline_attention": {"bound": "tensor", "kernel": "attention_kernel<64> (T <= 64; per (sample, head): QK^T and PV on "
                                    "tcgen05, bf16x3), 8 launches per step",
-                                   "achieved": (f_attn / (attn_ms / 1000.0) / 1e12) if attn_ms > 0 else 0.0,
-                                   "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                                   "frac": (f_attn / (attn_ms / 1000.0) / 1e12 / peaks["tf_sust"]) if attn_ms > 0 else 0.0,
-                                   "algorithmic_gbs": (8 * 16.0 * B * T * 512 / (attn_ms / 1000.0) / 1e9) if attn_ms > 0 else 0.0,
+                                   "achieved": attn_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                                   "frac": attn_tf / peaks["tf_sust"], "ms_per_step": attn_ms,
+                                   "algorithmic_gbs": 8 * 16.0 * B * T * 512 / (attn_ms / 1000.0) / 1e9,
                                    "note": "4*T*512 flops per token and layer (2.8 % of the step's flops); the kernel is bound by "
-                                           "its per-CTA latency chain (3 CTAs/SM), not by the tensor pipe: algorithmic_gbs = q|k|v "
-                                           "(hi, lo) read + output (hi, lo) written, 16 B per token and column of 512"},
-            "breakdown_ms": {"gemm": gemm_ms, "attention": attn_ms, "layernorm": ln_ms, "split_cfg": other_ms,
-                             "posterior_update": upd_ms, "step_total": ms_max / K},
+                                           "moving q|k|v (hi, lo) in and the output (hi, lo) out (algorithmic_gbs: 16 B per token "
+                                           "and column of 512), not by the tensor pipe"},
+            "breakdown_ms": {"gemm": gemm_ms, "attention": attn_ms, "elementwise_and_gaps": gap_ms,
+                             "timeline_step_total": span_ms + gap_ms, "step_total": ms_max / K},
             "algorithmic_gflop_per_step": (f_gemm + f_attn + f_small) / 1e9,
             "tensor_frac_whole_step": (f_gemm + f_attn + f_small) / ((ms_max / K) / 1000.0) / 1e12 / peaks["tf_sust"],
+            "tensor_frac_whole_step_sustained": (f_gemm + f_attn + f_small) / (sus_ms_step / 1000.0) / 1e12 / peaks["tf_sust"],
         }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(budget_s=15.0, T=T)
+        if world == 1 and not args.brief:
+            line["other_configs"] = other_configs(dev, peaks)
+
+            def ours_forward(x, t):
+                with torch.no_grad():
+                    return model(x, t, y=yc)
+            line["library_baseline"] = library_baseline(dev, B, T, ours_forward)
+            lb = line["library_baseline"]
+            lb["ours_vs_fp32_eager"] = line["sustained"]["value"] / lb["fp32"]["steps_per_s"]
+            lb["ours_vs_tf32_eager"] = line["sustained"]["value"] / lb["tf32"]["steps_per_s"]
+            line["cpu_baseline"] = cpu_baseline(budget_s=20.0, T=T)
         print(json.dumps(line))
     if world > 1:
-        import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
 
 
-def cpu_oracle_step_fn(Bs, T):
-    """One denoising step of the CPU oracle (port of the reference algorithm) at batch Bs."""
-    from oracle import cmdm_ref, sampler_ref
-    from regennet_b200 import synthetic
-    mk, sk = model_cfg()
-    sd = synthetic.make_state_dict(seed=0, **sk)
-    _, y = synthetic.make_inputs(Bs, 56, 6, T, seed=10)
-    smp = sampler_ref.Sampler()
-    kw = dict(num_layers=8, nhead=4, cond_mode="no_cond", cm_mode="concat")
-    state = {"x": torch.randn(Bs, 56, 6, T), "i": 999}
-
-    def step():
-        with torch.no_grad():
-            t = torch.tensor([state["i"]] * Bs)
-            state["x"], _ = smp.p_sample(lambda xx, tt: cmdm_ref.cmdm_forward(sd, xx, tt, y, **kw), state["x"], t,
-                                         torch.randn_like)
-            state["i"] -= 1
-    return step
-
-
-def cpu_baseline(budget_s, T, Bs=32):
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    step = cpu_oracle_step_fn(Bs, T)
-    step()
-    n, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < budget_s or n < 2:
-        step()
-        n += 1
-    dt = time.perf_counter() - t0
-    eq = (n / dt) * (Bs / float(B_DEFAULT))
-    return {"value": eq, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d p_sample steps of the CPU oracle (torch fp32, %d threads) at B=%d, T=%d in %.1f s; value is "
-                      "scaled by %d/%d to the B=256 step" % (n, cores, Bs, T, dt, Bs, B_DEFAULT)}
-
-
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path.  The reference is a Python tree
-    that cannot travel to the GPU box, so this times the CPU oracle (oracle/, a restatement pinned to the
-    reference by tests/golden) with all host threads.  Each step is a bounded sample (B=32 of the 256)."""
+    """Reference arm: the reference's OWN CPU implementation of the path -- its unmodified SpacedDiffusion.p_sample_loop +
+    CMDM files (oracle/_ref, staged by oracle/make_ref.sh; the oracle port only if that tree is missing) -- on all host
+    threads, at the true B = 256 of the GPU arm's config (no extrapolation).  Rank 0 only."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    K, W, T, Bs = args.steps, args.warmup, args.frames, 32
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    step = cpu_oracle_step_fn(Bs, T)
-    for _ in range(max(1, min(W, 3))):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        step()
-    dt = time.perf_counter() - t0
-    v = (K / dt) * (Bs / float(B_DEFAULT))
+    K, W, T = args.steps, args.warmup, args.frames
+    r = cpu_reference(K, W, T, B=args.batch)
+    v = r["value"]
     world = int(os.environ.get("WORLD_SIZE", 1))
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic (seeded random-init weights, random actor motion)",
-            "config": {"workload": "BASELINE configs[1] on host CPU: same model/config as the GPU arm; each step = one "
-                                   "p_sample at B=%d (bounded sample of B=256), value scaled by %d/256" % (Bs, Bs)},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d steps at B=%d, T=%d, %d threads, %.1f s" % (K, Bs, T, cores, dt)},
+    what = ("the reference's own SpacedDiffusion.p_sample_loop + CMDM (unmodified reference files: /root/reference in the "
+            "build container, their staged copy oracle/_ref on the GPU box), torch fp32"
+            if r["kind"] == "reference" else "the CPU oracle port of the reference algorithm (oracle/), torch fp32")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": r["steps"], "warmup": W,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": DATA,
+            "config": {"workload": "BASELINE configs[1] on the host CPU: same model / B=%d / T=%d as the GPU arm; each step = one "
+                                   "p_sample of the 1000-step loop over the whole batch; %s" % (args.batch, T, what),
+                       "batch_per_gpu": args.batch, "frames": T, "layers": 8,
+                       "steps_requested": K},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                             "sample": "%d consecutive steps at the true B=%d, T=%d, %d threads, %.1f s" % (
+                                 r["steps"], args.batch, T, r["cores"], r["seconds"])},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if world == 1 and not args.no_config1:
+        # BASELINE configs[0]: the reference's own CPU-runnable case, B = 1, the FULL 1000-step loop
+        kind, step, _, _ = reference_stepper(torch.device("cpu"), 1, T)
+        step()
+        t0 = time.perf_counter()
+        for _ in range(1000):
+            step()
+        dt = time.perf_counter() - t0
+        line["config1_cpu"] = {"workload": "B=1, T=%d, full 1000-step p_sample_loop" % T, "kind": kind, "seconds": dt,
+                               "steps_per_s": 1000 / dt, "frames_per_s": T / dt}
     print(json.dumps(line))
 
 
@@ -389,7 +688,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=B_DEFAULT)
     ap.add_argument("--frames", type=int, default=T_DEFAULT)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--brief", action="store_true", help="N=1: skip other_configs / library_baseline / cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", dest="brief", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-config1", action="store_true",
+                    help="reference arm: skip BASELINE configs[0] (B=1, full 1000-step loop on the CPU, ~30 s)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

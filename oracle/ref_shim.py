@@ -1,8 +1,10 @@
 """Import shim for the UNMODIFIED reference (liangxuy/ReGenNet) on CPU.
 
-Only usable where /root/reference exists (the build container); used by
-tests/golden/make_golden.py to generate golden vectors and by the optional
-``reference``-marked tests.  It never travels to the GPU box.
+Test / measurement infrastructure, never imported by the product path.  The reference tree is taken from
+``REGEN_REFERENCE_ROOT``, else /root/reference (the build container; used by tests/golden/make_golden*.py to generate
+golden vectors and by the ``reference``-marked tests), else ``oracle/_ref`` -- the 17 unmodified reference files of the
+sampling path staged by ``oracle/make_ref.sh`` (git-ignored; travels to the GPU box, where it lets ``bench.py --impl
+reference`` time the reference's own p_sample_loop on the host cores and on the GPU as the torch-eager baseline).
 
 The reference imports three packages that are absent here and irrelevant to the
 hot path (timm's DropPath, OpenAI clip, smplx body-model layers) and uses the
@@ -15,7 +17,17 @@ import types
 import numpy as np
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("REGEN_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _find_root():
+    for cand in (os.environ.get("REGEN_REFERENCE_ROOT"), "/root/reference", _STAGED):
+        if cand and os.path.isdir(os.path.join(cand, "model")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available():

@@ -26,7 +26,11 @@ def setup_dist(backend=None):
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if backend == "nccl":
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        local = int(os.environ.get("LOCAL_RANK", 0))
+        torch.cuda.set_device(local)
+        # binding the communicator to the device up front avoids the lazy init inside the first collective
+        dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        return
     dist.init_process_group(backend, rank=rank, world_size=world)
 
 
@@ -44,8 +48,10 @@ def shard_bounds(B, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def shard_kwargs(y, B, rank, world):
-    """Slice every tensor in the conditioning dict whose leading dim is the batch; share the rest."""
+def shard_kwargs(y, B, rank, world, device=None):
+    """Slice every tensor in the conditioning dict whose leading dim is the batch; share the rest.  With `device`, the
+    tensor entries (sliced or not) are moved there -- the shard of a (pinned) host-resident global batch is the only part
+    of it this rank ever copies."""
     lo, hi = shard_bounds(B, rank, world)
     out = {}
     for k, v in y.items():
@@ -55,11 +61,14 @@ def shard_kwargs(y, B, rank, world):
             out[k] = v[lo:hi]
         else:
             out[k] = v
+        if device is not None and torch.is_tensor(out[k]):
+            out[k] = out[k].to(device, non_blocking=True)
     return out
 
 
-def gather_batch(local, B, group=None):
-    """All-gather the per-rank shards [b_r, ...] into [B, ...] in rank order (shards may be ragged)."""
+def gather_batch(local, B, group=None, timing=None):
+    """All-gather the per-rank shards [b_r, ...] into [B, ...] in rank order (shards may be ragged).  `timing` (a dict,
+    CUDA only) receives a CUDA event pair around the collective under "collective_events"."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return local
@@ -70,7 +79,14 @@ def gather_batch(local, B, group=None):
     assert local.shape[0] == counts[rank]
     if len(set(counts)) == 1:
         out = torch.empty((B,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        ev = None
+        if timing is not None and local.is_cuda:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         dist.all_gather_into_tensor(out, local, group=group)
+        if ev is not None:
+            ev[1].record()
+            timing["collective_events"] = ev
         return out
     mx = max(counts)
     pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
@@ -80,9 +96,11 @@ def gather_batch(local, B, group=None):
     return torch.cat([buf[r * mx:r * mx + counts[r]] for r in range(world)], dim=0)
 
 
-def sharded_sample(sample_fn, model, shape, model_kwargs, seed=None, **kw):
+def sharded_sample(sample_fn, model, shape, model_kwargs, seed=None, device=None, timing=None, **kw):
     """Run ``sample_fn`` (``diffusion.p_sample_loop`` or ``ddim_sample_loop``) on this rank's shard and
-    return the full batch on every rank.  ``shape`` and ``model_kwargs`` describe the GLOBAL batch."""
+    return the full batch on every rank.  ``shape`` and ``model_kwargs`` describe the GLOBAL batch; the conditioning
+    tensors may live on the host (pass ``device`` and only this rank's shard is copied to it).  ``timing``: see
+    gather_batch; it also receives this rank's shard under "local"."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     B = shape[0]
@@ -91,6 +109,8 @@ def sharded_sample(sample_fn, model, shape, model_kwargs, seed=None, **kw):
         torch.manual_seed(seed + rank)
     local_kwargs = dict(model_kwargs or {})
     if isinstance(local_kwargs.get("y"), dict):
-        local_kwargs["y"] = shard_kwargs(local_kwargs["y"], B, rank, world)
+        local_kwargs["y"] = shard_kwargs(local_kwargs["y"], B, rank, world, device=device)
     local = sample_fn(model, (hi - lo,) + tuple(shape[1:]), model_kwargs=local_kwargs, **kw)
-    return gather_batch(local, B)
+    if timing is not None:
+        timing["local"] = local
+    return gather_batch(local, B, timing=timing)

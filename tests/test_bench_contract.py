@@ -1,4 +1,4 @@
-"""bench.py contract checks that run without a GPU: the reference arm (the CPU oracle timed on the host cores) prints ONE
+"""bench.py contract checks that run without a GPU: the reference arm (the reference's CPU path timed on the host cores) prints ONE
 JSON line with the keys the driver reads, and the torchrun convention (only rank 0 works) holds."""
 import json
 import os
@@ -11,7 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _run(env_extra=None):
     env = dict(os.environ)
     env.update(env_extra or {})
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--no-config1"],
                        capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
     return p.stdout.strip()
@@ -24,7 +25,9 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "denoising_steps_per_sec" and d["higher_is_better"] is True
     assert d["steps"] == 2 and d["n_gpus"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # "reference" where the reference tree (or its staged copy oracle/_ref) is present, the oracle port otherwise
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["config"]["batch_per_gpu"] == 256       # the true batch of the GPU arm, no extrapolation
     assert abs(d["cpu_baseline"]["value"] - d["value"]) < 1e-9
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["gpu_launches"] == 0

@@ -1,0 +1,105 @@
+"""Parity hardening beyond benign random-init weights and short loops.
+
+(a) Outlier stress: trained post-norm transformers carry LayerNorm-gain and FFN outlier channels; here 4 random channels of
+    every ``norm*.weight`` are scaled x20 and 4 random rows of every ``linear1.weight`` (+ bias) x8, and the B = 256 fused route
+    (bf16x3 products, bf16 (hi, lo) residual stream, fused LN epilogues, polynomial-erf GELU) must stay inside the path's
+    1e-3 tolerance against the fp32 oracle -- measured relative to the enlarged output range as well.
+(b) A full 1000-step ancestral sampling loop at the full batch (B = 256, T = 60, BASELINE config 2) against the oracle on two
+    samples with the noise the GPU run drew for them (recorded on the fly; samples are independent, so the oracle runs the
+    two-sample sub-batch).  Marked slow-ish (~1 min of CPU oracle)."""
+import pytest
+import torch
+
+import cases
+from oracle import cmdm_ref, sampler_ref
+from regennet_b200 import synthetic
+from regennet_b200.cmdm import CMDM
+from test_gpu_denoiser import _kw, get_model, to_cuda
+from test_gpu_sampler import _diffusion
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _outlier_state_dict(seed):
+    sd = synthetic.make_state_dict(seed=seed, **cases.synth_kw("ntu"))
+    g = torch.Generator().manual_seed(seed + 1000)
+    n_norm = n_l1 = 0
+    for k in sorted(sd):
+        if ".norm" in k and k.endswith(".weight"):
+            ch = torch.randperm(sd[k].numel(), generator=g)[:4]
+            sd[k] = sd[k].clone()
+            sd[k][ch] *= 20.0
+            n_norm += 1
+        elif k.endswith("linear1.weight"):
+            rows = torch.randperm(sd[k].shape[0], generator=g)[:4]
+            sd[k] = sd[k].clone()
+            sd[k][rows] *= 8.0
+            bk = k[:-len("weight")] + "bias"
+            sd[bk] = sd[bk].clone()
+            sd[bk][rows] *= 8.0
+            n_l1 += 1
+    assert n_norm == 24 and n_l1 == 8
+    return sd
+
+
+@pytest.mark.parametrize("B", [256, 8])       # fused GEMM+LN route (hi, lo residual) and the small-batch route (fp32 residual)
+def test_outlier_channels_stay_within_tolerance(built_lib, B):
+    mk = cases.MODELS["ntu"]
+    sd = _outlier_state_dict(5)
+    model = CMDM(**mk)
+    model.load_state_dict(sd, strict=False)
+    model = model.cuda().eval()
+    T = 60
+    x, y = synthetic.make_inputs(B, 56, 6, T, seed=900 + B)
+    t = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(B))
+    with torch.no_grad():
+        out = model(x.cuda(), t.cuda(), to_cuda(y)).cpu()
+    sel = torch.tensor([0, 1, B // 2, B - 1])
+    with torch.no_grad():
+        want = cmdm_ref.cmdm_forward(sd, x[sel], t[sel], {"cmotion": y["cmotion"][sel]}, **_kw(mk))
+        base = cmdm_ref.cmdm_forward(synthetic.make_state_dict(seed=5, **cases.synth_kw("ntu")), x[sel], t[sel],
+                                     {"cmotion": y["cmotion"][sel]}, **_kw(mk))
+    err = (out[sel] - want).abs().max().item()
+    print("outlier stress B=%d: max abs err vs oracle %.3e (output absmax %.2f; without outliers %.2f)" % (
+        B, err, want.abs().max(), base.abs().max()))
+    assert not torch.allclose(want, base, atol=1e-2)      # the outliers do change the function
+    assert err < TOL
+
+
+def test_full_1000_step_loop_matches_oracle_on_two_samples(built_lib):
+    model, sd = get_model("ntu", 0)
+    mk = cases.MODELS["ntu"]
+    B, T = 256, 60
+    shape = (B, 56, 6, T)
+    sel = torch.tensor([3, 200])
+    _, y = synthetic.make_inputs(B, 56, 6, T, seed=82)
+    d = _diffusion("")
+    assert d.num_timesteps == 1000
+    torch.manual_seed(31)
+    init = torch.randn(*shape, device="cuda")
+    noises = []
+    orig = torch.randn_like
+
+    def rec(x, **kw):
+        n = orig(x, **kw)
+        noises.append(n[sel.to(n.device)].cpu())      # two samples of the step's noise (same logical [B,J,F,T] indexing)
+        return n
+
+    torch.randn_like = rec
+    try:
+        out = d.p_sample_loop(model, shape, noise=init, clip_denoised=False, model_kwargs={"y": to_cuda(y)})
+    finally:
+        torch.randn_like = orig
+    assert len(noises) == 1000
+    it = iter(noises)
+    ysel = {"cmotion": y["cmotion"][sel]}
+    smp = sampler_ref.Sampler()
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    want, _ = smp.loop(lambda xx, tt: cmdm_ref.cmdm_forward(sd, xx, tt, ysel, **_kw(mk)), (2,) + shape[1:],
+                       noise_fn=lambda x: next(it), init_noise=init[sel.cuda()].cpu())
+    err = (out[sel.cuda()].cpu() - want).abs().max().item()
+    print("1000-step loop, B=256: max abs err vs oracle on samples %s: %.3e (absmax %.2f)" % (sel.tolist(), err,
+                                                                                             want.abs().max()))
+    assert torch.isfinite(out).all()
+    assert err < TOL

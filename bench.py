@@ -215,51 +215,49 @@ def in_graph_timeline(model, sess, diffusion, img, steps_logged=2):
 
 def hbm_kernels(dev, B, T, J=56, F=6):
     """The two elementwise kernels of the path timed ALONE over rotating buffer sets whose total exceeds the 126 MB L2
-    (every launch streams from / to HBM).  -> (update ms, rot6d ms, n_elem, n_rot)"""
-    from regennet_b200 import _lib, rotation_conversions
+    (every launch streams from / to HBM).  The launches are replayed from a CUDA graph -- enqueued from Python they are
+    host-bound (a ctypes call costs more than the 13 us kernel) and the events would time the host.
+    -> (update ms, rot6d ms, n_elem, n_rot)"""
+    from regennet_b200 import _lib
     d = make_diffusion([1000])
     n_elem = B * J * F * T
-    SETS = 8                                                      # 8 x 4 x 20.6 MB = 660 MB
+    SETS, REPS = 8, 5                                             # 8 x 4 x 20.6 MB = 660 MB
     xs = [torch.randn(T, B, J, F, device=dev).permute(1, 2, 3, 0) for _ in range(3 * SETS)]
     outs = [torch.empty(T, B, J, F, device=dev).permute(1, 2, 3, 0) for _ in range(SETS)]
     t = torch.full((B,), 500, dtype=torch.long, device=dev)
-    reps = 5
+    d._tables(dev)
 
-    def upd(i):
-        k = i % SETS
+    def upd(k):
         d._update("p", xs[3 * k], xs[3 * k + 1], xs[3 * k + 2], t, False, out=outs[k])
 
-    for i in range(SETS):
-        upd(i)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(reps * SETS):
-        upd(i)
-    e1.record()
-    torch.cuda.synchronize()
-    upd_ms = e0.elapsed_time(e1) / (reps * SETS)
     # rot6d -> rotmat at the size the sample of this config produces: B*T frames x 55 joints
     n_rot = B * T * (J - 1)
     lib = _lib.lib()
     srcs = [torch.randn(n_rot, 6, device=dev) for _ in range(SETS)]      # 8 x (20 + 30) MB
     dsts = [torch.empty(n_rot, 3, 3, device=dev) for _ in range(SETS)]
-    sp = _lib.stream_ptr(dev)
 
-    def rot(i):
-        k = i % SETS
-        _lib.check(lib.regen_rot6d_to_matrix(_lib.ptr(srcs[k]), _lib.ptr(dsts[k]), n_rot, sp), "rot6d")
+    def rot(k):
+        _lib.check(lib.regen_rot6d_to_matrix(_lib.ptr(srcs[k]), _lib.ptr(dsts[k]), n_rot, _lib.stream_ptr(dev)), "rot6d")
 
-    for i in range(SETS):
-        rot(i)
-    torch.cuda.synchronize()
-    e0.record()
-    for i in range(reps * SETS):
-        rot(i)
-    e1.record()
-    torch.cuda.synchronize()
-    rot_ms = e0.elapsed_time(e1) / (reps * SETS)
-    del rotation_conversions
+    def timed(fn):
+        for k in range(SETS):
+            fn(k)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(REPS * SETS):
+                fn(i % SETS)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (REPS * SETS)
+
+    upd_ms = timed(upd)
+    rot_ms = timed(rot)
     return upd_ms, rot_ms, n_elem, n_rot
 
 
@@ -604,12 +602,12 @@ def run_ours(args):
             "roofline_hbm": {"bound": "hbm", "kernel": "p_sample_update_kernel", "achieved": upd_gbs,
                              "peak": peaks["hbm"], "unit": "GB/s", "frac": upd_gbs / peaks["hbm"],
                              "bytes_per_element": 16, "ms": upd_ms,
-                             "how": "timed alone, 40 launches rotating over 8 buffer sets (660 MB > L2), CUDA events"},
+                             "how": "timed alone: 40 launches rotating over 8 buffer sets (660 MB > L2) replayed from a CUDA graph, CUDA events around the replay"},
             "roofline_rot6d": {"bound": "hbm", "kernel": "rot6d_kernel (rotation_6d_to_matrix)", "achieved": rot_gbs,
                                "peak": peaks["hbm"], "unit": "GB/s", "frac": rot_gbs / peaks["hbm"],
                                "bytes_per_rotation": 60, "rotations": n_rot, "ms": rot_ms,
                                "how": "B*T*55 rotations of one generated batch, 40 launches rotating over 8 buffer sets "
-                                      "(405 MB > L2), CUDA events"},
+                                      "(405 MB > L2) replayed from a CUDA graph, CUDA events around the replay"},
             "roofline_attention": {"bound": "tensor", "kernel": "attention_kernel<64> (T <= 64; per (sample, head): QK^T and PV on "
                                    "tcgen05, bf16x3), 8 launches per step",
                                    "achieved": attn_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s",

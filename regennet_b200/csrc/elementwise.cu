@@ -54,6 +54,14 @@ __device__ __forceinline__ float psample_one(float x, float x0, float nz, const 
   return __fadd_rn(mean, __fmul_rn(c.sig, nz));
 }
 
+// Streaming loads / stores: every operand of the update is touched exactly once per step, so nothing is worth keeping in
+// L1 and the lines are marked evict-first in L2 (ld.global.cs / st.global.cs).
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
+
+constexpr int kUpdUnroll = 4;        // float4 items per thread per block iteration (12 x 16 B loads in flight per thread)
+constexpr int kUpdCoefCap = 1024;    // per-sample coefficient table in shared memory up to this batch
+
 template <bool VEC>
 __global__ void __launch_bounds__(kThreads) p_sample_update_kernel(
     const float* __restrict__ x, const float* __restrict__ x0, const float* __restrict__ noise,
@@ -61,22 +69,60 @@ __global__ void __launch_bounds__(kThreads) p_sample_update_kernel(
     const float* __restrict__ coef1, const float* __restrict__ coef2, const float* __restrict__ logvar,
     uint32_t n_items, uint32_t inner_items, uint32_t B, int clip) {
   // one item = one float4 (VEC) or one float; inner_items = items per (sample, outer index)
-  for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n_items; i += gridDim.x * kThreads) {
-    int b = (int)((i / inner_items) % B);
-    PSampleCoef c = load_psample(t, coef1, coef2, logvar, b);
-    if (VEC) {
-      float4 vx = reinterpret_cast<const float4*>(x)[i];
-      float4 v0 = reinterpret_cast<const float4*>(x0)[i];
-      float4 vn = noise ? reinterpret_cast<const float4*>(noise)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      v0.x = clampf(v0.x, clip); v0.y = clampf(v0.y, clip); v0.z = clampf(v0.z, clip); v0.w = clampf(v0.w, clip);
-      float4 o;
-      o.x = psample_one(vx.x, v0.x, vn.x, c);
-      o.y = psample_one(vx.y, v0.y, vn.y, c);
-      o.z = psample_one(vx.z, v0.z, vn.z, c);
-      o.w = psample_one(vx.w, v0.w, vn.w, c);
-      reinterpret_cast<float4*>(out)[i] = o;
-      if (pred) reinterpret_cast<float4*>(pred)[i] = v0;
-    } else {
+  ptx::griddep_wait();    // PDL: launched while the producer of x0 / noise drains; its results are needed from here on
+  ptx::griddep_launch();
+  if (VEC) {
+    // Per-sample coefficients once per block (the gather chain t[b] -> table -> exp is two dependent global loads; per
+    // item it sat in front of every store), then kUpdUnroll independent float4 triples per thread and iteration.
+    __shared__ float s_c1[kUpdCoefCap], s_c2[kUpdCoefCap], s_sig[kUpdCoefCap];
+    const bool tab = B <= (uint32_t)kUpdCoefCap;
+    if (tab) {
+      for (uint32_t b = threadIdx.x; b < B; b += kThreads) {
+        PSampleCoef c = load_psample(t, coef1, coef2, logvar, (int)b);
+        s_c1[b] = c.c1; s_c2[b] = c.c2; s_sig[b] = c.sig;
+      }
+      __syncthreads();
+    }
+    // balanced contiguous partition: every block owns ceil(n_items / gridDim) items (rounded to whole 512-byte rows), so
+    // no block runs a whole extra iteration at the tail of the grid
+    const uint32_t per_iter = kThreads * kUpdUnroll;
+    const uint32_t ipb = ((n_items + gridDim.x - 1) / gridDim.x + 31u) & ~31u;
+    const uint32_t blk_begin = blockIdx.x * ipb;
+    const uint32_t blk_end = blk_begin + ipb < n_items ? blk_begin + ipb : n_items;
+    for (uint32_t base = blk_begin; base < blk_end; base += per_iter) {
+      float4 vx[kUpdUnroll], v0[kUpdUnroll], vn[kUpdUnroll];
+#pragma unroll
+      for (int u = 0; u < kUpdUnroll; ++u) {
+        const uint32_t i = base + u * kThreads + threadIdx.x;
+        if (i < blk_end) {
+          vx[u] = ld_stream(reinterpret_cast<const float4*>(x) + i);
+          v0[u] = ld_stream(reinterpret_cast<const float4*>(x0) + i);
+          vn[u] = noise ? ld_stream(reinterpret_cast<const float4*>(noise) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUpdUnroll; ++u) {
+        const uint32_t i = base + u * kThreads + threadIdx.x;
+        if (i >= blk_end) continue;
+        const int b = (int)((i / inner_items) % B);
+        PSampleCoef c;
+        if (tab) { c.c1 = s_c1[b]; c.c2 = s_c2[b]; c.sig = s_sig[b]; }
+        else c = load_psample(t, coef1, coef2, logvar, b);
+        float4 p0 = v0[u];
+        p0.x = clampf(p0.x, clip); p0.y = clampf(p0.y, clip); p0.z = clampf(p0.z, clip); p0.w = clampf(p0.w, clip);
+        float4 o;
+        o.x = psample_one(vx[u].x, p0.x, vn[u].x, c);
+        o.y = psample_one(vx[u].y, p0.y, vn[u].y, c);
+        o.z = psample_one(vx[u].z, p0.z, vn[u].z, c);
+        o.w = psample_one(vx[u].w, p0.w, vn[u].w, c);
+        st_stream(reinterpret_cast<float4*>(out) + i, o);
+        if (pred) st_stream(reinterpret_cast<float4*>(pred) + i, p0);
+      }
+    }
+  } else {
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n_items; i += gridDim.x * kThreads) {
+      int b = (int)((i / inner_items) % B);
+      PSampleCoef c = load_psample(t, coef1, coef2, logvar, b);
       float v0 = clampf(x0[i], clip);
       out[i] = psample_one(x[i], v0, noise ? noise[i] : 0.f, c);
       if (pred) pred[i] = v0;
@@ -117,6 +163,8 @@ __global__ void __launch_bounds__(kThreads) ddim_update_kernel(
     float* __restrict__ out, float* __restrict__ pred, const int64_t* __restrict__ t,
     const float* __restrict__ sra, const float* __restrict__ srm1, const float* __restrict__ ac,
     const float* __restrict__ acp, float eta, uint32_t n_items, uint32_t inner_items, uint32_t B, int clip) {
+  ptx::griddep_wait();
+  ptx::griddep_launch();
   for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n_items; i += gridDim.x * kThreads) {
     int b = (int)((i / inner_items) % B);
     DdimCoef c = load_ddim(t, sra, srm1, ac, acp, eta, b);
@@ -255,53 +303,71 @@ __global__ void __launch_bounds__(kThreads) plms_finish_kernel(const float* __re
   }
 }
 
-// utils/rotation_conversions.py:529-534.  One rotation per thread; the block's 6-float inputs and
-// 9-float outputs are staged through shared memory so global traffic is float4-coalesced.
-constexpr int kRotPerBlock = 256;
-__global__ void __launch_bounds__(kRotPerBlock) rot6d_kernel(const float* __restrict__ d6, float* __restrict__ R,
-                                                             int64_t n) {
-  __shared__ __align__(16) float s_in[kRotPerBlock * 6];
-  __shared__ __align__(16) float s_out[kRotPerBlock * 9];
-  for (int64_t base = (int64_t)blockIdx.x * kRotPerBlock; base < n; base += (int64_t)gridDim.x * kRotPerBlock) {
-    int cnt = (int)min((int64_t)kRotPerBlock, n - base);
-    const float* src = d6 + base * 6;  // 24*base bytes: 16B aligned because kRotPerBlock*24 % 16 == 0
-    int nin = cnt * 6;
-    for (int i = threadIdx.x * 4; i < nin; i += kRotPerBlock * 4) {
-      if (i + 4 <= nin) {
-        *reinterpret_cast<float4*>(s_in + i) = *reinterpret_cast<const float4*>(src + i);
-      } else {
-        for (int k = i; k < nin; ++k) s_in[k] = src[k];
-      }
+// utils/rotation_conversions.py:529-534.  Warp-private staging: each warp streams kRotPerWarp rotations per iteration
+// through its own slice of shared memory (float4-coalesced global traffic in both directions, 24 B in / 36 B out per
+// rotation) and synchronises with __syncwarp only -- no block barrier sits between a block's loads and its stores, so the
+// warps of an SM stay spread over the load / compute / store phases and keep bytes in flight.
+constexpr int kRotPerWarp = 128, kRotWarps = 4, kRotPerBlock = kRotPerWarp * kRotWarps;
+__device__ __forceinline__ void rot6d_one(const float* a, float* o) {
+  // three 8-byte shared loads: lanes are 24 bytes apart, which is conflict-free for 64-bit accesses (stride 3, odd)
+  const float2 p0 = reinterpret_cast<const float2*>(a)[0], p1 = reinterpret_cast<const float2*>(a)[1],
+               p2 = reinterpret_cast<const float2*>(a)[2];
+  float a1x = p0.x, a1y = p0.y, a1z = p1.x, a2x = p1.y, a2y = p2.x, a2z = p2.y;
+  // F.normalize: v / max(||v||, 1e-12)
+  float n1 = fmaxf(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(a1x, a1x), __fmul_rn(a1y, a1y)), __fmul_rn(a1z, a1z))), 1e-12f);
+  float b1x = __fdiv_rn(a1x, n1), b1y = __fdiv_rn(a1y, n1), b1z = __fdiv_rn(a1z, n1);
+  float d = __fadd_rn(__fadd_rn(__fmul_rn(b1x, a2x), __fmul_rn(b1y, a2y)), __fmul_rn(b1z, a2z));
+  float b2x = __fsub_rn(a2x, __fmul_rn(d, b1x)), b2y = __fsub_rn(a2y, __fmul_rn(d, b1y)), b2z = __fsub_rn(a2z, __fmul_rn(d, b1z));
+  float n2 = fmaxf(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(b2x, b2x), __fmul_rn(b2y, b2y)), __fmul_rn(b2z, b2z))), 1e-12f);
+  b2x = __fdiv_rn(b2x, n2); b2y = __fdiv_rn(b2y, n2); b2z = __fdiv_rn(b2z, n2);
+  o[0] = b1x; o[1] = b1y; o[2] = b1z;
+  o[3] = b2x; o[4] = b2y; o[5] = b2z;
+  o[6] = __fsub_rn(__fmul_rn(b1y, b2z), __fmul_rn(b1z, b2y));
+  o[7] = __fsub_rn(__fmul_rn(b1z, b2x), __fmul_rn(b1x, b2z));
+  o[8] = __fsub_rn(__fmul_rn(b1x, b2y), __fmul_rn(b1y, b2x));
+}
+
+__global__ void __launch_bounds__(kRotWarps * 32) rot6d_kernel(const float* __restrict__ d6, float* __restrict__ R,
+                                                                int64_t n) {
+  __shared__ __align__(16) float s_in[kRotWarps][kRotPerWarp * 6];
+  __shared__ __align__(16) float s_out[kRotWarps][kRotPerWarp * 9];
+  ptx::griddep_wait();
+  ptx::griddep_launch();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* in = s_in[warp];
+  float* ob = s_out[warp];
+  const int64_t n_chunks = (n + kRotPerWarp - 1) / kRotPerWarp;
+  for (int64_t chunk = (int64_t)blockIdx.x * kRotWarps + warp; chunk < n_chunks; chunk += (int64_t)gridDim.x * kRotWarps) {
+    const int64_t base = chunk * kRotPerWarp;
+    const int cnt = (int)min((int64_t)kRotPerWarp, n - base);
+    const float* src = d6 + base * 6;  // 24 * base bytes: 16 B aligned because kRotPerWarp * 24 % 16 == 0
+    const int nin = cnt * 6;
+    if (cnt == kRotPerWarp) {
+      float4 v[kRotPerWarp * 6 / 128];   // all of the warp's loads are issued before the first is consumed
+#pragma unroll
+      for (int k = 0; k < kRotPerWarp * 6 / 128; ++k) v[k] = __ldcs(reinterpret_cast<const float4*>(src) + k * 32 + lane);
+#pragma unroll
+      for (int k = 0; k < kRotPerWarp * 6 / 128; ++k) reinterpret_cast<float4*>(in)[k * 32 + lane] = v[k];
+    } else {
+      for (int i = lane; i < nin; i += 32) in[i] = src[i];
     }
-    __syncthreads();
-    if (threadIdx.x < cnt) {
-      const float* a = s_in + threadIdx.x * 6;
-      float a1x = a[0], a1y = a[1], a1z = a[2], a2x = a[3], a2y = a[4], a2z = a[5];
-      // F.normalize: v / max(||v||, 1e-12)
-      float n1 = fmaxf(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(a1x, a1x), __fmul_rn(a1y, a1y)), __fmul_rn(a1z, a1z))), 1e-12f);
-      float b1x = __fdiv_rn(a1x, n1), b1y = __fdiv_rn(a1y, n1), b1z = __fdiv_rn(a1z, n1);
-      float d = __fadd_rn(__fadd_rn(__fmul_rn(b1x, a2x), __fmul_rn(b1y, a2y)), __fmul_rn(b1z, a2z));
-      float b2x = __fsub_rn(a2x, __fmul_rn(d, b1x)), b2y = __fsub_rn(a2y, __fmul_rn(d, b1y)), b2z = __fsub_rn(a2z, __fmul_rn(d, b1z));
-      float n2 = fmaxf(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(b2x, b2x), __fmul_rn(b2y, b2y)), __fmul_rn(b2z, b2z))), 1e-12f);
-      b2x = __fdiv_rn(b2x, n2); b2y = __fdiv_rn(b2y, n2); b2z = __fdiv_rn(b2z, n2);
-      float* o = s_out + threadIdx.x * 9;
-      o[0] = b1x; o[1] = b1y; o[2] = b1z;
-      o[3] = b2x; o[4] = b2y; o[5] = b2z;
-      o[6] = __fsub_rn(__fmul_rn(b1y, b2z), __fmul_rn(b1z, b2y));
-      o[7] = __fsub_rn(__fmul_rn(b1z, b2x), __fmul_rn(b1x, b2z));
-      o[8] = __fsub_rn(__fmul_rn(b1x, b2y), __fmul_rn(b1y, b2x));
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < kRotPerWarp / 32; ++r) {
+      const int j = r * 32 + lane;       // lane-contiguous rotations: stride 6 / 9 words between lanes
+      if (j < cnt) rot6d_one(in + j * 6, ob + j * 9);
     }
-    __syncthreads();
-    float* dst = R + base * 9;  // 36*base bytes: 16B aligned because kRotPerBlock*36 % 16 == 0
-    int nout = cnt * 9;
-    for (int i = threadIdx.x * 4; i < nout; i += kRotPerBlock * 4) {
-      if (i + 4 <= nout) {
-        *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(s_out + i);
-      } else {
-        for (int k = i; k < nout; ++k) dst[k] = s_out[k];
-      }
+    __syncwarp();
+    float* dst = R + base * 9;  // 36 * base bytes: 16 B aligned because kRotPerWarp * 36 % 16 == 0
+    const int nout = cnt * 9;
+    if (cnt == kRotPerWarp) {
+#pragma unroll
+      for (int k = 0; k < kRotPerWarp * 9 / 128; ++k)
+        __stcs(reinterpret_cast<float4*>(dst) + k * 32 + lane, reinterpret_cast<const float4*>(ob)[k * 32 + lane]);
+    } else {
+      for (int i = lane; i < nout; i += 32) dst[i] = ob[i];
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -476,13 +542,13 @@ int regen_p_sample_update(const float* x, const float* x0, const float* noise, f
              aligned16(out) && (!pred_xstart || aligned16(pred_xstart));
   if (vec) {
     uint32_t items = (uint32_t)(n_elem / 4);
-    p_sample_update_kernel<true><<<grid_for(items), kThreads, 0, s>>>(x, x0, noise, out, pred_xstart, t, coef1, coef2,
-                                                                      logvar, items, (uint32_t)(inner / 4), (uint32_t)B,
-                                                                      clip_denoised);
+    REGEN_CUDA(launch_pdl(p_sample_update_kernel<true>, dim3(grid_for(ceil_div(items, kUpdUnroll))), dim3(kThreads), 0, s, x,
+                          x0, noise, out, pred_xstart, t, coef1, coef2, logvar, items, (uint32_t)(inner / 4), (uint32_t)B,
+                          (int)clip_denoised));
   } else {
-    p_sample_update_kernel<false><<<grid_for(n_elem), kThreads, 0, s>>>(x, x0, noise, out, pred_xstart, t, coef1, coef2,
-                                                                        logvar, (uint32_t)n_elem, (uint32_t)inner,
-                                                                        (uint32_t)B, clip_denoised);
+    REGEN_CUDA(launch_pdl(p_sample_update_kernel<false>, dim3(grid_for(n_elem)), dim3(kThreads), 0, s, x, x0, noise, out,
+                          pred_xstart, t, coef1, coef2, logvar, (uint32_t)n_elem, (uint32_t)inner, (uint32_t)B,
+                          (int)clip_denoised));
   }
   REGEN_LAUNCH_CHECK();
   count_launch();
@@ -503,13 +569,13 @@ int regen_ddim_update(const float* x, const float* x0, const float* noise, float
              aligned16(out) && (!pred_xstart || aligned16(pred_xstart));
   if (vec) {
     uint32_t items = (uint32_t)(n_elem / 4);
-    ddim_update_kernel<true><<<grid_for(items), kThreads, 0, s>>>(x, x0, noise, out, pred_xstart, t, sqrt_recip_ac,
-                                                                  sqrt_recipm1_ac, ac, ac_prev, eta, items,
-                                                                  (uint32_t)(inner / 4), (uint32_t)B, clip_denoised);
+    REGEN_CUDA(launch_pdl(ddim_update_kernel<true>, dim3(grid_for(items)), dim3(kThreads), 0, s, x, x0, noise, out,
+                          pred_xstart, t, sqrt_recip_ac, sqrt_recipm1_ac, ac, ac_prev, eta, items, (uint32_t)(inner / 4),
+                          (uint32_t)B, (int)clip_denoised));
   } else {
-    ddim_update_kernel<false><<<grid_for(n_elem), kThreads, 0, s>>>(x, x0, noise, out, pred_xstart, t, sqrt_recip_ac,
-                                                                    sqrt_recipm1_ac, ac, ac_prev, eta, (uint32_t)n_elem,
-                                                                    (uint32_t)inner, (uint32_t)B, clip_denoised);
+    REGEN_CUDA(launch_pdl(ddim_update_kernel<false>, dim3(grid_for(n_elem)), dim3(kThreads), 0, s, x, x0, noise, out,
+                          pred_xstart, t, sqrt_recip_ac, sqrt_recipm1_ac, ac, ac_prev, eta, (uint32_t)n_elem, (uint32_t)inner,
+                          (uint32_t)B, (int)clip_denoised));
   }
   REGEN_LAUNCH_CHECK();
   count_launch();
@@ -603,9 +669,9 @@ int regen_rot6d_to_matrix(const float* d6, float* R, int64_t n, void* stream) {
   REGEN_CHECK_ARG(d6 && R, "rot6d_to_matrix: null pointer");
   REGEN_CHECK_ARG(aligned16(d6) && aligned16(R), "rot6d_to_matrix: pointers must be 16-byte aligned");
   int64_t blocks = ceil_div(n, kRotPerBlock);
-  int64_t cap = (int64_t)kNumSMs * 8;
+  int64_t cap = (int64_t)kNumSMs * 12;   // 7.5 KB of staging per warp: 12 blocks of 4 warps per SM
   if (blocks > cap) blocks = cap;
-  rot6d_kernel<<<(int)blocks, kRotPerBlock, 0, (cudaStream_t)stream>>>(d6, R, n);
+  REGEN_CUDA(launch_pdl(rot6d_kernel, dim3((unsigned)blocks), dim3(kRotWarps * 32), 0, (cudaStream_t)stream, d6, R, n));
   REGEN_LAUNCH_CHECK();
   count_launch();
   return REGEN_OK;

@@ -727,6 +727,8 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     ptx::tmem_relinquish_2sm();
   }
   ptx::tcgen05_fence_before();
+  __syncthreads();      // CTA-level ordering of the TMEM base address (written by tcgen05.alloc) before it is read below;
+                        // the cluster barrier alone orders it too, but compute-sanitizer racecheck does not model that
   ptx::cluster_sync();  // barriers of both CTAs initialised before any remote arrive / multicast commit
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;

@@ -128,7 +128,27 @@ STGCN_CASES = {
     # single person, odd length (the stride-2 blocks round 37 -> 19 -> 10)
     "stgcn_p1_T37": dict(layout="ntu-rgb+d", in_channels=6, num_class=8, num_person=1, N=2, T=37, wseed=1, xseed=41),
 }
+# the evaluation's real shape (eval/a2m/stgcn/evaluate.py:15-20: layout 'smplx', 56 nodes, two persons x 6 rot6d features):
+# the reference reads the kinematic tree from the licensed SMPLX_NEUTRAL.npz; make_golden_stgcn.py hands it the tree below
+# through a temporary .npz instead
+STGCN_CASES["stgcn_smplx_p2"] = dict(layout="smplx", in_channels=12, num_class=26, num_person=2, N=3, T=60, wseed=2, xseed=42)
 STGCN_GRAPH_LAYOUTS = ["ntu-rgb+d", "ntu_edge", "openpose"]
+# a 55-joint kinematic tree shaped like SMPL-X's (22 body joints, jaw and two eyes on the head, 15 joints per hand in five
+# 3-joint chains on each wrist); parent of joint j
+STGCN_SMPLX_PARENTS = [-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 15, 15, 15,
+                       20, 25, 26, 20, 28, 29, 20, 31, 32, 20, 34, 35, 20, 37, 38,
+                       21, 40, 41, 21, 43, 44, 21, 46, 47, 21, 49, 50, 21, 52, 53]
+
+
+def stgcn_graph_args(c, ours):
+    """graph_args of an STGCN case: this package takes the kinematic tree of the 'smplx' layout as ``kintree``, the reference
+    reads it from a file (patched in by make_golden_stgcn.py)."""
+    import numpy as np
+    ga = {"layout": c["layout"], "strategy": "spatial"}
+    if ours and c["layout"] == "smplx":
+        ga["kintree"] = np.stack([np.array(STGCN_SMPLX_PARENTS), np.arange(55)])
+    return ga
+
 # the SMPL kinematic tree (parent of joint j), used to exercise the kintree-driven layouts without body-model files
 STGCN_SMPL_PARENTS = [-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21]
 

@@ -26,6 +26,14 @@ def main():
     torch.set_num_threads(8)
     ref_shim.install()
     from eval.a2m.recognition.models.stgcn import STGCN
+    from eval.a2m.recognition.models.stgcnutils import graph as ref_graph
+    import tempfile
+    # the 'smplx' layout reads kintree_table from SMPLX_NEUTRAL.npz (licensed, absent): point the UNMODIFIED reference at a
+    # temporary .npz that holds the synthetic SMPL-X-shaped tree of cases.STGCN_SMPLX_PARENTS
+    ktx = np.stack([np.array(cases.STGCN_SMPLX_PARENTS), np.arange(55)])
+    with tempfile.NamedTemporaryFile(suffix=".npz", delete=False) as f:
+        np.savez(f, kintree_table=ktx)
+    ref_graph.SMPLX_KINTREE_PATH = f.name
     out = {}
     for name, c in cases.STGCN_CASES.items():
         model = STGCN(in_channels=c["in_channels"], num_class=c["num_class"], num_person=c["num_person"],
@@ -80,6 +88,8 @@ def main():
     out["metrics.accuracy"] = np.float64(acc)
     out["metrics.confusion"] = conf.numpy()
     print("metrics: fid %.6f div/mm %s acc %.4f" % (out["metrics.fid"], out["metrics.div_mm"], acc))
+    out["graph.smplx.spatial.1"] = Graph(layout="smplx", strategy="spatial").A
+    os.unlink(ref_graph.SMPLX_KINTREE_PATH)
     np.savez(os.path.join(HERE, "stgcn.npz"), **out)
 
 

@@ -21,7 +21,8 @@ TOL = 1e-4   # fp32 CUDA-core arithmetic, summation order differs from torch's c
 
 def _model(c, layout, seed):
     m = STGCN(in_channels=c["in_channels"], num_class=c["num_class"], num_person=c["num_person"],
-              graph_args={"layout": layout, "strategy": "spatial"}, edge_importance_weighting=True, device="cuda")
+              graph_args=cases.stgcn_graph_args(dict(c, layout=layout), ours=True), edge_importance_weighting=True,
+              device="cuda")
     sd = stgcn_ref.make_state_dict(m.A.clone(), c["in_channels"], c["num_class"], c["num_person"], seed=seed)
     m.load_state_dict(sd, strict=True)
     return m.cuda().eval(), sd
@@ -54,6 +55,21 @@ def test_stgcn_chunking_and_odd_lengths_match_oracle(built_lib):
             wf, wy = stgcn_ref.stgcn_forward(sd, x[sel], P)
         assert (batch["features"].cpu()[sel] - wf).abs().max().item() < TOL, (P, N, T)
         assert (batch["yhat"].cpu()[sel] - wy).abs().max().item() < TOL, (P, N, T)
+
+
+def test_stgcn_full_eval_shape_matches_oracle(built_lib):
+    """The evaluation's real shape -- SMPL-X-shaped graph (56 nodes), two persons, T = 60, more samples than one chunk --
+    against the oracle on the rows around the chunk boundary."""
+    c = dict(cases.STGCN_CASES["stgcn_smplx_p2"])
+    model, sd = _model(c, c["layout"], 9)
+    N = 70
+    x = torch.randn(N, 56, 12, 60, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        batch = model({"output": x.cuda()})
+        sel = slice(28, 36)                                      # chunks hold 32 samples of two persons
+        wf, wy = stgcn_ref.stgcn_forward(sd, x[sel], 2)
+    assert (batch["features"].cpu()[sel] - wf).abs().max().item() < TOL
+    assert (batch["yhat"].cpu()[sel] - wy).abs().max().item() < TOL
 
 
 def test_stgcn_error_behaviour(built_lib):

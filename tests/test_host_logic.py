@@ -314,6 +314,11 @@ def test_stgcn_graph_adjacency_bit_exact():
     assert n == 18
     kt = np.stack([np.array(cases.STGCN_SMPL_PARENTS), np.arange(24)])
     assert np.array_equal(stgcn_graph.adjacency("smpl", "spatial", kintree=kt), g["graph.smpl.spatial.1"])
+    # the evaluation's own layout: 55 joints + the translation node, tree of cases.STGCN_SMPLX_PARENTS (the reference read it
+    # from a temporary SMPLX_NEUTRAL.npz when the golden was written)
+    ktx = np.stack([np.array(cases.STGCN_SMPLX_PARENTS), np.arange(55)])
+    Ax = stgcn_graph.adjacency("smplx", "spatial", kintree=ktx)
+    assert Ax.shape == (3, 56, 56) and np.array_equal(Ax, g["graph.smplx.spatial.1"])
     assert np.array_equal(g["stgcn_p2.A"], stgcn_graph.adjacency("ntu-rgb+d", "spatial").astype(np.float32))
     with pytest.raises(ValueError):
         stgcn_graph.adjacency("smplx", "spatial")          # needs the body model's kinematic tree

@@ -56,7 +56,7 @@ def test_kernel_arithmetic_matches_reference_golden(hostlib, name):
     c = cases.STGCN_CASES[name]
     g = np.load(os.path.join(HERE, "stgcn.npz"))
     model = STGCN(in_channels=c["in_channels"], num_class=c["num_class"], num_person=c["num_person"],
-                  graph_args={"layout": c["layout"], "strategy": "spatial"}, edge_importance_weighting=True, device="cpu")
+                  graph_args=cases.stgcn_graph_args(c, ours=True), edge_importance_weighting=True, device="cpu")
     sd = stgcn_ref.make_state_dict(model.A.clone(), c["in_channels"], c["num_class"], c["num_person"], seed=c["wseed"])
     model.load_state_dict(sd, strict=True)
     x = torch.randn(c["N"], model.A.size(1), c["in_channels"], c["T"], generator=torch.Generator().manual_seed(c["xseed"]))

@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libregen_sm100.so")
+# REGEN_LIB_PATH: A/B measurements of two builds of the library on one GPU box (bring-up only)
+LIB_PATH = os.environ.get("REGEN_LIB_PATH") or os.path.join(_HERE, "csrc", "libregen_sm100.so")
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int32

@@ -376,6 +376,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       uint32_t ra[32], rb[32];
       // ---- pass 1: v = acc + bias + residual, row statistics, v -> TMEM
       float sum = 0.f, sq = 0.f;
+      ptx::f32x2 psum = ptx::splat2(0.f), psq = ptx::splat2(0.f);   // (even, odd) column partial sums of the packed passes
       auto pass1 = [&](uint32_t (&r)[32], int sc) {
         if constexpr (R16) {
           // residual = hi + lo from the pair slot of sub-chunks (2u, 2u + 1): 32 rows x 64 bf16, 128-byte rows
@@ -385,24 +386,20 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           const uint8_t* hs = res_ring + slot * 2 * SLOT;
           const uint8_t* ls = hs + SLOT;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {  // 8 columns per 16-byte chunk of hi / lo
+          for (int c = 0; c < 4; ++c) {  // 8 columns per 16-byte chunk of hi / lo; packed fp32 pairs (even, odd column)
             const uint4 h4 = *reinterpret_cast<const uint4*>(hs + off_f32(lane, half * 4 + c));
             const uint4 l4 = *reinterpret_cast<const uint4*>(ls + off_f32(lane, half * 4 + c));
+            const float4 bA = *reinterpret_cast<const float4*>(s_bias + sc * SC + 8 * c);
+            const float4 bB = *reinterpret_cast<const float4*>(s_bias + sc * SC + 8 * c + 4);
             const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+            const ptx::f32x2 bp[4] = {ptx::pk2(bA.x, bA.y), ptx::pk2(bA.z, bA.w), ptx::pk2(bB.x, bB.y), ptx::pk2(bB.z, bB.w)};
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-              const int j = 2 * c + jj;
-              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + sc * SC + 4 * j);
-              const float r0 = __uint_as_float(hw[2 * jj] << 16) + __uint_as_float(lw[2 * jj] << 16);
-              const float r1 = __uint_as_float(hw[2 * jj] & 0xffff0000u) + __uint_as_float(lw[2 * jj] & 0xffff0000u);
-              const float r2 = __uint_as_float(hw[2 * jj + 1] << 16) + __uint_as_float(lw[2 * jj + 1] << 16);
-              const float r3 = __uint_as_float(hw[2 * jj + 1] & 0xffff0000u) + __uint_as_float(lw[2 * jj + 1] & 0xffff0000u);
-              float v0 = __uint_as_float(r[4 * j]) + b4.x + r0, v1 = __uint_as_float(r[4 * j + 1]) + b4.y + r1;
-              float v2 = __uint_as_float(r[4 * j + 2]) + b4.z + r2, v3 = __uint_as_float(r[4 * j + 3]) + b4.w + r3;
-              sum += (v0 + v1) + (v2 + v3);
-              sq = fmaf(v0, v0, sq); sq = fmaf(v1, v1, sq); sq = fmaf(v2, v2, sq); sq = fmaf(v3, v3, sq);
-              r[4 * j] = __float_as_uint(v0); r[4 * j + 1] = __float_as_uint(v1);
-              r[4 * j + 2] = __float_as_uint(v2); r[4 * j + 3] = __float_as_uint(v3);
+            for (int e = 0; e < 4; ++e) {
+              const ptx::f32x2 res = ptx::add2(ptx::bf16x2_to_f32x2(hw[e]), ptx::bf16x2_to_f32x2(lw[e]));
+              const ptx::f32x2 v = ptx::add2(ptx::add2(ptx::pk2u(r[8 * c + 2 * e], r[8 * c + 2 * e + 1]), bp[e]), res);
+              psum = ptx::add2(psum, v);
+              psq = ptx::fma2(v, v, psq);
+              ptx::upk2u(v, r[8 * c + 2 * e], r[8 * c + 2 * e + 1]);
             }
           }
           ptx::tmem_st_32x32b_x32(lane_addr + (uint32_t)(sc * SC), r);
@@ -449,6 +446,13 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       }
       ptx::tmem_st_wait();
       if (tr) REGEN_LTL(4);
+      if constexpr (R16) {
+        float a, b;
+        ptx::upk2(psum, a, b);
+        sum = a + b;
+        ptx::upk2(psq, a, b);
+        sq = a + b;
+      }
       // exchange the half-row statistics with the warp that owns the other 256 columns of the same rows
       s_stats[r_local * 4 + hf] = make_float2(sum, sq);
       named_bar_sync(1 + q, 32 * E::PARTS);
@@ -469,10 +473,31 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       if (CHAIN) {
         // ---- pass 2: y = LN1(v) + c, statistics of y, y -> TMEM
         float sum2 = 0.f, sq2 = 0.f;
+        ptx::f32x2 sum2b = ptx::splat2(0.f), sq2b = ptx::splat2(0.f);
         auto pass2 = [&](uint32_t (&r)[32], int sc) {
           constexpr int RING = RC;
           const int slot = sc % RING;
           ptx::mbar_wait(&rbar[4 + slot], (uint32_t)(it * ((E::NSC - slot + RING - 1) / RING) + sc / RING) & 1);
+          if constexpr (R16) {
+            const ptx::f32x2 rs2 = ptx::splat2(rstd), nm2 = ptx::splat2(nmr);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 g4 = *reinterpret_cast<const float4*>(s_g1 + sc * SC + 4 * j);
+              const float4 b4 = *reinterpret_cast<const float4*>(s_b1 + sc * SC + 4 * j);
+              const float4 cj = *reinterpret_cast<const float4*>(c_ring + slot * SLOT + off_f32(lane, j));
+              const ptx::f32x2 gp[2] = {ptx::pk2(g4.x, g4.y), ptx::pk2(g4.z, g4.w)};
+              const ptx::f32x2 bp[2] = {ptx::pk2(b4.x, b4.y), ptx::pk2(b4.z, b4.w)};
+              const ptx::f32x2 cp[2] = {ptx::pk2(cj.x, cj.y), ptx::pk2(cj.z, cj.w)};
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const ptx::f32x2 v = ptx::pk2u(r[4 * j + 2 * e], r[4 * j + 2 * e + 1]);
+                const ptx::f32x2 y = ptx::add2(ptx::fma2(ptx::fma2(v, rs2, nm2), gp[e], bp[e]), cp[e]);
+                sum2b = ptx::add2(sum2b, y);
+                sq2b = ptx::fma2(y, y, sq2b);
+                ptx::upk2u(y, r[4 * j + 2 * e], r[4 * j + 2 * e + 1]);
+              }
+            }
+          } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 g4 = *reinterpret_cast<const float4*>(s_g1 + sc * SC + 4 * j);
@@ -486,6 +511,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             sq2 = fmaf(y0, y0, sq2); sq2 = fmaf(y1, y1, sq2); sq2 = fmaf(y2, y2, sq2); sq2 = fmaf(y3, y3, sq2);
             r[4 * j] = __float_as_uint(y0); r[4 * j + 1] = __float_as_uint(y1);
             r[4 * j + 2] = __float_as_uint(y2); r[4 * j + 3] = __float_as_uint(y3);
+          }
           }
           ptx::tmem_st_32x32b_x32(lane_addr + (uint32_t)(sc * SC), r);
           __syncwarp();  // every lane has read the slot
@@ -507,6 +533,13 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         }
         ptx::tmem_st_wait();
         if (tr) REGEN_LTL(6);
+        if constexpr (R16) {
+          float a, b;
+          ptx::upk2(sum2b, a, b);
+          sum2 = a + b;
+          ptx::upk2(sq2b, a, b);
+          sq2 = a + b;
+        }
         s_stats[512 + r_local * 4 + hf] = make_float2(sum2, sq2);
         named_bar_sync(1 + q, 32 * E::PARTS);
         if (tr) REGEN_LTL(7);
@@ -550,6 +583,31 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         }
         __syncwarp();
         if (tr && sc == 2) REGEN_LTL(12);
+        if constexpr (R16) {
+          const ptx::f32x2 rs2 = ptx::splat2(rstd), nm2 = ptx::splat2(nmr);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {  // 8 columns -> one bf16 hi chunk, one bf16 lo chunk; packed fp32 pairs
+            uint32_t hw[4], lw[4];
+            const float4 gA = *reinterpret_cast<const float4*>(gg + sc * SC + 8 * c);
+            const float4 gB = *reinterpret_cast<const float4*>(gg + sc * SC + 8 * c + 4);
+            const float4 bA = *reinterpret_cast<const float4*>(bb + sc * SC + 8 * c);
+            const float4 bB = *reinterpret_cast<const float4*>(bb + sc * SC + 8 * c + 4);
+            const ptx::f32x2 gp[4] = {ptx::pk2(gA.x, gA.y), ptx::pk2(gA.z, gA.w), ptx::pk2(gB.x, gB.y), ptx::pk2(gB.z, gB.w)};
+            const ptx::f32x2 bp[4] = {ptx::pk2(bA.x, bA.y), ptx::pk2(bA.z, bA.w), ptx::pk2(bB.x, bB.y), ptx::pk2(bB.z, bB.w)};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const ptx::f32x2 z = ptx::fma2(ptx::fma2(ptx::pk2u(r[8 * c + 2 * e], r[8 * c + 2 * e + 1]), rs2, nm2), gp[e], bp[e]);
+              float z0, z1, l0, l1;
+              ptx::upk2(z, z0, z1);
+              hw[e] = gemm::pack_bf16x2(z0, z1);
+              ptx::upk2(ptx::sub2(z, ptx::bf16x2_to_f32x2(hw[e])), l0, l1);   // float(hi) = the bf16 bits in the upper half
+              lw[e] = gemm::pack_bf16x2(l0, l1);
+            }
+            // 16-byte chunk (half * 4 + c) of this row's 128-byte bf16 row (same SWIZZLE_128B pattern as the fp32 tile)
+            *reinterpret_cast<uint4*>(hb + off_f32(lane, half * 4 + c)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(lb + off_f32(lane, half * 4 + c)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        } else {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {  // 8 columns = two fp32 chunks, one bf16 hi chunk, one bf16 lo chunk
           uint32_t hw[4], lw[4];
@@ -572,6 +630,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           // 16-byte chunk (half * 4 + c) of this row's 128-byte bf16 row (same SWIZZLE_128B pattern as the fp32 tile)
           *reinterpret_cast<uint4*>(hb + off_f32(lane, half * 4 + c)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
           *reinterpret_cast<uint4*>(lb + off_f32(lane, half * 4 + c)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
         }
         if (tr && sc == 2) REGEN_LTL(13);
         if constexpr (R16) {

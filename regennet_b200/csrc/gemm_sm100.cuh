@@ -89,6 +89,28 @@ __device__ __forceinline__ float gelu_erf(float v) {
   return 0.5f * v + 0.5f * fabsf(v) * e;             // v/2 (1 + sign(v) e)
 }
 
+// The same GELU on a packed (even, odd column) fp32 pair: FFMA2 / FMUL2 halve the issue slots of the polynomial, the two
+// MUFU (reciprocal, exp2) stay scalar.  Bit-for-bit the scalar formula per half (each packed op is an IEEE fp32 op).
+__device__ __forceinline__ ptx::f32x2 gelu_erf2(ptx::f32x2 v) {
+  uint32_t v0, v1;
+  ptx::upk2u(v, v0, v1);
+  const ptx::f32x2 av = ptx::pk2u(v0 & 0x7fffffffu, v1 & 0x7fffffffu);                       // |v|
+  const ptx::f32x2 z = ptx::mul2(av, ptx::splat2(0.70710678118654752440f));
+  float d0, d1;
+  ptx::upk2(ptx::fma2(ptx::splat2(0.3275911f), z, ptx::splat2(1.0f)), d0, d1);
+  const ptx::f32x2 t = ptx::pk2(__fdividef(1.0f, d0), __fdividef(1.0f, d1));
+  ptx::f32x2 poly = ptx::fma2(ptx::splat2(1.061405429f), t, ptx::splat2(-1.453152027f));
+  poly = ptx::fma2(poly, t, ptx::splat2(1.421413741f));
+  poly = ptx::fma2(poly, t, ptx::splat2(-0.284496736f));
+  poly = ptx::fma2(poly, t, ptx::splat2(0.254829592f));
+  float q0, q1;
+  ptx::upk2(ptx::mul2(z, z), q0, q1);
+  const ptx::f32x2 nex = ptx::pk2(-__expf(-q0), -__expf(-q1));
+  const ptx::f32x2 e = ptx::fma2(ptx::mul2(poly, t), nex, ptx::splat2(1.0f));                // erf(|v| / sqrt 2)
+  const ptx::f32x2 half = ptx::splat2(0.5f);
+  return ptx::fma2(ptx::mul2(half, av), e, ptx::mul2(half, v));                              // v/2 (1 + sign(v) e)
+}
+
 // Epilogue of a 32-row x ncols slice of an accumulator tile, executed by one warp (lane = TMEM lane = output row).
 //   acc   TMEM address of (first lane of this warp's quarter, first column of the slice)
 //   row0  global row of lane 0, n0 global column of the slice's first column
@@ -409,14 +431,10 @@ __device__ __forceinline__ void epilogue_pair64(const Params& p, const CUtensorM
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
       const int src = 16 * g + (j >> 1);
-      float v0 = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, b2.x, src);
-      float v1 = __uint_as_float(r[j + 1]) + __shfl_sync(0xffffffffu, b2.y, src);
-      if (p.gelu) {
-        v0 = gelu_erf(v0);
-        v1 = gelu_erf(v1);
-      }
-      r[j] = __float_as_uint(v0);
-      r[j + 1] = __float_as_uint(v1);
+      ptx::f32x2 v = ptx::add2(ptx::pk2u(r[j], r[j + 1]),
+                               ptx::pk2(__shfl_sync(0xffffffffu, b2.x, src), __shfl_sync(0xffffffffu, b2.y, src)));
+      if (p.gelu) v = gelu_erf2(v);
+      ptx::upk2u(v, r[j], r[j + 1]);
     }
     uint32_t lw[16];
     if (issuer) ptx::bulk_wait_read<0>();  // the previous store from the shared tile has been read
@@ -428,7 +446,9 @@ __device__ __forceinline__ void epilogue_pair64(const Params& p, const CUtensorM
       for (int k = 0; k < 4; ++k) {
         const float a = __uint_as_float(r[8 * c + 2 * k]), b = __uint_as_float(r[8 * c + 2 * k + 1]);
         hw[k] = pack_bf16x2(a, b);
-        lw[4 * c + k] = pack_bf16x2(a - __uint_as_float(hw[k] << 16), b - __uint_as_float(hw[k] & 0xffff0000u));
+        float l0, l1;   // float(hi) is the bf16 bit pattern in the upper half of the word
+        ptx::upk2(ptx::sub2(ptx::pk2(a, b), ptx::bf16x2_to_f32x2(hw[k])), l0, l1);
+        lw[4 * c + k] = pack_bf16x2(l0, l1);
       }
       *reinterpret_cast<uint4*>(stg + stg_off_128(lane, 4 * sub + c)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     }

@@ -511,6 +511,22 @@ def run_ours(args):
             coll.append(timing["collective_events"][0].elapsed_time(timing["collective_events"][1]))
     e2e_s = sorted(e2e_runs)[1]
     coll_ms = sorted(coll)[len(coll) // 2] if coll else 0.0
+    # the same collective once more with all ranks aligned: the in-loop figure above includes waiting for the slowest rank
+    coll_alone_ms = 0.0
+    if world > 1:
+        loc = timing["local"].contiguous()
+        buf = torch.empty((world * B, J, F, T), device=dev)
+        alone = []
+        for _ in range(5):
+            torch.cuda.synchronize()
+            dist.barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            dist.all_gather_into_tensor(buf, loc)
+            a1.record()
+            torch.cuda.synchronize()
+            alone.append(a0.elapsed_time(a1))
+        coll_alone_ms = sorted(alone)[2]
     h2d = B * I * T * 4 / KE                       # this rank's shard of the conditioning, per step
     d2h = out_host.numel() * 4 / KE                # rank 0: the gathered batch
     # the gathered batch is in rank order and identical on every rank
@@ -520,14 +536,14 @@ def run_ours(args):
     chk_lo, chk_hi = chk.clone(), chk.clone()
 
     # ------------------------------------------------------------------ reduce over ranks (max time)
-    times = torch.tensor([ms, e2e_s * 1000.0, sus_ms / sus_K, coll_ms], device=dev, dtype=torch.float64)
+    times = torch.tensor([ms, e2e_s * 1000.0, sus_ms / sus_K, coll_ms, coll_alone_ms], device=dev, dtype=torch.float64)
     ok_t = torch.tensor([1.0 if gather_ok else 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
         dist.all_reduce(chk_lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(chk_hi, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max, sus_ms_step, coll_ms_max = times.tolist()
+    ms_max, e2e_ms_max, sus_ms_step, coll_ms_max, coll_alone_max = times.tolist()
     gather_ok = bool(ok_t.item() == 1.0) and chk_lo.item() == chk_hi.item()
 
     if rank == 0:
@@ -577,7 +593,10 @@ def run_ours(args):
                             "%d) with the conditioning in pinned host memory (each rank copies its shard), the all-gather of "
                             "the generated batch and the copy of the result to pinned host memory inside the timed region; "
                             "wall clock incl. Python, max over ranks of the median of 3 loops" % (world * B),
-                    "steps": KE, "collective_ms": coll_ms_max,
+                    "steps": KE, "collective_ms": coll_ms_max, "collective_alone_ms": coll_alone_max,
+                    "collective_note": "collective_ms: CUDA events around the all-gather inside the timed loop (includes waiting "
+                                       "for the slowest rank's 1000-step loop); collective_alone_ms: the same all-gather re-run "
+                                       "with the ranks aligned by a barrier (median of 5)",
                     "collective": "all_gather_into_tensor of [%d,%d,%d,%d] fp32 (%.1f MB total), CUDA events"
                                   % (world * B, J, F, T, world * B * I * T * 4 / 1e6) if world > 1 else "none (one rank)",
                     "gather_check": "rank order and cross-rank checksum ok" if gather_ok else "FAILED",

@@ -69,6 +69,9 @@ struct Params {
   unsigned long long* timeline;  // bring-up instrumentation (null in production): CTA 0 stamps clock64() at events
   unsigned long long* steplog;   // whole-step timeline (ptx::steplog_begin / steplog_end), null in production
   int steplog_slot, steplog_cta;  // steplog_cta: word offset of the per-CTA exit-time table (0 = off)
+  // L2 eviction-priority hints (ptx::kL2Evict*, 0 = none): q | k | v tiles are dead once read, the output is the next
+  // kernel's A operand
+  unsigned long long pol_load, pol_store;
 };
 
 #define REGEN_ATL(k)                                                                      \
@@ -150,10 +153,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       // ------------------------------------------------------------------ control thread: TMA + MMA issue
       auto load_operand = [&](uint8_t* dst, uint64_t* bar, int col0, int t0) {
         ptx::mbar_expect_tx(bar, C::OPERAND);
-        ptx::tma_load_3d(dst, &tm_hi, bar, col0, b, t0);
-        ptx::tma_load_3d(dst + C::TILE, &tm_hi, bar, col0 + 64, b, t0);
-        ptx::tma_load_3d(dst + 2 * C::TILE, &tm_lo, bar, col0, b, t0);
-        ptx::tma_load_3d(dst + 3 * C::TILE, &tm_lo, bar, col0 + 64, b, t0);
+        ptx::tma_load_3d(dst, &tm_hi, bar, col0, b, t0, p.pol_load);
+        ptx::tma_load_3d(dst + C::TILE, &tm_hi, bar, col0 + 64, b, t0, p.pol_load);
+        ptx::tma_load_3d(dst + 2 * C::TILE, &tm_lo, bar, col0, b, t0, p.pol_load);
+        ptx::tma_load_3d(dst + 3 * C::TILE, &tm_lo, bar, col0 + 64, b, t0, p.pol_load);
       };
       // Buffer rotation (TB = 128, two key chunks): K_0 -> sK and K_1 -> sV are both fetched at the start; V_0 takes sK as
       // soon as S_0 is complete and V_1 takes sV as soon as S_1 is, i.e. both V loads run behind the softmax passes and
@@ -385,8 +388,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     if (lane == 0 && q0 + q * 32 < p.T) {
 #pragma unroll
       for (int tile = 0; tile < DW / 64; ++tile) {
-        ptx::tma_store_3d(&tm_ohi, st + tile * 8192, h * HD + half * DW + tile * 64, b, q0 + q * 32);
-        ptx::tma_store_3d(&tm_olo, st + tile * 8192 + 4096, h * HD + half * DW + tile * 64, b, q0 + q * 32);
+        ptx::tma_store_3d(&tm_ohi, st + tile * 8192, h * HD + half * DW + tile * 64, b, q0 + q * 32, p.pol_store);
+        ptx::tma_store_3d(&tm_olo, st + tile * 8192 + 4096, h * HD + half * DW + tile * 64, b, q0 + q * 32, p.pol_store);
       }
       ptx::bulk_commit();
       // the staging tiles must have been read before the CTA exits; the kernel boundary orders the global writes
@@ -487,10 +490,10 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
       // ------------------------------------------------------------------ control thread: TMA + MMA issue
       auto load_operand = [&](uint8_t* dst, uint64_t* bar, int col0, int t0) {
         ptx::mbar_expect_tx(bar, C::OPERAND);
-        ptx::tma_load_3d(dst, &tm_hi, bar, col0, b, t0);
-        ptx::tma_load_3d(dst + C::TILE, &tm_hi, bar, col0 + 64, b, t0);
-        ptx::tma_load_3d(dst + 2 * C::TILE, &tm_lo, bar, col0, b, t0);
-        ptx::tma_load_3d(dst + 3 * C::TILE, &tm_lo, bar, col0 + 64, b, t0);
+        ptx::tma_load_3d(dst, &tm_hi, bar, col0, b, t0, p.pol_load);
+        ptx::tma_load_3d(dst + C::TILE, &tm_hi, bar, col0 + 64, b, t0, p.pol_load);
+        ptx::tma_load_3d(dst + 2 * C::TILE, &tm_lo, bar, col0, b, t0, p.pol_load);
+        ptx::tma_load_3d(dst + 3 * C::TILE, &tm_lo, bar, col0 + 64, b, t0, p.pol_load);
       };
       // operand j of the sequence K_0..K_{n-1}, V_0..V_{n-1} -> buffer j & 1
       auto load_op = [&](int j) {
@@ -655,8 +658,8 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        ptx::tma_store_3d(&tm_ohi, st_hi, h * HD + half * 64, b, q0 + q * 32);
-        ptx::tma_store_3d(&tm_olo, st_lo, h * HD + half * 64, b, q0 + q * 32);
+        ptx::tma_store_3d(&tm_ohi, st_hi, h * HD + half * 64, b, q0 + q * 32, p.pol_store);
+        ptx::tma_store_3d(&tm_olo, st_lo, h * HD + half * 64, b, q0 + q * 32, p.pol_store);
         ptx::bulk_commit();
         ptx::bulk_wait<0>();
       }

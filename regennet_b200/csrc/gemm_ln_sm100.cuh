@@ -72,6 +72,9 @@ struct Params {
   unsigned long long* timeline;  // bring-up instrumentation (null in production), see tools/ln_timeline.py
   unsigned long long* steplog;   // whole-step timeline (ptx::steplog_begin / steplog_end), null in production
   int steplog_slot, steplog_cta;  // steplog_cta: word offset of the per-CTA exit-time table (0 = off)
+  // L2 eviction-priority hints (ptx::kL2Evict*, 0 = none): A tiles (read once: attention output / FFN activations), W tiles
+  // (re-read by every row block), bf16 (hi, lo) outputs (operands of the next kernel)
+  unsigned long long pol_a, pol_w, pol_store;
 };
 
 #define REGEN_LTL(k)                                                                                   \
@@ -168,13 +171,13 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
           if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * (SPLIT ? STAGE_BYTES : STAGE_BYTES / 2));
-          ptx::tma_load_2d_2sm(st, &tm_a_hi, &full_bar[stage], kb * BK, m0);
-          ptx::tma_load_2d_2sm(st + 2 * 16384, &tm_w_hi, &full_bar[stage], kb * BK, (int)rank * 128);
-          ptx::tma_load_2d_2sm(st + 3 * 16384, &tm_w_hi, &full_bar[stage], kb * BK, 256 + (int)rank * 128);
+          ptx::tma_load_2d_2sm(st, &tm_a_hi, &full_bar[stage], kb * BK, m0, p.pol_a);
+          ptx::tma_load_2d_2sm(st + 2 * 16384, &tm_w_hi, &full_bar[stage], kb * BK, (int)rank * 128, p.pol_w);
+          ptx::tma_load_2d_2sm(st + 3 * 16384, &tm_w_hi, &full_bar[stage], kb * BK, 256 + (int)rank * 128, p.pol_w);
           if (SPLIT) {
-            ptx::tma_load_2d_2sm(st + 16384, &tm_a_lo, &full_bar[stage], kb * BK, m0);
-            ptx::tma_load_2d_2sm(st + 4 * 16384, &tm_w_lo, &full_bar[stage], kb * BK, (int)rank * 128);
-            ptx::tma_load_2d_2sm(st + 5 * 16384, &tm_w_lo, &full_bar[stage], kb * BK, 256 + (int)rank * 128);
+            ptx::tma_load_2d_2sm(st + 16384, &tm_a_lo, &full_bar[stage], kb * BK, m0, p.pol_a);
+            ptx::tma_load_2d_2sm(st + 4 * 16384, &tm_w_lo, &full_bar[stage], kb * BK, (int)rank * 128, p.pol_w);
+            ptx::tma_load_2d_2sm(st + 5 * 16384, &tm_w_lo, &full_bar[stage], kb * BK, 256 + (int)rank * 128, p.pol_w);
           }
           // The epilogue's first pass reads this CTA's 128 x 512 fp32 residual tile in one burst; by then h has been
           // evicted from L2 by the operand stream (ncu: the whole tile came from DRAM, pass 1 was HBM-bound).  Pull it
@@ -328,8 +331,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             }
             if (p.store_f32) ptx::tma_store_2d(&tm_c, fb, n_base + SC * sc, row0);
             if (half) {
-              ptx::tma_store_2d(&tm_ohi, hb, n_base + 2 * SC * u, row0);
-              ptx::tma_store_2d(&tm_olo, lb, n_base + 2 * SC * u, row0);
+              ptx::tma_store_2d(&tm_ohi, hb, n_base + 2 * SC * u, row0, p.pol_store);
+              ptx::tma_store_2d(&tm_olo, lb, n_base + 2 * SC * u, row0, p.pol_store);
             }
             ptx::bulk_commit();
           }
@@ -638,8 +641,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              ptx::tma_store_2d(&tm_ohi, hb, n_base + 2 * SC * u, row0);
-              ptx::tma_store_2d(&tm_olo, lb, n_base + 2 * SC * u, row0);
+              ptx::tma_store_2d(&tm_ohi, hb, n_base + 2 * SC * u, row0, p.pol_store);
+              ptx::tma_store_2d(&tm_olo, lb, n_base + 2 * SC * u, row0, p.pol_store);
               ptx::bulk_commit();
             }
           }
@@ -650,8 +653,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         if (lane == 0) {
           ptx::tma_store_2d(&tm_res, fb, n_base + SC * sc, row0);
           if (half) {
-            ptx::tma_store_2d(&tm_ohi, hb, n_base + 2 * SC * u, row0);
-            ptx::tma_store_2d(&tm_olo, lb, n_base + 2 * SC * u, row0);
+            ptx::tma_store_2d(&tm_ohi, hb, n_base + 2 * SC * u, row0, p.pol_store);
+            ptx::tma_store_2d(&tm_olo, lb, n_base + 2 * SC * u, row0, p.pol_store);
           }
           ptx::bulk_commit();
         }

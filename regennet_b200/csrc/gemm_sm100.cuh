@@ -67,6 +67,9 @@ struct Params {
   unsigned long long* timeline;
   unsigned long long* steplog;  // whole-step timeline (ptx::steplog_begin / steplog_end), null in production
   int steplog_slot, steplog_cta;  // steplog_cta: word offset of the per-CTA exit-time table (0 = off)
+  // L2 eviction-priority hints of the TMA traffic (ptx::kL2Evict*, 0 = none): W tiles (re-read by every row block) and
+  // bf16 (hi, lo) outputs (the next kernel's operands)
+  unsigned long long pol_w, pol_store;
 };
 
 #define REGEN_TL(slot)                                                        \
@@ -266,8 +269,8 @@ __device__ __forceinline__ void epilogue_slice(const Params& p, const CUtensorMa
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            ptx::tma_store_2d(tm_ohi, bh, n0 + c0, row0);
-            ptx::tma_store_2d(tm_olo, bl, n0 + c0, row0);
+            ptx::tma_store_2d(tm_ohi, bh, n0 + c0, row0, p.pol_store);
+            ptx::tma_store_2d(tm_olo, bl, n0 + c0, row0, p.pol_store);
             ptx::bulk_commit();
           }
         } else {
@@ -369,7 +372,7 @@ __device__ __forceinline__ void epilogue_slice32(const Params& p, const CUtensor
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        ptx::tma_store_2d(tm_ohi, stg, n0 + c0, row0);
+        ptx::tma_store_2d(tm_ohi, stg, n0 + c0, row0, p.pol_store);
         ptx::bulk_commit();
         ptx::bulk_wait_read<0>();
       }
@@ -380,7 +383,7 @@ __device__ __forceinline__ void epilogue_slice32(const Params& p, const CUtensor
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        ptx::tma_store_2d(tm_olo, stg, n0 + c0, row0);
+        ptx::tma_store_2d(tm_olo, stg, n0 + c0, row0, p.pol_store);
         ptx::bulk_commit();
       }
     } else {
@@ -455,7 +458,7 @@ __device__ __forceinline__ void epilogue_pair64(const Params& p, const CUtensorM
     ptx::fence_proxy_async_smem();
     pair_sync();  // both halves of the hi tile are staged
     if (issuer) {
-      ptx::tma_store_2d(tm_ohi, stg, n0 + 64 * g, row0);
+      ptx::tma_store_2d(tm_ohi, stg, n0 + 64 * g, row0, p.pol_store);
       ptx::bulk_commit();
       ptx::bulk_wait_read<0>();
     }
@@ -467,7 +470,7 @@ __device__ __forceinline__ void epilogue_pair64(const Params& p, const CUtensorM
     ptx::fence_proxy_async_smem();
     pair_sync();
     if (issuer) {
-      ptx::tma_store_2d(tm_olo, stg, n0 + 64 * g, row0);
+      ptx::tma_store_2d(tm_olo, stg, n0 + 64 * g, row0, p.pol_store);
       ptx::bulk_commit();
     }
   }
@@ -779,10 +782,10 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           uint8_t* st = smem + stage * C::STAGE_BYTES;
           if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * stage_tx);
           ptx::tma_load_2d_2sm(st, &tm_a_hi, &full_bar[stage], kb * BK, m0);
-          ptx::tma_load_2d_2sm(st + C::A_BYTES, wmap_hi, &full_bar[stage], kb * BK, nw);
+          ptx::tma_load_2d_2sm(st + C::A_BYTES, wmap_hi, &full_bar[stage], kb * BK, nw, p.pol_w);
           if (SPLIT) {
             ptx::tma_load_2d_2sm(st + C::A_BYTES + C::W_BYTES, &tm_a_lo, &full_bar[stage], kb * BK, m0);
-            ptx::tma_load_2d_2sm(st + 2 * C::A_BYTES + C::W_BYTES, wmap_lo, &full_bar[stage], kb * BK, nw);
+            ptx::tma_load_2d_2sm(st + 2 * C::A_BYTES + C::W_BYTES, wmap_lo, &full_bar[stage], kb * BK, nw, p.pol_w);
           }
           if (++stage == C::STAGES) {
             stage = 0;

@@ -84,6 +84,11 @@ struct regen_handle {
   float* cyc = nullptr;              // [L][max_batch + 32][512] row-cyclic cross-attention constants (per denoise)
   CUtensorMap tm_cyc[REGEN_MAX_LAYERS];
   bool simt_attention = false;       // REGEN_DEBUG_SIMT_ATTENTION=1: fp32 CUDA-core attention for A/B debugging
+  // L2 eviction-priority hints on the TMA traffic of the layer pipeline (REGEN_L2_HINTS bitmask, A/B switch):
+  //   1 attention reads q | k | v evict_first   2 bf16 (hi, lo) outputs of every kernel evict_last
+  //   4 weight tiles evict_last                  8 fused GEMM+LN A tiles (attention output / FFN activations) evict_first
+  int l2_hints = 0;
+  unsigned long long pol(int bit, unsigned long long policy) const { return (l2_hints & bit) ? policy : 0ull; }
   float *h = nullptr, *qkv = nullptr, *tmp = nullptr, *x0e = nullptr, *condbias = nullptr, *cmo_tbi = nullptr,
         *ccond = nullptr, *scratch = nullptr;
 
@@ -175,6 +180,8 @@ int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, gemm::Params
   gemm::OutMaps om;
   p.tma_store = 0;
   p.exit_wait_full = h->exit_wait_full ? 1 : 0;
+  p.pol_w = h->pol(4, ptx::kL2EvictLast);
+  p.pol_store = h->pol(2, ptx::kL2EvictLast);
   if (h->tma_store && (p.N & 3) == 0 && (!p.out_f32 || o32) && (!p.out_hi || osplit)) {
     p.tma_store = 1;
     // the 16-epilogue-warp pair kernel (no residual, one kind of output) stores 32-column boxes, everything else 16
@@ -275,6 +282,8 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
     h->nob16 = (e4d && e4d[0] == '3') ? 3 : 2;
     const char* e4c = getenv("REGEN_DEBUG_NO_STORE64");
     h->store64 = !(e4c && e4c[0] == '1');
+    const char* e5 = getenv("REGEN_L2_HINTS");
+    if (e5) h->l2_hints = atoi(e5);
   }
   const size_t Mx = (size_t)h->Mmax;
   int rc = REGEN_OK;
@@ -593,6 +602,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       memset(&q, 0, sizeof(q));
       q.M = Mf; q.K = h->Kin; q.Beff = Beff; q.ln_eps = layers::LN_EPS;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
+      q.pol_a = h->pol(8, ptx::kL2EvictFirst); q.pol_w = h->pol(4, ptx::kL2EvictLast); q.pol_store = h->pol(2, ptx::kL2EvictLast);
       q.store_f32 = h->res16 ? 0 : 1;  // the fused consumers rebuild the residual from (hi, lo)
       q.exit_wait_full = h->exit_wait_full ? 1 : 0;
       if (h->steplog && h->steplog_slot < h->steplog_cap) {
@@ -639,6 +649,8 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
         ap.out_hi = h->att.hi; ap.out_lo = h->att.lo; ap.T = S; ap.Beff = Beff; ap.causal = offline ? 0 : 1; ap.dbg = h->exit_wait_full ? 4 : 0;
         ap.timeline = nullptr;
         ap.steplog = nullptr; ap.steplog_slot = 0; ap.steplog_cta = 0;
+        ap.pol_load = h->pol(1, ptx::kL2EvictFirst);
+        ap.pol_store = h->pol(2, ptx::kL2EvictLast);
         if (h->steplog && h->steplog_slot < h->steplog_cap) { ap.steplog = h->steplog; ap.steplog_slot = h->steplog_slot++; }
         cudaError_t e = S <= 64 ? attn::launch<64>(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s)
                         : h->attn_mc
@@ -657,6 +669,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       q.M = M; q.K = D; q.Beff = Beff; q.bias = ld.bo; q.g1 = ld.n1w; q.b1 = ld.n1b; q.g2 = nullptr; q.b2 = nullptr;
       q.ln_eps = layers::LN_EPS; q.store_f32 = 0; q.nob16 = h->nob16; q.exit_wait_full = h->exit_wait_full ? 1 : 0;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
+      q.pol_a = h->pol(8, ptx::kL2EvictFirst); q.pol_w = h->pol(4, ptx::kL2EvictLast); q.pol_store = h->pol(2, ptx::kL2EvictLast);
       q.timeline = g_test_timeline;
       q.steplog = nullptr; q.steplog_slot = 0; q.steplog_cta = 0;
       if (h->steplog && h->steplog_slot < h->steplog_cap) {
@@ -678,6 +691,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       q.M = M; q.K = D; q.Beff = Beff; q.bias = ld.bo; q.g1 = ld.n1w; q.b1 = ld.n1b; q.g2 = ld.n2w; q.b2 = ld.n2b;
       q.ln_eps = layers::LN_EPS; q.store_f32 = 0; q.nob16 = h->nob16; q.exit_wait_full = h->exit_wait_full ? 1 : 0;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
+      q.pol_a = h->pol(8, ptx::kL2EvictFirst); q.pol_w = h->pol(4, ptx::kL2EvictLast); q.pol_store = h->pol(2, ptx::kL2EvictLast);
       q.timeline = g_test_timeline;
       q.steplog = nullptr; q.steplog_slot = 0; q.steplog_cta = 0;
       if (h->steplog && h->steplog_slot < h->steplog_cap) {
@@ -736,6 +750,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       q.g2 = nullptr; q.b2 = nullptr;
       q.ln_eps = layers::LN_EPS; q.store_f32 = 0; q.nob16 = h->nob16; q.exit_wait_full = h->exit_wait_full ? 1 : 0;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
+      q.pol_a = h->pol(8, ptx::kL2EvictFirst); q.pol_w = h->pol(4, ptx::kL2EvictLast); q.pol_store = h->pol(2, ptx::kL2EvictLast);
       q.timeline = g_test_timeline;
       q.steplog = nullptr; q.steplog_slot = 0; q.steplog_cta = 0;
       if (h->steplog && h->steplog_slot < h->steplog_cap) {
@@ -914,6 +929,7 @@ int regen_test_attention(const float* qkv, float* out, int32_t B, int32_t T, int
     ap.out_hi = oh; ap.out_lo = ol; ap.T = T; ap.Beff = B; ap.causal = (dbg & 2) ? 0 : 1; ap.dbg = dbg & 1;
     ap.timeline = g_test_timeline;
     ap.steplog = nullptr; ap.steplog_slot = 0; ap.steplog_cta = 0;
+    ap.pol_load = 0; ap.pol_store = 0;
     cudaError_t e = T <= 64 ? attn::launch<64>(th, tl, toh, tol, ap, s)
                     : mc    ? attn::launch_mc(th, tl, toh, tol, ap, s)
                             : attn::launch<128>(th, tl, toh, tol, ap, s);

@@ -88,8 +88,6 @@ int regen_ddim_update(const float* x, const float* x0, const float* noise, float
 int regen_cfg_combine(const float* cond, const float* uncond, const float* scale, float* out,
                       int64_t n_elem, int64_t inner, int32_t B, void* stream);
 
-/* rot6d -> rotation matrix (Gram-Schmidt).  Replaces utils/rotation_conversions.py:513-534.
- * d6 [n,6] contiguous -> R [n,3,3] contiguous, rows (b1,b2,b3).                         */
 /* Inpainting blend of the model output (motion editing, sample/edit.py:75-90).  Replaces
  * diffusion/gaussian_diffusion.py:319-323:  x0 = x0 * ~mask + motion * mask, in place, torch's operation order.
  * mask01 holds 0.0f / 1.0f; all three arrays share one memory layout (the sampler uses [T,B,I]). */
@@ -110,6 +108,9 @@ int regen_plms_finish(const float* x, const float* eps_prime, const float* pred,
                       const float* sqrt_recip_ac, const float* sqrt_recipm1_ac, const float* ac_prev, int64_t n_elem,
                       int64_t inner, int32_t B, int32_t n_table, int32_t mode, void* stream);
 
+/* rot6d -> rotation matrix (Gram-Schmidt).  Replaces utils/rotation_conversions.py:513-534
+ * (call sites model/rotation2xyz.py:56, 202, 270):
+ * d6 [n,6] contiguous -> R [n,3,3] contiguous, rows (b1,b2,b3); 60 bytes of HBM traffic per rotation. */
 int regen_rot6d_to_matrix(const float* d6, float* R, int64_t n, void* stream);
 
 /* Post-sampling tail.  Temporal Gaussian smoothing = scipy.ndimage.gaussian_filter1d(x, sigma,

@@ -70,6 +70,9 @@ struct Params {
   // L2 eviction-priority hints of the TMA traffic (ptx::kL2Evict*, 0 = none): W tiles (re-read by every row block) and
   // bf16 (hi, lo) outputs (the next kernel's operands)
   unsigned long long pol_w, pol_store;
+  int a_rows;               // single-CTA kernel: rows of the A box the tm_a_* maps load (0 = 128).  With at most 64 token rows
+                            // (one sample of T <= 64 frames) the 64-row box halves the A bytes per k-block; rows 64..127 of the
+                            // staged tile are then never written, and the accumulator rows they feed are never read
 };
 
 #define REGEN_TL(slot)                                                        \
@@ -544,7 +547,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
-          ptx::mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          ptx::mbar_expect_tx(&full_bar[stage],
+                              (SPLIT ? 2u : 1u) * (uint32_t)((p.a_rows ? p.a_rows : BM) * BK * 2 + C::W_BYTES));
           ptx::tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * BK, m0);
           ptx::tma_load_2d(st + C::A_BYTES, &tm_w_hi, &full_bar[stage], kb * BK, n0);
           if (SPLIT) {

@@ -27,6 +27,7 @@ struct SplitBuf {  // bf16 (hi, lo) operand pair + its TMA maps
   CUtensorMap st32_hi, st32_lo;  // same with box 32 x 32 (16-warp GEMM epilogue)
   CUtensorMap st64_hi, st64_lo;  // same with box 32 x 64, 128-byte rows (fused GEMM+LayerNorm epilogue)
   size_t cols = 0;
+  bool has64 = false;            // tm_hi3 / tm_lo3 (64-row boxes) are valid
 };
 
 struct LayerDev {
@@ -152,6 +153,7 @@ int alloc_split(regen_handle* h, SplitBuf* s, size_t rows, size_t cols, uint32_t
   TRY(make_tmap_bf16_2d(&s->tm_hi4, s->hi, rows, cols, cols, 32));
   TRY(make_tmap_bf16_2d(&s->tm_lo4, s->lo, rows, cols, cols, 32));
   s->cols = cols;
+  s->has64 = true;
   return REGEN_OK;
 }
 
@@ -210,9 +212,16 @@ int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, gemm::Params
     e = h->desc.precision == 0 ? gemm::launch2<256, true>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, om, p, s, sm)
                                : gemm::launch2<256, false>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, om, p, s, sm);
   }
-  else
-    e = h->desc.precision == 0 ? gemm::launch<64, true>(a.tm_hi, a.tm_lo, w.tm_hi3, w.tm_lo3, om, p, s)
-                               : gemm::launch<64, false>(a.tm_hi, a.tm_lo, w.tm_hi3, w.tm_lo3, om, p, s);
+  else {
+    // at most 64 token rows (a single sample of T <= 64 frames): the GEMM is bound by the bytes one SM can pull per
+    // k-block (measured ~50 B/clk), two thirds of which were the 128-row A box -- load the 64-row box instead
+    const bool a64 = p.M <= 64 && a.has64;
+    p.a_rows = a64 ? 64 : 0;
+    const CUtensorMap& ah = a64 ? a.tm_hi3 : a.tm_hi;
+    const CUtensorMap& al = a64 ? a.tm_lo3 : a.tm_lo;
+    e = h->desc.precision == 0 ? gemm::launch<64, true>(ah, al, w.tm_hi3, w.tm_lo3, om, p, s)
+                               : gemm::launch<64, false>(ah, al, w.tm_hi3, w.tm_lo3, om, p, s);
+  }
   if (e != cudaSuccess) {
     set_error("gemm launch (M=%d N=%d K=%d) failed: %s", p.M, p.N, p.K, cudaGetErrorString(e));
     return REGEN_ECUDA;

@@ -707,5 +707,96 @@ inline cudaError_t launch(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, co
                     tm_ohi, tm_olo, p);
 }
 
+// =====================================================================================================
+// Long sequences (more than 256 tokens per sample): streaming attention on the CUDA cores, exact fp32.
+//
+// The tcgen05 kernels above keep the scores of a whole key row resident in tensor memory, which bounds them at 256 keys;
+// the reference's positional table allows 5000 frames (model/cmdm.py:265-281), so longer sequences must not be an
+// error.  No dataset of the reference is longer than 196 frames, so this path is about completeness, not speed: one warp
+// per query row, keys / values streamed through shared memory in tiles of 32 (hi + lo recombined to fp32 while staging),
+// online softmax (running maximum and sum, fp32), output re-split into the bf16 (hi, lo) pair the output projection reads.
+// Reference semantics as above: nn.MultiheadAttention, additive causal mask (model/cmdm.py:168-171) or none.
+// =====================================================================================================
+constexpr int kLongWarps = 8, kLongTile = 32;
+
+__global__ void __launch_bounds__(kLongWarps * 32) attention_long_kernel(const __nv_bfloat16* __restrict__ qkv_hi,
+                                                                         const __nv_bfloat16* __restrict__ qkv_lo,
+                                                                         __nv_bfloat16* __restrict__ out_hi,
+                                                                         __nv_bfloat16* __restrict__ out_lo, int T, int Beff,
+                                                                         int causal) {
+  __shared__ float sK[kLongTile][HD + 1];
+  __shared__ float sV[kLongTile][HD];
+  __shared__ float sQ[kLongWarps][HD];
+  ptx::griddep_wait();
+  ptx::griddep_launch();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y >> 2, h = blockIdx.y & 3;
+  const int i0 = blockIdx.x * kLongWarps;                  // first query frame of this block
+  const int i = i0 + warp;                                 // this warp's query frame
+  const bool live = i < T;
+  const int last_q = min(i0 + kLongWarps, T) - 1;
+  const int kv_len = causal ? last_q + 1 : T;              // keys [0, kv_len) are needed by some row of the block
+  auto ld = [&](int t, int col) {                          // fp32 value of q | k | v element (frame t, column col)
+    const size_t off = ((size_t)t * Beff + b) * (3 * DM) + col;
+    return __bfloat162float(qkv_hi[off]) + __bfloat162float(qkv_lo[off]);
+  };
+  if (live)
+    for (int d = lane; d < HD; d += 32) sQ[warp][d] = ld(i, h * HD + d);
+  const float sc = 0.08838834764831845f;                   // 1/sqrt(128)
+  float m = -INFINITY, l = 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};                     // output dims lane, lane + 32, lane + 64, lane + 96
+  for (int j0 = 0; j0 < kv_len; j0 += kLongTile) {
+    __syncthreads();                                       // previous tile fully consumed (and sQ visible)
+    for (int e = threadIdx.x; e < kLongTile * HD; e += kLongWarps * 32) {
+      const int r = e / HD, d = e - r * HD;
+      const bool ok = j0 + r < kv_len;
+      sK[r][d] = ok ? ld(j0 + r, DM + h * HD + d) : 0.f;
+      sV[r][d] = ok ? ld(j0 + r, 2 * DM + h * HD + d) : 0.f;
+    }
+    __syncthreads();
+    if (!live) continue;
+    const int j = j0 + lane;                               // lane = key of the tile
+    const bool ok = j < T && (!causal || j <= i);
+    float s = -INFINITY;
+    if (ok) {
+      float a = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < HD; ++d) a = fmaf(sQ[warp][d], sK[lane][d], a);
+      s = a * sc;
+    }
+    const float mt = warp_max(s);
+    if (mt == -INFINITY) continue;                         // every key of this tile is masked for this row
+    const float m_new = fmaxf(m, mt);
+    const float corr = expf(m - m_new);                    // 0 at the first tile (m = -inf)
+    const float pj = ok ? expf(s - m_new) : 0.f;
+    l = l * corr + warp_sum(pj);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] *= corr;
+    for (int r = 0; r < kLongTile; ++r) {
+      const float pr = __shfl_sync(0xffffffffu, pj, r);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] = fmaf(pr, sV[r][lane + 32 * k], acc[k]);
+    }
+    m = m_new;
+  }
+  if (live) {
+    const float inv = 1.f / l;
+    const size_t row = ((size_t)i * Beff + b) * DM + h * HD;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(acc[k] * inv, hi, lo);
+      out_hi[row + lane + 32 * k] = hi;
+      out_lo[row + lane + 32 * k] = lo;
+    }
+  }
+}
+
+inline cudaError_t launch_long(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo, const Params& p, cudaStream_t s) {
+  if (p.Beff * 4 > 65535) return cudaErrorInvalidValue;
+  return launch_pdl(attention_long_kernel, dim3((unsigned)((p.T + kLongWarps - 1) / kLongWarps), (unsigned)(p.Beff * 4)),
+                    dim3(kLongWarps * 32), 0, s, qkv_hi, qkv_lo, p.out_hi, p.out_lo, p.T, p.Beff, p.causal);
+}
+
 }  // namespace attn
 }  // namespace regen

@@ -253,8 +253,8 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
   REGEN_CHECK_ARG(d->precision == 0 || d->precision == 1, "regen_create: precision must be 0 (bf16x3) or 1 (bf16)");
   REGEN_CHECK_ARG(d->arch == 0 || d->arch == 1, "regen_create: arch must be 0 ('online') or 1 ('offline')");
   REGEN_CHECK_ARG(d->max_batch >= 1 && d->max_frames >= 1 && d->num_table_steps >= 1, "regen_create: bad sizes");
-  REGEN_CHECK_ARG(d->max_frames + d->arch <= 256, "regen_create: max_frames=%d exceeds the attention kernel's limit of "
-                  "256 tokens (two key chunks of 128 resident in tensor memory)", d->max_frames);
+  // more than 256 tokens per sample run the streaming CUDA-core attention (attn::attention_long_kernel); the positional
+  // table bounds the length (checked against pe_len in regen_load_weights)
   REGEN_CHECK_ARG((int64_t)d->max_batch * d->max_frames < (1 << 24), "regen_create: max_batch*max_frames too large");
   {
     int ndev = 0;
@@ -661,7 +661,8 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
         ap.pol_load = h->pol(1, ptx::kL2EvictFirst);
         ap.pol_store = h->pol(2, ptx::kL2EvictLast);
         if (h->steplog && h->steplog_slot < h->steplog_cap) { ap.steplog = h->steplog; ap.steplog_slot = h->steplog_slot++; }
-        cudaError_t e = S <= 64 ? attn::launch<64>(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s)
+        cudaError_t e = S > 256 ? attn::launch_long(h->qkv_s.hi, h->qkv_s.lo, ap, s)
+                        : S <= 64 ? attn::launch<64>(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s)
                         : h->attn_mc
                                 ? attn::launch_mc(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s)
                                 : attn::launch<128>(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s);
@@ -918,7 +919,7 @@ int regen_test_gemm(const float* A, const float* W, const float* bias, const flo
 // Kernel-level test hook: causal multi-head self-attention on a seq-first q|k|v tensor through the tcgen05
 // attention kernel.  qkv fp32 [T*B, 1536] -> out fp32 [T*B, 512] (hi + lo recombined).  Synchronises.
 int regen_test_attention(const float* qkv, float* out, int32_t B, int32_t T, int32_t dbg, void* stream) {
-  REGEN_CHECK_ARG(qkv && out && B >= 1 && T >= 1 && T <= 256, "regen_test_attention: bad argument");
+  REGEN_CHECK_ARG(qkv && out && B >= 1 && T >= 1 && T <= 4096, "regen_test_attention: bad argument");
   cudaStream_t s = (cudaStream_t)stream;
   const size_t M = (size_t)B * T;
   bf16 *qh, *ql, *oh, *ol;
@@ -939,7 +940,8 @@ int regen_test_attention(const float* qkv, float* out, int32_t B, int32_t T, int
     ap.timeline = g_test_timeline;
     ap.steplog = nullptr; ap.steplog_slot = 0; ap.steplog_cta = 0;
     ap.pol_load = 0; ap.pol_store = 0;
-    cudaError_t e = T <= 64 ? attn::launch<64>(th, tl, toh, tol, ap, s)
+    cudaError_t e = T > 256 ? attn::launch_long(qh, ql, ap, s)
+                    : T <= 64 ? attn::launch<64>(th, tl, toh, tol, ap, s)
                     : mc    ? attn::launch_mc(th, tl, toh, tol, ap, s)
                             : attn::launch<128>(th, tl, toh, tol, ap, s);
     if (e == cudaSuccess) {

@@ -21,13 +21,26 @@ def ref_attention(qkv, B, T):
     return o.reshape(T * B, 512)
 
 
+def test_long_sequence_non_causal(built_lib):
+    """dbg bit 1 = no mask (arch 'offline') on the long-sequence kernel."""
+    B, T = 2, 301
+    qkv = torch.randn(T * B, 1536, generator=torch.Generator().manual_seed(9)).cuda()
+    out = run(built_lib, qkv, B, T, dbg=2)
+    x = qkv.double().view(T, B, 3, 4, 128)
+    s_ = torch.einsum("ibhd,jbhd->bhij", x[:, :, 0], x[:, :, 1]) / math.sqrt(128.0)
+    want = torch.einsum("bhij,jbhd->ibhd", torch.softmax(s_, dim=-1), x[:, :, 2]).reshape(T * B, 512)
+    assert (out.double() - want).abs().max().item() < 1e-4
+
+
 def run(lib, qkv, B, T, dbg=0):
     out = torch.full((T * B, 512), float("nan"), device="cuda")
     _lib.check(lib.regen_test_attention(_lib.ptr(qkv), _lib.ptr(out), B, T, dbg, _lib.stream_ptr()), "test_attention")
     return out
 
 
-@pytest.mark.parametrize("B,T", [(1, 1), (2, 7), (3, 60), (2, 64), (2, 65), (2, 128), (3, 150), (2, 196), (1, 256)])
+# T > 256: the streaming CUDA-core kernel (attention_long_kernel) -- the tcgen05 kernels keep a key row's scores in TMEM
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 7), (3, 60), (2, 64), (2, 65), (2, 128), (3, 150), (2, 196), (1, 256),
+                                 (2, 257), (1, 300), (2, 513)])
 def test_attention_matches_fp64(built_lib, B, T):
     g = torch.Generator().manual_seed(B * 1000 + T)
     qkv = torch.randn(T * B, 1536, generator=g).cuda()

@@ -97,6 +97,22 @@ def test_forward_matches_oracle_various_sizes(built_lib, B, T):
         assert torch.allclose(sub, out[:1], atol=1e-5 if B <= 33 else 1e-4)
 
 
+def test_sequences_longer_than_256_frames(built_lib):
+    """The reference's positional table allows 5000 frames (model/cmdm.py:265-281); beyond the 256 tokens the tcgen05
+    attention kernels hold in tensor memory the forward switches to the streaming attention kernel instead of failing."""
+    mk = cases.MODELS["ntu"]
+    model, sd = get_model("ntu", 0)
+    B, T = 2, 300
+    x, y = synthetic.make_inputs(B, 56, 6, T, seed=321)
+    t = torch.tensor([17, 803])
+    with torch.no_grad():
+        out = model(x.cuda(), t.cuda(), to_cuda(y)).cpu()
+        want = cmdm_ref.cmdm_forward(sd, x, t, y, **_kw(mk))
+    err = (out - want).abs().max().item()
+    print("T=300: max abs err vs oracle %.3e" % err)
+    assert err < TOL_TIGHT
+
+
 def test_causality_property(built_lib):
     """arch='online': frame f of the output depends only on frames <= f of x and cmotion."""
     model, _ = get_model("ntu", 0)

@@ -37,6 +37,13 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 B_DEFAULT, T_DEFAULT = 256, 60
+# operand scheme of the GPU arm: 'bf16x3', or 'mixed8' (bf16x3 + fp16/e4m3 linear2 on the fused route); REGEN_PRECISION overrides
+PRECISION = os.environ.get("REGEN_PRECISION", "bf16x3")
+DTYPES = {
+    "bf16x3": "bf16x3 (3 bf16 tcgen05 MMAs per product, fp32 accumulate; fp32 LN/softmax/update, residual stream as a bf16 (hi, lo) pair)",
+    "mixed8": "bf16x3 (3 bf16 tcgen05 MMAs per product) except linear2: fp16 MMA + two e4m3 correction MMAs per product "
+              "(2 MMA equivalents); fp32 accumulate, fp32 LN/softmax/update, residual stream as a bf16 (hi, lo) pair",
+}
 METRIC = "denoising_steps_per_sec"
 UNIT = "steps/s (1 step = one p_sample over B=256 x T=60 poses per GPU, summed over GPUs)"
 DATA = "synthetic (seeded random-init weights, random actor motion)"
@@ -130,7 +137,7 @@ def build_ours(device, B=None, T=None, name="ntu"):
     from regennet_b200 import synthetic
     from regennet_b200.cmdm import CMDM
     mk, sk = model_cfg(name)
-    model = CMDM(**mk)
+    model = CMDM(precision=PRECISION, **mk)
     model.load_state_dict(synthetic.make_state_dict(seed=0, **sk), strict=False)
     model = model.to(device).eval()
     return model, make_diffusion
@@ -572,7 +579,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": steps_per_s, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3 (3 bf16 tcgen05 MMAs per product, fp32 accumulate; fp32 LN/softmax/update, residual stream as a bf16 (hi, lo) pair)",
+            "dtype": DTYPES[PRECISION],
             "data": DATA,
             "config": {"workload": "BASELINE configs[1]: NTU120-AS online unconstrained 8-layer CMDM, SMPL-X rot6d "
                                    "56x6, T=%d, B=%d per GPU, 1000-step cosine DDPM p_sample_loop (steps %d..%d timed)"

@@ -99,6 +99,9 @@ class _Handle:
             pass
 
 
+_PRECISIONS = {'bf16x3': 0, 'bf16': 1, 'mixed8': 2}   # regen_model_desc.precision
+
+
 class CMDM(nn.Module):
     def __init__(self, modeltype, njoints, nfeats, num_actions, translation, pose_rep, glob, glob_rot,
                  num_frames=60, latent_dim=256, ff_size=1024, num_layers=8, num_heads=4, dropout=0.1,
@@ -136,8 +139,11 @@ class CMDM(nn.Module):
         self.emb_trans_dec = emb_trans_dec
         self.wo_pos_emb = wo_pos_emb
         self.body_model = body_model
-        #: 'bf16x3' (parity mode: three bf16 MMAs per product, ~2e-5 abs error) or 'bf16' (single pass)
+        #: 'bf16x3' (parity mode: three bf16 MMAs per product, ~2e-5 abs error), 'mixed8' (bf16x3 except linear2 of the
+        #: large-batch route: one fp16 MMA + two e4m3 correction MMAs per product, ~4e-5) or 'bf16' (single pass, ~1e-2)
         self.precision = kargs.get('precision', 'bf16x3')
+        if self.precision not in _PRECISIONS:
+            raise ValueError("precision must be one of %s (got %r)" % (sorted(_PRECISIONS), self.precision))
 
         # --- scope of the B200 path: everything else in the reference is a different model
         if arch not in ('online', 'offline'):
@@ -268,7 +274,7 @@ class CMDM(nn.Module):
                               cm_mode=1 if self.cm_mode == 'concat' else 0,
                               max_batch=max(batch_eff, h.max_batch if h else 0),
                               max_frames=max(frames, h.max_frames if h else 0, min(self.num_frames, 196)),
-                              num_table_steps=table_steps, precision=0 if self.precision == 'bf16x3' else 1,
+                              num_table_steps=table_steps, precision=_PRECISIONS[self.precision],
                               arch=1 if self.arch == 'offline' else 0)
         hp = ctypes.c_void_p()
         dev_index = device.index if device.index is not None else torch.cuda.current_device()

@@ -20,6 +20,18 @@
 // pass is bound by the TMA row rate (one box row per ~2.6 cycles), so dropping the fp32 copy halves its 128 row requests
 // per 64 columns and the bytes written.  The residual then carries 16 significand bits (forward error ~3e-5 instead of
 // ~1.5e-5, tolerance 1e-3).  R16 = false (REGEN_DEBUG_F32_RESIDUAL=1) keeps the fp32 copy of h.
+//
+// M8 = true (precision 'mixed8', linear2 + norm3): the product runs as ONE fp16 MMA plus two e4m3 correction MMAs at twice
+// the rate -- 2 bf16-MMA equivalents per product instead of 3 -- at the same 4 operand bytes per element:
+//   D  = (A_lo * 2^11) . (W_hi * 2^4)^T + A_hi . (W_lo * 2^15)^T        kind::f8f6f4, all four operands e4m3, K = 32 per MMA
+//   D  = A16 . W16^T + D * 2^-15                                         first kind::f16 MMA (scale-input-d = 15)
+//   D += A16 . W16^T                                                     remaining kind::f16 MMAs
+// with A16 = fp16(a), A_lo = a - A16, A_hi = e4m3(A16) (same for W).  The correction terms are 2^-11 of the result, so
+// 4 significand bits suffice for them (measured on B200: 4.0e-5 against 8.6e-6 for fp16 x3, tools/mixed8_probe.cu).
+// Operands: tm_a_hi = A16 [M, K] (16-bit), tm_a_lo = A8 [M, 2K] bytes (A_lo8 | A_hi8), tm_w_hi = W16 [512, K],
+// tm_w_lo = W8 [512, 2K] bytes (W_hi8 | W_lo8); the 8-bit boxes are 128 rows x 128 bytes.  The ring is then 4 stages of
+// 48 KB (A tile | two W half tiles of 16 KB), every stage feeds 8 MMAs (1 k cycles): first the 2 K / 128 correction stages,
+// then the K / 64 main-term stages.
 #pragma once
 #include "common.cuh"
 #include "gemm_sm100.cuh"
@@ -31,6 +43,9 @@ namespace gemmln {
 constexpr int BM = 128, BK = 64, UMMA_K = 16, ND = 512;
 constexpr int STAGE_BYTES = 6 * 16384;  // A_hi | A_lo | W_hi[0] | W_hi[1] | W_lo[0] | W_lo[1]
 constexpr int STAGES = 2;
+constexpr int RING_BYTES = STAGES * STAGE_BYTES;   // operand ring; re-used as epilogue staging
+constexpr int M8_STAGES = 4, M8_STAGE_BYTES = 3 * 16384;  // mixed8 ring: A | W[0] | W[1], same 192 KB
+static_assert(M8_STAGES * M8_STAGE_BYTES == RING_BYTES, "both ring shapes fill the same bytes");
 constexpr int SC = 32;                  // columns per epilogue sub-chunk (one tcgen05.ld/st x32, one TMA box)
 constexpr int SLOT = 32 * SC * 4;       // 4 KB: 32 rows x 32 fp32, 128-byte rows (SWIZZLE_128B)
 // Epilogue geometry for EW epilogue warps per CTA (EW / 4 warps share a TMEM lane quarter and split the 512 columns).
@@ -48,7 +63,7 @@ struct Epi {
   static constexpr int RING_R = CHAIN ? (EW == 16 ? 2 : 3) : (EW == 16 ? 3 : 6);
   static constexpr int RING_C = EW == 16 ? 1 : 3;
   static constexpr int NOB = EW == 16 ? 1 : 2;  // output staging depth (fp32 slots, and bf16 hi / lo tile pairs)
-  static constexpr int WARP_BYTES = (STAGES * STAGE_BYTES) / EW;
+  static constexpr int WARP_BYTES = RING_BYTES / EW;
   static constexpr int THREADS = 64 + 32 * EW;
   static_assert((RING_R + (CHAIN ? RING_C : 0)) * SLOT <= WARP_BYTES && 3 * NOB * SLOT <= WARP_BYTES,
                 "epilogue staging budget");
@@ -57,8 +72,8 @@ struct Epi {
 };
 constexpr int PARAM_BYTES = 5 * ND * 4; // bias, g1, b1, g2, b2
 constexpr int STATS_BYTES = 2 * 128 * 4 * 8;   // [2 exchanges][128 rows][<= 4 column parts] float2
-constexpr int BAR_BYTES = 2048;                // 8 pipeline barriers + 16 warps x 8 ring barriers
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PARAM_BYTES + STATS_BYTES + BAR_BYTES + 1024;
+constexpr int BAR_BYTES = 2048;                // 16 pipeline barrier slots + 16 warps x 8 ring barriers
+constexpr int SMEM_BYTES = RING_BYTES + PARAM_BYTES + STATS_BYTES + BAR_BYTES + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct Params {
@@ -95,7 +110,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // tm_res: fp32 [M, 512] residual stream h (box 32 x 32, SWIZZLE_128B) -- used for the residual LOAD and the h STORE
 // tm_c  : fp32 [Beff + 32, 512] cyclic per-sample constant (row r = c[r % Beff]); only read with CHAIN
 // tm_ohi / tm_olo: bf16 [M, 512] split of h (store, box 32 rows x 64 columns, SWIZZLE_128B)
-template <bool SPLIT, bool CHAIN, int EW, bool LN = true, bool R16 = false>
+template <bool SPLIT, bool CHAIN, int EW, bool LN = true, bool R16 = false, bool M8 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Epi<EW, CHAIN>::THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -105,14 +120,17 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   // 1 KB alignment by pointer arithmetic on the __shared__ array (NOT an integer round trip): the compiler keeps the
   // shared address space and emits LDS / STS instead of generic LD / ST for every staging access below
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* s_par = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);             // bias | g1 | b1 | g2 | b2
-  float2* s_stats = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + PARAM_BYTES);  // [2 exchanges][128 rows][2 halves]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + PARAM_BYTES + STATS_BYTES);
-  uint64_t* full_bar = bars;          // [2]
-  uint64_t* empty_bar = bars + 2;     // [2]
-  uint64_t* tmem_full_bar = bars + 4;
-  uint64_t* tmem_empty_bar = bars + 5;   // leader's copy: 16 arrivals (epilogue warps of both CTAs)
-  uint64_t* epi_done_bar = bars + 6;     // local: 8 arrivals, operand ring free again for the producer
+  static_assert(!M8 || (SPLIT && LN && R16), "mixed8 operands: built for the (hi, lo)-residual LayerNorm variants");
+  constexpr int NST = M8 ? M8_STAGES : STAGES;              // ring stages
+  constexpr int STB = M8 ? M8_STAGE_BYTES : STAGE_BYTES;    // bytes per stage
+  float* s_par = reinterpret_cast<float*>(smem + RING_BYTES);             // bias | g1 | b1 | g2 | b2
+  float2* s_stats = reinterpret_cast<float2*>(smem + RING_BYTES + PARAM_BYTES);  // [2 exchanges][128 rows][2 halves]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING_BYTES + PARAM_BYTES + STATS_BYTES);
+  uint64_t* full_bar = bars;          // [NST <= 4]
+  uint64_t* empty_bar = bars + 4;     // [NST <= 4]
+  uint64_t* tmem_full_bar = bars + 8;
+  uint64_t* tmem_empty_bar = bars + 9;   // leader's copy: 16 arrivals (epilogue warps of both CTAs)
+  uint64_t* epi_done_bar = bars + 10;    // local: 8 arrivals, operand ring free again for the producer
   using E = Epi<EW, CHAIN>;
   // R16: residual ring of RING_P pair slots (hi box | lo box, 8 KB, two sub-chunks each), c ring of RC fp32 slots
   static_assert(!R16 || (EW == 8 && LN), "the bf16 (hi, lo) residual variant is built for 8 epilogue warps");
@@ -120,8 +138,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   constexpr int RC = R16 ? 2 : E::RING_C;
   constexpr int NP = E::NSC / 2;         // sub-chunk pairs per warp
   static_assert(!R16 || (RING_P * 2 + (CHAIN ? RC : 0)) * SLOT <= E::WARP_BYTES, "R16 staging budget");
-  uint64_t* ring_bar = bars + 8;         // [EW warps][8]: res slots 0..3, c slots 4..7
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 8 + 8 * EW);
+  uint64_t* ring_bar = bars + 16;        // [EW warps][8]: res slots 0..3, c slots 4..7
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 16 + 8 * EW);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -135,7 +153,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       ptx::prefetch_tmap(&tm_a_hi);
       ptx::prefetch_tmap(&tm_w_hi);
       ptx::prefetch_tmap(&tm_res);
-      for (int s = 0; s < STAGES; ++s) {
+      for (int s = 0; s < NST; ++s) {
         ptx::mbar_init(&full_bar[s], 1);
         ptx::mbar_init(&empty_bar[s], 1);
       }
@@ -167,9 +185,23 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
         const int m0 = tile * (2 * BM) + (int)rank * BM;
         if (it > 0) ptx::mbar_wait(epi_done_bar, (it - 1) & 1);  // the epilogue staged in the operand ring
-        for (int kb = 0; kb < num_kb; ++kb) {
+        // pipeline iterations of one tile: k-blocks of 64, or (mixed8) 2 K / 128 correction stages + K / 64 main stages
+        const int n1 = M8 ? 2 * (p.K / 128) : 0;
+        const int nit = M8 ? n1 + num_kb : num_kb;
+        for (int kb = 0; kb < nit; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* st = smem + stage * STAGE_BYTES;
+          uint8_t* st = smem + stage * STB;
+          if constexpr (M8) {
+            if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * STB);
+            // correction stage i = 2 kb8 + sub: sub 0 = A_lo8 x W_hi8 (first K bytes of the rows), sub 1 = A_hi8 x W_lo8
+            const bool corr = kb < n1;
+            const CUtensorMap* ma = corr ? &tm_a_lo : &tm_a_hi;
+            const CUtensorMap* mw = corr ? &tm_w_lo : &tm_w_hi;
+            const int c0 = corr ? (kb & 1) * p.K + (kb >> 1) * 128 : (kb - n1) * BK;
+            ptx::tma_load_2d_2sm(st, ma, &full_bar[stage], c0, m0, p.pol_a);
+            ptx::tma_load_2d_2sm(st + 16384, mw, &full_bar[stage], c0, (int)rank * 128, p.pol_w);
+            ptx::tma_load_2d_2sm(st + 2 * 16384, mw, &full_bar[stage], c0, 256 + (int)rank * 128, p.pol_w);
+          } else {
           if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * (SPLIT ? STAGE_BYTES : STAGE_BYTES / 2));
           ptx::tma_load_2d_2sm(st, &tm_a_hi, &full_bar[stage], kb * BK, m0, p.pol_a);
           ptx::tma_load_2d_2sm(st + 2 * 16384, &tm_w_hi, &full_bar[stage], kb * BK, (int)rank * 128, p.pol_w);
@@ -179,11 +211,12 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             ptx::tma_load_2d_2sm(st + 4 * 16384, &tm_w_lo, &full_bar[stage], kb * BK, (int)rank * 128, p.pol_w);
             ptx::tma_load_2d_2sm(st + 5 * 16384, &tm_w_lo, &full_bar[stage], kb * BK, 256 + (int)rank * 128, p.pol_w);
           }
+          }
           // The epilogue's first pass reads this CTA's 128 x 512 fp32 residual tile in one burst; by then h has been
           // evicted from L2 by the operand stream (ncu: the whole tile came from DRAM, pass 1 was HBM-bound).  Pull it
           // into L2 during the main loop, which leaves DRAM bandwidth unused: 64 boxes of 32 x 32 spread over the k-blocks.
           if (p.prefetch_res) {
-            const int per_kb = (64 + num_kb - 1) / num_kb;
+            const int per_kb = (64 + nit - 1) / nit;
             for (int i = kb * per_kb; i < (kb + 1) * per_kb && i < 64; ++i) {
               if constexpr (R16) {  // 32 hi + 32 lo boxes of 32 rows x 64 columns
                 const int k = i >> 1;
@@ -193,7 +226,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               }
             }
           }
-          if (++stage == STAGES) {
+          if (++stage == NST) {
             stage = 0;
             phase ^= 1;
           }
@@ -209,11 +242,30 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
         ptx::mbar_wait(tmem_empty_bar, (it & 1) ^ 1);  // both CTAs' epilogues are done with the accumulator
         ptx::tcgen05_fence_after();
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int n1 = M8 ? 2 * (p.K / 128) : 0;
+        const int nit = M8 ? n1 + num_kb : num_kb;
+        for (int kb = 0; kb < nit; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           if (kb == 0 && it == 0) REGEN_LTL(1);
           ptx::tcgen05_fence_after();
-          const uint32_t st = ptx::smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t st = ptx::smem_u32(smem + stage * STB);
+          if constexpr (M8) {
+            // e4m3 x e4m3 and fp16 x fp16 share the descriptor bits (formats 0); 32 bytes per k-step in both phases
+            constexpr uint32_t idesc0 = ptx::umma_idesc_fmt0_f32(2 * BM, 256);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t adv = (uint32_t)k * 32;
+              const uint64_t a = ptx::umma_desc_k_sw128(st + adv);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint64_t w = ptx::umma_desc_k_sw128(st + (1 + j) * 16384 + adv);
+                const uint32_t acc = tmem_base + (uint32_t)(j * 256);
+                if (kb < n1) ptx::mma_f8_ss_2sm(acc, a, w, idesc0, (kb | k) != 0);
+                else if (kb == n1 && k == 0) ptx::mma_f16_ss_2sm_scale15(acc, a, w, idesc0);  // D = A.B + D * 2^-15
+                else ptx::mma_f16_ss_2sm(acc, a, w, idesc0, 1);
+              }
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint32_t adv = (uint32_t)k * 32;
@@ -233,8 +285,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               }
             }
           }
+          }
           ptx::tcgen05_commit_2sm(&empty_bar[stage]);
-          if (++stage == STAGES) {
+          if (++stage == NST) {
             stage = 0;
             phase ^= 1;
           }
@@ -701,20 +754,20 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
 }
 
-template <bool SPLIT, bool CHAIN, int EW, bool LN = true, bool R16 = false>
+template <bool SPLIT, bool CHAIN, int EW, bool LN = true, bool R16 = false, bool M8 = false>
 inline cudaError_t launch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                const CUtensorMap& w_lo, const CUtensorMap& res, const CUtensorMap& c,
                                const CUtensorMap& ohi, const CUtensorMap& olo, const Params& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_ln_kernel<SPLIT, CHAIN, EW, LN, R16>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_ln_kernel<SPLIT, CHAIN, EW, LN, R16, M8>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int64_t tiles = ceil_div(p.M, 2 * BM);
   const int clusters = (int)(tiles < kNumSMs / 2 ? tiles : kNumSMs / 2);
-  return launch_pdl(gemm_ln_kernel<SPLIT, CHAIN, EW, LN, R16>, dim3(2 * clusters), dim3(Epi<EW, CHAIN>::THREADS), SMEM_BYTES,
+  return launch_pdl(gemm_ln_kernel<SPLIT, CHAIN, EW, LN, R16, M8>, dim3(2 * clusters), dim3(Epi<EW, CHAIN>::THREADS), SMEM_BYTES,
                     stream, a_hi, a_lo, w_hi, w_lo, res, c, ohi, olo, p);
 }
 
@@ -735,6 +788,14 @@ inline cudaError_t launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, cons
   if (r16) return launch_impl<SPLIT, CHAIN, 8, true, true>(a_hi, a_lo, w_hi, w_lo, res, c, ohi, olo, p, stream);
   return ew == 16 ? launch_impl<SPLIT, CHAIN, 16>(a_hi, a_lo, w_hi, w_lo, res, c, ohi, olo, p, stream)
                   : launch_impl<SPLIT, CHAIN, 8>(a_hi, a_lo, w_hi, w_lo, res, c, ohi, olo, p, stream);
+}
+
+// mixed8 operands (see the header comment): a16 / a8 / w16 / w8 maps, (hi, lo) residual stream; K must be a multiple of 128
+template <bool CHAIN>
+inline cudaError_t launch_m8(const CUtensorMap& a16, const CUtensorMap& a8, const CUtensorMap& w16, const CUtensorMap& w8,
+                             const CUtensorMap& c, const CUtensorMap& ohi, const CUtensorMap& olo, const Params& p,
+                             cudaStream_t stream) {
+  return launch_impl<true, CHAIN, 8, true, true, true>(a16, a8, w16, w8, ohi, c, ohi, olo, p, stream);
 }
 
 // h <- A.W^T + bias + residual without LayerNorm (input projection): `res` = residual LOAD map, `out32` = fp32 STORE map

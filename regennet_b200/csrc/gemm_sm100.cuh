@@ -58,6 +58,9 @@ struct Params {
   int exit_wait_full;       // 1: wait for the bulk stores' global writes before exit (default; REGEN_DEBUG_EXIT_WAIT_READ=1 clears it, A/B: no measurable difference)
   int pair64;               // 16-warp pair kernel, bf16 (hi, lo) outputs only: 64-column store boxes through warp pairs (tm_ohi /
                             // tm_olo must then be the 32 x 64 box maps)
+  int m8;                   // pair64 epilogue only: outputs in the mixed8 operand format of the fused linear2 + LayerNorm kernel
+                            // (gemm_ln_sm100.cuh): tm_ohi = fp16 [M, N] (box 32 x 64), tm_olo = bytes [M, 2 N] (box 32 rows x 64 B,
+                            // SWIZZLE_64B) holding e4m3((v - fp16(v)) * 2^11) in columns [0, N) and e4m3(fp16(v)) in [N, 2 N)
   int slice_w_rows;         // pair kernel: rows of the W box the slice maps (tm_ws_*) load per CTA (set by launch2)
   int tail_split;           // pair kernel: the tiles of the last, partial wave are cut into 1 / 2 / 4 column slices (set by launch2)
   // bring-up instrumentation (test hook only, null in production): CTA 0 records clock64() at pipeline events
@@ -442,12 +445,27 @@ __device__ __forceinline__ void epilogue_pair64(const Params& p, const CUtensorM
       if (p.gelu) v = gelu_erf2(v);
       ptx::upk2u(v, r[j], r[j + 1]);
     }
-    uint32_t lw[16];
+    uint32_t lw[16];  // bf16 lo words, or (mixed8) 8 words of scaled-residual e4m3 bytes | 8 words of e4m3(hi) bytes
     if (issuer) ptx::bulk_wait_read<0>();  // the previous store from the shared tile has been read
     pair_sync();
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint32_t hw[4];
+      if (p.m8) {
+        float lo[8], hf[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a = __uint_as_float(r[8 * c + 2 * k]), b = __uint_as_float(r[8 * c + 2 * k + 1]);
+          hw[k] = ptx::pack_f16x2_sat(a, b);
+          const ptx::f32x2 h2 = ptx::f16x2_to_f32x2(hw[k]);
+          ptx::upk2(h2, hf[2 * k], hf[2 * k + 1]);
+          ptx::upk2(ptx::mul2(ptx::sub2(ptx::pk2(a, b), h2), ptx::splat2(2048.f)), lo[2 * k], lo[2 * k + 1]);
+        }
+        lw[2 * c] = ptx::pack_e4m3x4(lo[0], lo[1], lo[2], lo[3]);
+        lw[2 * c + 1] = ptx::pack_e4m3x4(lo[4], lo[5], lo[6], lo[7]);
+        lw[8 + 2 * c] = ptx::pack_e4m3x4(hf[0], hf[1], hf[2], hf[3]);
+        lw[8 + 2 * c + 1] = ptx::pack_e4m3x4(hf[4], hf[5], hf[6], hf[7]);
+      } else {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float a = __uint_as_float(r[8 * c + 2 * k]), b = __uint_as_float(r[8 * c + 2 * k + 1]);
@@ -455,6 +473,7 @@ __device__ __forceinline__ void epilogue_pair64(const Params& p, const CUtensorM
         float l0, l1;   // float(hi) is the bf16 bit pattern in the upper half of the word
         ptx::upk2(ptx::sub2(ptx::pk2(a, b), ptx::bf16x2_to_f32x2(hw[k])), l0, l1);
         lw[4 * c + k] = pack_bf16x2(l0, l1);
+      }
       }
       *reinterpret_cast<uint4*>(stg + stg_off_128(lane, 4 * sub + c)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     }
@@ -466,6 +485,24 @@ __device__ __forceinline__ void epilogue_pair64(const Params& p, const CUtensorM
       ptx::bulk_wait_read<0>();
     }
     pair_sync();  // hi tile read: the staging tile takes the lo halves
+    if (p.m8) {
+      // two byte tiles of 32 rows x 64 B (SWIZZLE_64B) in the 4 KB staging tile: residual bytes | e4m3(hi) bytes; this warp
+      // owns bytes [32 sub, 32 sub + 32) of every row
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          *reinterpret_cast<uint4*>(stg + t * 2048 + stg_off_f32(lane, 2 * sub + c)) =
+              make_uint4(lw[8 * t + 4 * c], lw[8 * t + 4 * c + 1], lw[8 * t + 4 * c + 2], lw[8 * t + 4 * c + 3]);
+      ptx::fence_proxy_async_smem();
+      pair_sync();
+      if (issuer) {
+        ptx::tma_store_2d(tm_olo, stg, n0 + 64 * g, row0, p.pol_store);
+        ptx::tma_store_2d(tm_olo, stg + 2048, p.N + n0 + 64 * g, row0, p.pol_store);
+        ptx::bulk_commit();
+      }
+      continue;
+    }
 #pragma unroll
     for (int c = 0; c < 4; ++c)
       *reinterpret_cast<uint4*>(stg + stg_off_128(lane, 4 * sub + c)) =

@@ -56,6 +56,27 @@ inline void launch_split_rows(const float* src, int ld_src, __nv_bfloat16* hi, _
 }
 
 // ------------------------------------------------------------------------------------------
+// fp32 W [R, C] -> the mixed8 operand pack of gemm_ln_sm100.cuh (setup only): w16 fp16 [R, C] and bytes [R, 2 C] with
+// e4m3(fp16(w) * 2^4) in columns [0, C) and e4m3((w - fp16(w)) * 2^15) in columns [C, 2 C).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_m8_weights_kernel(const float* __restrict__ src, uint16_t* __restrict__ w16,
+                                                              uint8_t* __restrict__ w8, int R, int C) {
+  const int64_t total = (int64_t)R * (C / 4);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int r = (int)(i / (C / 4)), c = (int)(i % (C / 4)) * 4;
+    const float4 f = *reinterpret_cast<const float4*>(src + (size_t)r * C + c);
+    const uint32_t h0 = ptx::pack_f16x2_sat(f.x, f.y), h1 = ptx::pack_f16x2_sat(f.z, f.w);
+    float a0, a1, a2, a3;
+    ptx::upk2(ptx::f16x2_to_f32x2(h0), a0, a1);
+    ptx::upk2(ptx::f16x2_to_f32x2(h1), a2, a3);
+    *reinterpret_cast<uint2*>(w16 + (size_t)r * C + c) = make_uint2(h0, h1);
+    *reinterpret_cast<uint32_t*>(w8 + (size_t)r * 2 * C + c) = ptx::pack_e4m3x4(a0 * 16.f, a1 * 16.f, a2 * 16.f, a3 * 16.f);
+    *reinterpret_cast<uint32_t*>(w8 + (size_t)r * 2 * C + C + c) =
+        ptx::pack_e4m3x4((f.x - a0) * 32768.f, (f.y - a1) * 32768.f, (f.z - a2) * 32768.f, (f.w - a3) * 32768.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Exact fp32 GEMM on CUDA cores for one-off setup work (weight folding, timestep table, the
 // loop-invariant cmotion embedding):
 //   C[m,n] = act( sum_k A[m*sam + k*sak] * Bm[k*sbk + n*sbn] + bias_n[n] + bias_m[m] )

@@ -32,6 +32,11 @@ struct SplitBuf {  // bf16 (hi, lo) operand pair + its TMA maps
 
 struct LayerDev {
   SplitBuf wqkv, wo, w1, w2;
+  // precision 'mixed8' only: linear2 weights as fp16 [512, 1024] + e4m3 bytes [512, 2048] (hi * 2^4 | lo * 2^15) for the
+  // fused linear2 + LayerNorm kernel (the bf16 pair above still serves the small-batch route)
+  uint16_t* w2_16 = nullptr;
+  uint8_t* w2_8 = nullptr;
+  CUtensorMap tm_w2_16, tm_w2_8;
   float *bqkv, *bo, *b1, *b2, *n1w, *n1b, *n2w, *n2b, *n3w, *n3b;
 };
 
@@ -66,6 +71,9 @@ struct regen_handle {
   float* e2tab = nullptr;            // offline: timestep-embedding table [num_table_steps, 512] (model/cmdm.py:291-298)
   CUtensorMap tm_qkv_hi, tm_qkv_lo;  // 3-D [T, Beff, 1536] views of qkv_s for the attention kernel (per prepare_cond)
   CUtensorMap tm_att_hi, tm_att_lo;  // 3-D [T, Beff, 512] store views of the attention output (box 32 frames x 64 d)
+  // precision 'mixed8', fused route: the FFN activations leave the FFN1 epilogue as fp16 in ffn.hi's memory and as e4m3
+  // bytes [M, 2048] ((v - fp16(v)) * 2^11 | fp16(v)) in ffn.lo's memory
+  CUtensorMap tm_ffn8, st_ffn8;      // load map (box 128 rows x 128 B) / store map (box 32 rows x 64 B, rows = M)
   CUtensorMap st_h, st_tmp, st_x0e;  // store-side maps of the fp32 activation buffers (rows = M)
   CUtensorMap st32_h;                // h with box 32 x 32: residual load + store of the fused GEMM+LayerNorm kernel
   bool tma_store = true;             // REGEN_DEBUG_NO_TMA_STORE=1: st.global epilogue (A/B measurements)
@@ -197,8 +205,13 @@ int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, gemm::Params
         p.pair64 = 1;
         om.hi = osplit->st64_hi;
         om.lo = osplit->st64_lo;
+        if (p.m8) om.lo = h->st_ffn8;  // mixed8 operand bytes (the fp16 halves use the 16-bit 32 x 64 box map)
       }
     }
+  }
+  if (p.m8 && !p.pair64) {
+    set_error("run_gemm: the mixed8 output format needs the 64-column store path");
+    return REGEN_EINVAL;
   }
   if (h->steplog && h->steplog_slot < h->steplog_cap) {
     p.steplog = h->steplog;
@@ -209,7 +222,7 @@ int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, gemm::Params
   if (use_pair_kernel(p.M)) {
     gemm::SliceMaps sm;
     if (h->narrow_slices) { sm.hi32 = &w.tm_hi4; sm.lo32 = &w.tm_lo4; sm.hi64 = &w.tm_hi3; sm.lo64 = &w.tm_lo3; }
-    e = h->desc.precision == 0 ? gemm::launch2<256, true>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, om, p, s, sm)
+    e = h->desc.precision != 1 ? gemm::launch2<256, true>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, om, p, s, sm)
                                : gemm::launch2<256, false>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, om, p, s, sm);
   }
   else {
@@ -219,7 +232,7 @@ int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, gemm::Params
     p.a_rows = a64 ? 64 : 0;
     const CUtensorMap& ah = a64 ? a.tm_hi3 : a.tm_hi;
     const CUtensorMap& al = a64 ? a.tm_lo3 : a.tm_lo;
-    e = h->desc.precision == 0 ? gemm::launch<64, true>(ah, al, w.tm_hi3, w.tm_lo3, om, p, s)
+    e = h->desc.precision != 1 ? gemm::launch<64, true>(ah, al, w.tm_hi3, w.tm_lo3, om, p, s)
                                : gemm::launch<64, false>(ah, al, w.tm_hi3, w.tm_lo3, om, p, s);
   }
   if (e != cudaSuccess) {
@@ -250,7 +263,8 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
                   d->num_layers);
   REGEN_CHECK_ARG(d->input_feats >= 1 && d->input_feats <= 4096, "regen_create: bad input_feats %d", d->input_feats);
   REGEN_CHECK_ARG(d->cm_mode == 0 || d->cm_mode == 1, "regen_create: cm_mode must be 0 (add) or 1 (concat)");
-  REGEN_CHECK_ARG(d->precision == 0 || d->precision == 1, "regen_create: precision must be 0 (bf16x3) or 1 (bf16)");
+  REGEN_CHECK_ARG(d->precision >= 0 && d->precision <= 2,
+                  "regen_create: precision must be 0 (bf16x3), 1 (bf16) or 2 (mixed8: bf16x3 + fp16/e4m3 linear2)");
   REGEN_CHECK_ARG(d->arch == 0 || d->arch == 1, "regen_create: arch must be 0 ('online') or 1 ('offline')");
   REGEN_CHECK_ARG(d->max_batch >= 1 && d->max_frames >= 1 && d->num_table_steps >= 1, "regen_create: bad sizes");
   // more than 256 tokens per sample run the streaming CUDA-core attention (attn::attention_long_kernel); the positional
@@ -306,6 +320,12 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
       if ((rc = alloc_split(h, &ld.wo, D, D, 256))) break;
       if ((rc = alloc_split(h, &ld.w1, FF, D, 256))) break;
       if ((rc = alloc_split(h, &ld.w2, D, FF, 256))) break;
+      if (d->precision == 2) {
+        if ((rc = h->alloc(&ld.w2_16, (size_t)D * FF))) break;
+        if ((rc = h->alloc(&ld.w2_8, (size_t)D * 2 * FF))) break;
+        if ((rc = make_tmap_bf16_2d(&ld.tm_w2_16, ld.w2_16, D, FF, FF, 128))) break;
+        if ((rc = make_tmap_u8_2d(&ld.tm_w2_8, ld.w2_8, D, 2 * FF, 2 * FF, 128, 128))) break;
+      }
     }
     if (rc) break;
     if ((rc = h->alloc(&h->w_c, (size_t)D * h->I))) break;
@@ -319,6 +339,7 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
     if ((rc = alloc_split(h, &h->h_s, Mx, D, 128))) break;
     if ((rc = alloc_split(h, &h->att, Mx, D, 128))) break;
     if ((rc = alloc_split(h, &h->ffn, Mx, FF, 128))) break;
+    if (d->precision == 2 && (rc = make_tmap_u8_2d(&h->tm_ffn8, h->ffn.lo, Mx, 2 * FF, 2 * FF, 128, 128))) break;
     if ((rc = alloc_split(h, &h->qkv_s, Mx, 3 * D, 128))) break;
     if ((rc = h->alloc(&h->h, Mx * D))) break;
     if ((rc = h->alloc(&h->qkv, Mx * 3 * D))) break;
@@ -421,6 +442,11 @@ int regen_load_weights(regen_handle* h, const regen_weight_ptrs* w, void* stream
     layers::launch_split_rows(lw.o_w, D, ld.wo.hi, ld.wo.lo, D, D, D, 1, 1, s);
     layers::launch_split_rows(lw.l1_w, D, ld.w1.hi, ld.w1.lo, D, D, FF, 1, 1, s);
     layers::launch_split_rows(lw.l2_w, FF, ld.w2.hi, ld.w2.lo, FF, FF, D, 1, 1, s);
+    if (h->desc.precision == 2) {
+      layers::pack_m8_weights_kernel<<<grid_cap(ceil_div((int64_t)D * FF / 4, 256)), 256, 0, s>>>(lw.l2_w, ld.w2_16,
+                                                                                                 ld.w2_8, D, FF);
+      count_launch();
+    }
     TRY(copy_vec(h, &ld.bqkv, lw.qkv_b, 3 * D, s));
     TRY(copy_vec(h, &ld.bo, lw.o_b, D, s));
     TRY(copy_vec(h, &ld.b1, lw.l1_b, FF, s));
@@ -503,6 +529,7 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
     TRY(make_tmap_store_2d(&sb->st64_hi, sb->hi, true, h->M, sb->cols, sb->cols, 64));
     TRY(make_tmap_store_2d(&sb->st64_lo, sb->lo, true, h->M, sb->cols, sb->cols, 64));
   }
+  if (h->desc.precision == 2) TRY(make_tmap_u8_2d(&h->st_ffn8, h->ffn.lo, h->M, 2 * FF, 2 * FF, 32, 64));
   TRY(make_tmap_store_2d(&h->st32_h, h->h, false, h->M, D, D, 32));
   TRY(make_tmap_store_2d(&h->ld32_condbias, h->condbias, false, Mf, D, D, 32));
   if (h->offline) {
@@ -579,6 +606,10 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
   // of the machine the N-tiled GEMM + a separate warp-per-row LayerNorm kernel is faster (measured crossover at M ~ 9 500:
   // B = 32, T = 60 runs 0.705 instead of 1.022 ms per step; single samples use the 64-column single-CTA GEMM tiles).
   const bool fused = h->fused_ln && ceil_div(M, 256) >= kNumSMs / 4;
+  // precision 'mixed8': on the fused route linear2 runs as one fp16 MMA + two e4m3 correction MMAs per product (2 instead
+  // of 3 bf16-MMA equivalents); FFN1's epilogue writes its activations in that operand format.  Everything else, and
+  // the whole small-batch route, is bf16x3.
+  const bool m8 = h->desc.precision == 2 && fused && h->tma_store && h->store64 && h->res16;
   const int Mf = T * Beff;                              // frame rows
   const size_t fr_off = offline ? (size_t)Beff * D : 0;  // offline: the frames follow the Beff condition-token rows
 
@@ -618,7 +649,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
         q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;
       }
       const SplitBuf& ob = offline ? h->h_fr : h->h_s;
-      cudaError_t e = h->desc.precision == 0
+      cudaError_t e = h->desc.precision != 1
           ? gemmln::launch_noln<true>(h->a_in.tm_hi, h->a_in.tm_lo, h->w_in.tm_hi2, h->w_in.tm_lo2, h->ld32_condbias,
                                       hmaps[1], ob.st64_hi, ob.st64_lo, q, s)
           : gemmln::launch_noln<false>(h->a_in.tm_hi, h->a_in.tm_lo, h->w_in.tm_hi2, h->w_in.tm_lo2, h->ld32_condbias,
@@ -685,7 +716,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       if (h->steplog && h->steplog_slot < h->steplog_cap) {
         q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;
       }
-      cudaError_t e = h->desc.precision == 0
+      cudaError_t e = h->desc.precision != 1
           ? gemmln::launch<true, false>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->st32_h,
                                         h->h_s.st64_hi, h->h_s.st64_lo, q, s, h->res16)
           : gemmln::launch<false, false>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->st32_h,
@@ -707,7 +738,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       if (h->steplog && h->steplog_slot < h->steplog_cap) {
         q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;
       }
-      cudaError_t e = h->desc.precision == 0
+      cudaError_t e = h->desc.precision != 1
           ? gemmln::launch<true, true>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->tm_cyc[l],
                                        h->h_s.st64_hi, h->h_s.st64_lo, q, s, h->res16)
           : gemmln::launch<false, true>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->tm_cyc[l],
@@ -749,7 +780,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
     }
     {  // ffn = gelu(h . W_1^T + b_1)
       gemm::Params p = gp(M, FF, D);
-      p.bias = ld.b1; p.gelu = 1;
+      p.bias = ld.b1; p.gelu = 1; p.m8 = m8 ? 1 : 0;
       p.out_hi = h->ffn.hi; p.out_lo = h->ffn.lo; p.ld_split = FF;
       TRY(run_gemm(h, h->h_s, ld.w1, p, nullptr, &h->ffn, s));
     }
@@ -766,7 +797,9 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       if (h->steplog && h->steplog_slot < h->steplog_cap) {
         q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;
       }
-      cudaError_t e = h->desc.precision == 0
+      cudaError_t e = m8 ? gemmln::launch_m8<false>(h->ffn.tm_hi, h->tm_ffn8, ld.tm_w2_16, ld.tm_w2_8, h->st32_h,
+                                                    h->h_s.st64_hi, h->h_s.st64_lo, q, s)
+          : h->desc.precision != 1
           ? gemmln::launch<true, false>(h->ffn.tm_hi, h->ffn.tm_lo, ld.w2.tm_hi2, ld.w2.tm_lo2, h->st32_h, h->st32_h,
                                         h->h_s.st64_hi, h->h_s.st64_lo, q, s, h->res16)
           : gemmln::launch<false, false>(h->ffn.tm_hi, h->ffn.tm_lo, ld.w2.tm_hi2, ld.w2.tm_lo2, h->st32_h, h->st32_h,

@@ -253,6 +253,30 @@ __device__ __forceinline__ void mma_f16_ss_2sm(uint32_t tmem_d, uint64_t adesc, 
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f8f6f4 (plain e4m3 x e4m3 -> fp32, K = 32 per instruction, twice the bf16 rate), CTA pair
+__device__ __forceinline__ void mma_f8_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::f16 with the scale-input-d immediate: D = A.B + D * 2^-15 (folds the 2^15-scaled e4m3 correction products of
+// the mixed8 scheme into the main term, see gemm_ln_sm100.cuh; measured on B200 with tools/mixed8_probe.cu)
+__device__ __forceinline__ void mma_f16_ss_2sm_scale15(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p, 15;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
+      : "memory");
+}
 // arrive (once all prior MMAs of this thread retire) on the mbarrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void tcgen05_commit_2sm(uint64_t* bar) {
   asm volatile(
@@ -354,6 +378,30 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 // both halves of a bf16x2 word as fp32: the low half is the even column, the high half the odd one
 __device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t w) { return pk2u(w << 16, w & 0xffff0000u); }
 
+// ---------------------------------------------------------------- mixed8 operand formats (fp16 + e4m3)
+// two fp32 -> fp16x2 (round to nearest, saturating at +-65504): low half = even column
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float even, float odd) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(odd), "f"(even));
+  return d;
+}
+// both halves of an fp16x2 word as fp32 (HADD2.F32, full rate)
+__device__ __forceinline__ f32x2 f16x2_to_f32x2(uint32_t w) {
+  float lo, hi;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}"
+      : "=f"(lo), "=f"(hi) : "r"(w));
+  return pk2(lo, hi);
+}
+// four fp32 -> four e4m3 bytes (round to nearest, saturating at +-448), byte i = value i
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  uint32_t r;
+  asm("mov.b32 %0, {%1, %2};" : "=r"(r) : "h"(lo), "h"(hi));
+  return r;
+}
+
 // ---------------------------------------------------------------- descriptors
 // UMMA shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of exactly 128 bytes
 // (64 bf16), 8-row swizzle atoms stacked every 1024 bytes (cute UMMA::SmemDescriptor):
@@ -375,6 +423,12 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
 // a_major[15]=0, b_major[16]=0 (K), n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Instruction descriptor with a_format = b_format = 0: fp16 x fp16 for kind::f16, e4m3 x e4m3 for kind::f8f6f4
+// (fp32 accumulate, both operands K-major)
+__host__ __device__ constexpr uint32_t umma_idesc_fmt0_f32(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace ptx

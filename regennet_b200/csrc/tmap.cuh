@@ -79,6 +79,31 @@ inline int make_tmap_store_2d(CUtensorMap* out, const void* base, bool is_bf16, 
   return REGEN_OK;
 }
 
+// Byte matrix [rows, cols] (e4m3 operands of the mixed8 scheme), box = box_rows x box_cols bytes; the swizzle equals the
+// box row size (64 B -> SWIZZLE_64B for the epilogue's store tiles, 128 B -> SWIZZLE_128B for the UMMA operand tiles).
+inline int make_tmap_u8_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+                           uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    return REGEN_ECUDA;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   box_cols == 64 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(u8) failed with CUresult %d (rows=%llu cols=%llu pitch=%llu box %u x %u)", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_bytes, box_rows, box_cols);
+    return REGEN_ECUDA;
+  }
+  return REGEN_OK;
+}
+
 // bf16 tensor [d2, d1, d0] (d0 contiguous), box = box2 x 1 x 64, 128-byte swizzle, zero fill out of bounds.
 // Used for q|k|v viewed as [T frames, Beff samples, 1536]: one box = one sample's frames x 64 head-dim columns.
 inline int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,

@@ -32,7 +32,7 @@ struct SplitBuf {  // bf16 (hi, lo) operand pair + its TMA maps
 
 struct LayerDev {
   SplitBuf wqkv, wo, w1, w2;
-  // precision 'mixed8' only: linear2 weights as fp16 [512, 1024] + e4m3 bytes [512, 2048] (hi * 2^4 | lo * 2^15) for the
+  // precision 'mixed8' only: linear2 weights as fp16 [512, 1024] + e4m3 bytes [512, 2048] (hi * 2^6 | lo * 2^17) for the
   // fused linear2 + LayerNorm kernel (the bf16 pair above still serves the small-batch route)
   uint16_t* w2_16 = nullptr;
   uint8_t* w2_8 = nullptr;
@@ -72,7 +72,7 @@ struct regen_handle {
   CUtensorMap tm_qkv_hi, tm_qkv_lo;  // 3-D [T, Beff, 1536] views of qkv_s for the attention kernel (per prepare_cond)
   CUtensorMap tm_att_hi, tm_att_lo;  // 3-D [T, Beff, 512] store views of the attention output (box 32 frames x 64 d)
   // precision 'mixed8', fused route: the FFN activations leave the FFN1 epilogue as fp16 in ffn.hi's memory and as e4m3
-  // bytes [M, 2048] ((v - fp16(v)) * 2^11 | fp16(v)) in ffn.lo's memory
+  // bytes [M, 2048] ((v - fp16(v)) * 2^9 | fp16(v) / 4) in ffn.lo's memory
   CUtensorMap tm_ffn8, st_ffn8;      // load map (box 128 rows x 128 B) / store map (box 32 rows x 64 B, rows = M)
   CUtensorMap st_h, st_tmp, st_x0e;  // store-side maps of the fp32 activation buffers (rows = M)
   CUtensorMap st32_h;                // h with box 32 x 32: residual load + store of the fused GEMM+LayerNorm kernel
@@ -605,7 +605,12 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
   // The fused GEMM+LayerNorm kernel gives one 256-row tile to a CTA pair, so it uses 2 * ceil(M / 256) SMs.  Below half
   // of the machine the N-tiled GEMM + a separate warp-per-row LayerNorm kernel is faster (measured crossover at M ~ 9 500:
   // B = 32, T = 60 runs 0.705 instead of 1.022 ms per step; single samples use the 64-column single-CTA GEMM tiles).
-  const bool fused = h->fused_ln && ceil_div(M, 256) >= kNumSMs / 4;
+  static int force_fused = -1;  // REGEN_DEBUG_FORCE_FUSED=1: fused route for any M > 128 (feed-bandwidth experiments)
+  if (force_fused < 0) {
+    const char* e = getenv("REGEN_DEBUG_FORCE_FUSED");
+    force_fused = (e && e[0] == '1') ? 1 : 0;
+  }
+  const bool fused = h->fused_ln && (ceil_div(M, 256) >= kNumSMs / 4 || (force_fused && M > 128));
   // precision 'mixed8': on the fused route linear2 runs as one fp16 MMA + two e4m3 correction MMAs per product (2 instead
   // of 3 bf16-MMA equivalents); FFN1's epilogue writes its activations in that operand format.  Everything else, and
   // the whole small-batch route, is bf16x3.
@@ -638,7 +643,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       // TMA and the outputs leave in one sweep (34.6 -> ~24 us at config 2; the generic residual epilogue is
       // bound by LSU round trips)
       ProfScope prof(h, CLS_GEMM, s);
-      gemmln::Params q;
+      gemmln::Params q{};
       memset(&q, 0, sizeof(q));
       q.M = Mf; q.K = h->Kin; q.Beff = Beff; q.ln_eps = layers::LN_EPS;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
@@ -706,7 +711,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
     }
     if (offline && fused) {  // encoder layer: h = LN1(h + attn . W_o^T + b_o)   (nn.TransformerEncoderLayer, post-norm)
       ProfScope prof(h, CLS_GEMM, s);
-      gemmln::Params q;
+      gemmln::Params q{};
       q.M = M; q.K = D; q.Beff = Beff; q.bias = ld.bo; q.g1 = ld.n1w; q.b1 = ld.n1b; q.g2 = nullptr; q.b2 = nullptr;
       q.ln_eps = layers::LN_EPS; q.store_f32 = 0; q.nob16 = h->nob16; q.exit_wait_full = h->exit_wait_full ? 1 : 0;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
@@ -728,7 +733,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       count_launch();
     } else if (fused) {  // h = LN2( LN1(h + attn . W_o^T + b_o) + c_l[b] )   -- one kernel
       ProfScope prof(h, CLS_GEMM, s);
-      gemmln::Params q;
+      gemmln::Params q{};
       q.M = M; q.K = D; q.Beff = Beff; q.bias = ld.bo; q.g1 = ld.n1w; q.b1 = ld.n1b; q.g2 = ld.n2w; q.b2 = ld.n2b;
       q.ln_eps = layers::LN_EPS; q.store_f32 = 0; q.nob16 = h->nob16; q.exit_wait_full = h->exit_wait_full ? 1 : 0;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
@@ -786,7 +791,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
     }
     if (fused) {  // h = LN3(h + ffn . W_2^T + b_2)   -- one kernel (encoder layer: norm2)
       ProfScope prof(h, CLS_GEMM, s);
-      gemmln::Params q;
+      gemmln::Params q{};
       q.M = M; q.K = FF; q.Beff = Beff; q.bias = ld.b2; q.g1 = offline ? ld.n2w : ld.n3w; q.b1 = offline ? ld.n2b : ld.n3b;
       q.g2 = nullptr; q.b2 = nullptr;
       q.ln_eps = layers::LN_EPS; q.store_f32 = 0; q.nob16 = h->nob16; q.exit_wait_full = h->exit_wait_full ? 1 : 0;

@@ -67,10 +67,13 @@ def test_small_batch_route_is_untouched(built_lib):
     assert torch.equal(a, b)
 
 
-def test_outlier_channels_stay_within_tolerance(built_lib):
+@pytest.mark.parametrize("l1_scale", [8.0, 100.0])
+def test_outlier_channels_stay_within_tolerance(built_lib, l1_scale):
+    """x100 on four linear1 rows pushes FFN activations past 448 (e4m3's largest finite value): the operand scales of the
+    fp8 copies keep |a| <= 1792 exact, anything larger saturates and falls back to fp16 accuracy for that element."""
     mk = cases.MODELS["ntu"]
-    sd = _outlier_state_dict(5)
-    model = _mixed8_model(sd, "outlier5")
+    sd = _outlier_state_dict(5, l1_scale)
+    model = _mixed8_model(sd, "outlier5_%g" % l1_scale)
     B, T = 256, 60
     x, y = synthetic.make_inputs(B, 56, 6, T, seed=900 + B)
     t = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(B))
@@ -80,7 +83,8 @@ def test_outlier_channels_stay_within_tolerance(built_lib):
     with torch.no_grad():
         want = cmdm_ref.cmdm_forward(sd, x[sel], t[sel], {"cmotion": y["cmotion"][sel]}, **_kw(mk))
     err = (out[sel] - want).abs().max().item()
-    print("mixed8 outlier stress: max abs err vs oracle %.3e (output absmax %.2f)" % (err, want.abs().max()))
+    print("mixed8 outlier stress (linear1 rows x%g): max abs err vs oracle %.3e (output absmax %.2f)" % (
+        l1_scale, err, want.abs().max()))
     assert torch.isfinite(out).all()
     assert err < TOL
 

@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
 
-def _outlier_state_dict(seed):
+def _outlier_state_dict(seed, l1_scale=8.0):
     sd = synthetic.make_state_dict(seed=seed, **cases.synth_kw("ntu"))
     g = torch.Generator().manual_seed(seed + 1000)
     n_norm = n_l1 = 0
@@ -34,10 +34,10 @@ def _outlier_state_dict(seed):
         elif k.endswith("linear1.weight"):
             rows = torch.randperm(sd[k].shape[0], generator=g)[:4]
             sd[k] = sd[k].clone()
-            sd[k][rows] *= 8.0
+            sd[k][rows] *= l1_scale
             bk = k[:-len("weight")] + "bias"
             sd[bk] = sd[bk].clone()
-            sd[bk][rows] *= 8.0
+            sd[bk][rows] *= l1_scale
             n_l1 += 1
     assert n_norm == 24 and n_l1 == 8
     return sd

@@ -9,12 +9,13 @@ from regennet_b200 import _lib, synthetic
 from regennet_b200.cmdm import CMDM
 
 lib = _lib.lib()
-m = CMDM(**cases.MODELS["ntu"])
+m = CMDM(precision=os.environ.get("REGEN_PRECISION", "bf16x3"), **cases.MODELS["ntu"])
 m.load_state_dict(synthetic.make_state_dict(seed=0, **cases.synth_kw("ntu")), strict=False)
 m = m.cuda().eval()
-x, y = synthetic.make_inputs(256, 56, 6, 60, seed=1)
+NB = int(os.environ.get("LN_TIMELINE_B", "256"))
+x, y = synthetic.make_inputs(NB, 56, 6, 60, seed=1)
 xc, yc = x.cuda(), {"cmotion": y["cmotion"].cuda()}
-t = torch.full((256,), 500, dtype=torch.long, device="cuda")
+t = torch.full((NB,), 500, dtype=torch.long, device="cuda")
 tl = torch.zeros(128, dtype=torch.int64, device="cuda")
 for rep in range(3):
     tl.zero_()
@@ -34,3 +35,7 @@ for base, label in [(0, "out_proj + LN1 + c + LN2 (K=512)"), (20, "linear2 + LN3
     for k, n in enumerate(names):
         if v[base + k]:
             print("   %-22s %8d" % (n, v[base + k] - t0))
+st = [x - v[20] for x in v[48:88] if x]
+print("== linear2 main loop: stage arrival times (cycles after entry) and cadence")
+print("   ", st)
+print("   ", [b - a for a, b in zip(st, st[1:])])

@@ -237,39 +237,81 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA)
-    if (rank == 0 && lane == 0) {
+    if (rank == 0 && (M8 || lane == 0)) {   // mixed8: the whole warp runs the loop, one elected lane per instruction
       constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(2 * BM, 256);
       int stage = 0, it = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
         ptx::mbar_wait(tmem_empty_bar, (it & 1) ^ 1);  // both CTAs' epilogues are done with the accumulator
         ptx::tcgen05_fence_after();
-        const int n1 = M8 ? 2 * (p.K / 128) : 0;
-        const int nit = M8 ? n1 + num_kb : num_kb;
-        for (int kb = 0; kb < nit; ++kb) {
+        if constexpr (M8) {
+          // Three straight-line loops (no per-MMA branches in the issuing thread): correction stages (e4m3 x e4m3), the
+          // first main-term stage (its two k = 0 MMAs fold the scaled corrections in: D = A.B + D * 2^-15), the remaining
+          // main-term stages.  e4m3 x e4m3 and fp16 x fp16 share the descriptor bits (formats 0); 32 bytes per k-step.
+          constexpr uint32_t idesc0 = ptx::umma_idesc_fmt0_f32(2 * BM, 256);
+          const int n1 = 2 * (p.K / 128);
+          int kb_log = 0;
+          auto stage_begin = [&]() -> uint32_t {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            if (kb_log == 0 && it == 0 && lane == 0) REGEN_LTL(1);
+            if (!CHAIN && p.timeline && blockIdx.x == 0 && it == 0 && kb_log < 40 && lane == 0)
+              p.timeline[48 + kb_log] = (unsigned long long)clock64();
+            ++kb_log;
+            ptx::tcgen05_fence_after();
+            return ptx::smem_u32(smem + stage * STB);
+          };
+          auto stage_end = [&]() {
+            if (ptx::elect_one()) ptx::tcgen05_commit_2sm(&empty_bar[stage]);
+            if (++stage == NST) {
+              stage = 0;
+              phase ^= 1;
+            }
+          };
+          for (int kb = 0; kb < n1; ++kb) {
+            const uint32_t st = stage_begin();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t a = ptx::umma_desc_k_sw128(st + k * 32);
+              if (ptx::elect_one()) ptx::mma_f8_ss_2sm(tmem_base, a, ptx::umma_desc_k_sw128(st + 16384 + k * 32), idesc0, (kb | k) != 0);
+              if (ptx::elect_one()) ptx::mma_f8_ss_2sm(tmem_base + 256, a, ptx::umma_desc_k_sw128(st + 2 * 16384 + k * 32), idesc0, (kb | k) != 0);
+            }
+            stage_end();
+          }
+          {
+            const uint32_t st = stage_begin();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t a = ptx::umma_desc_k_sw128(st + k * 32);
+              const uint64_t w0 = ptx::umma_desc_k_sw128(st + 16384 + k * 32);
+              const uint64_t w1 = ptx::umma_desc_k_sw128(st + 2 * 16384 + k * 32);
+              if (k == 0) {
+                if (ptx::elect_one()) ptx::mma_f16_ss_2sm_scale15(tmem_base, a, w0, idesc0);
+                if (ptx::elect_one()) ptx::mma_f16_ss_2sm_scale15(tmem_base + 256, a, w1, idesc0);
+              } else {
+                if (ptx::elect_one()) ptx::mma_f16_ss_2sm(tmem_base, a, w0, idesc0, 1);
+                if (ptx::elect_one()) ptx::mma_f16_ss_2sm(tmem_base + 256, a, w1, idesc0, 1);
+              }
+            }
+            stage_end();
+          }
+          for (int kb = 1; kb < num_kb; ++kb) {
+            const uint32_t st = stage_begin();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t a = ptx::umma_desc_k_sw128(st + k * 32);
+              if (ptx::elect_one()) ptx::mma_f16_ss_2sm(tmem_base, a, ptx::umma_desc_k_sw128(st + 16384 + k * 32), idesc0, 1);
+              if (ptx::elect_one()) ptx::mma_f16_ss_2sm(tmem_base + 256, a, ptx::umma_desc_k_sw128(st + 2 * 16384 + k * 32), idesc0, 1);
+            }
+            stage_end();
+          }
+        } else {
+        for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           if (kb == 0 && it == 0) REGEN_LTL(1);
           // bring-up: arrival time of every stage of the first tile (linear2 instance: slots 48..)
           if (!CHAIN && LN && p.timeline && blockIdx.x == 0 && it == 0 && kb < 40) p.timeline[48 + kb] = (unsigned long long)clock64();
           ptx::tcgen05_fence_after();
           const uint32_t st = ptx::smem_u32(smem + stage * STB);
-          if constexpr (M8) {
-            // e4m3 x e4m3 and fp16 x fp16 share the descriptor bits (formats 0); 32 bytes per k-step in both phases
-            constexpr uint32_t idesc0 = ptx::umma_idesc_fmt0_f32(2 * BM, 256);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t adv = (uint32_t)k * 32;
-              const uint64_t a = ptx::umma_desc_k_sw128(st + adv);
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const uint64_t w = ptx::umma_desc_k_sw128(st + (1 + j) * 16384 + adv);
-                const uint32_t acc = tmem_base + (uint32_t)(j * 256);
-                if (kb < n1) ptx::mma_f8_ss_2sm(acc, a, w, idesc0, (kb | k) != 0);
-                else if (kb == n1 && k == 0) ptx::mma_f16_ss_2sm_scale15(acc, a, w, idesc0);  // D = A.B + D * 2^-15
-                else ptx::mma_f16_ss_2sm(acc, a, w, idesc0, 1);
-              }
-            }
-          } else {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint32_t adv = (uint32_t)k * 32;
@@ -289,15 +331,15 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               }
             }
           }
-          }
           ptx::tcgen05_commit_2sm(&empty_bar[stage]);
           if (++stage == NST) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::tcgen05_commit_2sm(tmem_full_bar);
-        if (it == 0) REGEN_LTL(2);
+        }
+        if (!M8 || ptx::elect_one()) ptx::tcgen05_commit_2sm(tmem_full_bar);
+        if (it == 0 && lane == 0) REGEN_LTL(2);
       }
     }
   } else {

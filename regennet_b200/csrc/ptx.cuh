@@ -58,6 +58,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a converged warp (elect.sync): the MMA / TMA issuing warps run their loops warp-uniformly and elect a lane
+// per instruction, as CUTLASS does -- addresses and descriptors then live in uniform registers.  A loop that runs inside an
+// `if (lane == 0)` branch instead makes the compiler rebuild every tcgen05 / TMA operand with R2UR waterfall loops
+// (~15-20 instructions per MMA: measured 190 cycles per issued MMA against 106 of execution, tools/ln_timeline.py).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- clusters (CTA pairs)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -149,14 +149,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   if (threadIdx.x == 0) REGEN_ATL(1);
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ control thread: TMA + MMA issue
+    {
+      // ------------------------------------------------------------------ control warp: TMA + MMA issue
+      // The whole warp runs this code warp-uniformly and elects one lane per TMA / tcgen05 instruction (ptx::elect_one):
+      // a loop inside `if (lane == 0)` costs more issue cycles per MMA than these small MMAs take to execute.
       auto load_operand = [&](uint8_t* dst, uint64_t* bar, int col0, int t0) {
-        ptx::mbar_expect_tx(bar, C::OPERAND);
-        ptx::tma_load_3d(dst, &tm_hi, bar, col0, b, t0, p.pol_load);
-        ptx::tma_load_3d(dst + C::TILE, &tm_hi, bar, col0 + 64, b, t0, p.pol_load);
-        ptx::tma_load_3d(dst + 2 * C::TILE, &tm_lo, bar, col0, b, t0, p.pol_load);
-        ptx::tma_load_3d(dst + 3 * C::TILE, &tm_lo, bar, col0 + 64, b, t0, p.pol_load);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(bar, C::OPERAND);
+          ptx::tma_load_3d(dst, &tm_hi, bar, col0, b, t0, p.pol_load);
+          ptx::tma_load_3d(dst + C::TILE, &tm_hi, bar, col0 + 64, b, t0, p.pol_load);
+          ptx::tma_load_3d(dst + 2 * C::TILE, &tm_lo, bar, col0, b, t0, p.pol_load);
+          ptx::tma_load_3d(dst + 3 * C::TILE, &tm_lo, bar, col0 + 64, b, t0, p.pol_load);
+        }
       };
       // Buffer rotation (TB = 128, two key chunks): K_0 -> sK and K_1 -> sV are both fetched at the start; V_0 takes sK as
       // soon as S_0 is complete and V_1 takes sV as soon as S_1 is, i.e. both V loads run behind the softmax passes and
@@ -188,11 +192,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
           const uint64_t q_lo = ptx::umma_desc_k_sw128(aQ + 2 * C::TILE + tile + adv);
           const uint64_t k_hi = ptx::umma_desc_k_sw128(aKc + tile + adv);
           const uint64_t k_lo = ptx::umma_desc_k_sw128(aKc + 2 * C::TILE + tile + adv);
-          ptx::mma_f16_ss(accS, q_lo, k_hi, idesc_s, k != 0);
-          ptx::mma_f16_ss(accS, q_hi, k_lo, idesc_s, 1);
-          ptx::mma_f16_ss(accS, q_hi, k_hi, idesc_s, 1);
+          if (ptx::elect_one()) ptx::mma_f16_ss(accS, q_lo, k_hi, idesc_s, k != 0);
+          if (ptx::elect_one()) ptx::mma_f16_ss(accS, q_hi, k_lo, idesc_s, 1);
+          if (ptx::elect_one()) ptx::mma_f16_ss(accS, q_hi, k_hi, idesc_s, 1);
         }
-        ptx::tcgen05_commit(&barS[kc]);
+        if (ptx::elect_one()) ptx::tcgen05_commit(&barS[kc]);
         ptx::mbar_wait(&barS[kc], 0);  // this chunk's K buffer (and finally Q) free again
         if (kc == 0) REGEN_ATL(3);
         if (rotate) load_operand(kc == 0 ? sK : sV, kc == 0 ? barV : barV1, 2 * DM + h * HD, kc * TB);  // V_kc -> K_kc's buffer
@@ -216,11 +220,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
           const uint32_t lbo = (p.dbg & 1) ? 1024u : (uint32_t)C::TILE, sbo = (p.dbg & 1) ? (uint32_t)C::TILE : 1024u;
           const uint64_t v_hi = umma_desc_mn_sw128(aVc + (uint32_t)k * 2048, lbo, sbo);
           const uint64_t v_lo = umma_desc_mn_sw128(aVc + 2 * C::TILE + (uint32_t)k * 2048, lbo, sbo);
-          ptx::mma_f16_ss(accO, p_lo, v_hi, idesc_o, (kc | k) != 0);
-          ptx::mma_f16_ss(accO, p_hi, v_lo, idesc_o, 1);
-          ptx::mma_f16_ss(accO, p_hi, v_hi, idesc_o, 1);
+          if (ptx::elect_one()) ptx::mma_f16_ss(accO, p_lo, v_hi, idesc_o, (kc | k) != 0);
+          if (ptx::elect_one()) ptx::mma_f16_ss(accO, p_hi, v_lo, idesc_o, 1);
+          if (ptx::elect_one()) ptx::mma_f16_ss(accO, p_hi, v_hi, idesc_o, 1);
         }
-        ptx::tcgen05_commit(barO);
+        if (ptx::elect_one()) ptx::tcgen05_commit(barO);
       }
     }
   } else {
@@ -486,14 +490,17 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
   ptx::steplog_begin(p.steplog, p.steplog_slot);
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ control thread: TMA + MMA issue
+    {
+      // ------------------------------------------------------------------ control warp: TMA + MMA issue (warp-uniform,
+      // one elected lane per TMA / tcgen05 instruction, see attention_kernel)
       auto load_operand = [&](uint8_t* dst, uint64_t* bar, int col0, int t0) {
-        ptx::mbar_expect_tx(bar, C::OPERAND);
-        ptx::tma_load_3d(dst, &tm_hi, bar, col0, b, t0, p.pol_load);
-        ptx::tma_load_3d(dst + C::TILE, &tm_hi, bar, col0 + 64, b, t0, p.pol_load);
-        ptx::tma_load_3d(dst + 2 * C::TILE, &tm_lo, bar, col0, b, t0, p.pol_load);
-        ptx::tma_load_3d(dst + 3 * C::TILE, &tm_lo, bar, col0 + 64, b, t0, p.pol_load);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(bar, C::OPERAND);
+          ptx::tma_load_3d(dst, &tm_hi, bar, col0, b, t0, p.pol_load);
+          ptx::tma_load_3d(dst + C::TILE, &tm_hi, bar, col0 + 64, b, t0, p.pol_load);
+          ptx::tma_load_3d(dst + 2 * C::TILE, &tm_lo, bar, col0, b, t0, p.pol_load);
+          ptx::tma_load_3d(dst + 3 * C::TILE, &tm_lo, bar, col0 + 64, b, t0, p.pol_load);
+        }
       };
       // operand j of the sequence K_0..K_{n-1}, V_0..V_{n-1} -> buffer j & 1
       auto load_op = [&](int j) {
@@ -524,11 +531,11 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
           const uint64_t q_lo = ptx::umma_desc_k_sw128(aQ + 2 * C::TILE + tile + adv);
           const uint64_t k_hi = ptx::umma_desc_k_sw128(aK + tile + adv);
           const uint64_t k_lo = ptx::umma_desc_k_sw128(aK + 2 * C::TILE + tile + adv);
-          ptx::mma_f16_ss(accS, q_lo, k_hi, idesc_s, k != 0);
-          ptx::mma_f16_ss(accS, q_hi, k_lo, idesc_s, 1);
-          ptx::mma_f16_ss(accS, q_hi, k_hi, idesc_s, 1);
+          if (ptx::elect_one()) ptx::mma_f16_ss(accS, q_lo, k_hi, idesc_s, k != 0);
+          if (ptx::elect_one()) ptx::mma_f16_ss(accS, q_hi, k_lo, idesc_s, 1);
+          if (ptx::elect_one()) ptx::mma_f16_ss(accS, q_hi, k_hi, idesc_s, 1);
         }
-        ptx::tcgen05_commit(&barS[kc]);
+        if (ptx::elect_one()) ptx::tcgen05_commit(&barS[kc]);
         ptx::mbar_wait(&barS[kc], 0);              // K_kc consumed: its buffer takes operand kc + 2
         if (kc + 2 < 2 * n) load_op(kc + 2);
       }
@@ -547,11 +554,11 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
           const uint64_t p_lo = ptx::umma_desc_k_sw128(aP + 8192u + (uint32_t)k * 32);
           const uint64_t v_hi = umma_desc_mn_sw128(aV + (uint32_t)k * 2048, (uint32_t)C::TILE, 1024u);
           const uint64_t v_lo = umma_desc_mn_sw128(aV + 2 * C::TILE + (uint32_t)k * 2048, (uint32_t)C::TILE, 1024u);
-          ptx::mma_f16_ss(accO, p_lo, v_hi, idesc_o, (kc | k) != 0);
-          ptx::mma_f16_ss(accO, p_hi, v_lo, idesc_o, 1);
-          ptx::mma_f16_ss(accO, p_hi, v_hi, idesc_o, 1);
+          if (ptx::elect_one()) ptx::mma_f16_ss(accO, p_lo, v_hi, idesc_o, (kc | k) != 0);
+          if (ptx::elect_one()) ptx::mma_f16_ss(accO, p_hi, v_lo, idesc_o, 1);
+          if (ptx::elect_one()) ptx::mma_f16_ss(accO, p_hi, v_hi, idesc_o, 1);
         }
-        ptx::tcgen05_commit(&barPV[kc]);
+        if (ptx::elect_one()) ptx::tcgen05_commit(&barPV[kc]);
         if (n + kc + 2 < 2 * n) {                   // V_kc consumed: its buffer takes V_{kc + 2}
           ptx::mbar_wait(&barPV[kc], 0);
           load_op(n + kc + 2);

@@ -237,7 +237,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA)
-    if (rank == 0 && (M8 || lane == 0)) {   // mixed8: the whole warp runs the loop, one elected lane per instruction
+    // The whole warp runs the loop (warp-uniform control flow and operands); one elected lane issues each tcgen05
+    // instruction (ptx::elect_one: a single-lane loop costs more cycles per MMA in issue than the MMA takes to execute).
+    if (rank == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(2 * BM, 256);
       int stage = 0, it = 0;
       uint32_t phase = 0;
@@ -307,9 +309,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         } else {
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
-          if (kb == 0 && it == 0) REGEN_LTL(1);
+          if (kb == 0 && it == 0 && lane == 0) REGEN_LTL(1);
           // bring-up: arrival time of every stage of the first tile (linear2 instance: slots 48..)
-          if (!CHAIN && LN && p.timeline && blockIdx.x == 0 && it == 0 && kb < 40) p.timeline[48 + kb] = (unsigned long long)clock64();
+          if (!CHAIN && LN && p.timeline && blockIdx.x == 0 && it == 0 && kb < 40 && lane == 0) p.timeline[48 + kb] = (unsigned long long)clock64();
           ptx::tcgen05_fence_after();
           const uint32_t st = ptx::smem_u32(smem + stage * STB);
 #pragma unroll
@@ -323,22 +325,22 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               const uint64_t w_lo = ptx::umma_desc_k_sw128(st + (4 + j) * 16384 + adv);
               const uint32_t acc = tmem_base + (uint32_t)(j * 256);
               if (SPLIT) {
-                ptx::mma_f16_ss_2sm(acc, a_lo, w_hi, idesc, (kb | k) != 0);
-                ptx::mma_f16_ss_2sm(acc, a_hi, w_lo, idesc, 1);
-                ptx::mma_f16_ss_2sm(acc, a_hi, w_hi, idesc, 1);
+                if (ptx::elect_one()) ptx::mma_f16_ss_2sm(acc, a_lo, w_hi, idesc, (kb | k) != 0);
+                if (ptx::elect_one()) ptx::mma_f16_ss_2sm(acc, a_hi, w_lo, idesc, 1);
+                if (ptx::elect_one()) ptx::mma_f16_ss_2sm(acc, a_hi, w_hi, idesc, 1);
               } else {
-                ptx::mma_f16_ss_2sm(acc, a_hi, w_hi, idesc, (kb | k) != 0);
+                if (ptx::elect_one()) ptx::mma_f16_ss_2sm(acc, a_hi, w_hi, idesc, (kb | k) != 0);
               }
             }
           }
-          ptx::tcgen05_commit_2sm(&empty_bar[stage]);
+          if (ptx::elect_one()) ptx::tcgen05_commit_2sm(&empty_bar[stage]);
           if (++stage == NST) {
             stage = 0;
             phase ^= 1;
           }
         }
         }
-        if (!M8 || ptx::elect_one()) ptx::tcgen05_commit_2sm(tmem_full_bar);
+        if (ptx::elect_one()) ptx::tcgen05_commit_2sm(tmem_full_bar);
         if (it == 0 && lane == 0) REGEN_LTL(2);
       }
     }

@@ -600,8 +600,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform; one elected lane per
+    // tcgen05 instruction, see ptx::elect_one)
+    {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -625,20 +626,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const uint64_t adv = (uint64_t)(k * UMMA_K * 2 >> 4);
             if (SPLIT) {
               // small cross terms first, the dominant hi.hi product last
-              ptx::mma_f16_ss(acc, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);
-              ptx::mma_f16_ss(acc, a_hi + adv, w_lo + adv, idesc, 1);
-              ptx::mma_f16_ss(acc, a_hi + adv, w_hi + adv, idesc, 1);
+              if (ptx::elect_one()) ptx::mma_f16_ss(acc, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);
+              if (ptx::elect_one()) ptx::mma_f16_ss(acc, a_hi + adv, w_lo + adv, idesc, 1);
+              if (ptx::elect_one()) ptx::mma_f16_ss(acc, a_hi + adv, w_hi + adv, idesc, 1);
             } else {
-              ptx::mma_f16_ss(acc, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+              if (ptx::elect_one()) ptx::mma_f16_ss(acc, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
             }
           }
-          ptx::tcgen05_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          if (ptx::elect_one()) ptx::tcgen05_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::tcgen05_commit(&tmem_full_bar[buf]);  // accumulator complete
+        if (ptx::elect_one()) ptx::tcgen05_commit(&tmem_full_bar[buf]);  // accumulator complete
       }
     }
   } else {
@@ -837,7 +838,9 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (rank == 0 && lane == 0) {
+    // The whole warp runs the loop (warp-uniform control flow and operands); one elected lane issues each tcgen05
+    // instruction (ptx::elect_one: a single-lane loop costs more cycles per MMA in issue than the MMA takes to execute).
+    if (rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -851,7 +854,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
-          if (kb == 0 && it < 16) REGEN_TL(8 + 2 * it);
+          if (kb == 0 && it < 16 && lane == 0) REGEN_TL(8 + 2 * it);
           ptx::tcgen05_fence_after();
           const uint32_t st = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t a_hi = ptx::umma_desc_k_sw128(st);
@@ -862,21 +865,21 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)(k * UMMA_K * 2 >> 4);
             if (SPLIT) {
-              ptx::mma_f16_ss_2sm(acc, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);
-              ptx::mma_f16_ss_2sm(acc, a_hi + adv, w_lo + adv, idesc, 1);
-              ptx::mma_f16_ss_2sm(acc, a_hi + adv, w_hi + adv, idesc, 1);
+              if (ptx::elect_one()) ptx::mma_f16_ss_2sm(acc, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);
+              if (ptx::elect_one()) ptx::mma_f16_ss_2sm(acc, a_hi + adv, w_lo + adv, idesc, 1);
+              if (ptx::elect_one()) ptx::mma_f16_ss_2sm(acc, a_hi + adv, w_hi + adv, idesc, 1);
             } else {
-              ptx::mma_f16_ss_2sm(acc, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+              if (ptx::elect_one()) ptx::mma_f16_ss_2sm(acc, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
             }
           }
-          ptx::tcgen05_commit_2sm(&empty_bar[stage]);  // frees this stage in BOTH CTAs
+          if (ptx::elect_one()) ptx::tcgen05_commit_2sm(&empty_bar[stage]);  // frees this stage in BOTH CTAs
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::tcgen05_commit_2sm(&tmem_full_bar[buf]);  // accumulator complete, signalled to both epilogues
-        if (it < 16) REGEN_TL(9 + 2 * it);
+        if (ptx::elect_one()) ptx::tcgen05_commit_2sm(&tmem_full_bar[buf]);  // accumulator complete, signalled to both epilogues
+        if (it < 16 && lane == 0) REGEN_TL(9 + 2 * it);
       }
     }
   } else {

@@ -64,6 +64,9 @@ struct Params {
   __nv_bfloat16* out_lo;
   int T, Beff;
   int causal;  // 1: additive causal mask of model/cmdm.py:168-171 (arch 'online'); 0: no mask (arch 'offline')
+  int m8;   // 1: outputs in the mixed8 operand format of the fused out_proj + LayerNorm kernel (gemm_ln_sm100.cuh): tm_ohi
+            // stores fp16 (same [T, Beff, 512] 16-bit map), tm_olo is the byte map [T, Beff, 1024] (box 32 frames x 64 B,
+            // SWIZZLE_64B): e4m3((o - fp16(o)) * 2^9) in bytes [0, 512) of a row, e4m3(fp16(o) / 4) in bytes [512, 1024)
   int dbg;  // bit 0 (test hook only) swaps the LBO / SBO fields of the V descriptor (bring-up A/B switch);
             // bit 2: wait for the bulk stores' global writes before exit (default; REGEN_DEBUG_EXIT_WAIT_READ=1 clears it, A/B: no measurable difference)
   unsigned long long* timeline;  // bring-up instrumentation (null in production): CTA 0 stamps clock64() at events
@@ -78,6 +81,59 @@ struct Params {
   do {                                                                                    \
     if (p.timeline && blockIdx.x == 0) p.timeline[(k)] = (unsigned long long)clock64();   \
   } while (0)
+
+// 32 accumulator columns of one output row -> staged operand chunks.  bf16 pair: four 16-byte chunks of the hi tile and
+// of the lo tile (32 rows x 128 B, SWIZZLE_128B, chunk index chunk0 + i).  mixed8: the same four chunks of the fp16 tile at
+// st_hi, and two 16-byte chunks each of the two byte tiles (32 rows x 64 B, SWIZZLE_64B) at st_lo / st_lo + 2048.
+__device__ __forceinline__ void stage_out32(const uint32_t (&v)[32], float inv, uint8_t* st_hi, uint8_t* st_lo, int lane,
+                                            int c0, bool m8) {
+  if (m8) {
+#pragma unroll
+    for (int j16 = 0; j16 < 32; j16 += 16) {
+      uint32_t hw[8], l8[4], h8[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {  // 4 columns -> two fp16x2 words, one word of residual bytes, one word of hi bytes
+        float lo[4], hf[4];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float a = __uint_as_float(v[j16 + 4 * g + 2 * e]) * inv, b2 = __uint_as_float(v[j16 + 4 * g + 2 * e + 1]) * inv;
+          hw[2 * g + e] = ptx::pack_f16x2_sat(a, b2);
+          const ptx::f32x2 h2 = ptx::f16x2_to_f32x2(hw[2 * g + e]);
+          ptx::upk2(ptx::mul2(h2, ptx::splat2(0.25f)), hf[2 * e], hf[2 * e + 1]);
+          ptx::upk2(ptx::mul2(ptx::sub2(ptx::pk2(a, b2), h2), ptx::splat2(512.f)), lo[2 * e], lo[2 * e + 1]);
+        }
+        l8[g] = ptx::pack_e4m3x4(lo[0], lo[1], lo[2], lo[3]);
+        h8[g] = ptx::pack_e4m3x4(hf[0], hf[1], hf[2], hf[3]);
+      }
+      const int col = (c0 & 63) + j16;  // column inside the warp's 64-column tile
+      const uint32_t off16 = (uint32_t)lane * 128;
+      *reinterpret_cast<uint4*>(st_hi + off16 + ((((uint32_t)col >> 3) ^ ((uint32_t)lane & 7)) << 4)) =
+          make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(st_hi + off16 + (((((uint32_t)col >> 3) + 1) ^ ((uint32_t)lane & 7)) << 4)) =
+          make_uint4(hw[4], hw[5], hw[6], hw[7]);
+      const uint32_t off8 = (uint32_t)lane * 64 + ((((uint32_t)col >> 4) ^ (((uint32_t)lane >> 1) & 3)) << 4);
+      *reinterpret_cast<uint4*>(st_lo + off8) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+      *reinterpret_cast<uint4*>(st_lo + 2048 + off8) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+    }
+    return;
+  }
+#pragma unroll
+  for (int j8 = 0; j8 < 32; j8 += 8) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = __uint_as_float(v[j8 + 2 * e]) * inv, b2 = __uint_as_float(v[j8 + 2 * e + 1]) * inv;
+      __nv_bfloat162 hh = __floats2bfloat162_rn(a, b2);
+      hw[e] = *reinterpret_cast<uint32_t*>(&hh);
+      __nv_bfloat162 ll = __floats2bfloat162_rn(a - __uint_as_float(hw[e] << 16), b2 - __uint_as_float(hw[e] & 0xffff0000u));
+      lw[e] = *reinterpret_cast<uint32_t*>(&ll);
+    }
+    const int chunk = ((c0 & 63) + j8) >> 3;  // 16-byte chunk of the 128-byte row
+    const uint32_t off = (uint32_t)lane * 128 + (((uint32_t)chunk ^ ((uint32_t)lane & 7)) << 4);
+    *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(st_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
 
 template <int TB>
 __global__ void __launch_bounds__(Cfg<TB>::THREADS, TB == 64 ? 3 : 1)
@@ -353,23 +409,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     uint8_t* st = (C::COMPACT ? sQ : sK) + (warp - 1) * (DW / 64) * 8192;
     auto stage_o = [&](const uint32_t (&v)[32], int c0) {
       uint8_t* st_hi = st + (c0 >> 6) * 8192;
-      uint8_t* st_lo = st_hi + 4096;
-#pragma unroll
-      for (int j8 = 0; j8 < 32; j8 += 8) {
-        uint32_t hw[4], lw[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float a = __uint_as_float(v[j8 + 2 * e]) * inv, b2 = __uint_as_float(v[j8 + 2 * e + 1]) * inv;
-          __nv_bfloat162 hh = __floats2bfloat162_rn(a, b2);
-          hw[e] = *reinterpret_cast<uint32_t*>(&hh);
-          __nv_bfloat162 ll = __floats2bfloat162_rn(a - __uint_as_float(hw[e] << 16), b2 - __uint_as_float(hw[e] & 0xffff0000u));
-          lw[e] = *reinterpret_cast<uint32_t*>(&ll);
-        }
-        const int chunk = ((c0 & 63) + j8) >> 3;  // 16-byte chunk of the 128-byte row
-        const uint32_t off = (uint32_t)lane * 128 + (((uint32_t)chunk ^ ((uint32_t)lane & 7)) << 4);
-        *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(st_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-      }
+      stage_out32(v, inv, st_hi, st_hi + 4096, lane, c0, p.m8 != 0);
     };
     {  // the next 32 columns of O are in flight while the current ones are scaled, split and staged
       static_assert((DW / 32) % 2 == 0, "O columns are processed in (va, vb) pairs");
@@ -392,8 +432,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     if (lane == 0 && q0 + q * 32 < p.T) {
 #pragma unroll
       for (int tile = 0; tile < DW / 64; ++tile) {
-        ptx::tma_store_3d(&tm_ohi, st + tile * 8192, h * HD + half * DW + tile * 64, b, q0 + q * 32, p.pol_store);
-        ptx::tma_store_3d(&tm_olo, st + tile * 8192 + 4096, h * HD + half * DW + tile * 64, b, q0 + q * 32, p.pol_store);
+        const int col = h * HD + half * DW + tile * 64;
+        ptx::tma_store_3d(&tm_ohi, st + tile * 8192, col, b, q0 + q * 32, p.pol_store);
+        if (p.m8) {  // residual bytes | hi bytes (two 32 x 64 B tiles behind the fp16 tile)
+          ptx::tma_store_3d(&tm_olo, st + tile * 8192 + 4096, col, b, q0 + q * 32, p.pol_store);
+          ptx::tma_store_3d(&tm_olo, st + tile * 8192 + 4096 + 2048, DM + col, b, q0 + q * 32, p.pol_store);
+        } else {
+          ptx::tma_store_3d(&tm_olo, st + tile * 8192 + 4096, col, b, q0 + q * 32, p.pol_store);
+        }
       }
       ptx::bulk_commit();
       // the staging tiles must have been read before the CTA exits; the kernel boundary orders the global writes
@@ -645,28 +691,14 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         __syncwarp();
         ptx::tmem_ld_32x32b_x32(o_addr + (uint32_t)c0, v);
         ptx::tmem_ld_wait(v);
-#pragma unroll
-        for (int j8 = 0; j8 < 32; j8 += 8) {
-          uint32_t hw[4], lw[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float a = __uint_as_float(v[j8 + 2 * e]) * inv, b2 = __uint_as_float(v[j8 + 2 * e + 1]) * inv;
-            __nv_bfloat162 hh = __floats2bfloat162_rn(a, b2);
-            hw[e] = *reinterpret_cast<uint32_t*>(&hh);
-            __nv_bfloat162 ll = __floats2bfloat162_rn(a - __uint_as_float(hw[e] << 16), b2 - __uint_as_float(hw[e] & 0xffff0000u));
-            lw[e] = *reinterpret_cast<uint32_t*>(&ll);
-          }
-          const int chunk = (c0 + j8) >> 3;
-          const uint32_t off = (uint32_t)lane * 128 + (((uint32_t)chunk ^ ((uint32_t)lane & 7)) << 4);
-          *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          *reinterpret_cast<uint4*>(st_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        }
+        stage_out32(v, inv, st_hi, st_lo, lane, c0, p.m8 != 0);
       }
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
         ptx::tma_store_3d(&tm_ohi, st_hi, h * HD + half * 64, b, q0 + q * 32, p.pol_store);
         ptx::tma_store_3d(&tm_olo, st_lo, h * HD + half * 64, b, q0 + q * 32, p.pol_store);
+        if (p.m8) ptx::tma_store_3d(&tm_olo, st_lo + 2048, DM + h * HD + half * 64, b, q0 + q * 32, p.pol_store);
         ptx::bulk_commit();
         ptx::bulk_wait<0>();
       }

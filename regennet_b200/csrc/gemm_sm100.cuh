@@ -855,6 +855,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           if (kb == 0 && it < 16 && lane == 0) REGEN_TL(8 + 2 * it);
+          if (it < 3 && kb < 8 && lane == 0) REGEN_TL(104 + 8 * it + kb);  // bring-up: k-block arrival times of the first tiles
           ptx::tcgen05_fence_after();
           const uint32_t st = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t a_hi = ptx::umma_desc_k_sw128(st);

@@ -34,9 +34,9 @@ struct LayerDev {
   SplitBuf wqkv, wo, w1, w2;
   // precision 'mixed8' only: linear2 weights as fp16 [512, 1024] + e4m3 bytes [512, 2048] (hi * 2^6 | lo * 2^17) for the
   // fused linear2 + LayerNorm kernel (the bf16 pair above still serves the small-batch route)
-  uint16_t* w2_16 = nullptr;
-  uint8_t* w2_8 = nullptr;
-  CUtensorMap tm_w2_16, tm_w2_8;
+  uint16_t *w2_16 = nullptr, *wo_16 = nullptr;
+  uint8_t *w2_8 = nullptr, *wo_8 = nullptr;
+  CUtensorMap tm_w2_16, tm_w2_8, tm_wo_16, tm_wo_8;   // wo_*: the same pack of the attention output projection [512, 512]
   float *bqkv, *bo, *b1, *b2, *n1w, *n1b, *n2w, *n2b, *n3w, *n3b;
 };
 
@@ -74,6 +74,8 @@ struct regen_handle {
   // precision 'mixed8', fused route: the FFN activations leave the FFN1 epilogue as fp16 in ffn.hi's memory and as e4m3
   // bytes [M, 2048] ((v - fp16(v)) * 2^9 | fp16(v) / 4) in ffn.lo's memory
   CUtensorMap tm_ffn8, st_ffn8;      // load map (box 128 rows x 128 B) / store map (box 32 rows x 64 B, rows = M)
+  // the attention output the same way: fp16 in att.hi's memory, bytes [M, 1024] in att.lo's memory
+  CUtensorMap tm_att8, st_att8;      // 2-D load map (box 128 rows x 128 B) / 3-D store map [S, Beff, 1024] (box 32 frames x 64 B)
   CUtensorMap st_h, st_tmp, st_x0e;  // store-side maps of the fp32 activation buffers (rows = M)
   CUtensorMap st32_h;                // h with box 32 x 32: residual load + store of the fused GEMM+LayerNorm kernel
   bool tma_store = true;             // REGEN_DEBUG_NO_TMA_STORE=1: st.global epilogue (A/B measurements)
@@ -325,6 +327,10 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
         if ((rc = h->alloc(&ld.w2_8, (size_t)D * 2 * FF))) break;
         if ((rc = make_tmap_bf16_2d(&ld.tm_w2_16, ld.w2_16, D, FF, FF, 128))) break;
         if ((rc = make_tmap_u8_2d(&ld.tm_w2_8, ld.w2_8, D, 2 * FF, 2 * FF, 128, 128))) break;
+        if ((rc = h->alloc(&ld.wo_16, (size_t)D * D))) break;
+        if ((rc = h->alloc(&ld.wo_8, (size_t)D * 2 * D))) break;
+        if ((rc = make_tmap_bf16_2d(&ld.tm_wo_16, ld.wo_16, D, D, D, 128))) break;
+        if ((rc = make_tmap_u8_2d(&ld.tm_wo_8, ld.wo_8, D, 2 * D, 2 * D, 128, 128))) break;
       }
     }
     if (rc) break;
@@ -340,6 +346,7 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
     if ((rc = alloc_split(h, &h->att, Mx, D, 128))) break;
     if ((rc = alloc_split(h, &h->ffn, Mx, FF, 128))) break;
     if (d->precision == 2 && (rc = make_tmap_u8_2d(&h->tm_ffn8, h->ffn.lo, Mx, 2 * FF, 2 * FF, 128, 128))) break;
+    if (d->precision == 2 && (rc = make_tmap_u8_2d(&h->tm_att8, h->att.lo, Mx, 2 * D, 2 * D, 128, 128))) break;
     if ((rc = alloc_split(h, &h->qkv_s, Mx, 3 * D, 128))) break;
     if ((rc = h->alloc(&h->h, Mx * D))) break;
     if ((rc = h->alloc(&h->qkv, Mx * 3 * D))) break;
@@ -445,6 +452,8 @@ int regen_load_weights(regen_handle* h, const regen_weight_ptrs* w, void* stream
     if (h->desc.precision == 2) {
       layers::pack_m8_weights_kernel<<<grid_cap(ceil_div((int64_t)D * FF / 4, 256)), 256, 0, s>>>(lw.l2_w, ld.w2_16,
                                                                                                  ld.w2_8, D, FF);
+      layers::pack_m8_weights_kernel<<<grid_cap(ceil_div((int64_t)D * D / 4, 256)), 256, 0, s>>>(lw.o_w, ld.wo_16,
+                                                                                                ld.wo_8, D, D);
       count_launch();
     }
     TRY(copy_vec(h, &ld.bqkv, lw.qkv_b, 3 * D, s));
@@ -563,6 +572,7 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
   TRY(make_tmap_bf16_3d(&h->tm_qkv_lo, h->qkv_s.lo, 3 * D, Beff, S, qkv_box));
   TRY(make_tmap_bf16_3d(&h->tm_att_hi, h->att.hi, D, Beff, S, 32));
   TRY(make_tmap_bf16_3d(&h->tm_att_lo, h->att.lo, D, Beff, S, 32));
+  if (h->desc.precision == 2) TRY(make_tmap_u8_3d(&h->st_att8, h->att.lo, 2 * D, Beff, S, 32, 64));
   if (h->has_cond) {
     // cond_emb[b'] for b' in [0, Beff): conditional rows [0,B), unconditional rows [B,2B) under guidance
     if (text_model) {
@@ -615,6 +625,8 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
   // of 3 bf16-MMA equivalents); FFN1's epilogue writes its activations in that operand format.  Everything else, and
   // the whole small-batch route, is bf16x3.
   const bool m8 = h->desc.precision == 2 && fused && h->tma_store && h->store64 && h->res16;
+  // ... and the attention output projection the same way when a tcgen05 attention kernel (which can write that format) runs
+  const bool m8_att = m8 && !h->simt_attention && S <= 256;
   const int Mf = T * Beff;                              // frame rows
   const size_t fr_off = offline ? (size_t)Beff * D : 0;  // offline: the frames follow the Beff condition-token rows
 
@@ -692,16 +704,18 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       } else {
         attn::Params ap;
         ap.out_hi = h->att.hi; ap.out_lo = h->att.lo; ap.T = S; ap.Beff = Beff; ap.causal = offline ? 0 : 1; ap.dbg = h->exit_wait_full ? 4 : 0;
+        ap.m8 = m8_att ? 1 : 0;
+        const CUtensorMap& att_lo_map = m8_att ? h->st_att8 : h->tm_att_lo;
         ap.timeline = nullptr;
         ap.steplog = nullptr; ap.steplog_slot = 0; ap.steplog_cta = 0;
         ap.pol_load = h->pol(1, ptx::kL2EvictFirst);
         ap.pol_store = h->pol(2, ptx::kL2EvictLast);
         if (h->steplog && h->steplog_slot < h->steplog_cap) { ap.steplog = h->steplog; ap.steplog_slot = h->steplog_slot++; }
         cudaError_t e = S > 256 ? attn::launch_long(h->qkv_s.hi, h->qkv_s.lo, ap, s)
-                        : S <= 64 ? attn::launch<64>(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s)
+                        : S <= 64 ? attn::launch<64>(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, att_lo_map, ap, s)
                         : h->attn_mc
-                                ? attn::launch_mc(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s)
-                                : attn::launch<128>(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, h->tm_att_lo, ap, s);
+                                ? attn::launch_mc(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, att_lo_map, ap, s)
+                                : attn::launch<128>(h->tm_qkv_hi, h->tm_qkv_lo, h->tm_att_hi, att_lo_map, ap, s);
         if (e != cudaSuccess) {
           set_error("attention launch (T=%d Beff=%d) failed: %s", T, Beff, cudaGetErrorString(e));
           return REGEN_ECUDA;
@@ -721,7 +735,9 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       if (h->steplog && h->steplog_slot < h->steplog_cap) {
         q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;
       }
-      cudaError_t e = h->desc.precision != 1
+      cudaError_t e = m8_att ? gemmln::launch_m8<false>(h->att.tm_hi, h->tm_att8, ld.tm_wo_16, ld.tm_wo_8, h->st32_h,
+                                                        h->h_s.st64_hi, h->h_s.st64_lo, q, s)
+          : h->desc.precision != 1
           ? gemmln::launch<true, false>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->st32_h,
                                         h->h_s.st64_hi, h->h_s.st64_lo, q, s, h->res16)
           : gemmln::launch<false, false>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->st32_h,
@@ -743,7 +759,9 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       if (h->steplog && h->steplog_slot < h->steplog_cap) {
         q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;
       }
-      cudaError_t e = h->desc.precision != 1
+      cudaError_t e = m8_att ? gemmln::launch_m8<true>(h->att.tm_hi, h->tm_att8, ld.tm_wo_16, ld.tm_wo_8, h->tm_cyc[l],
+                                                       h->h_s.st64_hi, h->h_s.st64_lo, q, s)
+          : h->desc.precision != 1
           ? gemmln::launch<true, true>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->tm_cyc[l],
                                        h->h_s.st64_hi, h->h_s.st64_lo, q, s, h->res16)
           : gemmln::launch<false, true>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->tm_cyc[l],
@@ -974,7 +992,7 @@ int regen_test_attention(const float* qkv, float* out, int32_t B, int32_t T, int
   if (!rc) rc = make_tmap_bf16_3d(&tol, ol, D, B, T, 32);
   if (!rc) {
     attn::Params ap;
-    ap.out_hi = oh; ap.out_lo = ol; ap.T = T; ap.Beff = B; ap.causal = (dbg & 2) ? 0 : 1; ap.dbg = dbg & 1;
+    ap.out_hi = oh; ap.out_lo = ol; ap.T = T; ap.Beff = B; ap.causal = (dbg & 2) ? 0 : 1; ap.dbg = dbg & 1; ap.m8 = 0;
     ap.timeline = g_test_timeline;
     ap.steplog = nullptr; ap.steplog_slot = 0; ap.steplog_cta = 0;
     ap.pol_load = 0; ap.pol_store = 0;

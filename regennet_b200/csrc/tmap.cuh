@@ -128,4 +128,28 @@ inline int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, ui
   return REGEN_OK;
 }
 
+// Byte tensor [d2, d1, d0] (d0 contiguous): the attention output's e4m3 operand bytes viewed as [T frames, Beff samples,
+// 1024 B]; box = 32 frames x 1 sample x 64 bytes, SWIZZLE_64B (store side of the attention kernels under precision 'mixed8').
+inline int make_tmap_u8_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box2,
+                           uint32_t box0) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    return REGEN_ECUDA;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0, d0 * d1};
+  cuuint32_t box[3] = {box0, 1, box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box0 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(u8 3d) failed with CUresult %d (dims %llu x %llu x %llu, box %u x %u)", (int)r,
+              (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, box2, box0);
+    return REGEN_ECUDA;
+  }
+  return REGEN_OK;
+}
+
 }  // namespace regen

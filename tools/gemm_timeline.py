@@ -29,6 +29,9 @@ for name, N, K, res, gelu in [("qkv", 1536, 512, False, False), ("out_proj", 512
             break
         print("  tile %d: mma start %7d issue-end %7d | epi start %7d end %7d (epi %6d)" % (
             i, t[8 + 2 * i] - t0, t[9 + 2 * i] - t0, t[40 + 2 * i] - t0, t[41 + 2 * i] - t0, t[41 + 2 * i] - t[40 + 2 * i]))
+    for i in range(3):
+        kb = [x - t0 for x in t[104 + 8 * i:112 + 8 * i] if x]
+        print("  tile %d k-block arrivals %s cadence %s" % (i, kb, [b - a for a, b in zip(kb, kb[1:])]))
     for sc in range(3):
         b0 = 80 + sc * 8
         if t[b0]:

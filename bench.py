@@ -38,11 +38,12 @@ import torch  # noqa: E402
 
 B_DEFAULT, T_DEFAULT = 256, 60
 # operand scheme of the GPU arm: 'bf16x3', or 'mixed8' (bf16x3 + fp16/e4m3 linear2 on the fused route); REGEN_PRECISION overrides
-PRECISION = os.environ.get("REGEN_PRECISION", "bf16x3")
+PRECISION = os.environ.get("REGEN_PRECISION", "mixed8")
 DTYPES = {
     "bf16x3": "bf16x3 (3 bf16 tcgen05 MMAs per product, fp32 accumulate; fp32 LN/softmax/update, residual stream as a bf16 (hi, lo) pair)",
-    "mixed8": "bf16x3 (3 bf16 tcgen05 MMAs per product) except linear2: fp16 MMA + two e4m3 correction MMAs per product "
-              "(2 MMA equivalents); fp32 accumulate, fp32 LN/softmax/update, residual stream as a bf16 (hi, lo) pair",
+    "mixed8": "mixed8 = bf16x3 (3 bf16 tcgen05 MMAs per product: input / QKV / FFN1 / output projections, attention) + "
+              "fp16 MMA with two e4m3 correction MMAs per product (2 MMA equivalents: attention out_proj and linear2, the "
+              "two fused GEMM+LayerNorm kernels); fp32 accumulate, fp32 LN/softmax/update, residual stream as a bf16 (hi, lo) pair",
 }
 METRIC = "denoising_steps_per_sec"
 UNIT = "steps/s (1 step = one p_sample over B=256 x T=60 poses per GPU, summed over GPUs)"
@@ -133,11 +134,11 @@ def make_diffusion(respacing):
                                    model_var_type=gd.ModelVarType.FIXED_SMALL, loss_type=gd.LossType.MSE)
 
 
-def build_ours(device, B=None, T=None, name="ntu"):
+def build_ours(device, B=None, T=None, name="ntu", precision=None):
     from regennet_b200 import synthetic
     from regennet_b200.cmdm import CMDM
     mk, sk = model_cfg(name)
-    model = CMDM(precision=PRECISION, **mk)
+    model = CMDM(precision=precision or PRECISION, **mk)
     model.load_state_dict(synthetic.make_state_dict(seed=0, **sk), strict=False)
     model = model.to(device).eval()
     return model, make_diffusion
@@ -611,8 +612,8 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "tcgen05 GEMM class: gemm2_tn_kernel<256,bf16x3> (QKV, FFN1, output projection) + "
-                                   "gemm_ln_kernel (input projection, out_proj+LN1+LN2, linear2+LN3 fused), %d launches per step"
-                                   % gemm_launches,
+                                   "gemm_ln_kernel (input projection: bf16x3; out_proj+LN1+LN2, linear2+LN3 fused: %s), %d "
+                                   "launches per step" % (PRECISION if PRECISION == "mixed8" else "bf16x3", gemm_launches),
                          "achieved": gemm_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
                          "frac": gemm_tf / peaks["tf_sust"], "traffic": traffic,
                          "ms_per_step": gemm_ms,
@@ -622,8 +623,9 @@ def run_ours(args):
                          "traffic_note": "DRAM bytes per GEMM-class launch (ncu dram__bytes_read+write, profiles/); "
                                          "algorithmic operand+result bytes per launch: QKV 129 MB, FFN1 100 MB, fused N=512 GEMMs 96-128 MB",
                          "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json)" % peaks["src"],
-                         "note": "achieved counts ALGORITHMIC flops (1 MAC per product); the bf16x3 parity mode "
-                                 "executes 3 MMAs per product, so frac is capped at 1/3"},
+                         "note": "achieved counts ALGORITHMIC flops (1 MAC per product); bf16x3 executes 3 MMAs per product "
+                                 "(frac capped at 1/3), the mixed8 kernels (out+LN, lin2+LN under precision 'mixed8') 2 "
+                                 "bf16-MMA equivalents (cap 1/2)"},
             "kernels": kernels,
             "roofline_hbm": {"bound": "hbm", "kernel": "p_sample_update_kernel", "achieved": upd_gbs,
                              "peak": peaks["hbm"], "unit": "GB/s", "frac": upd_gbs / peaks["hbm"],
@@ -650,6 +652,15 @@ def run_ours(args):
         }
         if world == 1 and not args.brief:
             line["other_configs"] = other_configs(dev, peaks)
+            if PRECISION != "bf16x3":
+                # the same K device-resident steps with every product in bf16x3 (the library's default precision)
+                m3, _ = build_ours(dev, precision="bf16x3")
+                s3 = full._fast_session(m3, shape, {"y": yc}, None, None, False, False, img)
+                ms3, K3, _, _ = device_steps(s3, full, "p", img, K, W, U, barrier)
+                line["precision_ab"] = {PRECISION: steps_per_s, "bf16x3": 1000.0 * K3 / ms3, "unit": UNIT,
+                                        "what": "device-resident value of this run vs the same %d steps with precision="
+                                                "'bf16x3' (library default) on the same GPU" % K3}
+                del m3, s3
 
             def ours_forward(x, t):
                 with torch.no_grad():

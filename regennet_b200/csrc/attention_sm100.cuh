@@ -65,8 +65,8 @@ struct Params {
   int T, Beff;
   int causal;  // 1: additive causal mask of model/cmdm.py:168-171 (arch 'online'); 0: no mask (arch 'offline')
   int m8;   // 1: outputs in the mixed8 operand format of the fused out_proj + LayerNorm kernel (gemm_ln_sm100.cuh): tm_ohi
-            // stores fp16 (same [T, Beff, 512] 16-bit map), tm_olo is the byte map [T, Beff, 1024] (box 32 frames x 64 B,
-            // SWIZZLE_64B): e4m3((o - fp16(o)) * 2^9) in bytes [0, 512) of a row, e4m3(fp16(o) / 4) in bytes [512, 1024)
+            // stores fp16 (same [T, Beff, 512] 16-bit map), tm_olo is the byte map [T, Beff, 1024] (box 32 frames x 128 B,
+            // SWIZZLE_128B): per group of 64 columns, 64 bytes e4m3((o - fp16(o)) * 2^9) | 64 bytes e4m3(fp16(o) / 4)
   int dbg;  // bit 0 (test hook only) swaps the LBO / SBO fields of the V descriptor (bring-up A/B switch);
             // bit 2: wait for the bulk stores' global writes before exit (default; REGEN_DEBUG_EXIT_WAIT_READ=1 clears it, A/B: no measurable difference)
   unsigned long long* timeline;  // bring-up instrumentation (null in production): CTA 0 stamps clock64() at events
@@ -84,7 +84,8 @@ struct Params {
 
 // 32 accumulator columns of one output row -> staged operand chunks.  bf16 pair: four 16-byte chunks of the hi tile and
 // of the lo tile (32 rows x 128 B, SWIZZLE_128B, chunk index chunk0 + i).  mixed8: the same four chunks of the fp16 tile at
-// st_hi, and two 16-byte chunks each of the two byte tiles (32 rows x 64 B, SWIZZLE_64B) at st_lo / st_lo + 2048.
+// st_hi, and one 16-byte chunk in each half of the byte tile at st_lo (32 rows x 128 B, SWIZZLE_128B: 64 residual bytes |
+// 64 hi bytes per row).
 __device__ __forceinline__ void stage_out32(const uint32_t (&v)[32], float inv, uint8_t* st_hi, uint8_t* st_lo, int lane,
                                             int c0, bool m8) {
   if (m8) {
@@ -111,9 +112,11 @@ __device__ __forceinline__ void stage_out32(const uint32_t (&v)[32], float inv, 
           make_uint4(hw[0], hw[1], hw[2], hw[3]);
       *reinterpret_cast<uint4*>(st_hi + off16 + (((((uint32_t)col >> 3) + 1) ^ ((uint32_t)lane & 7)) << 4)) =
           make_uint4(hw[4], hw[5], hw[6], hw[7]);
-      const uint32_t off8 = (uint32_t)lane * 64 + ((((uint32_t)col >> 4) ^ (((uint32_t)lane >> 1) & 3)) << 4);
-      *reinterpret_cast<uint4*>(st_lo + off8) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
-      *reinterpret_cast<uint4*>(st_lo + 2048 + off8) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+      // byte tile: 32 rows x 128 B (SWIZZLE_128B), residual bytes in chunks 0..3, hi bytes in chunks 4..7
+      *reinterpret_cast<uint4*>(st_lo + off16 + ((((uint32_t)col >> 4) ^ ((uint32_t)lane & 7)) << 4)) =
+          make_uint4(l8[0], l8[1], l8[2], l8[3]);
+      *reinterpret_cast<uint4*>(st_lo + off16 + (((4 + ((uint32_t)col >> 4)) ^ ((uint32_t)lane & 7)) << 4)) =
+          make_uint4(h8[0], h8[1], h8[2], h8[3]);
     }
     return;
   }
@@ -434,12 +437,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       for (int tile = 0; tile < DW / 64; ++tile) {
         const int col = h * HD + half * DW + tile * 64;
         ptx::tma_store_3d(&tm_ohi, st + tile * 8192, col, b, q0 + q * 32, p.pol_store);
-        if (p.m8) {  // residual bytes | hi bytes (two 32 x 64 B tiles behind the fp16 tile)
-          ptx::tma_store_3d(&tm_olo, st + tile * 8192 + 4096, col, b, q0 + q * 32, p.pol_store);
-          ptx::tma_store_3d(&tm_olo, st + tile * 8192 + 4096 + 2048, DM + col, b, q0 + q * 32, p.pol_store);
-        } else {
-          ptx::tma_store_3d(&tm_olo, st + tile * 8192 + 4096, col, b, q0 + q * 32, p.pol_store);
-        }
+        // mixed8: the byte tile (residual bytes | hi bytes of these 64 columns) lands at byte column 2 col of the [.., 1024] rows
+        ptx::tma_store_3d(&tm_olo, st + tile * 8192 + 4096, p.m8 ? 2 * col : col, b, q0 + q * 32, p.pol_store);
       }
       ptx::bulk_commit();
       // the staging tiles must have been read before the CTA exits; the kernel boundary orders the global writes
@@ -697,8 +696,7 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
       __syncwarp();
       if (lane == 0) {
         ptx::tma_store_3d(&tm_ohi, st_hi, h * HD + half * 64, b, q0 + q * 32, p.pol_store);
-        ptx::tma_store_3d(&tm_olo, st_lo, h * HD + half * 64, b, q0 + q * 32, p.pol_store);
-        if (p.m8) ptx::tma_store_3d(&tm_olo, st_lo + 2048, DM + h * HD + half * 64, b, q0 + q * 32, p.pol_store);
+        ptx::tma_store_3d(&tm_olo, st_lo, (p.m8 ? 2 : 1) * (h * HD + half * 64), b, q0 + q * 32, p.pol_store);
         ptx::bulk_commit();
         ptx::bulk_wait<0>();
       }

@@ -30,8 +30,11 @@
 // 4 significand bits suffice for them (measured on B200: 4.0e-5 against 8.6e-6 for fp16 x3, tools/mixed8_probe.cu).
 // The power-of-two operand scales (product 2^15 in both terms, undone by scale-input-d) place |a| <= 1792 and |w| <= 7 inside
 // e4m3's range; beyond that the fp8 copies saturate and the element falls back to plain fp16 accuracy.
-// Operands: tm_a_hi = A16 [M, K] (16-bit), tm_a_lo = A8 [M, 2K] bytes (A_lo8 | A_hi8), tm_w_hi = W16 [512, K],
-// tm_w_lo = W8 [512, 2K] bytes (W_hi8 | W_lo8); the 8-bit boxes are 128 rows x 128 bytes.  The ring is then 4 stages of
+// Operands: tm_a_hi = A16 [M, K] (16-bit), tm_a_lo = A8 [M, 2K] bytes, tm_w_hi = W16 [512, K], tm_w_lo = W8 [512, 2K] bytes.
+// The byte rows interleave the two correction operands per group of 64 K elements: A8 = [A_lo8 (64) | A_hi8 (64)] ...,
+// W8 = [W_hi8 (64) | W_lo8 (64)] ..., so that one 128-byte row segment of A8 against the same segment of W8 is the sum of
+// both correction products of those 64 elements (and the producing epilogues emit ONE 32 x 128-byte box per 64 columns);
+// the 8-bit boxes are 128 rows x 128 bytes.  The ring is then 4 stages of
 // 48 KB (A tile | two W half tiles of 16 KB), every stage feeds 8 MMAs (1 k cycles): first the 2 K / 128 correction stages,
 // then the K / 64 main-term stages.
 #pragma once
@@ -195,11 +198,12 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           uint8_t* st = smem + stage * STB;
           if constexpr (M8) {
             if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * STB);
-            // correction stage i = 2 kb8 + sub: sub 0 = A_lo8 x W_hi8 (first K bytes of the rows), sub 1 = A_hi8 x W_lo8
+            // correction stage i: bytes [128 i, 128 i + 128) of the byte rows = the residual-times-hi and hi-times-residual
+            // operand bytes of 64 K elements (see the header comment: the two correction products are one dot product over 2 K)
             const bool corr = kb < n1;
             const CUtensorMap* ma = corr ? &tm_a_lo : &tm_a_hi;
             const CUtensorMap* mw = corr ? &tm_w_lo : &tm_w_hi;
-            const int c0 = corr ? (kb & 1) * p.K + (kb >> 1) * 128 : (kb - n1) * BK;
+            const int c0 = corr ? kb * 128 : (kb - n1) * BK;
             ptx::tma_load_2d_2sm(st, ma, &full_bar[stage], c0, m0, p.pol_a);
             ptx::tma_load_2d_2sm(st + 16384, mw, &full_bar[stage], c0, (int)rank * 128, p.pol_w);
             ptx::tma_load_2d_2sm(st + 2 * 16384, mw, &full_bar[stage], c0, 256 + (int)rank * 128, p.pol_w);

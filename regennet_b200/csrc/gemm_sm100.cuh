@@ -59,8 +59,8 @@ struct Params {
   int pair64;               // 16-warp pair kernel, bf16 (hi, lo) outputs only: 64-column store boxes through warp pairs (tm_ohi /
                             // tm_olo must then be the 32 x 64 box maps)
   int m8;                   // pair64 epilogue only: outputs in the mixed8 operand format of the fused linear2 + LayerNorm kernel
-                            // (gemm_ln_sm100.cuh): tm_ohi = fp16 [M, N] (box 32 x 64), tm_olo = bytes [M, 2 N] (box 32 rows x 64 B,
-                            // SWIZZLE_64B) holding e4m3((v - fp16(v)) * 2^9) in columns [0, N) and e4m3(fp16(v) / 4) in [N, 2 N)
+                            // (gemm_ln_sm100.cuh): tm_ohi = fp16 [M, N] (box 32 x 64), tm_olo = bytes [M, 2 N] (box 32 rows x 128 B,
+                            // SWIZZLE_128B): per group of 64 columns, 64 bytes e4m3((v - fp16(v)) * 2^9) | 64 bytes e4m3(fp16(v) / 4)
   int slice_w_rows;         // pair kernel: rows of the W box the slice maps (tm_ws_*) load per CTA (set by launch2)
   int tail_split;           // pair kernel: the tiles of the last, partial wave are cut into 1 / 2 / 4 column slices (set by launch2)
   // bring-up instrumentation (test hook only, null in production): CTA 0 records clock64() at pipeline events
@@ -486,19 +486,18 @@ __device__ __forceinline__ void epilogue_pair64(const Params& p, const CUtensorM
     }
     pair_sync();  // hi tile read: the staging tile takes the lo halves
     if (p.m8) {
-      // two byte tiles of 32 rows x 64 B (SWIZZLE_64B) in the 4 KB staging tile: residual bytes | e4m3(hi) bytes; this warp
-      // owns bytes [32 sub, 32 sub + 32) of every row
+      // one byte tile of 32 rows x 128 B (SWIZZLE_128B): residual bytes of the 64 columns | e4m3(hi) bytes of the 64 columns;
+      // this warp owns bytes [32 sub, 32 sub + 32) of each half
 #pragma unroll
       for (int t = 0; t < 2; ++t)
 #pragma unroll
         for (int c = 0; c < 2; ++c)
-          *reinterpret_cast<uint4*>(stg + t * 2048 + stg_off_f32(lane, 2 * sub + c)) =
+          *reinterpret_cast<uint4*>(stg + stg_off_128(lane, 4 * t + 2 * sub + c)) =
               make_uint4(lw[8 * t + 4 * c], lw[8 * t + 4 * c + 1], lw[8 * t + 4 * c + 2], lw[8 * t + 4 * c + 3]);
       ptx::fence_proxy_async_smem();
       pair_sync();
       if (issuer) {
-        ptx::tma_store_2d(tm_olo, stg, n0 + 64 * g, row0, p.pol_store);
-        ptx::tma_store_2d(tm_olo, stg + 2048, p.N + n0 + 64 * g, row0, p.pol_store);
+        ptx::tma_store_2d(tm_olo, stg, 2 * (n0 + 64 * g), row0, p.pol_store);
         ptx::bulk_commit();
       }
       continue;

@@ -56,8 +56,8 @@ inline void launch_split_rows(const float* src, int ld_src, __nv_bfloat16* hi, _
 }
 
 // ------------------------------------------------------------------------------------------
-// fp32 W [R, C] -> the mixed8 operand pack of gemm_ln_sm100.cuh (setup only): w16 fp16 [R, C] and bytes [R, 2 C] with
-// e4m3(fp16(w) * 2^6) in columns [0, C) and e4m3((w - fp16(w)) * 2^17) in columns [C, 2 C).
+// fp32 W [R, C] -> the mixed8 operand pack of gemm_ln_sm100.cuh (setup only): w16 fp16 [R, C] and bytes [R, 2 C]: per group
+// of 64 columns, 64 bytes e4m3(fp16(w) * 2^6) followed by 64 bytes e4m3((w - fp16(w)) * 2^17).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_m8_weights_kernel(const float* __restrict__ src, uint16_t* __restrict__ w16,
                                                               uint8_t* __restrict__ w8, int R, int C) {
@@ -70,8 +70,9 @@ __global__ void __launch_bounds__(256) pack_m8_weights_kernel(const float* __res
     ptx::upk2(ptx::f16x2_to_f32x2(h0), a0, a1);
     ptx::upk2(ptx::f16x2_to_f32x2(h1), a2, a3);
     *reinterpret_cast<uint2*>(w16 + (size_t)r * C + c) = make_uint2(h0, h1);
-    *reinterpret_cast<uint32_t*>(w8 + (size_t)r * 2 * C + c) = ptx::pack_e4m3x4(a0 * 64.f, a1 * 64.f, a2 * 64.f, a3 * 64.f);
-    *reinterpret_cast<uint32_t*>(w8 + (size_t)r * 2 * C + C + c) =
+    uint8_t* grp = w8 + (size_t)r * 2 * C + (c >> 6) * 128 + (c & 63);   // group of 64 K elements: hi bytes | residual bytes
+    *reinterpret_cast<uint32_t*>(grp) = ptx::pack_e4m3x4(a0 * 64.f, a1 * 64.f, a2 * 64.f, a3 * 64.f);
+    *reinterpret_cast<uint32_t*>(grp + 64) =
         ptx::pack_e4m3x4((f.x - a0) * 131072.f, (f.y - a1) * 131072.f, (f.z - a2) * 131072.f, (f.w - a3) * 131072.f);
   }
 }

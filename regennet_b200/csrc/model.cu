@@ -32,7 +32,7 @@ struct SplitBuf {  // bf16 (hi, lo) operand pair + its TMA maps
 
 struct LayerDev {
   SplitBuf wqkv, wo, w1, w2;
-  // precision 'mixed8' only: linear2 weights as fp16 [512, 1024] + e4m3 bytes [512, 2048] (hi * 2^6 | lo * 2^17) for the
+  // precision 'mixed8' only: linear2 weights as fp16 [512, 1024] + e4m3 bytes [512, 2048] (per 64 columns: hi * 2^6 | lo * 2^17) for the
   // fused linear2 + LayerNorm kernel (the bf16 pair above still serves the small-batch route)
   uint16_t *w2_16 = nullptr, *wo_16 = nullptr;
   uint8_t *w2_8 = nullptr, *wo_8 = nullptr;
@@ -72,10 +72,10 @@ struct regen_handle {
   CUtensorMap tm_qkv_hi, tm_qkv_lo;  // 3-D [T, Beff, 1536] views of qkv_s for the attention kernel (per prepare_cond)
   CUtensorMap tm_att_hi, tm_att_lo;  // 3-D [T, Beff, 512] store views of the attention output (box 32 frames x 64 d)
   // precision 'mixed8', fused route: the FFN activations leave the FFN1 epilogue as fp16 in ffn.hi's memory and as e4m3
-  // bytes [M, 2048] ((v - fp16(v)) * 2^9 | fp16(v) / 4) in ffn.lo's memory
-  CUtensorMap tm_ffn8, st_ffn8;      // load map (box 128 rows x 128 B) / store map (box 32 rows x 64 B, rows = M)
+  // bytes [M, 2048] (per 64 columns: (v - fp16(v)) * 2^9 | fp16(v) / 4) in ffn.lo's memory
+  CUtensorMap tm_ffn8, st_ffn8;      // load map (box 128 rows x 128 B) / store map (box 32 rows x 128 B, rows = M)
   // the attention output the same way: fp16 in att.hi's memory, bytes [M, 1024] in att.lo's memory
-  CUtensorMap tm_att8, st_att8;      // 2-D load map (box 128 rows x 128 B) / 3-D store map [S, Beff, 1024] (box 32 frames x 64 B)
+  CUtensorMap tm_att8, st_att8;      // 2-D load map (box 128 rows x 128 B) / 3-D store map [S, Beff, 1024] (box 32 frames x 128 B)
   CUtensorMap st_h, st_tmp, st_x0e;  // store-side maps of the fp32 activation buffers (rows = M)
   CUtensorMap st32_h;                // h with box 32 x 32: residual load + store of the fused GEMM+LayerNorm kernel
   bool tma_store = true;             // REGEN_DEBUG_NO_TMA_STORE=1: st.global epilogue (A/B measurements)
@@ -538,7 +538,7 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
     TRY(make_tmap_store_2d(&sb->st64_hi, sb->hi, true, h->M, sb->cols, sb->cols, 64));
     TRY(make_tmap_store_2d(&sb->st64_lo, sb->lo, true, h->M, sb->cols, sb->cols, 64));
   }
-  if (h->desc.precision == 2) TRY(make_tmap_u8_2d(&h->st_ffn8, h->ffn.lo, h->M, 2 * FF, 2 * FF, 32, 64));
+  if (h->desc.precision == 2) TRY(make_tmap_u8_2d(&h->st_ffn8, h->ffn.lo, h->M, 2 * FF, 2 * FF, 32, 128));
   TRY(make_tmap_store_2d(&h->st32_h, h->h, false, h->M, D, D, 32));
   TRY(make_tmap_store_2d(&h->ld32_condbias, h->condbias, false, Mf, D, D, 32));
   if (h->offline) {
@@ -572,7 +572,7 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
   TRY(make_tmap_bf16_3d(&h->tm_qkv_lo, h->qkv_s.lo, 3 * D, Beff, S, qkv_box));
   TRY(make_tmap_bf16_3d(&h->tm_att_hi, h->att.hi, D, Beff, S, 32));
   TRY(make_tmap_bf16_3d(&h->tm_att_lo, h->att.lo, D, Beff, S, 32));
-  if (h->desc.precision == 2) TRY(make_tmap_u8_3d(&h->st_att8, h->att.lo, 2 * D, Beff, S, 32, 64));
+  if (h->desc.precision == 2) TRY(make_tmap_u8_3d(&h->st_att8, h->att.lo, 2 * D, Beff, S, 32, 128));
   if (h->has_cond) {
     // cond_emb[b'] for b' in [0, Beff): conditional rows [0,B), unconditional rows [B,2B) under guidance
     if (text_model) {

@@ -184,6 +184,17 @@ bool use_pair_kernel(int M) {
   return !force1 && M > 128;
 }
 
+// REGEN_DEBUG_QKV_TIMELINE=1: the regen_test_gemm_timeline buffer receives the stamps of the (last) QKV GEMM of a forward
+// instead of those of the fused GEMM+LN kernels (tools/qkv_timeline.py)
+bool qkv_timeline() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("REGEN_DEBUG_QKV_TIMELINE");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
+}
+
 // o32: store-side maps {box 16, box 32} of the fp32 output named in p; osplit: the bf16-pair output buffer
 // (null -> st.global epilogue)
 int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, gemm::Params p, const CUtensorMap* o32,
@@ -220,6 +231,7 @@ int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, gemm::Params
     p.steplog_slot = h->steplog_slot++;
     p.steplog_cta = 2 * h->steplog_cap;
   }
+  if (qkv_timeline() && p.N == 3 * D) p.timeline = g_test_timeline;  // bring-up: pipeline stamps of the QKV GEMM inside a real forward
   cudaError_t e;
   if (use_pair_kernel(p.M)) {
     gemm::SliceMaps sm;
@@ -730,7 +742,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       q.ln_eps = layers::LN_EPS; q.store_f32 = 0; q.nob16 = h->nob16; q.exit_wait_full = h->exit_wait_full ? 1 : 0;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
       q.pol_a = h->pol(8, ptx::kL2EvictFirst); q.pol_w = h->pol(4, ptx::kL2EvictLast); q.pol_store = h->pol(2, ptx::kL2EvictLast);
-      q.timeline = g_test_timeline;
+      q.timeline = qkv_timeline() ? nullptr : g_test_timeline;
       q.steplog = nullptr; q.steplog_slot = 0; q.steplog_cta = 0;
       if (h->steplog && h->steplog_slot < h->steplog_cap) {
         q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;
@@ -754,7 +766,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       q.ln_eps = layers::LN_EPS; q.store_f32 = 0; q.nob16 = h->nob16; q.exit_wait_full = h->exit_wait_full ? 1 : 0;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
       q.pol_a = h->pol(8, ptx::kL2EvictFirst); q.pol_w = h->pol(4, ptx::kL2EvictLast); q.pol_store = h->pol(2, ptx::kL2EvictLast);
-      q.timeline = g_test_timeline;
+      q.timeline = qkv_timeline() ? nullptr : g_test_timeline;
       q.steplog = nullptr; q.steplog_slot = 0; q.steplog_cta = 0;
       if (h->steplog && h->steplog_slot < h->steplog_cap) {
         q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;
@@ -815,7 +827,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       q.ln_eps = layers::LN_EPS; q.store_f32 = 0; q.nob16 = h->nob16; q.exit_wait_full = h->exit_wait_full ? 1 : 0;
       q.prefetch_res = h->prefetch_res ? 1 : 0;
       q.pol_a = h->pol(8, ptx::kL2EvictFirst); q.pol_w = h->pol(4, ptx::kL2EvictLast); q.pol_store = h->pol(2, ptx::kL2EvictLast);
-      q.timeline = g_test_timeline;
+      q.timeline = qkv_timeline() ? nullptr : g_test_timeline;
       q.steplog = nullptr; q.steplog_slot = 0; q.steplog_cta = 0;
       if (h->steplog && h->steplog_slot < h->steplog_cap) {
         q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;

@@ -243,17 +243,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         ptx::tcgen05_fence_after();
         const uint32_t accS = tmem_base + S_COL + (uint32_t)(kc * TB);
         const uint32_t aKc = kc == 0 ? aK : aV;                      // K_1 sits in the V buffer
+        // one elected lane issues the chunk's 24 MMAs back to back; descriptors: base of each operand tile built once,
+        // + 2 in the address field per 32-byte k-step (the per-MMA issue cost, ~80 cycles when every MMA was elected and
+        // its descriptors rebuilt, exceeded the 32 cycles such a 128 x 64 x 16 MMA executes)
+        {
+          const uint64_t dq_hi0 = ptx::umma_desc_k_sw128(aQ), dq_hi1 = ptx::umma_desc_k_sw128(aQ + C::TILE);
+          const uint64_t dq_lo0 = ptx::umma_desc_k_sw128(aQ + 2 * C::TILE), dq_lo1 = ptx::umma_desc_k_sw128(aQ + 3 * C::TILE);
+          const uint64_t dk_hi0 = ptx::umma_desc_k_sw128(aKc), dk_hi1 = ptx::umma_desc_k_sw128(aKc + C::TILE);
+          const uint64_t dk_lo0 = ptx::umma_desc_k_sw128(aKc + 2 * C::TILE), dk_lo1 = ptx::umma_desc_k_sw128(aKc + 3 * C::TILE);
+          if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t tile = (uint32_t)(k >> 2) * C::TILE;        // d 0-63 | d 64-127
-          const uint32_t adv = (uint32_t)(k & 3) * 32;               // 16 bf16 inside the swizzle row
-          const uint64_t q_hi = ptx::umma_desc_k_sw128(aQ + tile + adv);
-          const uint64_t q_lo = ptx::umma_desc_k_sw128(aQ + 2 * C::TILE + tile + adv);
-          const uint64_t k_hi = ptx::umma_desc_k_sw128(aKc + tile + adv);
-          const uint64_t k_lo = ptx::umma_desc_k_sw128(aKc + 2 * C::TILE + tile + adv);
-          if (ptx::elect_one()) ptx::mma_f16_ss(accS, q_lo, k_hi, idesc_s, k != 0);
-          if (ptx::elect_one()) ptx::mma_f16_ss(accS, q_hi, k_lo, idesc_s, 1);
-          if (ptx::elect_one()) ptx::mma_f16_ss(accS, q_hi, k_hi, idesc_s, 1);
+            for (int k = 0; k < 8; ++k) {
+              const uint64_t adv = (uint64_t)(2 * (k & 3));          // 16 bf16 = 32 bytes inside the swizzle row
+              const uint64_t q_hi = ((k >> 2) ? dq_hi1 : dq_hi0) + adv, q_lo = ((k >> 2) ? dq_lo1 : dq_lo0) + adv;
+              const uint64_t k_hi = ((k >> 2) ? dk_hi1 : dk_hi0) + adv, k_lo = ((k >> 2) ? dk_lo1 : dk_lo0) + adv;
+              ptx::mma_f16_ss(accS, q_lo, k_hi, idesc_s, k != 0);
+              ptx::mma_f16_ss(accS, q_hi, k_lo, idesc_s, 1);
+              ptx::mma_f16_ss(accS, q_hi, k_hi, idesc_s, 1);
+            }
+          }
         }
         if (ptx::elect_one()) ptx::tcgen05_commit(&barS[kc]);
         ptx::mbar_wait(&barS[kc], 0);  // this chunk's K buffer (and finally Q) free again
@@ -269,19 +277,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         ptx::tcgen05_fence_after();
         const uint32_t accO = tmem_base + O_COL;
         const uint32_t aVc = (rotate && kc == 0) ? aK : aV;          // rotation: V_0 in sK, V_1 in sV
-#pragma unroll
-        for (int k = 0; k < TB / 16; ++k) {
-          // A = P: [128 rows x 64 keys] tiles, K-major; k-step = 16 keys
-          const uint32_t ptile = (uint32_t)(k >> 2) * C::P_TILE + (uint32_t)(k & 3) * 32;
-          const uint64_t p_hi = ptx::umma_desc_k_sw128(aQ + ptile);
-          const uint64_t p_lo = ptx::umma_desc_k_sw128(aQ + (TB / 64) * C::P_TILE + ptile);
-          // B = V: [TB keys x 64 d] tiles; 16 keys = 16 rows of 128 bytes; second d half at +TILE
+        {
+          // A = P: [128 rows x 64 keys] tiles, K-major, k-step = 16 keys (+2 in the address field); B = V: [TB keys x 64 d]
+          // tiles, 16 keys = 16 rows of 128 bytes (+128 in the address field), second d half at +TILE
           const uint32_t lbo = (p.dbg & 1) ? 1024u : (uint32_t)C::TILE, sbo = (p.dbg & 1) ? (uint32_t)C::TILE : 1024u;
-          const uint64_t v_hi = umma_desc_mn_sw128(aVc + (uint32_t)k * 2048, lbo, sbo);
-          const uint64_t v_lo = umma_desc_mn_sw128(aVc + 2 * C::TILE + (uint32_t)k * 2048, lbo, sbo);
-          if (ptx::elect_one()) ptx::mma_f16_ss(accO, p_lo, v_hi, idesc_o, (kc | k) != 0);
-          if (ptx::elect_one()) ptx::mma_f16_ss(accO, p_hi, v_lo, idesc_o, 1);
-          if (ptx::elect_one()) ptx::mma_f16_ss(accO, p_hi, v_hi, idesc_o, 1);
+          const uint64_t dv_hi = umma_desc_mn_sw128(aVc, lbo, sbo), dv_lo = umma_desc_mn_sw128(aVc + 2 * C::TILE, lbo, sbo);
+          uint64_t dp_hi[TB / 64], dp_lo[TB / 64];
+#pragma unroll
+          for (int t = 0; t < TB / 64; ++t) {
+            dp_hi[t] = ptx::umma_desc_k_sw128(aQ + (uint32_t)t * C::P_TILE);
+            dp_lo[t] = ptx::umma_desc_k_sw128(aQ + (TB / 64) * C::P_TILE + (uint32_t)t * C::P_TILE);
+          }
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < TB / 16; ++k) {
+              const uint64_t p_hi = dp_hi[k >> 2] + (uint64_t)(2 * (k & 3)), p_lo = dp_lo[k >> 2] + (uint64_t)(2 * (k & 3));
+              const uint64_t v_hi = dv_hi + (uint64_t)(128 * k), v_lo = dv_lo + (uint64_t)(128 * k);
+              ptx::mma_f16_ss(accO, p_lo, v_hi, idesc_o, (kc | k) != 0);
+              ptx::mma_f16_ss(accO, p_hi, v_lo, idesc_o, 1);
+              ptx::mma_f16_ss(accO, p_hi, v_hi, idesc_o, 1);
+            }
+          }
         }
         if (ptx::elect_one()) ptx::tcgen05_commit(barO);
       }
@@ -568,17 +584,22 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         ptx::tcgen05_fence_after();
         const uint32_t accS = tmem_base + (uint32_t)(kc * 64);
         const uint32_t aK = (kc & 1) ? aB1 : aB0;
+        {  // one elected lane issues the chunk's 24 MMAs back to back (descriptor bases built once, see attention_kernel)
+          const uint64_t dq_hi0 = ptx::umma_desc_k_sw128(aQ), dq_hi1 = ptx::umma_desc_k_sw128(aQ + C::TILE);
+          const uint64_t dq_lo0 = ptx::umma_desc_k_sw128(aQ + 2 * C::TILE), dq_lo1 = ptx::umma_desc_k_sw128(aQ + 3 * C::TILE);
+          const uint64_t dk_hi0 = ptx::umma_desc_k_sw128(aK), dk_hi1 = ptx::umma_desc_k_sw128(aK + C::TILE);
+          const uint64_t dk_lo0 = ptx::umma_desc_k_sw128(aK + 2 * C::TILE), dk_lo1 = ptx::umma_desc_k_sw128(aK + 3 * C::TILE);
+          if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t tile = (uint32_t)(k >> 2) * C::TILE;
-          const uint32_t adv = (uint32_t)(k & 3) * 32;
-          const uint64_t q_hi = ptx::umma_desc_k_sw128(aQ + tile + adv);
-          const uint64_t q_lo = ptx::umma_desc_k_sw128(aQ + 2 * C::TILE + tile + adv);
-          const uint64_t k_hi = ptx::umma_desc_k_sw128(aK + tile + adv);
-          const uint64_t k_lo = ptx::umma_desc_k_sw128(aK + 2 * C::TILE + tile + adv);
-          if (ptx::elect_one()) ptx::mma_f16_ss(accS, q_lo, k_hi, idesc_s, k != 0);
-          if (ptx::elect_one()) ptx::mma_f16_ss(accS, q_hi, k_lo, idesc_s, 1);
-          if (ptx::elect_one()) ptx::mma_f16_ss(accS, q_hi, k_hi, idesc_s, 1);
+            for (int k = 0; k < 8; ++k) {
+              const uint64_t adv = (uint64_t)(2 * (k & 3));
+              const uint64_t q_hi = ((k >> 2) ? dq_hi1 : dq_hi0) + adv, q_lo = ((k >> 2) ? dq_lo1 : dq_lo0) + adv;
+              const uint64_t k_hi = ((k >> 2) ? dk_hi1 : dk_hi0) + adv, k_lo = ((k >> 2) ? dk_lo1 : dk_lo0) + adv;
+              ptx::mma_f16_ss(accS, q_lo, k_hi, idesc_s, k != 0);
+              ptx::mma_f16_ss(accS, q_hi, k_lo, idesc_s, 1);
+              ptx::mma_f16_ss(accS, q_hi, k_hi, idesc_s, 1);
+            }
+          }
         }
         if (ptx::elect_one()) ptx::tcgen05_commit(&barS[kc]);
         ptx::mbar_wait(&barS[kc], 0);              // K_kc consumed: its buffer takes operand kc + 2
@@ -593,15 +614,18 @@ attention_mc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         const uint32_t accO = tmem_base;
         const uint32_t aV = ((n + kc) & 1) ? aB1 : aB0;
         const uint32_t aP = aQ + (uint32_t)(kc & 1) * 16384u;   // P buffer kc & 1: hi at +0, lo at +8 KB
+        {
+          const uint64_t dp_hi = ptx::umma_desc_k_sw128(aP), dp_lo = ptx::umma_desc_k_sw128(aP + 8192u);
+          const uint64_t dv_hi = umma_desc_mn_sw128(aV, (uint32_t)C::TILE, 1024u);
+          const uint64_t dv_lo = umma_desc_mn_sw128(aV + 2 * C::TILE, (uint32_t)C::TILE, 1024u);
+          if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t p_hi = ptx::umma_desc_k_sw128(aP + (uint32_t)k * 32);
-          const uint64_t p_lo = ptx::umma_desc_k_sw128(aP + 8192u + (uint32_t)k * 32);
-          const uint64_t v_hi = umma_desc_mn_sw128(aV + (uint32_t)k * 2048, (uint32_t)C::TILE, 1024u);
-          const uint64_t v_lo = umma_desc_mn_sw128(aV + 2 * C::TILE + (uint32_t)k * 2048, (uint32_t)C::TILE, 1024u);
-          if (ptx::elect_one()) ptx::mma_f16_ss(accO, p_lo, v_hi, idesc_o, (kc | k) != 0);
-          if (ptx::elect_one()) ptx::mma_f16_ss(accO, p_hi, v_lo, idesc_o, 1);
-          if (ptx::elect_one()) ptx::mma_f16_ss(accO, p_hi, v_hi, idesc_o, 1);
+            for (int k = 0; k < 4; ++k) {   // 16 keys per step: +32 bytes in P (K-major), +2048 bytes in V (MN-major)
+              ptx::mma_f16_ss(accO, dp_lo + (uint64_t)(2 * k), dv_hi + (uint64_t)(128 * k), idesc_o, (kc | k) != 0);
+              ptx::mma_f16_ss(accO, dp_hi + (uint64_t)(2 * k), dv_lo + (uint64_t)(128 * k), idesc_o, 1);
+              ptx::mma_f16_ss(accO, dp_hi + (uint64_t)(2 * k), dv_hi + (uint64_t)(128 * k), idesc_o, 1);
+            }
+          }
         }
         if (ptx::elect_one()) ptx::tcgen05_commit(&barPV[kc]);
         if (n + kc + 2 < 2 * n) {                   // V_kc consumed: its buffer takes V_{kc + 2}

@@ -619,17 +619,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           const uint64_t w_hi = ptx::umma_desc_k_sw128(st + C::A_BYTES);
           const uint64_t a_lo = ptx::umma_desc_k_sw128(st + C::A_BYTES + C::W_BYTES);
           const uint64_t w_lo = ptx::umma_desc_k_sw128(st + 2 * C::A_BYTES + C::W_BYTES);
+          // one elected lane issues the k-block's MMAs back to back: with BN = 64 tiles (small batches) an MMA executes in
+          // 32 cycles, less than electing a lane for each costs
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            const uint64_t adv = (uint64_t)(k * UMMA_K * 2 >> 4);
-            if (SPLIT) {
-              // small cross terms first, the dominant hi.hi product last
-              if (ptx::elect_one()) ptx::mma_f16_ss(acc, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);
-              if (ptx::elect_one()) ptx::mma_f16_ss(acc, a_hi + adv, w_lo + adv, idesc, 1);
-              if (ptx::elect_one()) ptx::mma_f16_ss(acc, a_hi + adv, w_hi + adv, idesc, 1);
-            } else {
-              if (ptx::elect_one()) ptx::mma_f16_ss(acc, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+              const uint64_t adv = (uint64_t)(k * UMMA_K * 2 >> 4);
+              if (SPLIT) {
+                // small cross terms first, the dominant hi.hi product last
+                ptx::mma_f16_ss(acc, a_lo + adv, w_hi + adv, idesc, (kb | k) != 0);
+                ptx::mma_f16_ss(acc, a_hi + adv, w_lo + adv, idesc, 1);
+                ptx::mma_f16_ss(acc, a_hi + adv, w_hi + adv, idesc, 1);
+              } else {
+                ptx::mma_f16_ss(acc, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+              }
             }
           }
           if (ptx::elect_one()) ptx::tcgen05_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire

@@ -21,7 +21,7 @@
 // per 64 columns and the bytes written.  The residual then carries 16 significand bits (forward error ~3e-5 instead of
 // ~1.5e-5, tolerance 1e-3).  R16 = false (REGEN_DEBUG_F32_RESIDUAL=1) keeps the fp32 copy of h.
 //
-// M8 = true (precision 'mixed8', linear2 + norm3): the product runs as ONE fp16 MMA plus two e4m3 correction MMAs at twice
+// M8 = true (precision 'mixed8': attention out_proj + norm1 + norm2 and linear2 + norm3): the product runs as ONE fp16 MMA plus two e4m3 correction MMAs at twice
 // the rate -- 2 bf16-MMA equivalents per product instead of 3 -- at the same 4 operand bytes per element:
 //   D  = (A_lo * 2^9) . (W_hi * 2^6)^T + (A_hi * 2^-2) . (W_lo * 2^17)^T   kind::f8f6f4, all four operands e4m3, K = 32 per MMA
 //   D  = A16 . W16^T + D * 2^-15                                         first kind::f16 MMA (scale-input-d = 15)

@@ -130,3 +130,19 @@ def test_offline_arch_stays_close_to_bf16x3(built_lib):
     print("offline mixed8 vs bf16x3 at B=%d: max abs diff %.3e (absmax %.2f)" % (B, d, b.abs().max()))
     assert torch.isfinite(a).all()
     assert 0.0 < d < 2 * TOL_M8
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "mixed8"])
+def test_repeated_forwards_are_bit_identical(built_lib, precision):
+    """Race / pipeline-hazard guard: 60 forwards of the same B = 256 input through the fused route (persistent tcgen05
+    kernels, mbarrier rings, TMEM double buffers, no atomics anywhere) must return the same bits every time."""
+    ref_model, sd = get_model("ntu", 0)
+    model = _mixed8_model(sd, "w0") if precision == "mixed8" else ref_model
+    B, T = 256, 60
+    x, y = synthetic.make_inputs(B, 56, 6, T, seed=5)
+    xc, yc = x.cuda(), to_cuda(y)
+    t = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(3)).cuda()
+    with torch.no_grad():
+        first = model(xc, t, yc).clone()
+        for _ in range(60):
+            assert torch.equal(model(xc, t, yc), first)

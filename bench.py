@@ -20,6 +20,8 @@ Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   other_configs    device-resident step time of BASELINE configs 1, 3, 5 (per-GPU shapes), N = 1 only
   library_baseline the reference's own torch-eager path on this GPU (fp32 and TF32), N = 1 only
   cpu_baseline     the reference's own p_sample_loop on this box's host cores at the true B = 256, N = 1 only
+  precision_ab     device-resident steps/s of this run (precision='mixed8', the GPU arm's operand scheme) and of the same K steps
+                   with the library default precision='bf16x3' on the same GPU, N = 1 only (REGEN_PRECISION selects the arm's scheme)
 """
 import argparse
 import json

@@ -729,7 +729,14 @@ struct Cfg2 {
 // EW = 8: general epilogue (residual, fp32 and/or bf16-pair outputs), double-buffered staging.
 // EW = 16 (RES = false): 4 epilogue warps per scheduler for the bias/GELU/bf16-split epilogues, which are bound by
 // instruction issue and latency, not bandwidth; 576 threads -> at most 112 registers, so the residual path is compiled out.
-template <int BN, bool SPLIT, int EW, bool RES>
+// M8 = true (precision 'mixed8h', operand pack of gemm_ln_sm100.cuh): tm_a_hi / tm_w_hi are the fp16 halves, tm_a_lo / tm_w_lo
+// the byte rows [.., 2K] (per 64 K elements: A residual bytes | A hi bytes against W hi bytes | W residual bytes), tm_ws_hi /
+// tm_ws_lo the narrow W boxes of both for the tail slices.  Ring, barriers and transaction bytes are those of the bf16x3 loop
+// (3 stages of 64 KB, four 128-byte-row boxes per CTA and stage: A | W | A' | W'); a stage holds TWO consecutive 128-byte
+// blocks of the current phase -- first the 2K/128 correction blocks (kind::f8f6f4, 32 K elements per MMA), then the K/64
+// main-term blocks (kind::f16; the very first one folds the 2^15-scaled corrections in through scale-input-d) -- i.e. 8 MMAs
+// per stage instead of 12 over the same K/64 stages per tile: two thirds of the tensor time at the same bytes.
+template <int BN, bool SPLIT, int EW, bool RES, bool M8 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -826,11 +833,26 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
           if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * stage_tx);
+          if constexpr (M8) {
+            // stage kb carries blocks 2 kb and 2 kb + 1 of the sequence [2K/128 correction blocks | K/64 main-term blocks]
+            // (num_kb = K/64 is even: K % 128 == 0); every box row is 128 bytes: 128 e4m3 bytes or 64 fp16
+            const int n1 = 2 * (p.K / 128);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int blk = 2 * kb + h;
+              const bool corr = blk < n1;
+              const int c0 = corr ? blk * 128 : (blk - n1) * BK;
+              ptx::tma_load_2d_2sm(st + h * (C::A_BYTES + C::W_BYTES), corr ? &tm_a_lo : &tm_a_hi, &full_bar[stage], c0, m0);
+              ptx::tma_load_2d_2sm(st + h * (C::A_BYTES + C::W_BYTES) + C::A_BYTES, corr ? wmap_lo : wmap_hi, &full_bar[stage], c0,
+                                   nw, p.pol_w);
+            }
+          } else {
           ptx::tma_load_2d_2sm(st, &tm_a_hi, &full_bar[stage], kb * BK, m0);
           ptx::tma_load_2d_2sm(st + C::A_BYTES, wmap_hi, &full_bar[stage], kb * BK, nw, p.pol_w);
           if (SPLIT) {
             ptx::tma_load_2d_2sm(st + C::A_BYTES + C::W_BYTES, &tm_a_lo, &full_bar[stage], kb * BK, m0);
             ptx::tma_load_2d_2sm(st + 2 * C::A_BYTES + C::W_BYTES, wmap_lo, &full_bar[stage], kb * BK, nw, p.pol_w);
+          }
           }
           if (++stage == C::STAGES) {
             stage = 0;
@@ -865,6 +887,31 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
           const uint64_t w_hi = ptx::umma_desc_k_sw128(st + C::A_BYTES);
           const uint64_t a_lo = ptx::umma_desc_k_sw128(st + C::A_BYTES + C::W_BYTES);
           const uint64_t w_lo = ptx::umma_desc_k_sw128(st + 2 * C::A_BYTES + C::W_BYTES);
+          if constexpr (M8) {
+            // (a_hi, w_hi) = first block of the stage, (a_lo, w_lo) = second; formats 0 = e4m3 x e4m3 / fp16 x fp16
+            const uint32_t idesc0 = ptx::umma_idesc_fmt0_f32(2 * BM, width);
+            const int ncs = p.K / 128;   // correction stages; stage ncs starts the main term (straight-line code per stage kind)
+            if (kb < ncs) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint64_t adv = (uint64_t)(2 * (i & 3));   // 32 bytes per k-step
+                if (ptx::elect_one())
+                  ptx::mma_f8_ss_2sm(acc, ((i >> 2) ? a_lo : a_hi) + adv, ((i >> 2) ? w_lo : w_hi) + adv, idesc0, (kb | i) != 0);
+              }
+            } else {
+              if (kb == ncs) {
+                if (ptx::elect_one()) ptx::mma_f16_ss_2sm_scale15(acc, a_hi, w_hi, idesc0);   // D = A.B + D * 2^-15
+              } else {
+                if (ptx::elect_one()) ptx::mma_f16_ss_2sm(acc, a_hi, w_hi, idesc0, 1);
+              }
+#pragma unroll
+              for (int i = 1; i < 8; ++i) {
+                const uint64_t adv = (uint64_t)(2 * (i & 3));
+                if (ptx::elect_one())
+                  ptx::mma_f16_ss_2sm(acc, ((i >> 2) ? a_lo : a_hi) + adv, ((i >> 2) ? w_lo : w_hi) + adv, idesc0, 1);
+              }
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)(k * UMMA_K * 2 >> 4);
@@ -875,6 +922,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
             } else {
               if (ptx::elect_one()) ptx::mma_f16_ss_2sm(acc, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
             }
+          }
           }
           if (ptx::elect_one()) ptx::tcgen05_commit_2sm(&empty_bar[stage]);  // frees this stage in BOTH CTAs
           if (++stage == C::STAGES) {
@@ -949,14 +997,14 @@ struct SliceMaps {
   const CUtensorMap *hi64 = nullptr, *lo64 = nullptr;  // box {64, 64}: half slices (tail_split = 2)
 };
 
-template <int BN, bool SPLIT, int EW, bool RES>
+template <int BN, bool SPLIT, int EW, bool RES, bool M8 = false>
 inline cudaError_t launch2_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                 const CUtensorMap& w_lo, const OutMaps& o, const Params& p, cudaStream_t stream,
                                 const SliceMaps& sm) {
   using C = Cfg2<BN, SPLIT, EW>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_tn_kernel<BN, SPLIT, EW, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm2_tn_kernel<BN, SPLIT, EW, RES, M8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
@@ -990,8 +1038,17 @@ inline cudaError_t launch2_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo
   } else if (q.tail_split == 2 && sm.hi64 && sm.lo64) {
     ws_hi = sm.hi64; ws_lo = sm.lo64; q.slice_w_rows = 64;
   }
-  return launch_pdl(gemm2_tn_kernel<BN, SPLIT, EW, RES>, dim3(2 * clusters), dim3(64 + 32 * EW), C::SMEM_BYTES, stream, a_hi,
+  return launch_pdl(gemm2_tn_kernel<BN, SPLIT, EW, RES, M8>, dim3(2 * clusters), dim3(64 + 32 * EW), C::SMEM_BYTES, stream, a_hi,
                     a_lo, w_hi, w_lo, o.f32, o.hi, o.lo, *ws_hi, *ws_lo, q);
+}
+
+// mixed8 operands (K % 128 == 0, no residual, TMA-store epilogue): a16 / a8 / w16 / w8 maps; sm: narrow W boxes of the tail
+// slices (hi32 / hi64 = 16-bit halves, lo32 / lo64 = byte rows), else the slices load the full-height boxes
+template <int BN>
+inline cudaError_t launch2_m8(const CUtensorMap& a16, const CUtensorMap& a8, const CUtensorMap& w16, const CUtensorMap& w8,
+                              const OutMaps& o, const Params& p, cudaStream_t stream, const SliceMaps& sm) {
+  if (p.residual || !p.tma_store || (p.out_f32 && p.out_hi) || (p.K & 127)) return cudaErrorInvalidValue;
+  return launch2_impl<BN, true, 16, false, true>(a16, a8, w16, w8, o, p, stream, sm);
 }
 
 template <int BN, bool SPLIT>

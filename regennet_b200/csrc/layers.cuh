@@ -56,12 +56,15 @@ inline void launch_split_rows(const float* src, int ld_src, __nv_bfloat16* hi, _
 }
 
 // ------------------------------------------------------------------------------------------
-// fp32 W [R, C] -> the mixed8 operand pack of gemm_ln_sm100.cuh (setup only): w16 fp16 [R, C] and bytes [R, 2 C]: per group
-// of 64 columns, 64 bytes e4m3(fp16(w) * 2^6) followed by 64 bytes e4m3((w - fp16(w)) * 2^17).
+// fp32 [R, C] -> the mixed8 operand pack of gemm_ln_sm100.cuh / gemm_sm100.cuh: x16 fp16 [R, C] and bytes [R, 2 C], per group
+// of 64 columns.  Weights (act = 0, setup only): 64 bytes e4m3(fp16(w) * 2^6) | 64 bytes e4m3((w - fp16(w)) * 2^17).
+// Activations (act = 1; test hook and the split of the sampler state x -- everywhere else the producing epilogues write
+// the pack themselves): 64 bytes e4m3((a - fp16(a)) * 2^9) | 64 bytes e4m3(fp16(a) * 2^-2).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pack_m8_weights_kernel(const float* __restrict__ src, uint16_t* __restrict__ w16,
-                                                              uint8_t* __restrict__ w8, int R, int C) {
+__global__ void __launch_bounds__(256) pack_m8_kernel(const float* __restrict__ src, uint16_t* __restrict__ x16,
+                                                      uint8_t* __restrict__ x8, int R, int C, int act) {
   const int64_t total = (int64_t)R * (C / 4);
+  const float s_hi = act ? 0.25f : 64.f, s_lo = act ? 512.f : 131072.f;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
     const int r = (int)(i / (C / 4)), c = (int)(i % (C / 4)) * 4;
     const float4 f = *reinterpret_cast<const float4*>(src + (size_t)r * C + c);
@@ -69,11 +72,12 @@ __global__ void __launch_bounds__(256) pack_m8_weights_kernel(const float* __res
     float a0, a1, a2, a3;
     ptx::upk2(ptx::f16x2_to_f32x2(h0), a0, a1);
     ptx::upk2(ptx::f16x2_to_f32x2(h1), a2, a3);
-    *reinterpret_cast<uint2*>(w16 + (size_t)r * C + c) = make_uint2(h0, h1);
-    uint8_t* grp = w8 + (size_t)r * 2 * C + (c >> 6) * 128 + (c & 63);   // group of 64 K elements: hi bytes | residual bytes
-    *reinterpret_cast<uint32_t*>(grp) = ptx::pack_e4m3x4(a0 * 64.f, a1 * 64.f, a2 * 64.f, a3 * 64.f);
-    *reinterpret_cast<uint32_t*>(grp + 64) =
-        ptx::pack_e4m3x4((f.x - a0) * 131072.f, (f.y - a1) * 131072.f, (f.z - a2) * 131072.f, (f.w - a3) * 131072.f);
+    *reinterpret_cast<uint2*>(x16 + (size_t)r * C + c) = make_uint2(h0, h1);
+    uint8_t* grp = x8 + (size_t)r * 2 * C + (c >> 6) * 128 + (c & 63);
+    const uint32_t hi8 = ptx::pack_e4m3x4(a0 * s_hi, a1 * s_hi, a2 * s_hi, a3 * s_hi);
+    const uint32_t lo8 = ptx::pack_e4m3x4((f.x - a0) * s_lo, (f.y - a1) * s_lo, (f.z - a2) * s_lo, (f.w - a3) * s_lo);
+    *reinterpret_cast<uint32_t*>(grp) = act ? lo8 : hi8;
+    *reinterpret_cast<uint32_t*>(grp + 64) = act ? hi8 : lo8;
   }
 }
 

@@ -462,10 +462,8 @@ int regen_load_weights(regen_handle* h, const regen_weight_ptrs* w, void* stream
     layers::launch_split_rows(lw.l1_w, D, ld.w1.hi, ld.w1.lo, D, D, FF, 1, 1, s);
     layers::launch_split_rows(lw.l2_w, FF, ld.w2.hi, ld.w2.lo, FF, FF, D, 1, 1, s);
     if (h->desc.precision == 2) {
-      layers::pack_m8_weights_kernel<<<grid_cap(ceil_div((int64_t)D * FF / 4, 256)), 256, 0, s>>>(lw.l2_w, ld.w2_16,
-                                                                                                 ld.w2_8, D, FF);
-      layers::pack_m8_weights_kernel<<<grid_cap(ceil_div((int64_t)D * D / 4, 256)), 256, 0, s>>>(lw.o_w, ld.wo_16,
-                                                                                                ld.wo_8, D, D);
+      layers::pack_m8_kernel<<<grid_cap(ceil_div((int64_t)D * FF / 4, 256)), 256, 0, s>>>(lw.l2_w, ld.w2_16, ld.w2_8, D, FF, 0);
+      layers::pack_m8_kernel<<<grid_cap(ceil_div((int64_t)D * D / 4, 256)), 256, 0, s>>>(lw.o_w, ld.wo_16, ld.wo_8, D, D, 0);
       count_launch();
     }
     TRY(copy_vec(h, &ld.bqkv, lw.qkv_b, 3 * D, s));
@@ -944,6 +942,41 @@ int regen_test_gemm(const float* A, const float* W, const float* bias, const flo
   REGEN_CHECK_ARG(A && W && out, "regen_test_gemm: null argument");
   REGEN_CHECK_ARG(M >= 1 && N >= 1 && K >= 1, "regen_test_gemm: bad sizes");
   cudaStream_t s = (cudaStream_t)stream;
+  if (precision == 2) {
+    // mixed8 main loop of the pair kernel (fp16 + e4m3 operand pack, packed here from the fp32 inputs)
+    REGEN_CHECK_ARG(use_pair_kernel(M) && (K & 127) == 0 && (N & 3) == 0 && !residual,
+                    "regen_test_gemm: precision 2 needs M > 128, K %% 128 == 0, N %% 4 == 0 and no residual");
+    uint16_t *a16, *w16;
+    uint8_t *a8, *w8;
+    REGEN_CUDA(cudaMalloc(&a16, (size_t)M * K * 2));
+    REGEN_CUDA(cudaMalloc(&a8, (size_t)M * K * 2));
+    REGEN_CUDA(cudaMalloc(&w16, (size_t)N * K * 2));
+    REGEN_CUDA(cudaMalloc(&w8, (size_t)N * K * 2));
+    layers::pack_m8_kernel<<<grid_cap(ceil_div((int64_t)M * K / 4, 256)), 256, 0, s>>>(A, a16, a8, M, K, 1);
+    layers::pack_m8_kernel<<<grid_cap(ceil_div((int64_t)N * K / 4, 256)), 256, 0, s>>>(W, w16, w8, N, K, 0);
+    CUtensorMap ta16, ta8, tw16, tw8;
+    int rc = make_tmap_bf16_2d(&ta16, a16, M, K, K, 128);
+    if (!rc) rc = make_tmap_u8_2d(&ta8, a8, M, 2 * K, 2 * K, 128, 128);
+    if (!rc) rc = make_tmap_bf16_2d(&tw16, w16, N, K, K, 128);
+    if (!rc) rc = make_tmap_u8_2d(&tw8, w8, N, 2 * K, 2 * K, 128, 128);
+    if (!rc) {
+      gemm::Params p = gp(M, N, K);
+      p.bias = bias; p.out_f32 = out; p.ld_out = N; p.gelu = gelu; p.tma_store = 1; p.exit_wait_full = 1;
+      p.timeline = g_test_timeline;
+      gemm::OutMaps om;
+      rc = make_tmap_store_2d(&om.f32, out, false, M, N, N, 16);
+      if (!rc) {
+        cudaError_t e = gemm::launch2_m8<256>(ta16, ta8, tw16, tw8, om, p, s, gemm::SliceMaps());
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) {
+          set_error("regen_test_gemm(mixed8): %s", cudaGetErrorString(e));
+          rc = REGEN_ECUDA;
+        }
+      }
+    }
+    cudaFree(a16); cudaFree(a8); cudaFree(w16); cudaFree(w8);
+    return rc;
+  }
   const int Kp = (int)ceil_div(K, 64) * 64;
   bf16 *ah, *al, *wh, *wl;
   REGEN_CUDA(cudaMalloc(&ah, (size_t)M * Kp * 2));

@@ -46,6 +46,9 @@ DTYPES = {
     "mixed8": "mixed8 = bf16x3 (3 bf16 tcgen05 MMAs per product: input / QKV / FFN1 / output projections, attention) + "
               "fp16 MMA with two e4m3 correction MMAs per product (2 MMA equivalents: attention out_proj and linear2, the "
               "two fused GEMM+LayerNorm kernels); fp32 accumulate, fp32 LN/softmax/update, residual stream as a bf16 (hi, lo) pair",
+    "mixed8h": "mixed8h = fp16 MMA with two e4m3 correction MMAs per product (2 MMA equivalents) in every GEMM of the decoder "
+               "stack (QKV, out_proj, FFN1, linear2, output projection), bf16x3 in the input projection and attention; fp32 "
+               "accumulate, fp32 LN/softmax/update, residual stream as fp16 + e4m3 residual bytes",
 }
 METRIC = "denoising_steps_per_sec"
 UNIT = "steps/s (1 step = one p_sample over B=256 x T=60 poses per GPU, summed over GPUs)"
@@ -615,7 +618,7 @@ def run_ours(args):
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "tcgen05 GEMM class: gemm2_tn_kernel<256,bf16x3> (QKV, FFN1, output projection) + "
                                    "gemm_ln_kernel (input projection: bf16x3; out_proj+LN1+LN2, linear2+LN3 fused: %s), %d "
-                                   "launches per step" % (PRECISION if PRECISION == "mixed8" else "bf16x3", gemm_launches),
+                                   "launches per step" % (PRECISION if PRECISION.startswith("mixed8") else "bf16x3", gemm_launches),
                          "achieved": gemm_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
                          "frac": gemm_tf / peaks["tf_sust"], "traffic": traffic,
                          "ms_per_step": gemm_ms,

@@ -145,8 +145,9 @@ typedef struct {
   int32_t max_batch;       /* largest effective batch (2x the user batch under CFG) */
   int32_t max_frames;      /* largest T */
   int32_t num_table_steps; /* size of the timestep-embedding table; timesteps must be < this */
-  int32_t precision;       /* 0 = bf16x3 split (parity mode), 1 = single-pass bf16 (fast), 2 = mixed8: bf16x3 except linear2
-                              of the large-batch route, which runs as one fp16 + two e4m3 correction MMAs per product */
+  int32_t precision;       /* 0 = bf16x3 split (parity mode), 1 = single-pass bf16 (fast), 2 = mixed8: bf16x3 except the two
+                              fused GEMM+LayerNorm kernels of the large-batch route, which run one fp16 + two e4m3 correction
+                              MMAs per product, 3 = mixed8h: all GEMMs of that route (arch 0 only; otherwise like 2) */
   int32_t arch;            /* 0 = 'online': causal nn.TransformerDecoder, 1-token memory (model/cmdm.py:75-81, 203-227);
                               1 = 'offline': nn.TransformerEncoder over [condition token | frames], no mask (:63-71, 228-238) */
 } regen_model_desc;

@@ -99,7 +99,7 @@ class _Handle:
             pass
 
 
-_PRECISIONS = {'bf16x3': 0, 'bf16': 1, 'mixed8': 2}   # regen_model_desc.precision
+_PRECISIONS = {'bf16x3': 0, 'bf16': 1, 'mixed8': 2, 'mixed8h': 3}   # regen_model_desc.precision
 
 
 class CMDM(nn.Module):
@@ -140,7 +140,8 @@ class CMDM(nn.Module):
         self.wo_pos_emb = wo_pos_emb
         self.body_model = body_model
         #: 'bf16x3' (parity mode: three bf16 MMAs per product, ~2e-5 abs error), 'mixed8' (bf16x3 except linear2 of the
-        #: large-batch route: one fp16 MMA + two e4m3 correction MMAs per product, ~4e-5) or 'bf16' (single pass, ~1e-2)
+        #: large-batch route: one fp16 MMA + two e4m3 correction MMAs per product, ~4e-5), 'mixed8h' (arch 'online': every
+        #: GEMM of the large-batch route that way, the residual stream kept as fp16 + e4m3 residual bytes) or 'bf16' (single pass, ~1e-2)
         self.precision = kargs.get('precision', 'bf16x3')
         if self.precision not in _PRECISIONS:
             raise ValueError("precision must be one of %s (got %r)" % (sorted(_PRECISIONS), self.precision))

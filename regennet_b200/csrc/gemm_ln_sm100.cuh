@@ -115,7 +115,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // tm_res: fp32 [M, 512] residual stream h (box 32 x 32, SWIZZLE_128B) -- used for the residual LOAD and the h STORE
 // tm_c  : fp32 [Beff + 32, 512] cyclic per-sample constant (row r = c[r % Beff]); only read with CHAIN
 // tm_ohi / tm_olo: bf16 [M, 512] split of h (store, box 32 rows x 64 columns, SWIZZLE_128B)
-template <bool SPLIT, bool CHAIN, int EW, bool LN = true, bool R16 = false, bool M8 = false>
+template <bool SPLIT, bool CHAIN, int EW, bool LN = true, bool R16 = false, bool M8 = false, bool H8 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Epi<EW, CHAIN>::THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -126,6 +126,12 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   // shared address space and emits LDS / STS instead of generic LD / ST for every staging access below
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   static_assert(!M8 || (SPLIT && LN && R16), "mixed8 operands: built for the (hi, lo)-residual LayerNorm variants");
+  // H8 (precision 'mixed8h'): the residual stream h itself lives in HBM as the mixed8 operand pack -- tm_ohi = fp16 [M, 512]
+  // (box 32 x 64), tm_olo = bytes [M, 1024] (box 32 rows x 128 B: per 64 columns 64 bytes e4m3((h - fp16(h)) * 2^9) | 64 bytes
+  // e4m3(fp16(h) / 4)), loaded as the residual (fp16 + residual byte * 2^-9: ~15 significand bits) and stored by the final
+  // pass, so that the QKV / FFN1 / output GEMMs read h with the mixed8 main loop too.  Same box sizes and staging as R16.
+  static_assert(!H8 || (EW == 8 && (R16 || !LN)), "the mixed8 residual-stream format shares the R16 staging layout");
+  constexpr int OLO = H8 ? 2 : 1;   // column coordinate scale of tm_olo (bytes: two per column)
   constexpr int NST = M8 ? M8_STAGES : STAGES;              // ring stages
   constexpr int STB = M8 ? M8_STAGE_BYTES : STAGE_BYTES;    // bytes per stage
   float* s_par = reinterpret_cast<float*>(smem + RING_BYTES);             // bias | g1 | b1 | g2 | b2
@@ -226,7 +232,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             for (int i = kb * per_kb; i < (kb + 1) * per_kb && i < 64; ++i) {
               if constexpr (R16) {  // 32 hi + 32 lo boxes of 32 rows x 64 columns
                 const int k = i >> 1;
-                ptx::tma_prefetch_l2_2d((i & 1) ? &tm_olo : &tm_ohi, (k & 7) * 2 * SC, m0 + (k >> 3) * 32);
+                ptx::tma_prefetch_l2_2d((i & 1) ? &tm_olo : &tm_ohi, ((i & 1) ? OLO : 1) * (k & 7) * 2 * SC, m0 + (k >> 3) * 32);
               } else {
                 ptx::tma_prefetch_l2_2d(&tm_res, (i & 15) * SC, m0 + (i >> 4) * 32);
               }
@@ -424,8 +430,29 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               lw[2 * jj] = gemm::pack_bf16x2(z0 - __uint_as_float(h0 << 16), z1 - __uint_as_float(h0 & 0xffff0000u));
               lw[2 * jj + 1] = gemm::pack_bf16x2(z2 - __uint_as_float(h1 << 16), z3 - __uint_as_float(h1 & 0xffff0000u));
             }
+            if constexpr (H8) {
+              // re-encode the 8 values of this chunk as fp16 + residual / hi bytes (z is rebuilt from the bf16 pair exactly)
+              uint32_t fw[4];
+              float lo8[8], hi8[8];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const ptx::f32x2 z = ptx::add2(ptx::bf16x2_to_f32x2(hw[e]), ptx::bf16x2_to_f32x2(lw[e]));
+                float z0, z1;
+                ptx::upk2(z, z0, z1);
+                fw[e] = ptx::pack_f16x2_sat(z0, z1);
+                const ptx::f32x2 h2 = ptx::f16x2_to_f32x2(fw[e]);
+                ptx::upk2(ptx::mul2(ptx::sub2(z, h2), ptx::splat2(512.f)), lo8[2 * e], lo8[2 * e + 1]);
+                ptx::upk2(ptx::mul2(h2, ptx::splat2(0.25f)), hi8[2 * e], hi8[2 * e + 1]);
+              }
+              *reinterpret_cast<uint4*>(hb + off_f32(lane, half * 4 + c)) = make_uint4(fw[0], fw[1], fw[2], fw[3]);
+              *reinterpret_cast<uint2*>(lb + off_f32(lane, half * 2 + (c >> 1)) + (c & 1) * 8) =
+                  make_uint2(ptx::pack_e4m3x4(lo8[0], lo8[1], lo8[2], lo8[3]), ptx::pack_e4m3x4(lo8[4], lo8[5], lo8[6], lo8[7]));
+              *reinterpret_cast<uint2*>(lb + off_f32(lane, 4 + half * 2 + (c >> 1)) + (c & 1) * 8) =
+                  make_uint2(ptx::pack_e4m3x4(hi8[0], hi8[1], hi8[2], hi8[3]), ptx::pack_e4m3x4(hi8[4], hi8[5], hi8[6], hi8[7]));
+            } else {
             *reinterpret_cast<uint4*>(hb + off_f32(lane, half * 4 + c)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
             *reinterpret_cast<uint4*>(lb + off_f32(lane, half * 4 + c)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();  // staging complete, every lane has read the residual slot
@@ -437,7 +464,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             if (p.store_f32) ptx::tma_store_2d(&tm_c, fb, n_base + SC * sc, row0);
             if (half) {
               ptx::tma_store_2d(&tm_ohi, hb, n_base + 2 * SC * u, row0, p.pol_store);
-              ptx::tma_store_2d(&tm_olo, lb, n_base + 2 * SC * u, row0, p.pol_store);
+              ptx::tma_store_2d(&tm_olo, lb, OLO * (n_base + 2 * SC * u), row0, p.pol_store);
             }
             ptx::bulk_commit();
           }
@@ -461,7 +488,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           for (int s = 0; s < RING_P; ++s) {
             ptx::mbar_expect_tx(&rbar[s], 2 * SLOT);
             ptx::tma_load_2d(res_ring + s * 2 * SLOT, &tm_ohi, &rbar[s], n_base + 2 * SC * s, row0);
-            ptx::tma_load_2d(res_ring + s * 2 * SLOT + SLOT, &tm_olo, &rbar[s], n_base + 2 * SC * s, row0);
+            ptx::tma_load_2d(res_ring + s * 2 * SLOT + SLOT, &tm_olo, &rbar[s], OLO * (n_base + 2 * SC * s), row0);
           }
         } else {
 #pragma unroll
@@ -496,6 +523,23 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
           for (int c = 0; c < 4; ++c) {  // 8 columns per 16-byte chunk of hi / lo; packed fp32 pairs (even, odd column)
             const uint4 h4 = *reinterpret_cast<const uint4*>(hs + off_f32(lane, half * 4 + c));
+            if constexpr (H8) {
+              // residual = fp16 + residual byte * 2^-9 (8 residual bytes of these columns: first half of the byte row)
+              const uint2 l2 = *reinterpret_cast<const uint2*>(ls + off_f32(lane, half * 2 + (c >> 1)) + (c & 1) * 8);
+              const float4 bA = *reinterpret_cast<const float4*>(s_bias + sc * SC + 8 * c);
+              const float4 bB = *reinterpret_cast<const float4*>(s_bias + sc * SC + 8 * c + 4);
+              const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, l8[4] = {l2.x, l2.x >> 16, l2.y, l2.y >> 16};
+              const ptx::f32x2 bp[4] = {ptx::pk2(bA.x, bA.y), ptx::pk2(bA.z, bA.w), ptx::pk2(bB.x, bB.y), ptx::pk2(bB.z, bB.w)};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const ptx::f32x2 res = ptx::fma2(ptx::e4m3x2_to_f32x2(l8[e]), ptx::splat2(0.001953125f), ptx::f16x2_to_f32x2(hw[e]));
+                const ptx::f32x2 v = ptx::add2(ptx::add2(ptx::pk2u(r[8 * c + 2 * e], r[8 * c + 2 * e + 1]), bp[e]), res);
+                psum = ptx::add2(psum, v);
+                psq = ptx::fma2(v, v, psq);
+                ptx::upk2u(v, r[8 * c + 2 * e], r[8 * c + 2 * e + 1]);
+              }
+              continue;
+            }
             const uint4 l4 = *reinterpret_cast<const uint4*>(ls + off_f32(lane, half * 4 + c));
             const float4 bA = *reinterpret_cast<const float4*>(s_bias + sc * SC + 8 * c);
             const float4 bB = *reinterpret_cast<const float4*>(s_bias + sc * SC + 8 * c + 4);
@@ -515,7 +559,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           if (half == 1 && lane == 0 && u + RING_P < NP) {
             ptx::mbar_expect_tx(&rbar[slot], 2 * SLOT);
             ptx::tma_load_2d(res_ring + slot * 2 * SLOT, &tm_ohi, &rbar[slot], n_base + 2 * SC * (u + RING_P), row0);
-            ptx::tma_load_2d(res_ring + slot * 2 * SLOT + SLOT, &tm_olo, &rbar[slot], n_base + 2 * SC * (u + RING_P), row0);
+            ptx::tma_load_2d(res_ring + slot * 2 * SLOT + SLOT, &tm_olo, &rbar[slot], OLO * (n_base + 2 * SC * (u + RING_P)), row0);
           }
         } else {
         constexpr int RING = E::RING_R;
@@ -696,6 +740,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 #pragma unroll
           for (int c = 0; c < 4; ++c) {  // 8 columns -> one bf16 hi chunk, one bf16 lo chunk; packed fp32 pairs
             uint32_t hw[4], lw[4];
+            float lo8[8], hi8[8];   // H8 only
             const float4 gA = *reinterpret_cast<const float4*>(gg + sc * SC + 8 * c);
             const float4 gB = *reinterpret_cast<const float4*>(gg + sc * SC + 8 * c + 4);
             const float4 bA = *reinterpret_cast<const float4*>(bb + sc * SC + 8 * c);
@@ -710,10 +755,23 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               hw[e] = gemm::pack_bf16x2(z0, z1);
               ptx::upk2(ptx::sub2(z, ptx::bf16x2_to_f32x2(hw[e])), l0, l1);   // float(hi) = the bf16 bits in the upper half
               lw[e] = gemm::pack_bf16x2(l0, l1);
+              if constexpr (H8) {   // fp16 + residual / hi bytes instead of the bf16 pair
+                hw[e] = ptx::pack_f16x2_sat(z0, z1);
+                const ptx::f32x2 h2 = ptx::f16x2_to_f32x2(hw[e]);
+                ptx::upk2(ptx::mul2(ptx::sub2(z, h2), ptx::splat2(512.f)), lo8[2 * e], lo8[2 * e + 1]);
+                ptx::upk2(ptx::mul2(h2, ptx::splat2(0.25f)), hi8[2 * e], hi8[2 * e + 1]);
+              }
             }
             // 16-byte chunk (half * 4 + c) of this row's 128-byte bf16 row (same SWIZZLE_128B pattern as the fp32 tile)
             *reinterpret_cast<uint4*>(hb + off_f32(lane, half * 4 + c)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            if constexpr (H8) {  // byte tile: residual bytes in chunks 0..3, hi bytes in chunks 4..7, 8 bytes per 8 columns
+              *reinterpret_cast<uint2*>(lb + off_f32(lane, half * 2 + (c >> 1)) + (c & 1) * 8) =
+                  make_uint2(ptx::pack_e4m3x4(lo8[0], lo8[1], lo8[2], lo8[3]), ptx::pack_e4m3x4(lo8[4], lo8[5], lo8[6], lo8[7]));
+              *reinterpret_cast<uint2*>(lb + off_f32(lane, 4 + half * 2 + (c >> 1)) + (c & 1) * 8) =
+                  make_uint2(ptx::pack_e4m3x4(hi8[0], hi8[1], hi8[2], hi8[3]), ptx::pack_e4m3x4(hi8[4], hi8[5], hi8[6], hi8[7]));
+            } else {
             *reinterpret_cast<uint4*>(lb + off_f32(lane, half * 4 + c)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
           }
         } else {
 #pragma unroll
@@ -747,7 +805,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             __syncwarp();
             if (lane == 0) {
               ptx::tma_store_2d(&tm_ohi, hb, n_base + 2 * SC * u, row0, p.pol_store);
-              ptx::tma_store_2d(&tm_olo, lb, n_base + 2 * SC * u, row0, p.pol_store);
+              ptx::tma_store_2d(&tm_olo, lb, OLO * (n_base + 2 * SC * u), row0, p.pol_store);
               ptx::bulk_commit();
             }
           }
@@ -806,20 +864,20 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
 }
 
-template <bool SPLIT, bool CHAIN, int EW, bool LN = true, bool R16 = false, bool M8 = false>
+template <bool SPLIT, bool CHAIN, int EW, bool LN = true, bool R16 = false, bool M8 = false, bool H8 = false>
 inline cudaError_t launch_impl(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                                const CUtensorMap& w_lo, const CUtensorMap& res, const CUtensorMap& c,
                                const CUtensorMap& ohi, const CUtensorMap& olo, const Params& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_ln_kernel<SPLIT, CHAIN, EW, LN, R16, M8>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_ln_kernel<SPLIT, CHAIN, EW, LN, R16, M8, H8>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const int64_t tiles = ceil_div(p.M, 2 * BM);
   const int clusters = (int)(tiles < kNumSMs / 2 ? tiles : kNumSMs / 2);
-  return launch_pdl(gemm_ln_kernel<SPLIT, CHAIN, EW, LN, R16, M8>, dim3(2 * clusters), dim3(Epi<EW, CHAIN>::THREADS), SMEM_BYTES,
+  return launch_pdl(gemm_ln_kernel<SPLIT, CHAIN, EW, LN, R16, M8, H8>, dim3(2 * clusters), dim3(Epi<EW, CHAIN>::THREADS), SMEM_BYTES,
                     stream, a_hi, a_lo, w_hi, w_lo, res, c, ohi, olo, p);
 }
 
@@ -843,10 +901,12 @@ inline cudaError_t launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, cons
 }
 
 // mixed8 operands (see the header comment): a16 / a8 / w16 / w8 maps, (hi, lo) residual stream; K must be a multiple of 128
+// h8: the residual stream is the mixed8 pack too (ohi = fp16 map, olo = byte map [M, 1024] with 32 x 128-byte boxes)
 template <bool CHAIN>
 inline cudaError_t launch_m8(const CUtensorMap& a16, const CUtensorMap& a8, const CUtensorMap& w16, const CUtensorMap& w8,
                              const CUtensorMap& c, const CUtensorMap& ohi, const CUtensorMap& olo, const Params& p,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, bool h8 = false) {
+  if (h8) return launch_impl<true, CHAIN, 8, true, true, true, true>(a16, a8, w16, w8, ohi, c, ohi, olo, p, stream);
   return launch_impl<true, CHAIN, 8, true, true, true>(a16, a8, w16, w8, ohi, c, ohi, olo, p, stream);
 }
 
@@ -857,6 +917,12 @@ inline cudaError_t launch_noln(const CUtensorMap& a_hi, const CUtensorMap& a_lo,
                                const CUtensorMap& w_lo, const CUtensorMap& res, const CUtensorMap& out32,
                                const CUtensorMap& ohi, const CUtensorMap& olo, const Params& p, cudaStream_t stream) {
   return launch_impl<SPLIT, false, 8, false>(a_hi, a_lo, w_hi, w_lo, res, out32, ohi, olo, p, stream);
+}
+// the same with h written as the mixed8 pack (ohi = fp16 map, olo = byte map): input projection under precision 'mixed8h'
+inline cudaError_t launch_noln_h8(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                                  const CUtensorMap& w_lo, const CUtensorMap& res, const CUtensorMap& out32,
+                                  const CUtensorMap& ohi, const CUtensorMap& olo, const Params& p, cudaStream_t stream) {
+  return launch_impl<true, false, 8, false, false, false, true>(a_hi, a_lo, w_hi, w_lo, res, out32, ohi, olo, p, stream);
 }
 
 }  // namespace gemmln

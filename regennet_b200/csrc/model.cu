@@ -30,8 +30,17 @@ struct SplitBuf {  // bf16 (hi, lo) operand pair + its TMA maps
   bool has64 = false;            // tm_hi3 / tm_lo3 (64-row boxes) are valid
 };
 
+// mixed8 pack of one weight matrix [rows, K] for the pair GEMM's mixed8 main loop: fp16 halves + byte rows [rows, 2K], with
+// the 128- (tile), 64- and 32-row (tail slice) boxes of both
+struct M8W {
+  uint16_t* w16 = nullptr;
+  uint8_t* w8 = nullptr;
+  CUtensorMap tm16, tm8, tm16_64, tm8_64, tm16_32, tm8_32;
+};
+
 struct LayerDev {
   SplitBuf wqkv, wo, w1, w2;
+  M8W m_qkv, m_w1;   // precision 'mixed8h' only
   // precision 'mixed8' only: linear2 weights as fp16 [512, 1024] + e4m3 bytes [512, 2048] (per 64 columns: hi * 2^6 | lo * 2^17) for the
   // fused linear2 + LayerNorm kernel (the bf16 pair above still serves the small-batch route)
   uint16_t *w2_16 = nullptr, *wo_16 = nullptr;
@@ -76,6 +85,10 @@ struct regen_handle {
   CUtensorMap tm_ffn8, st_ffn8;      // load map (box 128 rows x 128 B) / store map (box 32 rows x 128 B, rows = M)
   // the attention output the same way: fp16 in att.hi's memory, bytes [M, 1024] in att.lo's memory
   CUtensorMap tm_att8, st_att8;      // 2-D load map (box 128 rows x 128 B) / 3-D store map [S, Beff, 1024] (box 32 frames x 128 B)
+  // precision 'mixed8h', fused route, arch 'online': the residual stream h the same way (fp16 in h_s.hi's memory, bytes
+  // [M, 1024] in h_s.lo's memory), read by the mixed8 main loop of the QKV / FFN1 / output GEMMs (A operand) and as the residual
+  CUtensorMap tm_h8, st_h8;          // load map (box 128 rows x 128 B) / store + residual map (box 32 rows x 128 B, rows = M)
+  M8W m_out;                         // output projection weights in the mixed8 pack
   CUtensorMap st_h, st_tmp, st_x0e;  // store-side maps of the fp32 activation buffers (rows = M)
   CUtensorMap st32_h;                // h with box 32 x 32: residual load + store of the fused GEMM+LayerNorm kernel
   bool tma_store = true;             // REGEN_DEBUG_NO_TMA_STORE=1: st.global epilogue (A/B measurements)
@@ -167,6 +180,25 @@ int alloc_split(regen_handle* h, SplitBuf* s, size_t rows, size_t cols, uint32_t
   return REGEN_OK;
 }
 
+int alloc_m8w(regen_handle* h, M8W* w, size_t rows, size_t K) {
+  TRY(h->alloc(&w->w16, rows * K));
+  TRY(h->alloc(&w->w8, rows * 2 * K));
+  REGEN_CUDA(cudaMemset(w->w16, 0, rows * K * 2));
+  REGEN_CUDA(cudaMemset(w->w8, 0, rows * 2 * K));
+  TRY(make_tmap_bf16_2d(&w->tm16, w->w16, rows, K, K, 128));
+  TRY(make_tmap_bf16_2d(&w->tm16_64, w->w16, rows, K, K, 64));
+  TRY(make_tmap_bf16_2d(&w->tm16_32, w->w16, rows, K, K, 32));
+  TRY(make_tmap_u8_2d(&w->tm8, w->w8, rows, 2 * K, 2 * K, 128, 128));
+  TRY(make_tmap_u8_2d(&w->tm8_64, w->w8, rows, 2 * K, 2 * K, 64, 128));
+  TRY(make_tmap_u8_2d(&w->tm8_32, w->w8, rows, 2 * K, 2 * K, 32, 128));
+  return REGEN_OK;
+}
+
+void pack_m8w(const float* src, M8W* w, int rows, int K, cudaStream_t s) {
+  layers::pack_m8_kernel<<<grid_cap(ceil_div((int64_t)rows * K / 4, 256)), 256, 0, s>>>(src, w->w16, w->w8, rows, K, 0);
+  count_launch();
+}
+
 int copy_vec(regen_handle* h, float** dst, const float* src, size_t n, cudaStream_t s) {
   TRY(h->alloc(dst, n));
   REGEN_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -197,8 +229,9 @@ bool qkv_timeline() {
 
 // o32: store-side maps {box 16, box 32} of the fp32 output named in p; osplit: the bf16-pair output buffer
 // (null -> st.global epilogue)
+// m8w != null: A (a.tm_hi = fp16 halves, *a8 = byte rows) and W (*m8w) are the mixed8 operand pack: pair kernel, mixed8 main loop
 int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, gemm::Params p, const CUtensorMap* o32,
-             const SplitBuf* osplit, cudaStream_t s) {
+             const SplitBuf* osplit, cudaStream_t s, const CUtensorMap* a8 = nullptr, const M8W* m8w = nullptr) {
   ProfScope prof(h, CLS_GEMM, s);
   gemm::OutMaps om;
   p.tma_store = 0;
@@ -233,7 +266,15 @@ int run_gemm(regen_handle* h, const SplitBuf& a, const SplitBuf& w, gemm::Params
   }
   if (qkv_timeline() && p.N == 3 * D) p.timeline = g_test_timeline;  // bring-up: pipeline stamps of the QKV GEMM inside a real forward
   cudaError_t e;
-  if (use_pair_kernel(p.M)) {
+  if (m8w) {
+    if (!use_pair_kernel(p.M) || !p.tma_store) {
+      set_error("run_gemm: the mixed8 main loop needs the pair kernel with TMA stores");
+      return REGEN_EINVAL;
+    }
+    gemm::SliceMaps sm;
+    if (h->narrow_slices) { sm.hi32 = &m8w->tm16_32; sm.lo32 = &m8w->tm8_32; sm.hi64 = &m8w->tm16_64; sm.lo64 = &m8w->tm8_64; }
+    e = gemm::launch2_m8<256>(a.tm_hi, *a8, m8w->tm16, m8w->tm8, om, p, s, sm);
+  } else if (use_pair_kernel(p.M)) {
     gemm::SliceMaps sm;
     if (h->narrow_slices) { sm.hi32 = &w.tm_hi4; sm.lo32 = &w.tm_lo4; sm.hi64 = &w.tm_hi3; sm.lo64 = &w.tm_lo3; }
     e = h->desc.precision != 1 ? gemm::launch2<256, true>(a.tm_hi, a.tm_lo, w.tm_hi2, w.tm_lo2, om, p, s, sm)
@@ -277,8 +318,8 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
                   d->num_layers);
   REGEN_CHECK_ARG(d->input_feats >= 1 && d->input_feats <= 4096, "regen_create: bad input_feats %d", d->input_feats);
   REGEN_CHECK_ARG(d->cm_mode == 0 || d->cm_mode == 1, "regen_create: cm_mode must be 0 (add) or 1 (concat)");
-  REGEN_CHECK_ARG(d->precision >= 0 && d->precision <= 2,
-                  "regen_create: precision must be 0 (bf16x3), 1 (bf16) or 2 (mixed8: bf16x3 + fp16/e4m3 linear2)");
+  REGEN_CHECK_ARG(d->precision >= 0 && d->precision <= 3,
+                  "regen_create: precision must be 0 (bf16x3), 1 (bf16), 2 (mixed8) or 3 (mixed8h)");
   REGEN_CHECK_ARG(d->arch == 0 || d->arch == 1, "regen_create: arch must be 0 ('online') or 1 ('offline')");
   REGEN_CHECK_ARG(d->max_batch >= 1 && d->max_frames >= 1 && d->num_table_steps >= 1, "regen_create: bad sizes");
   // more than 256 tokens per sample run the streaming CUDA-core attention (attn::attention_long_kernel); the positional
@@ -334,7 +375,7 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
       if ((rc = alloc_split(h, &ld.wo, D, D, 256))) break;
       if ((rc = alloc_split(h, &ld.w1, FF, D, 256))) break;
       if ((rc = alloc_split(h, &ld.w2, D, FF, 256))) break;
-      if (d->precision == 2) {
+      if (d->precision >= 2) {
         if ((rc = h->alloc(&ld.w2_16, (size_t)D * FF))) break;
         if ((rc = h->alloc(&ld.w2_8, (size_t)D * 2 * FF))) break;
         if ((rc = make_tmap_bf16_2d(&ld.tm_w2_16, ld.w2_16, D, FF, FF, 128))) break;
@@ -343,6 +384,10 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
         if ((rc = h->alloc(&ld.wo_8, (size_t)D * 2 * D))) break;
         if ((rc = make_tmap_bf16_2d(&ld.tm_wo_16, ld.wo_16, D, D, D, 128))) break;
         if ((rc = make_tmap_u8_2d(&ld.tm_wo_8, ld.wo_8, D, 2 * D, 2 * D, 128, 128))) break;
+      }
+      if (d->precision == 3) {
+        if ((rc = alloc_m8w(h, &ld.m_qkv, 3 * D, D))) break;
+        if ((rc = alloc_m8w(h, &ld.m_w1, FF, D))) break;
       }
     }
     if (rc) break;
@@ -357,8 +402,10 @@ int regen_create(regen_handle** out, int32_t device, const regen_model_desc* d) 
     if ((rc = alloc_split(h, &h->h_s, Mx, D, 128))) break;
     if ((rc = alloc_split(h, &h->att, Mx, D, 128))) break;
     if ((rc = alloc_split(h, &h->ffn, Mx, FF, 128))) break;
-    if (d->precision == 2 && (rc = make_tmap_u8_2d(&h->tm_ffn8, h->ffn.lo, Mx, 2 * FF, 2 * FF, 128, 128))) break;
-    if (d->precision == 2 && (rc = make_tmap_u8_2d(&h->tm_att8, h->att.lo, Mx, 2 * D, 2 * D, 128, 128))) break;
+    if (d->precision >= 2 && (rc = make_tmap_u8_2d(&h->tm_ffn8, h->ffn.lo, Mx, 2 * FF, 2 * FF, 128, 128))) break;
+    if (d->precision >= 2 && (rc = make_tmap_u8_2d(&h->tm_att8, h->att.lo, Mx, 2 * D, 2 * D, 128, 128))) break;
+    if (d->precision == 3 && (rc = make_tmap_u8_2d(&h->tm_h8, h->h_s.lo, Mx, 2 * D, 2 * D, 128, 128))) break;
+    if (d->precision == 3 && (rc = alloc_m8w(h, &h->m_out, h->I, D))) break;
     if ((rc = alloc_split(h, &h->qkv_s, Mx, 3 * D, 128))) break;
     if ((rc = h->alloc(&h->h, Mx * D))) break;
     if ((rc = h->alloc(&h->qkv, Mx * 3 * D))) break;
@@ -448,6 +495,7 @@ int regen_load_weights(regen_handle* h, const regen_weight_ptrs* w, void* stream
     layers::launch_sgemm(w->in_b, 1, 1, one_d, 1, 1, nullptr, w->cmo_b, h->b_c, 1, D, 1, 1, 0, s);
   }
   layers::launch_split_rows(w->out_w, D, h->w_out.hi, h->w_out.lo, D, D, I, 1, 1, s);
+  if (h->desc.precision == 3) pack_m8w(w->out_w, &h->m_out, I, D, s);
 
   for (int l = 0; l < L; ++l) {
     const regen_layer_weights& lw = w->layers[l];
@@ -461,10 +509,14 @@ int regen_load_weights(regen_handle* h, const regen_weight_ptrs* w, void* stream
     layers::launch_split_rows(lw.o_w, D, ld.wo.hi, ld.wo.lo, D, D, D, 1, 1, s);
     layers::launch_split_rows(lw.l1_w, D, ld.w1.hi, ld.w1.lo, D, D, FF, 1, 1, s);
     layers::launch_split_rows(lw.l2_w, FF, ld.w2.hi, ld.w2.lo, FF, FF, D, 1, 1, s);
-    if (h->desc.precision == 2) {
+    if (h->desc.precision >= 2) {
       layers::pack_m8_kernel<<<grid_cap(ceil_div((int64_t)D * FF / 4, 256)), 256, 0, s>>>(lw.l2_w, ld.w2_16, ld.w2_8, D, FF, 0);
       layers::pack_m8_kernel<<<grid_cap(ceil_div((int64_t)D * D / 4, 256)), 256, 0, s>>>(lw.o_w, ld.wo_16, ld.wo_8, D, D, 0);
       count_launch();
+    }
+    if (h->desc.precision == 3) {
+      pack_m8w(lw.qkv_w, &ld.m_qkv, 3 * D, D, s);
+      pack_m8w(lw.l1_w, &ld.m_w1, FF, D, s);
     }
     TRY(copy_vec(h, &ld.bqkv, lw.qkv_b, 3 * D, s));
     TRY(copy_vec(h, &ld.bo, lw.o_b, D, s));
@@ -548,7 +600,7 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
     TRY(make_tmap_store_2d(&sb->st64_hi, sb->hi, true, h->M, sb->cols, sb->cols, 64));
     TRY(make_tmap_store_2d(&sb->st64_lo, sb->lo, true, h->M, sb->cols, sb->cols, 64));
   }
-  if (h->desc.precision == 2) TRY(make_tmap_u8_2d(&h->st_ffn8, h->ffn.lo, h->M, 2 * FF, 2 * FF, 32, 128));
+  if (h->desc.precision >= 2) TRY(make_tmap_u8_2d(&h->st_ffn8, h->ffn.lo, h->M, 2 * FF, 2 * FF, 32, 128));
   TRY(make_tmap_store_2d(&h->st32_h, h->h, false, h->M, D, D, 32));
   TRY(make_tmap_store_2d(&h->ld32_condbias, h->condbias, false, Mf, D, D, 32));
   if (h->offline) {
@@ -582,7 +634,8 @@ int regen_prepare_cond(regen_handle* h, const float* cmotion_bjft, const int64_t
   TRY(make_tmap_bf16_3d(&h->tm_qkv_lo, h->qkv_s.lo, 3 * D, Beff, S, qkv_box));
   TRY(make_tmap_bf16_3d(&h->tm_att_hi, h->att.hi, D, Beff, S, 32));
   TRY(make_tmap_bf16_3d(&h->tm_att_lo, h->att.lo, D, Beff, S, 32));
-  if (h->desc.precision == 2) TRY(make_tmap_u8_3d(&h->st_att8, h->att.lo, 2 * D, Beff, S, 32, 128));
+  if (h->desc.precision == 3) TRY(make_tmap_u8_2d(&h->st_h8, h->h_s.lo, h->M, 2 * D, 2 * D, 32, 128));
+  if (h->desc.precision >= 2) TRY(make_tmap_u8_3d(&h->st_att8, h->att.lo, 2 * D, Beff, S, 32, 128));
   if (h->has_cond) {
     // cond_emb[b'] for b' in [0, Beff): conditional rows [0,B), unconditional rows [B,2B) under guidance
     if (text_model) {
@@ -634,10 +687,13 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
   // precision 'mixed8': on the fused route linear2 runs as one fp16 MMA + two e4m3 correction MMAs per product (2 instead
   // of 3 bf16-MMA equivalents); FFN1's epilogue writes its activations in that operand format.  Everything else, and
   // the whole small-batch route, is bf16x3.
-  const bool m8 = h->desc.precision == 2 && fused && h->tma_store && h->store64 && h->res16;
+  const bool m8 = h->desc.precision >= 2 && fused && h->tma_store && h->store64 && h->res16;
   // ... and the attention output projection the same way when a tcgen05 attention kernel (which can write that format) runs
   const bool m8_att = m8 && !h->simt_attention && S <= 256;
   const int Mf = T * Beff;                              // frame rows
+  // precision 'mixed8h' (arch 'online'): the residual stream h is the mixed8 pack as well, so the input projection writes it,
+  // both fused kernels load / store it, and QKV / FFN1 / the output projection run the mixed8 main loop on it
+  const bool m8h = m8_att && h->desc.precision == 3 && !offline && Mf > 128 && (I & 3) == 0;
   const size_t fr_off = offline ? (size_t)Beff * D : 0;  // offline: the frames follow the Beff condition-token rows
 
   // A operand of the input projection: split x into bf16 (hi, lo), K padded to a multiple of 64,
@@ -676,7 +732,9 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
         q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;
       }
       const SplitBuf& ob = offline ? h->h_fr : h->h_s;
-      cudaError_t e = h->desc.precision != 1
+      cudaError_t e = m8h ? gemmln::launch_noln_h8(h->a_in.tm_hi, h->a_in.tm_lo, h->w_in.tm_hi2, h->w_in.tm_lo2,
+                                                     h->ld32_condbias, hmaps[1], ob.st64_hi, h->st_h8, q, s)
+          : h->desc.precision != 1
           ? gemmln::launch_noln<true>(h->a_in.tm_hi, h->a_in.tm_lo, h->w_in.tm_hi2, h->w_in.tm_lo2, h->ld32_condbias,
                                       hmaps[1], ob.st64_hi, ob.st64_lo, q, s)
           : gemmln::launch_noln<false>(h->a_in.tm_hi, h->a_in.tm_lo, h->w_in.tm_hi2, h->w_in.tm_lo2, h->ld32_condbias,
@@ -704,7 +762,8 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       p.bias = ld.bqkv;
       p.out_hi = h->qkv_s.hi; p.out_lo = h->qkv_s.lo; p.ld_split = 3 * D;
       if (h->simt_attention) { p.out_f32 = h->qkv; p.ld_out = 3 * D; }
-      TRY(run_gemm(h, h->h_s, ld.wqkv, p, nullptr, h->simt_attention ? nullptr : &h->qkv_s, s));
+      TRY(run_gemm(h, h->h_s, ld.wqkv, p, nullptr, h->simt_attention ? nullptr : &h->qkv_s, s, m8h ? &h->tm_h8 : nullptr,
+                   m8h ? &ld.m_qkv : nullptr));
     }
     {
       ProfScope prof(h, CLS_ATTN, s);
@@ -770,7 +829,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
         q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;
       }
       cudaError_t e = m8_att ? gemmln::launch_m8<true>(h->att.tm_hi, h->tm_att8, ld.tm_wo_16, ld.tm_wo_8, h->tm_cyc[l],
-                                                       h->h_s.st64_hi, h->h_s.st64_lo, q, s)
+                                                       h->h_s.st64_hi, m8h ? h->st_h8 : h->h_s.st64_lo, q, s, m8h)
           : h->desc.precision != 1
           ? gemmln::launch<true, true>(h->att.tm_hi, h->att.tm_lo, ld.wo.tm_hi2, ld.wo.tm_lo2, h->st32_h, h->tm_cyc[l],
                                        h->h_s.st64_hi, h->h_s.st64_lo, q, s, h->res16)
@@ -815,7 +874,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       gemm::Params p = gp(M, FF, D);
       p.bias = ld.b1; p.gelu = 1; p.m8 = m8 ? 1 : 0;
       p.out_hi = h->ffn.hi; p.out_lo = h->ffn.lo; p.ld_split = FF;
-      TRY(run_gemm(h, h->h_s, ld.w1, p, nullptr, &h->ffn, s));
+      TRY(run_gemm(h, h->h_s, ld.w1, p, nullptr, &h->ffn, s, m8h ? &h->tm_h8 : nullptr, m8h ? &ld.m_w1 : nullptr));
     }
     if (fused) {  // h = LN3(h + ffn . W_2^T + b_2)   -- one kernel (encoder layer: norm2)
       ProfScope prof(h, CLS_GEMM, s);
@@ -831,7 +890,7 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
         q.steplog = h->steplog; q.steplog_slot = h->steplog_slot++; q.steplog_cta = 2 * h->steplog_cap;
       }
       cudaError_t e = m8 ? gemmln::launch_m8<false>(h->ffn.tm_hi, h->tm_ffn8, ld.tm_w2_16, ld.tm_w2_8, h->st32_h,
-                                                    h->h_s.st64_hi, h->h_s.st64_lo, q, s)
+                                                    h->h_s.st64_hi, m8h ? h->st_h8 : h->h_s.st64_lo, q, s, m8h)
           : h->desc.precision != 1
           ? gemmln::launch<true, false>(h->ffn.tm_hi, h->ffn.tm_lo, ld.w2.tm_hi2, ld.w2.tm_lo2, h->st32_h, h->st32_h,
                                         h->h_s.st64_hi, h->h_s.st64_lo, q, s, h->res16)
@@ -876,7 +935,8 @@ int regen_denoise(regen_handle* h, const float* x_tbi, const int64_t* t, const f
       TRY(make_tmap_store_2d(&st_x0[1], dst, false, Mf, I, I, 32));
       om = st_x0;
     }
-    TRY(run_gemm(h, offline ? h->h_fr : h->h_s, h->w_out, p, om, nullptr, s));
+    TRY(run_gemm(h, offline ? h->h_fr : h->h_s, h->w_out, p, om, nullptr, s, m8h ? &h->tm_h8 : nullptr,
+                 m8h ? &h->m_out : nullptr));
   }
   if (h->guidance) {
     int64_t total = (int64_t)T * B * I;

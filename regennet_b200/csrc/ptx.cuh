@@ -418,6 +418,15 @@ __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float
   return r;
 }
 
+// two e4m3 bytes (low 16 bits of w) as fp32: e4m3x2 -> f16x2 is exact, then f16 -> f32
+__device__ __forceinline__ f32x2 e4m3x2_to_f32x2(uint32_t w) {
+  float lo, hi;
+  asm("{\n\t.reg .b16 e, l, h;\n\t.reg .b32 t;\n\tcvt.u16.u32 e, %2;\n\tcvt.rn.f16x2.e4m3x2 t, e;\n\tmov.b32 {l, h}, t;\n\t"
+      "cvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}"
+      : "=f"(lo), "=f"(hi) : "r"(w));
+  return pk2(lo, hi);
+}
+
 // ---------------------------------------------------------------- descriptors
 // UMMA shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of exactly 128 bytes
 // (64 bf16), 8-row swizzle atoms stacked every 1024 bytes (cute UMMA::SmemDescriptor):

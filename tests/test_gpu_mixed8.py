@@ -9,6 +9,7 @@ import torch
 import cases
 from oracle import cmdm_ref
 from regennet_b200 import synthetic
+from regennet_b200.cfg_sampler import ClassifierFreeSampleModel
 from regennet_b200.cmdm import CMDM
 from test_gpu_denoiser import _kw, get_model, to_cuda
 from test_gpu_parity_stress import _outlier_state_dict
@@ -60,6 +61,36 @@ def test_forward_matches_oracle_and_bf16x3(built_lib, B, T, precision):
     assert err < (TOL_M8 if precision == "mixed8" else 2 * TOL_M8)
     assert d < 2 * TOL_M8
     assert d > 0.0   # the route really ran (a silent bf16x3 fallback would be bit-identical)
+
+
+@pytest.mark.parametrize("precision", ["mixed8", "mixed8h"])
+@pytest.mark.parametrize("name,model_name,B,T", [("config3", "chi3d", 128, 150), ("config5", "hml", 64, 196)])
+def test_guided_configs_match_oracle_on_a_subset(built_lib, name, model_name, B, T, precision):
+    """BASELINE configs 3 (Chi3D, action-conditioned) and 5 (HumanML-shaped text model, 263 input features: not a multiple of
+    4, so 'mixed8h' keeps the bf16-pair residual stream there and runs like 'mixed8') under classifier-free guidance at their
+    full per-GPU sizes -- the shapes bench.py's other_configs runs with the GPU arm's precision."""
+    mk = cases.MODELS[model_name]
+    _, sd = get_model(model_name, 0)
+    key = (model_name, precision)
+    if key not in _m8:
+        m = CMDM(precision=precision, **mk)
+        m.load_state_dict(sd, strict=False)
+        _m8[key] = m.cuda().eval()
+    run = ClassifierFreeSampleModel(_m8[key])
+    x, y = synthetic.make_inputs(B, mk["njoints"], mk["nfeats"], T, seed=400 + B, cond_mode=mk["cond_mode"],
+                                 num_actions=mk["num_actions"], scale=2.5)
+    t = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(B + T))
+    with torch.no_grad():
+        out = run(x.cuda(), t.cuda(), to_cuda(y)).cpu()
+    assert out.shape == x.shape and torch.isfinite(out).all()
+    sel = torch.tensor([0, B // 2 - 1, B - 1])
+    ysel = {k: (v[sel] if torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == B else v) for k, v in y.items()}
+    with torch.no_grad():
+        want = cmdm_ref.cfg_forward(sd, x[sel], t[sel], ysel, **_kw(mk))
+    err = (out[sel] - want).abs().max().item()
+    print("%s %s (B=%d, T=%d, CFG 2.5): max abs err vs oracle on 3 samples %.3e (absmax %.2f)" % (
+        precision, name, B, T, err, want.abs().max()))
+    assert err < TOL   # guidance amplifies the difference of the two forwards (2.5 x cond - 1.5 x uncond)
 
 
 @pytest.mark.parametrize("precision", ["mixed8", "mixed8h"])

@@ -67,3 +67,48 @@ def test_beyond_the_range_degrades_to_fp16_accuracy_not_worse():
     rel1 = ((fp16_x1(a, w).double() - want).abs().max() / want.abs().max()).item()
     print("saturated: mixed8 rel %.3e, fp16 single rel %.3e" % (rel, rel1))
     assert math.isfinite(rel) and rel < 3 * rel1 + 1e-6
+
+
+# ---------------------------------------------------------------- precision 'mixed8h': the residual stream in that pack
+def h8_roundtrip(h):
+    """What gemm_ln_kernel<.., H8> stores for the residual stream h and what its next residual load rebuilds:
+    fp16(h) + e4m3((h - fp16(h)) * 2^9) * 2^-9  (the third byte, e4m3(fp16(h) / 4), only feeds the correction MMAs)."""
+    h16 = _f16(h)
+    return h16 + _e4m3((h - h16) * 2.0 ** 9) * 2.0 ** -9
+
+
+def test_h8_residual_stream_keeps_about_15_significand_bits():
+    g = torch.Generator().manual_seed(3)
+    h = torch.randn(4096, 512, generator=g) * 1.5          # LayerNorm outputs: O(1) with a tail of a few units
+    back = h8_roundtrip(h)
+    err = (back - h).abs()
+    # residual <= 2^-11 |h| (half an fp16 ulp), kept to 4 significand bits by e4m3 -> 2^-15 |h|; below |h| ~ 1/16 the scaled
+    # residual falls into e4m3's subnormals (step 2^-9): absolute error <= 2^-10 * 2^-9
+    bound = torch.maximum(h.abs() * 2.0 ** -15, torch.tensor(2.0 ** -19))
+    bf16_pair = h.to(torch.bfloat16).float()
+    bf16_pair = bf16_pair + (h - bf16_pair).to(torch.bfloat16).float()
+    print("h8 round trip: max abs err %.3e (bf16 pair: %.3e), max err / bound %.3f" % (
+        err.max(), (bf16_pair - h).abs().max(), (err / bound).max()))
+    assert (err <= bound).all()
+    assert err.max().item() < 2e-4 * 1.5
+
+
+def test_h8_subnormal_and_large_values_degrade_gracefully():
+    h = torch.tensor([0.0, 1e-6, -3e-5, 0.37, -5.0, 250.0, 1500.0, 40000.0, 1e6])
+    back = h8_roundtrip(h)
+    assert torch.isfinite(back).all()
+    assert back[0].item() == 0.0
+    assert (back[:7] - h[:7]).abs().max().item() <= 2.0 ** -13 * 1500.0 / 2   # residual of 1500: (ulp 1) * 2^-5
+    assert abs(back[7].item() - 40000.0) <= 16.0 + 1.0       # fp16 ulp 32 at 4e4; the scaled residual (<= 16 * 2^9) saturates at 448
+    assert back[8].item() == pytest.approx(65504.0 + 448.0 / 512.0)   # satfinite fp16, saturated residual byte
+
+
+def test_h8_operands_give_the_same_product_accuracy():
+    """QKV / FFN1 under mixed8h: A = the stored pack of h (fp16 | residual byte | hi byte), i.e. mixed8_matmul on h itself."""
+    g = torch.Generator().manual_seed(11)
+    h = torch.randn(256, 512, generator=g)
+    w = (torch.rand(384, 512, generator=g) * 2 - 1) / math.sqrt(512)
+    want = h.double() @ w.double().t()
+    err = (mixed8_matmul(h, w).double() - want).abs().max().item()
+    print("mixed8h QKV-shaped product: %.3e" % err)
+    assert err < 5e-5

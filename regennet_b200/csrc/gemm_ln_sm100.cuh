@@ -450,8 +450,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               *reinterpret_cast<uint2*>(lb + off_f32(lane, 4 + half * 2 + (c >> 1)) + (c & 1) * 8) =
                   make_uint2(ptx::pack_e4m3x4(hi8[0], hi8[1], hi8[2], hi8[3]), ptx::pack_e4m3x4(hi8[4], hi8[5], hi8[6], hi8[7]));
             } else {
-            *reinterpret_cast<uint4*>(hb + off_f32(lane, half * 4 + c)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(lb + off_f32(lane, half * 4 + c)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              *reinterpret_cast<uint4*>(hb + off_f32(lane, half * 4 + c)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(lb + off_f32(lane, half * 4 + c)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
           }
           ptx::fence_proxy_async_smem();
@@ -770,7 +770,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
               *reinterpret_cast<uint2*>(lb + off_f32(lane, 4 + half * 2 + (c >> 1)) + (c & 1) * 8) =
                   make_uint2(ptx::pack_e4m3x4(hi8[0], hi8[1], hi8[2], hi8[3]), ptx::pack_e4m3x4(hi8[4], hi8[5], hi8[6], hi8[7]));
             } else {
-            *reinterpret_cast<uint4*>(lb + off_f32(lane, half * 4 + c)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              *reinterpret_cast<uint4*>(lb + off_f32(lane, half * 4 + c)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
           }
         } else {

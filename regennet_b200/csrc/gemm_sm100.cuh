@@ -467,13 +467,13 @@ __device__ __forceinline__ void epilogue_pair64(const Params& p, const CUtensorM
         lw[8 + 2 * c + 1] = ptx::pack_e4m3x4(hf[4], hf[5], hf[6], hf[7]);
       } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float a = __uint_as_float(r[8 * c + 2 * k]), b = __uint_as_float(r[8 * c + 2 * k + 1]);
-        hw[k] = pack_bf16x2(a, b);
-        float l0, l1;   // float(hi) is the bf16 bit pattern in the upper half of the word
-        ptx::upk2(ptx::sub2(ptx::pk2(a, b), ptx::bf16x2_to_f32x2(hw[k])), l0, l1);
-        lw[4 * c + k] = pack_bf16x2(l0, l1);
-      }
+        for (int k = 0; k < 4; ++k) {
+          const float a = __uint_as_float(r[8 * c + 2 * k]), b = __uint_as_float(r[8 * c + 2 * k + 1]);
+          hw[k] = pack_bf16x2(a, b);
+          float l0, l1;   // float(hi) is the bf16 bit pattern in the upper half of the word
+          ptx::upk2(ptx::sub2(ptx::pk2(a, b), ptx::bf16x2_to_f32x2(hw[k])), l0, l1);
+          lw[4 * c + k] = pack_bf16x2(l0, l1);
+        }
       }
       *reinterpret_cast<uint4*>(stg + stg_off_128(lane, 4 * sub + c)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     }

@@ -78,3 +78,16 @@ def test_gpu_arm_line_has_every_contract_key():
             bound |= {t.id for t in n.targets if isinstance(t, ast.Name)}
     used = {n.id for n in ast.walk(d) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)}
     assert used <= bound, sorted(used - bound)
+
+
+def test_bench_describes_every_operand_scheme_it_can_be_switched_to():
+    """REGEN_PRECISION selects the GPU arm's operand scheme; the `dtype` string of the line is looked up per scheme."""
+    import re
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    cm = open(os.path.join(ROOT, "regennet_b200", "cmdm.py")).read()
+    schemes = set(re.findall(r"'(\w+)': \d", re.search(r"_PRECISIONS = \{([^}]*)\}", cm).group(1)))
+    assert {"bf16x3", "mixed8", "mixed8h"} <= schemes
+    dtypes = set(re.findall(r'^    "(\w+)": ', re.search(r"DTYPES = \{(.*?)\n\}", src, re.S).group(1), re.M))
+    assert schemes - {"bf16"} <= dtypes, (schemes, dtypes)          # 'bf16' (single pass, ~1e-2) is outside the path's tolerance
+    default = re.search(r'os\.environ\.get\("REGEN_PRECISION", "(\w+)"\)', src).group(1)
+    assert default in dtypes
